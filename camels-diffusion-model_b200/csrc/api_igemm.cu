@@ -1,0 +1,271 @@
+// C-ABI entry points for the tcgen05 kernels (+ library-wide error plumbing).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.h"
+#include "igemm.cuh"
+
+namespace cdm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_device() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDevice failed: %s (no CUDA device? this library has no CPU path)", cudaGetErrorString(e));
+    return CDM_ERR_CUDA;
+  }
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) {
+    set_error("cudaDeviceGetAttribute failed: %s", cudaGetErrorString(e));
+    return CDM_ERR_CUDA;
+  }
+  if (major != 10) {
+    set_error("device compute capability %d.x is not sm_100: kernels are built for sm_100a only", major);
+    return CDM_ERR_ARCH;
+  }
+  return CDM_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// libcuda is reached through the runtime so that the .so loads on a box without a driver.
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+    set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return CDM_ERR_CUDA;
+  cuuint64_t gd[5];
+  cuuint64_t gs[5];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) gs[i] = strides_bytes[i];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu, box %u %u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return CDM_ERR_CUDA;
+  }
+  return CDM_OK;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n) return n;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+
+template <int MODE>
+static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvKParams& p,
+                       cudaStream_t st) {
+  constexpr int smem = conv_smem_bytes<MODE>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    CDM_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
+  conv3x3_kernel<MODE><<<grid, kConvThreads, smem, st>>>(a0, a1, b, p);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
+}  // namespace cdm
+
+using namespace cdm;
+
+extern "C" int cdm_version(void) { return 100; }
+extern "C" const char* cdm_last_error(void) { return g_err; }
+extern "C" int cdm_device_ok(void) { return check_device(); }
+
+extern "C" int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream) {
+  CDM_CHECK_ARG(a != nullptr);
+  CDM_CHECK_ARG(a->src0 && a->weight && a->scale && a->shift && a->out);
+  CDM_CHECK_ARG(a->c0 > 0 && a->c0 % 64 == 0 && a->c1 >= 0 && a->c1 % 64 == 0);
+  CDM_CHECK_ARG((a->c1 == 0) == (a->src1 == nullptr));
+  CDM_CHECK_ARG(a->n_img > 0 && a->H >= 16 && a->W >= 16 && a->H % 16 == 0 && a->W % 16 == 0);
+  CDM_CHECK_ARG(a->cout > 0 && a->cout % 128 == 0 && a->cout <= 256);
+  CDM_CHECK_ARG(a->mode >= 0 && a->mode <= 2);
+  if (a->flags & CDM_EPI_SHORTCUT)
+    CDM_CHECK_ARG(a->sc_x && a->sc_tab && a->sc_nx > 0 && a->n_img % a->sc_nx == 0);
+  if (a->flags & CDM_EPI_FILM) CDM_CHECK_ARG(a->film_scale && a->film_shift && a->film_shift_rows >= 1);
+  if (a->flags & CDM_EPI_GNSTATS) CDM_CHECK_ARG(a->gn_partial && a->cout == 128 && !(a->flags & CDM_EPI_POOL));
+  int rc = check_device();
+  if (rc) return rc;
+
+  static const int pitch_of_mode[3] = {16, 24, 18};
+  const uint32_t pitch = pitch_of_mode[a->mode];
+  CUtensorMap mA0, mA1, mB;
+  {
+    uint64_t dims[4] = {(uint64_t)a->c0, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
+    uint64_t str[3] = {(uint64_t)a->c0 * 2, (uint64_t)a->W * a->c0 * 2, (uint64_t)a->H * a->W * a->c0 * 2};
+    uint32_t box[4] = {64, pitch, 18, 1};
+    rc = make_tmap_bf16(&mA0, a->src0, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  if (a->src1) {
+    uint64_t dims[4] = {(uint64_t)a->c1, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
+    uint64_t str[3] = {(uint64_t)a->c1 * 2, (uint64_t)a->W * a->c1 * 2, (uint64_t)a->H * a->W * a->c1 * 2};
+    uint32_t box[4] = {64, pitch, 18, 1};
+    rc = make_tmap_bf16(&mA1, a->src1, 4, dims, str, box);
+    if (rc) return rc;
+  } else {
+    mA1 = mA0;
+  }
+  const int cin = a->c0 + a->c1;
+  {
+    uint64_t dims[2] = {(uint64_t)9 * cin, (uint64_t)a->cout};
+    uint64_t str[1] = {(uint64_t)9 * cin * 2};
+    uint32_t box[2] = {64, 128};
+    rc = make_tmap_bf16(&mB, a->weight, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  ConvKParams p;
+  memset(&p, 0, sizeof(p));
+  p.H = a->H;
+  p.W = a->W;
+  p.n_img = a->n_img;
+  p.chunks0 = a->c0 / 64;
+  p.chunks = cin / 64;
+  p.n_tiles = a->cout / 128;
+  p.cout = a->cout;
+  p.strips_x = a->W / 16;
+  p.strips_y = a->H / 16;
+  p.n_units = a->n_img * p.strips_x * p.strips_y * p.n_tiles;
+  p.flags = a->flags;
+  p.scale = a->scale;
+  p.shift = a->shift;
+  p.out = reinterpret_cast<bf16*>(a->out);
+  p.sc_x = a->sc_x;
+  p.sc_nx = a->sc_nx > 0 ? a->sc_nx : 1;
+  p.sc_tab = a->sc_tab;
+  p.sc_halves = a->n_img / p.sc_nx;
+  p.film_scale = a->film_scale;
+  p.film_shift = a->film_shift;
+  p.film_shift_rows = a->film_shift_rows;
+  p.step_ptr = a->step_ptr;
+  p.gn_partial = a->gn_partial;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (a->mode) {
+    case 0: return launch_conv<0>(mA0, mA1, mB, p, st);
+    case 1: return launch_conv<1>(mA0, mA1, mB, p, st);
+    default: return launch_conv<2>(mA0, mA1, mB, p, st);
+  }
+}
+
+extern "C" int cdm_gemm(const cdm_gemm_args* a, void* stream) {
+  CDM_CHECK_ARG(a != nullptr);
+  CDM_CHECK_ARG(a->a0 && a->bw && a->shift && a->out);
+  CDM_CHECK_ARG(a->k0 > 0 && a->k0 % 64 == 0 && a->k1 >= 0 && a->k1 % 64 == 0);
+  CDM_CHECK_ARG((a->k1 == 0) == (a->a1 == nullptr));
+  CDM_CHECK_ARG(a->M > 0 && a->N > 0 && a->N % 128 == 0 && a->shift_mod > 0);
+  CDM_CHECK_ARG(a->out_mode == 0 || (a->out_mode == 1 && a->N == 512 && a->H > 0 && a->W > 0 &&
+                                     a->M % (a->H * a->W) == 0));
+  int rc = check_device();
+  if (rc) return rc;
+  CUtensorMap mA0, mA1, mB;
+  {
+    uint64_t dims[2] = {(uint64_t)a->k0, (uint64_t)a->M};
+    uint64_t str[1] = {(uint64_t)a->k0 * 2};
+    uint32_t box[2] = {64, 128};
+    rc = make_tmap_bf16(&mA0, a->a0, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  if (a->a1) {
+    uint64_t dims[2] = {(uint64_t)a->k1, (uint64_t)a->M};
+    uint64_t str[1] = {(uint64_t)a->k1 * 2};
+    uint32_t box[2] = {64, 128};
+    rc = make_tmap_bf16(&mA1, a->a1, 2, dims, str, box);
+    if (rc) return rc;
+  } else {
+    mA1 = mA0;
+  }
+  const int K = a->k0 + a->k1;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)a->N};
+    uint64_t str[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {64, 128};
+    rc = make_tmap_bf16(&mB, a->bw, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  GemmKParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->M;
+  p.N = a->N;
+  p.chunks0 = a->k0 / 64;
+  p.chunks = K / 64;
+  p.m_tiles = (a->M + 127) / 128;
+  p.n_tiles = a->N / 128;
+  p.n_units = p.m_tiles * p.n_tiles;
+  p.shift = a->shift;
+  p.shift_mod = a->shift_mod;
+  p.out_mode = a->out_mode;
+  p.H = a->H;
+  p.W = a->W;
+  p.out = reinterpret_cast<bf16*>(a->out);
+  constexpr int smem = gemm_smem_bytes();
+  static bool attr_set = false;
+  if (!attr_set) {
+    CDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
+  gemm_kernel<<<grid, kConvThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(mA0, mA1, mB, p);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
+extern "C" int cdm_probe_tma_l2(const void* buf, int n_rows, int iters, void* stream) {
+  CDM_CHECK_ARG(buf && n_rows >= 128 && n_rows % 128 == 0 && iters > 0);
+  int rc = check_device();
+  if (rc) return rc;
+  CUtensorMap m;
+  uint64_t dims[2] = {64, (uint64_t)n_rows};
+  uint64_t str[1] = {128};
+  uint32_t box[2] = {64, 128};
+  rc = make_tmap_bf16(&m, buf, 2, dims, str, box);
+  if (rc) return rc;
+  const int smem = 8 * 16384 + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CDM_CHECK_CUDA(cudaFuncSetAttribute(probe_tma_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  probe_tma_l2_kernel<<<num_sms(), 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(m, n_rows, iters);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}

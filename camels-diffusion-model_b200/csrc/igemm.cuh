@@ -1,0 +1,596 @@
+// tcgen05 implicit-GEMM kernels of the ContextUnet hot path (sm_100a only).
+//
+//   conv3x3_kernel : 3x3/s1/p1 convolution, NHWC bf16, K-split over two sources
+//                    (replaces nn.Conv2d + eval BatchNorm2d + ReLU [+ MaxPool2d,
+//                    FiLM, shortcut, GroupNorm statistics] — see cdm_b200.h)
+//   gemm_kernel    : plain K-major GEMM (ConvTranspose2d 2x2/s2 and the 16x16/s16
+//                    up0 transposed conv are GEMMs + a scatter epilogue)
+//
+// Shared structure (one CTA per SM, persistent over work units, 8 warps):
+//   warp 0  lane 0 : TMA producer of the activation (A) operand
+//   warp 3  lane 0 : TMA producer of the weight (B) operand
+//   warp 1  lane 0 : tcgen05.mma issuer (accumulators in TMEM, double buffered)
+//   warp 2         : TMEM allocator
+//   warps 4..7     : epilogue (tcgen05.ld -> fp32 math -> bf16 -> smem transpose -> coalesced stores)
+#pragma once
+#include "../../include/cdm_b200.h"
+#include "ptx.cuh"
+
+namespace cdm {
+
+typedef __nv_bfloat16 bf16;
+
+// --------------------------------------------------------------------------
+// conv3x3: geometry
+//   M-tile (one 128-row UMMA) = a patch of 8 pixels (along W) x 16 rows; TMEM
+//   lane m = row*8 + px.  The A descriptor walks the 16 rows with its stride
+//   byte offset (SBO = smem pitch * 128 B), so a patch is a strided window of
+//   one resident halo tile and every tap (kh,kw) is just a different start
+//   address: + kh*pitch rows, + kw rows.
+//   CTA work unit = strip of 16x16 pixels = 2 patches (2 accumulators), one
+//   128-wide slice of Cout.
+// --------------------------------------------------------------------------
+struct ConvKParams {
+  int H, W, n_img;
+  int chunks0, chunks;  // 64-channel K chunks from src0 / in total
+  int n_tiles, cout;
+  int strips_x, strips_y;
+  int n_units;
+  int flags;
+  const float* scale;
+  const float* shift;
+  bf16* out;
+  const float* sc_x;
+  int sc_nx;
+  const float* sc_tab;
+  int sc_halves;
+  const float* film_scale;
+  const float* film_shift;
+  int film_shift_rows;
+  const int* step_ptr;
+  float* gn_partial;
+};
+
+template <int MODE>
+struct ConvCfg;
+template <>
+struct ConvCfg<0> {  // three kw-shifted copies; descriptor starts stay 1024B-atom aligned
+  static constexpr int PITCH = 16, A_PER_CHUNK = 3, TAPS_PER_A = 3, NA = 3;
+  static constexpr int A_BYTES = 18 * PITCH * 128, A_STRIDE = 36864;
+};
+template <>
+struct ConvCfg<1> {  // one halo tile, pitch 24 (kh shift stays atom aligned, kw shift is +128 B)
+  static constexpr int PITCH = 24, A_PER_CHUNK = 1, TAPS_PER_A = 9, NA = 2;
+  static constexpr int A_BYTES = 18 * PITCH * 128, A_STRIDE = 55296;
+};
+template <>
+struct ConvCfg<2> {  // one halo tile, pitch 18 (no padding columns; SBO = 2304 B)
+  static constexpr int PITCH = 18, A_PER_CHUNK = 1, TAPS_PER_A = 9, NA = 2;
+  static constexpr int A_BYTES = 18 * PITCH * 128, A_STRIDE = 41984;
+};
+
+constexpr int kNB = 4;               // weight stages
+constexpr int kBBytes = 128 * 128;   // 128 Cout rows x 64 ch x 2 B
+constexpr int kStageBytes = 4 * 8192;  // epilogue transpose buffers, one per epilogue warp
+constexpr int kConvThreads = 256;
+
+template <int MODE>
+constexpr int conv_smem_bytes() {
+  return ConvCfg<MODE>::NA * ConvCfg<MODE>::A_STRIDE + kNB * kBBytes + kStageBytes + 2 * 256 * 4 + 256 + 1024;
+}
+
+// Epilogue of one 128x128 accumulator tile held by this warp's 32 TMEM lanes.
+// Converts to bf16 into the warp-private staging buffer (XOR-swizzled 16 B units,
+// conflict free for both the row-per-thread writes and the row-contiguous reads).
+struct EpiCtx {
+  const float* s_scale;  // smem, this n-tile's 128 entries
+  const float* s_shift;
+  int flags;
+  // shortcut
+  float xpix;
+  const float* sc_w;
+  const float* sc_b;
+  // film
+  const float* film_scale;
+  const float* film_shift;
+};
+
+__device__ __forceinline__ void epi_tile_to_staging(uint32_t taddr, uint32_t stg, int lane, const EpiCtx& e,
+                                                    float* gn_sum, float* gn_sq) {
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    uint32_t v[32];
+    tmem_ld_x32(taddr + cc * 32, v);
+    tmem_wait_ld();
+    float f[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int c = cc * 32 + i;
+      float y = fmaf(__uint_as_float(v[i]), e.s_scale[c], e.s_shift[c]);
+      if (e.flags & CDM_EPI_RELU) y = fmaxf(y, 0.f);
+      f[i] = y;
+    }
+    if (e.flags & CDM_EPI_SHORTCUT) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] += fmaf(__ldg(e.sc_w + cc * 32 + i), e.xpix, __ldg(e.sc_b + cc * 32 + i));
+    }
+    if (e.flags & CDM_EPI_FILM) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        f[i] = fmaf(__ldg(e.film_scale + cc * 32 + i), f[i], __ldg(e.film_shift + cc * 32 + i));
+    }
+    if (e.flags & CDM_EPI_GNSTATS) {
+      float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        s0 += f[i];
+        q0 = fmaf(f[i], f[i], q0);
+        s1 += f[16 + i];
+        q1 = fmaf(f[16 + i], f[16 + i], q1);
+      }
+      gn_sum[cc * 2] = s0;
+      gn_sq[cc * 2] = q0;
+      gn_sum[cc * 2 + 1] = s1;
+      gn_sq[cc * 2 + 1] = q1;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int u = cc * 4 + j;  // 16-byte unit inside this pixel's 256-byte row
+      const uint32_t addr = stg + lane * 256 + ((u ^ (lane & 7)) << 4);
+      st_shared_v4(addr, pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]), pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]),
+                   pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]), pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]));
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               const __grid_constant__ CUtensorMap mapB, const ConvKParams p) {
+  using C = ConvCfg<MODE>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smemA + C::NA * C::A_STRIDE;
+  uint8_t* smemStage = smemB + kNB * kBBytes;
+  float* s_scale = reinterpret_cast<float*>(smemStage + kStageBytes);
+  float* s_shift = s_scale + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + C::NA;
+  uint64_t* b_full = a_empty + C::NA;
+  uint64_t* b_empty = b_full + kNB;
+  uint64_t* t_full = b_empty + kNB;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < p.cout; i += blockDim.x) {
+    s_scale[i] = p.scale[i];
+    s_shift[i] = p.shift[i];
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::NA; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < kNB; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int cin = p.chunks * 64;
+  const int units_per_img = p.strips_x * p.strips_y * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------ A producer (activations)
+    tma_prefetch_desc(&mapA0);
+    tma_prefetch_desc(&mapA1);
+    int sa = 0;
+    uint32_t pa = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int img = u / units_per_img;
+      const int s = (u % units_per_img) / p.n_tiles;
+      const int sx = s % p.strips_x, sy = s / p.strips_x;
+      for (int ch = 0; ch < p.chunks; ++ch) {
+        const CUtensorMap* m = ch < p.chunks0 ? &mapA0 : &mapA1;
+        const int c_off = (ch < p.chunks0 ? ch : ch - p.chunks0) * 64;
+        for (int j = 0; j < C::A_PER_CHUNK; ++j) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          mbar_arrive_expect_tx(&a_full[sa], C::A_BYTES);
+          const int w0 = sx * 16 - 1 + (MODE == 0 ? j : 0);
+          tma_load_4d(smemA + sa * C::A_STRIDE, m, &a_full[sa], c_off, w0, sy * 16 - 1, img);
+          if (++sa == C::NA) {
+            sa = 0;
+            pa ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ------------------------------------------------ B producer (weights)
+    tma_prefetch_desc(&mapB);
+    int sb = 0;
+    uint32_t pb = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int n_tile = u % p.n_tiles;
+      for (int ch = 0; ch < p.chunks; ++ch)
+        for (int j = 0; j < C::A_PER_CHUNK; ++j)
+          for (int t = 0; t < C::TAPS_PER_A; ++t) {
+            const int tap = MODE == 0 ? t * 3 + j : t;
+            mbar_wait(&b_empty[sb], pb ^ 1);
+            mbar_arrive_expect_tx(&b_full[sb], kBBytes);
+            tma_load_2d(smemB + sb * kBBytes, &mapB, &b_full[sb], tap * cin + ch * 64, n_tile * 128);
+            if (++sb == kNB) {
+              sb = 0;
+              pb ^= 1;
+            }
+          }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    int it = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      bool first = true;
+      for (int ch = 0; ch < p.chunks; ++ch)
+        for (int j = 0; j < C::A_PER_CHUNK; ++j) {
+          mbar_wait(&a_full[sa], pa);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smemA + sa * C::A_STRIDE);
+          for (int t = 0; t < C::TAPS_PER_A; ++t) {
+            const int kh = MODE == 0 ? t : t / 3;
+            const int kw = MODE == 0 ? 0 : t % 3;  // MODE 0: the copy itself is kw-shifted
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(smemB + sb * kBBytes);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              const uint32_t a_addr = a_base + (uint32_t)(kh * C::PITCH + mt * 8 + kw) * 128u;
+              const uint32_t d_tmem = tmem_base + (uint32_t)((buf * 2 + mt) * 128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, C::PITCH * 128),
+                          umma_desc_sw128(b_base + k * 32, 1024), idesc, (first && k == 0) ? 0u : 1u);
+            }
+            first = false;
+            umma_commit(&b_empty[sb]);
+            if (++sb == kNB) {
+              sb = 0;
+              pb ^= 1;
+            }
+          }
+          umma_commit(&a_empty[sa]);
+          if (++sa == C::NA) {
+            sa = 0;
+            pa ^= 1;
+          }
+        }
+      umma_commit(&t_full[buf]);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ epilogue
+    const int q = warp - 4;  // TMEM lane quadrant == warp % 4
+    const uint32_t stg = smem_u32(smemStage + q * 8192);
+    const int step = p.step_ptr ? *p.step_ptr : 0;
+    int it = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int img = u / units_per_img;
+      const int n_tile = (u % units_per_img) % p.n_tiles;
+      const int s = (u % units_per_img) / p.n_tiles;
+      const int sx = s % p.strips_x, sy = s / p.strips_x;
+      mbar_wait(&t_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+
+      EpiCtx e;
+      e.s_scale = s_scale + n_tile * 128;
+      e.s_shift = s_shift + n_tile * 128;
+      e.flags = p.flags;
+      e.xpix = 0.f;
+      e.sc_w = e.sc_b = e.film_scale = e.film_shift = nullptr;
+      if (p.flags & CDM_EPI_SHORTCUT) {
+        const int half = img / p.sc_nx;
+        const float* row = p.sc_tab + ((size_t)(step * p.sc_halves + half) * 2) * p.cout + n_tile * 128;
+        e.sc_w = row;
+        e.sc_b = row + p.cout;
+      }
+      if (p.flags & CDM_EPI_FILM) {
+        e.film_scale = p.film_scale + (size_t)img * p.cout + n_tile * 128;
+        const int r = p.film_shift_rows == 1 ? 0 : img;
+        e.film_shift = p.film_shift + ((size_t)step * p.film_shift_rows + r) * p.cout + n_tile * 128;
+      }
+
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        const int oh0 = sy * 16, ow0 = sx * 16 + mt * 8;
+        const int my_r = 4 * q + (lane >> 3), my_j = lane & 7;  // this thread's pixel inside the patch
+        if (p.flags & CDM_EPI_SHORTCUT)
+          e.xpix = __ldg(p.sc_x + ((size_t)(img % p.sc_nx) * p.H + oh0 + my_r) * p.W + ow0 + my_j);
+        float gsum[8], gsq[8];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + mt) * 128);
+        epi_tile_to_staging(taddr, stg, lane, e, gsum, gsq);
+        if (p.flags & CDM_EPI_GNSTATS) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              gsum[g] += __shfl_xor_sync(0xffffffffu, gsum[g], o);
+              gsq[g] += __shfl_xor_sync(0xffffffffu, gsq[g], o);
+            }
+          }
+          if (lane == 0) {
+            const int slots = p.strips_x * p.strips_y * 8;
+            const int slot = (s * 2 + mt) * 4 + q;
+            float* dst = p.gn_partial + ((size_t)img * slots + slot) * 16;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              dst[g * 2] = gsum[g];
+              dst[g * 2 + 1] = gsq[g];
+            }
+          }
+        }
+        __syncwarp();
+        if (!(p.flags & CDM_EPI_POOL)) {
+          // 32 pixels x 256 B; one instruction stores two pixels = 512 contiguous bytes
+#pragma unroll 4
+          for (int i2 = 0; i2 < 16; ++i2) {
+            const int px = 2 * i2 + (lane >> 4), un = lane & 15;
+            const uint4 val = ld_shared_v4(stg + px * 256 + ((un ^ (px & 7)) << 4));
+            const int r = 4 * q + (px >> 3), jx = px & 7;
+            bf16* g = p.out + (((size_t)img * p.H + oh0 + r) * p.W + ow0 + jx) * p.cout + n_tile * 128;
+            reinterpret_cast<uint4*>(g)[un] = val;
+          }
+        } else {
+          // 2x2 max-pool inside the warp's 4 rows x 8 px -> 2 rows x 4 px
+          const int Ho = p.H >> 1, Wo = p.W >> 1;
+#pragma unroll
+          for (int i2 = 0; i2 < 4; ++i2) {
+            const int item = i2 * 32 + lane;
+            const int pp = item >> 4, un = item & 15;
+            const int pr = pp >> 2, pj = pp & 3;
+            const int p00 = (2 * pr) * 8 + 2 * pj;
+            const uint4 a = ld_shared_v4(stg + p00 * 256 + ((un ^ (p00 & 7)) << 4));
+            const uint4 b = ld_shared_v4(stg + (p00 + 1) * 256 + ((un ^ ((p00 + 1) & 7)) << 4));
+            const uint4 c = ld_shared_v4(stg + (p00 + 8) * 256 + ((un ^ ((p00 + 8) & 7)) << 4));
+            const uint4 d = ld_shared_v4(stg + (p00 + 9) * 256 + ((un ^ ((p00 + 9) & 7)) << 4));
+            uint4 m;
+            m.x = bf16x2_max(bf16x2_max(a.x, b.x), bf16x2_max(c.x, d.x));
+            m.y = bf16x2_max(bf16x2_max(a.y, b.y), bf16x2_max(c.y, d.y));
+            m.z = bf16x2_max(bf16x2_max(a.z, b.z), bf16x2_max(c.z, d.z));
+            m.w = bf16x2_max(bf16x2_max(a.w, b.w), bf16x2_max(c.w, d.w));
+            const int orow = (oh0 >> 1) + 2 * q + pr, ocol = (ow0 >> 1) + pj;
+            bf16* g = p.out + (((size_t)img * Ho + orow) * Wo + ocol) * p.cout + n_tile * 128;
+            reinterpret_cast<uint4*>(g)[un] = m;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// --------------------------------------------------------------------------
+// gemm: C[M][N] = A[M][K] * Bw[N][K]^T, work unit = one 128x128 output tile.
+// --------------------------------------------------------------------------
+struct GemmKParams {
+  int M, N;
+  int chunks0, chunks;
+  int m_tiles, n_tiles, n_units;
+  const float* shift;
+  int shift_mod;
+  int out_mode, H, W;
+  bf16* out;
+};
+constexpr int kGemmStages = 5;
+constexpr int kGemmStageBytes = 2 * 16384;
+constexpr int gemm_smem_bytes() { return kGemmStages * kGemmStageBytes + kStageBytes + 256 + 1024; }
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+            const __grid_constant__ CUtensorMap mapB, const GemmKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smemAB = smem;
+  uint8_t* smemStage = smemAB + kGemmStages * kGemmStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemStage + kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = full + kGemmStages;
+  uint64_t* t_full = empty + kGemmStages;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kGemmStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // unit -> (m_tile, n_tile): n fastest so concurrently running CTAs share the A rows in L2
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0);
+    tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapB);
+    int st = 0;
+    uint32_t ph = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int m_tile = u / p.n_tiles, n_tile = u % p.n_tiles;
+      for (int ch = 0; ch < p.chunks; ++ch) {
+        const CUtensorMap* m = ch < p.chunks0 ? &mapA0 : &mapA1;
+        const int c_off = (ch < p.chunks0 ? ch : ch - p.chunks0) * 64;
+        mbar_wait(&empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&full[st], kGemmStageBytes);
+        tma_load_2d(smemAB + st * kGemmStageBytes, m, &full[st], c_off, m_tile * 128);
+        tma_load_2d(smemAB + st * kGemmStageBytes + 16384, &mapB, &full[st], ch * 64, n_tile * 128);
+        if (++st == kGemmStages) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+    int st = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int ch = 0; ch < p.chunks; ++ch) {
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smemAB + st * kGemmStageBytes);
+        const uint32_t b_base = a_base + 16384;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + buf * 128, umma_desc_sw128(a_base + k * 32, 1024),
+                    umma_desc_sw128(b_base + k * 32, 1024), idesc, (ch == 0 && k == 0) ? 0u : 1u);
+        umma_commit(&empty[st]);
+        if (++st == kGemmStages) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+      umma_commit(&t_full[buf]);
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const uint32_t stg = smem_u32(smemStage + q * 8192);
+    int it = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int m_tile = u / p.n_tiles, n_tile = u % p.n_tiles;
+      mbar_wait(&t_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128);
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t v[32];
+        tmem_ld_x32(taddr + cc * 32, v);
+        tmem_wait_ld();
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          f[i] = __uint_as_float(v[i]) + __ldg(p.shift + (n_tile * 128 + cc * 32 + i) % p.shift_mod);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int un = cc * 4 + j;
+          st_shared_v4(stg + lane * 256 + ((un ^ (lane & 7)) << 4), pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]),
+                       pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]), pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]),
+                       pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]));
+        }
+      }
+      __syncwarp();
+#pragma unroll 4
+      for (int i2 = 0; i2 < 16; ++i2) {
+        const int rw = 2 * i2 + (lane >> 4), un = lane & 15;
+        const int m = m_tile * 128 + q * 32 + rw;
+        if (m < p.M) {
+          const uint4 val = ld_shared_v4(stg + rw * 256 + ((un ^ (rw & 7)) << 4));
+          bf16* g;
+          if (p.out_mode == 0) {
+            g = p.out + (size_t)m * p.N + n_tile * 128;
+          } else {
+            const int w = m % p.W, h = (m / p.W) % p.H, img = m / (p.W * p.H);
+            const int kh = n_tile >> 1, kw = n_tile & 1;
+            g = p.out + (((size_t)img * 2 * p.H + 2 * h + kh) * (2 * p.W) + 2 * w + kw) * 128;
+          }
+          reinterpret_cast<uint4*>(g)[un] = val;
+        }
+      }
+      __syncwarp();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
+// --------------------------------------------------------------------------
+// probe: how fast can TMA refill shared memory from L2?  Each CTA streams
+// 16 KB boxes (128 rows x 128 B) of an L2-resident [n_rows][64] bf16 buffer.
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+probe_tma_l2_kernel(const __grid_constant__ CUtensorMap map, int n_rows, int iters) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int NS = 8;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * 16384);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) mbar_init(&full[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int n_tiles = n_rows / 128;
+    int tile = (blockIdx.x * 37) % n_tiles;
+    // keep NS loads in flight; a completed stage is immediately re-armed
+    for (int i = 0; i < NS; ++i) {
+      mbar_arrive_expect_tx(&full[i], 16384);
+      tma_load_2d(smem + i * 16384, &map, &full[i], 0, tile * 128);
+      tile = (tile + 1) % n_tiles;
+    }
+    for (int it = 0; it < iters; ++it) {
+      const int st = it % NS;
+      mbar_wait(&full[st], (it / NS) & 1);
+      mbar_arrive_expect_tx(&full[st], 16384);
+      tma_load_2d(smem + st * 16384, &map, &full[st], 0, tile * 128);
+      tile = (tile + 1) % n_tiles;
+    }
+    // drain
+    for (int i = 0; i < NS; ++i) {
+      const int it = iters + i;
+      mbar_wait(&full[it % NS], (it / NS) & 1);
+    }
+  }
+}
+
+}  // namespace cdm
