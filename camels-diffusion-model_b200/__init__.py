@@ -4,3 +4,8 @@ Python mirrors the reference's nn.Module / function API; all arithmetic runs in
 hand-written sm_100a CUDA kernels behind the C ABI in include/cdm_b200.h.
 """
 __version__ = "0.1.0"
+
+from ._lib import CdmError  # noqa: F401
+from .unet import ContextUnet, EmbedFC, ResidualConvBlock, UnetDown, UnetUp  # noqa: F401
+from .diffusion import (DDPM, calculate_elbo_and_bpd, calculate_elbo_and_bpd_batch,  # noqa: F401
+                        calculate_likelihood, denoise_add_noise, make_schedule, perturb_input, sample_ddpm)

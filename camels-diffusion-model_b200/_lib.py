@@ -25,7 +25,7 @@ class Conv3x3Args(C.Structure):
         ("n_img", C.c_int), ("H", C.c_int), ("W", C.c_int),
         ("weight", C.c_void_p), ("cout", C.c_int),
         ("scale", C.c_void_p), ("shift", C.c_void_p), ("flags", C.c_int), ("out", C.c_void_p),
-        ("sc_x", C.c_void_p), ("sc_nx", C.c_int), ("sc_tab", C.c_void_p),
+        ("sc_x", C.c_void_p), ("sc_reps", C.c_int), ("sc_tab", C.c_void_p),
         ("film_scale", C.c_void_p), ("film_shift", C.c_void_p), ("film_shift_rows", C.c_int),
         ("step_ptr", C.c_void_p), ("gn_partial", C.c_void_p), ("mode", C.c_int),
     ]
@@ -37,6 +37,43 @@ class GemmArgs(C.Structure):
         ("M", C.c_int), ("N", C.c_int), ("bw", C.c_void_p), ("shift", C.c_void_p),
         ("shift_mod", C.c_int), ("out_mode", C.c_int), ("H", C.c_int), ("W", C.c_int), ("out", C.c_void_p),
     ]
+
+
+class ConvInArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("n_img", C.c_int), ("H", C.c_int), ("W", C.c_int), ("weight", C.c_void_p),
+                ("cout", C.c_int), ("scale", C.c_void_p), ("shift", C.c_void_p), ("relu", C.c_int),
+                ("out", C.c_void_p)]
+
+
+class ConvOutArgs(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("n_img", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
+                ("mean_rstd", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("weight", C.c_void_p),
+                ("bias", C.c_void_p), ("out", C.c_void_p)]
+
+
+class GnReluFilmArgs(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("n_img", C.c_int), ("P", C.c_int), ("C", C.c_int), ("groups", C.c_int),
+                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float), ("film_scale", C.c_void_p),
+                ("film_shift", C.c_void_p), ("film_rows", C.c_int), ("step_ptr", C.c_void_p), ("out", C.c_void_p)]
+
+
+class DdpmStepArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("eps", C.c_void_p), ("n", C.c_int), ("hw", C.c_int), ("reps", C.c_int),
+                ("guide_w", C.c_float), ("coef", C.c_void_p), ("step_ptr", C.c_void_p), ("step", C.c_int),
+                ("timesteps", C.c_int), ("z", C.c_void_p), ("z_iter_stride", C.c_longlong),
+                ("seed", C.c_ulonglong), ("snap", C.c_void_p), ("snap_slot", C.c_void_p)]
+
+
+class PerturbArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("noise", C.c_void_p), ("out", C.c_void_p), ("n", C.c_int), ("hw", C.c_int),
+                ("ca", C.c_void_p), ("cb", C.c_void_p), ("t_idx", C.c_void_p), ("t_shared", C.c_int),
+                ("step_ptr", C.c_void_p), ("seed", C.c_ulonglong), ("stream_id", C.c_uint), ("noise_out", C.c_void_p)]
+
+
+class MseAccumArgs(C.Structure):
+    _fields_ = [("pred", C.c_void_p), ("target", C.c_void_p), ("n", C.c_int), ("hw", C.c_int),
+                ("weight_tab", C.c_void_p), ("t_idx", C.c_void_p), ("t_shared", C.c_int),
+                ("step_ptr", C.c_void_p), ("mse_out", C.c_void_p), ("acc", C.c_void_p)]
 
 
 _lib = None
@@ -63,6 +100,8 @@ def lib():
 EXPORTS = [
     "cdm_version", "cdm_last_error", "cdm_device_ok",
     "cdm_conv3x3", "cdm_gemm", "cdm_probe_tma_l2",
+    "cdm_conv_in", "cdm_conv_out", "cdm_embed_fc", "cdm_avgpool_gelu", "cdm_gn_relu_film", "cdm_gn_finalize",
+    "cdm_ddpm_step", "cdm_step_advance", "cdm_perturb", "cdm_mse_accum",
 ]
 
 
@@ -83,9 +122,9 @@ def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def conv3x3(src0, weight, scale, shift, out, *, src1=None, flags=EPI_RELU, sc_x=None, sc_tab=None,
+def conv3x3(src0, weight, scale, shift, out, *, src1=None, flags=EPI_RELU, sc_x=None, sc_tab=None, sc_reps=1,
             film_scale=None, film_shift=None, film_shift_rows=1, step_ptr=None, gn_partial=None,
-            mode=CONV_MODE_COPIES):
+            mode=CONV_MODE_SHIFT18):
     """src*: bf16 [n,H,W,c]; weight bf16 [cout,3,3,cin]; out bf16 NHWC. See cdm_conv3x3 in cdm_b200.h."""
     n, H, W, c0 = src0.shape
     a = Conv3x3Args()
@@ -95,7 +134,7 @@ def conv3x3(src0, weight, scale, shift, out, *, src1=None, flags=EPI_RELU, sc_x=
     a.weight, a.cout = ptr(weight), weight.shape[0]
     assert weight.shape[3] == a.c0 + a.c1
     a.scale, a.shift, a.flags, a.out = ptr(scale), ptr(shift), flags, ptr(out)
-    a.sc_x, a.sc_nx, a.sc_tab = ptr(sc_x), (sc_x.shape[0] if sc_x is not None else 0), ptr(sc_tab)
+    a.sc_x, a.sc_reps, a.sc_tab = ptr(sc_x), sc_reps, ptr(sc_tab)
     a.film_scale, a.film_shift, a.film_shift_rows = ptr(film_scale), ptr(film_shift), film_shift_rows
     a.step_ptr, a.gn_partial, a.mode = ptr(step_ptr), ptr(gn_partial), mode
     check(lib().cdm_conv3x3(C.byref(a), stream_ptr()), "cdm_conv3x3")
@@ -118,3 +157,95 @@ def gemm(a0, bw, shift, out, *, a1=None, shift_mod=None, out_mode=0, H=0, W=0):
 
 def probe_tma_l2(buf, n_rows, iters):
     check(lib().cdm_probe_tma_l2(C.c_void_p(ptr(buf)), n_rows, iters, stream_ptr()), "cdm_probe_tma_l2")
+
+
+def conv_in(x, weight, scale, shift, out, relu=True):
+    """x fp32 [n,H,W]; weight fp32 [9,cout]; out bf16 [n,H,W,cout]."""
+    a = ConvInArgs()
+    a.x, (a.n_img, a.H, a.W) = ptr(x), x.shape
+    a.weight, a.cout, a.scale, a.shift, a.relu, a.out = ptr(weight), weight.shape[1], ptr(scale), ptr(shift), int(relu), ptr(out)
+    check(lib().cdm_conv_in(C.byref(a), stream_ptr()), "cdm_conv_in")
+    return out
+
+
+def conv_out(src, mean_rstd, gamma, beta, weight, bias, out):
+    """src bf16 [n,H,W,128]; weight fp32 [9,128]; out fp32 [n,H,W]."""
+    a = ConvOutArgs()
+    a.src, (a.n_img, a.H, a.W, a.C) = ptr(src), src.shape
+    a.mean_rstd, a.gamma, a.beta, a.weight, a.bias, a.out = (ptr(mean_rstd), ptr(gamma), ptr(beta), ptr(weight),
+                                                             ptr(bias), ptr(out))
+    check(lib().cdm_conv_out(C.byref(a), stream_ptr()), "cdm_conv_out")
+    return out
+
+
+def embed_fc(inp, w1, b1, w2, b2, out):
+    """inp fp32 [rows,din]; w1 [emb,din]; w2 [emb,emb]; out fp32 [rows,emb]."""
+    rows, din = inp.shape
+    check(lib().cdm_embed_fc(C.c_void_p(ptr(inp)), rows, din, C.c_void_p(ptr(w1)), C.c_void_p(ptr(b1)),
+                             C.c_void_p(ptr(w2)), C.c_void_p(ptr(b2)), w2.shape[0], C.c_void_p(ptr(out)),
+                             stream_ptr()), "cdm_embed_fc")
+    return out
+
+
+def avgpool_gelu(src, out):
+    """src bf16 [n,P,C] -> out bf16 [n,C]."""
+    n, P, Cc = src.shape
+    check(lib().cdm_avgpool_gelu(C.c_void_p(ptr(src)), n, P, Cc, C.c_void_p(ptr(out)), stream_ptr()),
+          "cdm_avgpool_gelu")
+    return out
+
+
+def gn_relu_film(src, gamma, beta, out, *, groups=8, eps=1e-5, film_scale=None, film_shift=None, film_rows=1,
+                 step_ptr=None):
+    """src/out bf16 [n,P,C]."""
+    a = GnReluFilmArgs()
+    a.src, (a.n_img, a.P, a.C) = ptr(src), src.shape
+    a.groups, a.gamma, a.beta, a.eps = groups, ptr(gamma), ptr(beta), eps
+    a.film_scale, a.film_shift, a.film_rows, a.step_ptr, a.out = (ptr(film_scale), ptr(film_shift), film_rows,
+                                                                  ptr(step_ptr), ptr(out))
+    check(lib().cdm_gn_relu_film(C.byref(a), stream_ptr()), "cdm_gn_relu_film")
+    return out
+
+
+def gn_finalize(partial, count, mean_rstd, eps=1e-5):
+    """partial fp32 [n,slots,8,2] -> mean_rstd fp32 [n,8,2]."""
+    n, slots = partial.shape[0], partial.shape[1]
+    check(lib().cdm_gn_finalize(C.c_void_p(ptr(partial)), n, slots, C.c_float(count), C.c_float(eps),
+                                C.c_void_p(ptr(mean_rstd)), stream_ptr()), "cdm_gn_finalize")
+    return mean_rstd
+
+
+def ddpm_step(x, eps, coef, timesteps, *, reps=1, guide_w=0.0, step=0, step_ptr=None, z=None, z_iter_stride=0,
+              seed=0, snap=None, snap_slot=None):
+    """x fp32 [n,...] in place; eps fp32 [reps*n,...]; coef fp32 [T+1,4]."""
+    a = DdpmStepArgs()
+    n = x.shape[0]
+    a.x, a.eps, a.n, a.hw, a.reps, a.guide_w = ptr(x), ptr(eps), n, x.numel() // n, reps, guide_w
+    a.coef, a.step_ptr, a.step, a.timesteps = ptr(coef), ptr(step_ptr), step, timesteps
+    a.z, a.z_iter_stride, a.seed, a.snap, a.snap_slot = ptr(z), z_iter_stride, seed, ptr(snap), ptr(snap_slot)
+    check(lib().cdm_ddpm_step(C.byref(a), stream_ptr()), "cdm_ddpm_step")
+    return x
+
+
+def step_advance(step_ptr, delta):
+    check(lib().cdm_step_advance(C.c_void_p(ptr(step_ptr)), delta, stream_ptr()), "cdm_step_advance")
+
+
+def perturb(x, out, ca, cb, *, noise=None, t_idx=None, t_shared=0, step_ptr=None, seed=0, stream_id=0,
+            noise_out=None):
+    a = PerturbArgs()
+    n = x.shape[0]
+    a.x, a.noise, a.out, a.n, a.hw = ptr(x), ptr(noise), ptr(out), n, x.numel() // n
+    a.ca, a.cb, a.t_idx, a.t_shared, a.step_ptr = ptr(ca), ptr(cb), ptr(t_idx), t_shared, ptr(step_ptr)
+    a.seed, a.stream_id, a.noise_out = seed, stream_id, ptr(noise_out)
+    check(lib().cdm_perturb(C.byref(a), stream_ptr()), "cdm_perturb")
+    return out
+
+
+def mse_accum(pred, target, *, weight_tab=None, t_idx=None, t_shared=0, step_ptr=None, mse_out=None, acc=None):
+    a = MseAccumArgs()
+    n = pred.shape[0]
+    a.pred, a.target, a.n, a.hw = ptr(pred), ptr(target), n, pred.numel() // n
+    a.weight_tab, a.t_idx, a.t_shared, a.step_ptr = ptr(weight_tab), ptr(t_idx), t_shared, ptr(step_ptr)
+    a.mse_out, a.acc = ptr(mse_out), ptr(acc)
+    check(lib().cdm_mse_accum(C.byref(a), stream_ptr()), "cdm_mse_accum")

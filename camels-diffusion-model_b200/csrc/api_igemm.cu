@@ -121,7 +121,7 @@ extern "C" int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream) {
   CDM_CHECK_ARG(a->cout > 0 && a->cout % 128 == 0 && a->cout <= 256);
   CDM_CHECK_ARG(a->mode >= 0 && a->mode <= 2);
   if (a->flags & CDM_EPI_SHORTCUT)
-    CDM_CHECK_ARG(a->sc_x && a->sc_tab && a->sc_nx > 0 && a->n_img % a->sc_nx == 0);
+    CDM_CHECK_ARG(a->sc_x && a->sc_tab && a->sc_reps >= 1);
   if (a->flags & CDM_EPI_FILM) CDM_CHECK_ARG(a->film_scale && a->film_shift && a->film_shift_rows >= 1);
   if (a->flags & CDM_EPI_GNSTATS) CDM_CHECK_ARG(a->gn_partial && a->cout == 128 && !(a->flags & CDM_EPI_POOL));
   int rc = check_device();
@@ -171,9 +171,8 @@ extern "C" int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream) {
   p.shift = a->shift;
   p.out = reinterpret_cast<bf16*>(a->out);
   p.sc_x = a->sc_x;
-  p.sc_nx = a->sc_nx > 0 ? a->sc_nx : 1;
   p.sc_tab = a->sc_tab;
-  p.sc_halves = a->n_img / p.sc_nx;
+  p.sc_reps = a->sc_reps > 0 ? a->sc_reps : 1;
   p.film_scale = a->film_scale;
   p.film_shift = a->film_shift;
   p.film_shift_rows = a->film_shift_rows;

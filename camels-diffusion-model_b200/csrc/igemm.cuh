@@ -41,9 +41,8 @@ struct ConvKParams {
   const float* shift;
   bf16* out;
   const float* sc_x;
-  int sc_nx;
   const float* sc_tab;
-  int sc_halves;
+  int sc_reps;
   const float* film_scale;
   const float* film_shift;
   int film_shift_rows;
@@ -310,82 +309,88 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       e.flags = p.flags;
       e.xpix = 0.f;
       e.sc_w = e.sc_b = e.film_scale = e.film_shift = nullptr;
-      if (p.flags & CDM_EPI_SHORTCUT) {
-        const int half = img / p.sc_nx;
-        const float* row = p.sc_tab + ((size_t)(step * p.sc_halves + half) * 2) * p.cout + n_tile * 128;
-        e.sc_w = row;
-        e.sc_b = row + p.cout;
-      }
       if (p.flags & CDM_EPI_FILM) {
         e.film_scale = p.film_scale + (size_t)img * p.cout + n_tile * 128;
         const int r = p.film_shift_rows == 1 ? 0 : img;
         e.film_shift = p.film_shift + ((size_t)step * p.film_shift_rows + r) * p.cout + n_tile * 128;
       }
+      // The G1 shortcut can fan one input image out to `sc_reps` outputs (the CFG cond / uncond
+      // passes share x and init_conv, and differ only in the fresh 1x1 shortcut).
+      const int reps = (p.flags & CDM_EPI_SHORTCUT) ? p.sc_reps : 1;
 
 #pragma unroll 1
       for (int mt = 0; mt < 2; ++mt) {
         const int oh0 = sy * 16, ow0 = sx * 16 + mt * 8;
         const int my_r = 4 * q + (lane >> 3), my_j = lane & 7;  // this thread's pixel inside the patch
         if (p.flags & CDM_EPI_SHORTCUT)
-          e.xpix = __ldg(p.sc_x + ((size_t)(img % p.sc_nx) * p.H + oh0 + my_r) * p.W + ow0 + my_j);
-        float gsum[8], gsq[8];
+          e.xpix = __ldg(p.sc_x + ((size_t)img * p.H + oh0 + my_r) * p.W + ow0 + my_j);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + mt) * 128);
-        epi_tile_to_staging(taddr, stg, lane, e, gsum, gsq);
-        if (p.flags & CDM_EPI_GNSTATS) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              gsum[g] += __shfl_xor_sync(0xffffffffu, gsum[g], o);
-              gsq[g] += __shfl_xor_sync(0xffffffffu, gsq[g], o);
-            }
+#pragma unroll 1
+        for (int rep = 0; rep < reps; ++rep) {
+          if (p.flags & CDM_EPI_SHORTCUT) {
+            const float* row = p.sc_tab + ((size_t)(step * p.sc_reps + rep) * 2) * p.cout + n_tile * 128;
+            e.sc_w = row;
+            e.sc_b = row + p.cout;
           }
-          if (lane == 0) {
-            const int slots = p.strips_x * p.strips_y * 8;
-            const int slot = (s * 2 + mt) * 4 + q;
-            float* dst = p.gn_partial + ((size_t)img * slots + slot) * 16;
+          const int oimg = rep * p.n_img + img;
+          float gsum[8], gsq[8];
+          epi_tile_to_staging(taddr, stg, lane, e, gsum, gsq);
+          if (p.flags & CDM_EPI_GNSTATS) {
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-              dst[g * 2] = gsum[g];
-              dst[g * 2 + 1] = gsq[g];
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                gsum[g] += __shfl_xor_sync(0xffffffffu, gsum[g], o);
+                gsq[g] += __shfl_xor_sync(0xffffffffu, gsq[g], o);
+              }
+            }
+            if (lane == 0) {
+              const int slots = p.strips_x * p.strips_y * 8;
+              const int slot = (s * 2 + mt) * 4 + q;
+              float* dst = p.gn_partial + ((size_t)oimg * slots + slot) * 16;
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                dst[g * 2] = gsum[g];
+                dst[g * 2 + 1] = gsq[g];
+              }
             }
           }
-        }
-        __syncwarp();
-        if (!(p.flags & CDM_EPI_POOL)) {
-          // 32 pixels x 256 B; one instruction stores two pixels = 512 contiguous bytes
+          __syncwarp();
+          if (!(p.flags & CDM_EPI_POOL)) {
+            // 32 pixels x 256 B; one instruction stores two pixels = 512 contiguous bytes
 #pragma unroll 4
-          for (int i2 = 0; i2 < 16; ++i2) {
-            const int px = 2 * i2 + (lane >> 4), un = lane & 15;
-            const uint4 val = ld_shared_v4(stg + px * 256 + ((un ^ (px & 7)) << 4));
-            const int r = 4 * q + (px >> 3), jx = px & 7;
-            bf16* g = p.out + (((size_t)img * p.H + oh0 + r) * p.W + ow0 + jx) * p.cout + n_tile * 128;
-            reinterpret_cast<uint4*>(g)[un] = val;
-          }
-        } else {
-          // 2x2 max-pool inside the warp's 4 rows x 8 px -> 2 rows x 4 px
-          const int Ho = p.H >> 1, Wo = p.W >> 1;
+            for (int i2 = 0; i2 < 16; ++i2) {
+              const int px = 2 * i2 + (lane >> 4), un = lane & 15;
+              const uint4 val = ld_shared_v4(stg + px * 256 + ((un ^ (px & 7)) << 4));
+              const int r = 4 * q + (px >> 3), jx = px & 7;
+              bf16* g = p.out + (((size_t)oimg * p.H + oh0 + r) * p.W + ow0 + jx) * p.cout + n_tile * 128;
+              reinterpret_cast<uint4*>(g)[un] = val;
+            }
+          } else {
+            // 2x2 max-pool inside the warp's 4 rows x 8 px -> 2 rows x 4 px
+            const int Ho = p.H >> 1, Wo = p.W >> 1;
 #pragma unroll
-          for (int i2 = 0; i2 < 4; ++i2) {
-            const int item = i2 * 32 + lane;
-            const int pp = item >> 4, un = item & 15;
-            const int pr = pp >> 2, pj = pp & 3;
-            const int p00 = (2 * pr) * 8 + 2 * pj;
-            const uint4 a = ld_shared_v4(stg + p00 * 256 + ((un ^ (p00 & 7)) << 4));
-            const uint4 b = ld_shared_v4(stg + (p00 + 1) * 256 + ((un ^ ((p00 + 1) & 7)) << 4));
-            const uint4 c = ld_shared_v4(stg + (p00 + 8) * 256 + ((un ^ ((p00 + 8) & 7)) << 4));
-            const uint4 d = ld_shared_v4(stg + (p00 + 9) * 256 + ((un ^ ((p00 + 9) & 7)) << 4));
-            uint4 m;
-            m.x = bf16x2_max(bf16x2_max(a.x, b.x), bf16x2_max(c.x, d.x));
-            m.y = bf16x2_max(bf16x2_max(a.y, b.y), bf16x2_max(c.y, d.y));
-            m.z = bf16x2_max(bf16x2_max(a.z, b.z), bf16x2_max(c.z, d.z));
-            m.w = bf16x2_max(bf16x2_max(a.w, b.w), bf16x2_max(c.w, d.w));
-            const int orow = (oh0 >> 1) + 2 * q + pr, ocol = (ow0 >> 1) + pj;
-            bf16* g = p.out + (((size_t)img * Ho + orow) * Wo + ocol) * p.cout + n_tile * 128;
-            reinterpret_cast<uint4*>(g)[un] = m;
+            for (int i2 = 0; i2 < 4; ++i2) {
+              const int item = i2 * 32 + lane;
+              const int pp = item >> 4, un = item & 15;
+              const int pr = pp >> 2, pj = pp & 3;
+              const int p00 = (2 * pr) * 8 + 2 * pj;
+              const uint4 a = ld_shared_v4(stg + p00 * 256 + ((un ^ (p00 & 7)) << 4));
+              const uint4 b = ld_shared_v4(stg + (p00 + 1) * 256 + ((un ^ ((p00 + 1) & 7)) << 4));
+              const uint4 c = ld_shared_v4(stg + (p00 + 8) * 256 + ((un ^ ((p00 + 8) & 7)) << 4));
+              const uint4 d = ld_shared_v4(stg + (p00 + 9) * 256 + ((un ^ ((p00 + 9) & 7)) << 4));
+              uint4 m;
+              m.x = bf16x2_max(bf16x2_max(a.x, b.x), bf16x2_max(c.x, d.x));
+              m.y = bf16x2_max(bf16x2_max(a.y, b.y), bf16x2_max(c.y, d.y));
+              m.z = bf16x2_max(bf16x2_max(a.z, b.z), bf16x2_max(c.z, d.z));
+              m.w = bf16x2_max(bf16x2_max(a.w, b.w), bf16x2_max(c.w, d.w));
+              const int orow = (oh0 >> 1) + 2 * q + pr, ocol = (ow0 >> 1) + pj;
+              bf16* g = p.out + (((size_t)oimg * Ho + orow) * Wo + ocol) * p.cout + n_tile * 128;
+              reinterpret_cast<uint4*>(g)[un] = m;
+            }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();

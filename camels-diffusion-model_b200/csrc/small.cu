@@ -1,0 +1,561 @@
+// Memory-bound kernels of the ContextUnet / DDPM hot path (everything that is
+// not a dense contraction): first/last convolution, EmbedFC, GroupNorm, pooling,
+// the sampler tail, the training noise perturbation and the per-sample MSE.
+// All of them are single-pass, vectorised (16 B per thread access) and coalesced.
+#include <math.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace cdm {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// Block-wide sum (blockDim.x multiple of 32, <= 1024); result broadcast to all threads.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; ++i) t += red[i];  // fixed order: deterministic
+  return t;
+}
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  v.x = pack_bf16x2(f[0], f[1]);
+  v.y = pack_bf16x2(f[2], f[3]);
+  v.z = pack_bf16x2(f[4], f[5]);
+  v.w = pack_bf16x2(f[6], f[7]);
+  return v;
+}
+
+// ------------------------------------------------------------------ conv_in
+// Conv2d(1, C, 3, 1, 1) + folded BatchNorm + ReLU.  K = 9: CUDA cores, bound by the
+// bf16 NHWC write (256 B / pixel).  One thread = one pixel x 8 channels.
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, int n_img, int H, int W, int C,
+                                                      const float* __restrict__ wgt, const float* __restrict__ scale,
+                                                      const float* __restrict__ shift, int relu,
+                                                      bf16* __restrict__ out) {
+  extern __shared__ float s_par[];  // [9][C] weights, [C] scale, [C] shift
+  float* s_w = s_par;
+  float* s_scale = s_w + 9 * C;
+  float* s_shift = s_scale + C;
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i] = wgt[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    s_scale[i] = scale[i];
+    s_shift[i] = shift[i];
+  }
+  __syncthreads();
+  const int groups = C >> 3;
+  const size_t total = (size_t)n_img * H * W * groups;
+  for (size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(gid % groups);
+    const size_t p = gid / groups;
+    const int w = (int)(p % W), h = (int)((p / W) % H);
+    const size_t n = p / ((size_t)W * H);
+    float xin[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ih = h + kh - 1, iw = w + kw - 1;
+        xin[kh * 3 + kw] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(x + (n * H + ih) * W + iw) : 0.f;
+      }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float4 w0 = *reinterpret_cast<const float4*>(s_w + t * C + cg * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(s_w + t * C + cg * 8 + 4);
+      acc[0] = fmaf(xin[t], w0.x, acc[0]);
+      acc[1] = fmaf(xin[t], w0.y, acc[1]);
+      acc[2] = fmaf(xin[t], w0.z, acc[2]);
+      acc[3] = fmaf(xin[t], w0.w, acc[3]);
+      acc[4] = fmaf(xin[t], w1.x, acc[4]);
+      acc[5] = fmaf(xin[t], w1.y, acc[5]);
+      acc[6] = fmaf(xin[t], w1.z, acc[6]);
+      acc[7] = fmaf(xin[t], w1.w, acc[7]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = fmaf(acc[j], s_scale[cg * 8 + j], s_shift[cg * 8 + j]);
+      acc[j] = relu ? fmaxf(y, 0.f) : y;
+    }
+    *reinterpret_cast<uint4*>(out + p * C + cg * 8) = pack8(acc);
+  }
+}
+
+// ----------------------------------------------------------------- conv_out
+// GroupNorm(8, 128) + ReLU applied on load, then Conv2d(128, 1, 3, 1, 1): N = 1, so
+// CUDA cores.  One warp walks a 16-pixel row segment; lane l owns channels 4l..4l+3.
+__global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ src, int n_img, int H, int W,
+                                                       const float* __restrict__ mean_rstd,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ wgt, const float* __restrict__ bias,
+                                                       float* __restrict__ out) {
+  constexpr int C = 128, SEG = 16;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int segs_per_row = W / SEG;
+  const size_t n_items = (size_t)n_img * H * segs_per_row;
+  float wr[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 w4 = *reinterpret_cast<const float4*>(wgt + t * C + lane * 4);
+    wr[t][0] = w4.x;
+    wr[t][1] = w4.y;
+    wr[t][2] = w4.z;
+    wr[t][3] = w4.w;
+  }
+  const float4 g4 = *reinterpret_cast<const float4*>(gamma + lane * 4);
+  const float4 b4 = *reinterpret_cast<const float4*>(beta + lane * 4);
+  const float bias0 = __ldg(bias);
+  for (size_t item = (size_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < n_items;
+       item += (size_t)gridDim.x * warps_per_block) {
+    const int seg = (int)(item % segs_per_row);
+    const int h = (int)((item / segs_per_row) % H);
+    const size_t n = item / ((size_t)segs_per_row * H);
+    const int grp = lane >> 2;  // 16 channels per group, 4 per lane
+    const float mean = __ldg(mean_rstd + (n * 8 + grp) * 2), rstd = __ldg(mean_rstd + (n * 8 + grp) * 2 + 1);
+    float a[4], b[4];
+    a[0] = rstd * g4.x;
+    a[1] = rstd * g4.y;
+    a[2] = rstd * g4.z;
+    a[3] = rstd * g4.w;
+    b[0] = b4.x - mean * a[0];
+    b[1] = b4.y - mean * a[1];
+    b[2] = b4.z - mean * a[2];
+    b[3] = b4.w - mean * a[3];
+    for (int w = seg * SEG; w < seg * SEG + SEG; ++w) {
+      float acc = 0.f;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ih = h + kh - 1;
+        if (ih < 0 || ih >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int iw = w + kw - 1;
+          if (iw < 0 || iw >= W) continue;
+          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(src + ((n * H + ih) * W + iw) * C + lane * 4));
+          const float2 v01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+          const float2 v23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+          const int t = kh * 3 + kw;
+          acc = fmaf(fmaxf(fmaf(v01.x, a[0], b[0]), 0.f), wr[t][0], acc);
+          acc = fmaf(fmaxf(fmaf(v01.y, a[1], b[1]), 0.f), wr[t][1], acc);
+          acc = fmaf(fmaxf(fmaf(v23.x, a[2], b[2]), 0.f), wr[t][2], acc);
+          acc = fmaf(fmaxf(fmaf(v23.y, a[3], b[3]), 0.f), wr[t][3], acc);
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) out[(n * H + h) * W + w] = acc + bias0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ embed_fc
+// EmbedFC: out = W2 * gelu(W1 * v + b1) + b2, one block per input row.
+__global__ void __launch_bounds__(256) embed_fc_kernel(const float* __restrict__ in, int din,
+                                                       const float* __restrict__ w1, const float* __restrict__ b1,
+                                                       const float* __restrict__ w2, const float* __restrict__ b2,
+                                                       int emb, float* __restrict__ out) {
+  extern __shared__ float s_h[];  // [emb]
+  const int row = blockIdx.x;
+  for (int j = threadIdx.x; j < emb; j += blockDim.x) {
+    float s = b1[j];
+    for (int i = 0; i < din; ++i) s = fmaf(w1[j * din + i], in[(size_t)row * din + i], s);
+    s_h[j] = gelu_erf(s);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = warp; j < emb; j += nw) {
+    float s = 0.f;
+    for (int k = lane; k < emb; k += 32) s = fmaf(w2[(size_t)j * emb + k], s_h[k], s);
+    s = warp_sum(s);
+    if (lane == 0) out[(size_t)row * emb + j] = s + b2[j];
+  }
+}
+
+// ------------------------------------------------------------ avgpool + gelu
+// to_vec: AvgPool2d over all P pixels + GELU; src bf16 [n][P][C] -> out bf16 [n][C].
+__global__ void __launch_bounds__(256) avgpool_gelu_kernel(const bf16* __restrict__ src, int P, int C,
+                                                           bf16* __restrict__ out) {
+  const size_t n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < P; ++p) s += __bfloat162float(src[(n * P + p) * C + c]);
+    out[n * C + c] = __float2bfloat16(gelu_erf(s / (float)P));
+  }
+}
+
+// ----------------------------------------------- GroupNorm + ReLU + FiLM (up0)
+// One block per (image, group): statistics over P pixels x cpg channels, then
+// y = film_scale * relu(gn(x)) + film_shift.  src/out bf16 [n][P][C].
+__global__ void __launch_bounds__(256) gn_relu_film_kernel(const bf16* __restrict__ src, int P, int C, int groups,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps,
+                                                           const float* __restrict__ film_scale,
+                                                           const float* __restrict__ film_shift, int film_rows,
+                                                           const int* __restrict__ step_ptr, bf16* __restrict__ out) {
+  __shared__ float red[32];
+  const int n = blockIdx.x / groups, g = blockIdx.x % groups;
+  const int cpg = C / groups;      // multiple of 8
+  const int vec_per_px = cpg / 8;  // uint4 per pixel
+  const int n_vec = P * vec_per_px;
+  const bf16* base = src + (size_t)n * P * C + g * cpg;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
+    const int p = i / vec_per_px, v = i % vec_per_px;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(base + (size_t)p * C + v * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += f[j];
+  }
+  const float cnt = (float)(P * cpg);
+  const float mean = block_sum(s, red) / cnt;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
+    const int p = i / vec_per_px, v = i % vec_per_px;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(base + (size_t)p * C + v * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q = fmaf(f[j] - mean, f[j] - mean, q);
+  }
+  const float rstd = rsqrtf(block_sum(q, red) / cnt + eps);
+  const int step = step_ptr ? *step_ptr : 0;
+  const float* fs = film_scale ? film_scale + (size_t)n * C + g * cpg : nullptr;
+  const float* fb =
+      film_shift ? film_shift + ((size_t)step * film_rows + (film_rows == 1 ? 0 : n)) * C + g * cpg : nullptr;
+  for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
+    const int p = i / vec_per_px, v = i % vec_per_px;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(base + (size_t)p * C + v * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * cpg + v * 8 + j;
+      float y = fmaxf(fmaf((f[j] - mean) * rstd, gamma[c], beta[c]), 0.f);
+      if (fs) y = fmaf(fs[v * 8 + j], y, fb[v * 8 + j]);
+      f[j] = y;
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)n * P * C + (size_t)p * C + g * cpg + v * 8) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------- gn_finalize
+// Reduce the per-tile partial sums the out.0 convolution emitted, in a fixed order
+// (deterministic), into mean / rstd per (image, group).  One warp per (image, group).
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int n_img, int slots, float count, float eps,
+                                   float* __restrict__ mean_rstd) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= n_img * 8) return;
+  const int n = wid >> 3, g = wid & 7;
+  float s = 0.f, q = 0.f;
+  for (int k = lane; k < slots; k += 32) {
+    const float* p = partial + (((size_t)n * slots + k) * 8 + g) * 2;
+    s += p[0];
+    q += p[1];
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane == 0) {
+    const float mean = s / count;
+    const float var = fmaxf(q / count - mean * mean, 0.f);
+    mean_rstd[(size_t)wid * 2] = mean;
+    mean_rstd[(size_t)wid * 2 + 1] = rsqrtf(var + eps);
+  }
+}
+
+// ---------------------------------------------------------------- RNG (Philox)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, uint32_t idx, uint32_t stream) {
+  const uint4 r = philox4x32_10(make_uint4(idx, stream, 0x1234567u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float k = 5.9604644775390625e-8f;  // 2^-24
+  const float u0 = ((r.x >> 8) + 0.5f) * k, u1 = ((r.y >> 8) + 0.5f) * k;
+  const float u2 = ((r.z >> 8) + 0.5f) * k, u3 = ((r.w >> 8) + 0.5f) * k;
+  const float r0 = sqrtf(-2.f * logf(u0)), r1 = sqrtf(-2.f * logf(u2));
+  float s0, c0, s1, c1;
+  sincosf(6.283185307179586f * u1, &s0, &c0);
+  sincosf(6.283185307179586f * u3, &s1, &c1);
+  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+
+// --------------------------------------------------------------- ddpm step
+// eps = eps_u + w (eps_c - eps_u)  (iff reps == 2);  x <- (x - eps*k2)/sqrt(a) + sqrt(b) z.
+// Every fp32 operation is rounded separately (no FMA contraction, IEEE division) so the
+// trajectory matches the reference's chain of torch elementwise ops bit for bit.
+struct DdpmKParams {
+  float* x;
+  const float* eps;
+  int n, hw, reps;
+  float guide_w;
+  const float* coef;
+  const int* step_ptr;
+  int step, timesteps;
+  const float* z;
+  long long z_iter_stride;
+  unsigned long long seed;
+  float* snap;
+  const int* snap_slot;
+};
+__global__ void __launch_bounds__(256) ddpm_step_kernel(const DdpmKParams p) {
+  const int i = p.step_ptr ? *p.step_ptr : p.step;
+  const float k2 = p.coef[i * 4 + 0], sa = p.coef[i * 4 + 1], sb = p.coef[i * 4 + 2];
+  const size_t total4 = (size_t)p.n * p.hw / 4;
+  const size_t half = (size_t)p.n * p.hw;
+  const float* zbase = p.z ? p.z + (size_t)(p.timesteps - i) * p.z_iter_stride : nullptr;
+  const int slot = p.snap_slot ? p.snap_slot[i] : -1;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total4; v += (size_t)gridDim.x * blockDim.x) {
+    float4 x4 = reinterpret_cast<float4*>(p.x)[v];
+    float4 e4 = reinterpret_cast<const float4*>(p.eps)[v];
+    if (p.reps == 2 && p.guide_w > 0.f) {
+      const float4 u4 = reinterpret_cast<const float4*>(p.eps + half)[v];
+      e4.x = __fadd_rn(u4.x, __fmul_rn(p.guide_w, __fsub_rn(e4.x, u4.x)));
+      e4.y = __fadd_rn(u4.y, __fmul_rn(p.guide_w, __fsub_rn(e4.y, u4.y)));
+      e4.z = __fadd_rn(u4.z, __fmul_rn(p.guide_w, __fsub_rn(e4.z, u4.z)));
+      e4.w = __fadd_rn(u4.w, __fmul_rn(p.guide_w, __fsub_rn(e4.w, u4.w)));
+    }
+    float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i > 1) z4 = zbase ? reinterpret_cast<const float4*>(zbase)[v] : philox_normal4(p.seed, (uint32_t)v, (uint32_t)i);
+    x4.x = __fadd_rn(__fdiv_rn(__fsub_rn(x4.x, __fmul_rn(e4.x, k2)), sa), __fmul_rn(sb, z4.x));
+    x4.y = __fadd_rn(__fdiv_rn(__fsub_rn(x4.y, __fmul_rn(e4.y, k2)), sa), __fmul_rn(sb, z4.y));
+    x4.z = __fadd_rn(__fdiv_rn(__fsub_rn(x4.z, __fmul_rn(e4.z, k2)), sa), __fmul_rn(sb, z4.z));
+    x4.w = __fadd_rn(__fdiv_rn(__fsub_rn(x4.w, __fmul_rn(e4.w, k2)), sa), __fmul_rn(sb, z4.w));
+    reinterpret_cast<float4*>(p.x)[v] = x4;
+    if (slot >= 0) reinterpret_cast<float4*>(p.snap + (size_t)slot * half)[v] = x4;
+  }
+}
+__global__ void step_advance_kernel(int* step_ptr, int delta) { *step_ptr += delta; }
+
+// ----------------------------------------------------------------- perturb
+// x_t = ca[t] * x + cb[t] * noise (ca = sqrt(ab_t); cb = 1 - ab_t in the training / NLL form,
+// sqrt(1 - ab_t) in the dataloader-ELBO form).  t per sample (t_idx) or shared (t_shared).
+__global__ void __launch_bounds__(256) perturb_kernel(const float* __restrict__ x, const float* __restrict__ noise,
+                                                      float* __restrict__ out, int n, int hw,
+                                                      const float* __restrict__ ca, const float* __restrict__ cb,
+                                                      const long long* __restrict__ t_idx, int t_shared,
+                                                      const int* __restrict__ step_ptr, unsigned long long seed,
+                                                      uint32_t stream, float* __restrict__ noise_out) {
+  const int hw4 = hw / 4;
+  if (step_ptr) {
+    t_shared = *step_ptr;
+    stream += (uint32_t)t_shared;
+  }
+  const size_t total4 = (size_t)n * hw4;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total4; v += (size_t)gridDim.x * blockDim.x) {
+    const int s = (int)(v / hw4);
+    const int t = t_idx ? (int)t_idx[s] : t_shared;
+    const float a = ca[t], b = cb[t];
+    const float4 x4 = reinterpret_cast<const float4*>(x)[v];
+    float4 n4;
+    if (noise) {
+      n4 = reinterpret_cast<const float4*>(noise)[v];
+    } else {
+      n4 = philox_normal4(seed, (uint32_t)v, stream);
+      reinterpret_cast<float4*>(noise_out)[v] = n4;
+    }
+    float4 o;
+    o.x = __fadd_rn(__fmul_rn(a, x4.x), __fmul_rn(b, n4.x));
+    o.y = __fadd_rn(__fmul_rn(a, x4.y), __fmul_rn(b, n4.y));
+    o.z = __fadd_rn(__fmul_rn(a, x4.z), __fmul_rn(b, n4.z));
+    o.w = __fadd_rn(__fmul_rn(a, x4.w), __fmul_rn(b, n4.w));
+    reinterpret_cast<float4*>(out)[v] = o;
+  }
+}
+
+// --------------------------------------------------------------- mse_accum
+// mse[s] = mean((pred - target)^2) per sample; optionally acc[s] += weight[t] * mse[s].
+__global__ void __launch_bounds__(256) mse_accum_kernel(const float* __restrict__ pred,
+                                                        const float* __restrict__ target, int hw,
+                                                        const float* __restrict__ weight_tab,
+                                                        const long long* __restrict__ t_idx, int t_shared,
+                                                        const int* __restrict__ step_ptr,
+                                                        float* __restrict__ mse_out, float* __restrict__ acc) {
+  __shared__ float red[32];
+  if (step_ptr) t_shared = *step_ptr;
+  const size_t s = blockIdx.x;
+  const float4* p4 = reinterpret_cast<const float4*>(pred + s * hw);
+  const float4* t4 = reinterpret_cast<const float4*>(target + s * hw);
+  float q = 0.f;
+  for (int v = threadIdx.x; v < hw / 4; v += blockDim.x) {
+    const float4 a = p4[v], b = t4[v];
+    const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+    q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+  }
+  const float tot = block_sum(q, red);
+  if (threadIdx.x == 0) {
+    const float mse = tot / (float)hw;
+    if (mse_out) mse_out[s] = mse;
+    if (acc) {
+      const int t = t_idx ? (int)t_idx[s] : t_shared;
+      acc[s] += (weight_tab ? weight_tab[t] : 1.f) * mse;
+    }
+  }
+}
+
+static int grid_for(size_t work_items, int block) {
+  size_t g = (work_items + block - 1) / block;
+  const size_t cap = 148 * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace cdm
+
+using namespace cdm;
+
+extern "C" int cdm_conv_in(const cdm_conv_in_args* a, void* stream) {
+  CDM_CHECK_ARG(a && a->x && a->weight && a->scale && a->shift && a->out);
+  CDM_CHECK_ARG(a->n_img > 0 && a->H > 0 && a->W > 0 && a->cout > 0 && a->cout % 8 == 0 && a->cout <= 512);
+  int rc = check_device();
+  if (rc) return rc;
+  const size_t total = (size_t)a->n_img * a->H * a->W * (a->cout / 8);
+  const int smem = 11 * a->cout * (int)sizeof(float);
+  conv_in_kernel<<<grid_for(total, 256), 256, smem, (cudaStream_t)stream>>>(
+      a->x, a->n_img, a->H, a->W, a->cout, a->weight, a->scale, a->shift, a->relu, (bf16*)a->out);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
+extern "C" int cdm_conv_out(const cdm_conv_out_args* a, void* stream) {
+  CDM_CHECK_ARG(a && a->src && a->mean_rstd && a->gamma && a->beta && a->weight && a->bias && a->out);
+  CDM_CHECK_ARG(a->n_img > 0 && a->H > 0 && a->W > 0 && a->W % 16 == 0 && a->C == 128);
+  int rc = check_device();
+  if (rc) return rc;
+  const size_t items = (size_t)a->n_img * a->H * (a->W / 16);
+  conv_out_kernel<<<grid_for(items, 8), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)a->src, a->n_img, a->H, a->W, a->mean_rstd, a->gamma, a->beta, a->weight, a->bias, a->out);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
+extern "C" int cdm_embed_fc(const float* in, int rows, int din, const float* w1, const float* b1, const float* w2,
+                            const float* b2, int emb, float* out, void* stream) {
+  CDM_CHECK_ARG(in && w1 && b1 && w2 && b2 && out && rows > 0 && din > 0 && emb > 0 && emb <= 4096);
+  int rc = check_device();
+  if (rc) return rc;
+  embed_fc_kernel<<<rows, 256, emb * sizeof(float), (cudaStream_t)stream>>>(in, din, w1, b1, w2, b2, emb, out);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
+extern "C" int cdm_avgpool_gelu(const void* src, int n_img, int P, int C, void* out, void* stream) {
+  CDM_CHECK_ARG(src && out && n_img > 0 && P > 0 && C > 0);
+  int rc = check_device();
+  if (rc) return rc;
+  avgpool_gelu_kernel<<<n_img, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, P, C, (bf16*)out);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
+extern "C" int cdm_gn_relu_film(const cdm_gn_relu_film_args* a, void* stream) {
+  CDM_CHECK_ARG(a && a->src && a->gamma && a->beta && a->out);
+  CDM_CHECK_ARG(a->n_img > 0 && a->P > 0 && a->groups > 0 && a->C % a->groups == 0 && (a->C / a->groups) % 8 == 0);
+  CDM_CHECK_ARG((a->film_scale == nullptr) == (a->film_shift == nullptr));
+  CDM_CHECK_ARG(!a->film_scale || a->film_rows >= 1);
+  int rc = check_device();
+  if (rc) return rc;
+  gn_relu_film_kernel<<<a->n_img * a->groups, 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)a->src, a->P, a->C, a->groups, a->gamma, a->beta, a->eps, a->film_scale, a->film_shift,
+      a->film_rows, a->step_ptr, (bf16*)a->out);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
+extern "C" int cdm_gn_finalize(const float* partial, int n_img, int slots, float count, float eps, float* mean_rstd,
+                               void* stream) {
+  CDM_CHECK_ARG(partial && mean_rstd && n_img > 0 && slots > 0 && count > 0);
+  int rc = check_device();
+  if (rc) return rc;
+  const int warps = n_img * 8;
+  gn_finalize_kernel<<<(warps * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(partial, n_img, slots, count, eps,
+                                                                                 mean_rstd);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
+extern "C" int cdm_ddpm_step(const cdm_ddpm_step_args* a, void* stream) {
+  CDM_CHECK_ARG(a && a->x && a->eps && a->coef);
+  CDM_CHECK_ARG(a->n > 0 && a->hw > 0 && a->hw % 4 == 0 && (a->reps == 1 || a->reps == 2) && a->timesteps > 0);
+  CDM_CHECK_ARG(a->step_ptr || (a->step >= 1 && a->step <= a->timesteps));
+  CDM_CHECK_ARG((a->snap == nullptr) == (a->snap_slot == nullptr));
+  int rc = check_device();
+  if (rc) return rc;
+  DdpmKParams p;
+  p.x = a->x;
+  p.eps = a->eps;
+  p.n = a->n;
+  p.hw = a->hw;
+  p.reps = a->reps;
+  p.guide_w = a->guide_w;
+  p.coef = a->coef;
+  p.step_ptr = a->step_ptr;
+  p.step = a->step;
+  p.timesteps = a->timesteps;
+  p.z = a->z;
+  p.z_iter_stride = a->z_iter_stride;
+  p.seed = a->seed;
+  p.snap = a->snap;
+  p.snap_slot = a->snap_slot;
+  ddpm_step_kernel<<<grid_for((size_t)a->n * a->hw / 4, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
+extern "C" int cdm_step_advance(int* step_ptr, int delta, void* stream) {
+  CDM_CHECK_ARG(step_ptr);
+  int rc = check_device();
+  if (rc) return rc;
+  step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_ptr, delta);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
+extern "C" int cdm_perturb(const cdm_perturb_args* a, void* stream) {
+  CDM_CHECK_ARG(a && a->x && a->out && a->ca && a->cb && a->n > 0 && a->hw > 0 && a->hw % 4 == 0);
+  CDM_CHECK_ARG(a->noise || a->noise_out);
+  int rc = check_device();
+  if (rc) return rc;
+  perturb_kernel<<<grid_for((size_t)a->n * a->hw / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+      a->x, a->noise, a->out, a->n, a->hw, a->ca, a->cb, a->t_idx, a->t_shared, a->step_ptr, a->seed, a->stream_id,
+      a->noise_out);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
+extern "C" int cdm_mse_accum(const cdm_mse_accum_args* a, void* stream) {
+  CDM_CHECK_ARG(a && a->pred && a->target && a->n > 0 && a->hw > 0 && a->hw % 4 == 0 && (a->mse_out || a->acc));
+  int rc = check_device();
+  if (rc) return rc;
+  mse_accum_kernel<<<a->n, 256, 0, (cudaStream_t)stream>>>(a->pred, a->target, a->hw, a->weight_tab, a->t_idx,
+                                                           a->t_shared, a->step_ptr, a->mse_out, a->acc);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}

@@ -1,0 +1,384 @@
+"""DDPM process around ContextUnet: schedule, perturb_input, denoise_add_noise, the
+1500-step ancestral sampler with classifier-free guidance, the all-timestep NLL and the
+two ELBO/BPD variants.  Mirrors the closures / functions of the reference scripts
+(code/train_diffusion_paper.py:77-183,205-217,320-321,548-686; code/sample_power_spectra.py:64-110;
+code/train_diffusion_elbo.py:74-105) — same names, argument meaning and return values.
+
+The sampling step (1 or 2 U-Net passes + CFG mix + x_{t-1} update) is captured once as a CUDA
+graph and replayed `timesteps` times; the step index lives in a device int that the kernels
+read (time-embedding row, shortcut row, schedule coefficients, noise offset, snapshot slot).
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+# --------------------------------------------------------------------------- schedule
+def make_schedule(timesteps, beta1=1e-4, beta2=0.02, device="cuda"):
+    """b_t, a_t, ab_t with T+1 entries (train_diffusion_paper.py:205-217)."""
+    b_t = (beta2 - beta1) * torch.linspace(0, 1, timesteps + 1, device=device) + beta1
+    a_t = 1 - b_t
+    ab_t = torch.cumsum(a_t.log(), dim=0).exp()
+    ab_t[0] = 1
+    return b_t, a_t, ab_t
+
+
+def _coef_table(b_t, a_t, ab_t):
+    """[T+1][4] fp32: (1-a_t)/sqrt(1-ab_t), sqrt(a_t), sqrt(b_t), 0 — the scalars of
+    denoise_add_noise evaluated with the reference's own torch expressions (paper.py:551-552)."""
+    k2 = (1 - a_t) / (1 - ab_t).sqrt()
+    return torch.stack([k2, a_t.sqrt(), b_t.sqrt(), torch.zeros_like(b_t)], 1).float().contiguous()
+
+
+def _time_table(model, timesteps, dev):
+    """temb1/temb2 for every t = i/T, i = 0..T: [T+1, 2nf], [T+1, nf] (row i <-> tensor([i / timesteps]))."""
+    tv = (torch.arange(timesteps + 1, dtype=torch.float64) / timesteps).float().to(dev).view(-1, 1)
+    return model.timeembed1(tv), model.timeembed2(tv)
+
+
+def draw_shortcut_table(timesteps, reps, n_feat=128):
+    """Shortcut (w_c, b_c) draws for a whole sampling run, in the order the reference's loop consumes the
+    global CPU generator (one fresh nn.Conv2d(1,n_feat,1) per forward: weight U(-1,1)[n_feat] then
+    bias U(-1,1)[n_feat]; conditional pass before the unconditional one).  Returns [T+1][reps][2][n_feat]
+    indexed by the step i (row 0 unused)."""
+    tab = torch.zeros(timesteps + 1, reps, 2, n_feat)
+    for i in range(timesteps, 0, -1):
+        for r in range(reps):
+            tab[i, r, 0].uniform_(-1, 1)
+            tab[i, r, 1].uniform_(-1, 1)
+    return tab
+
+
+def shortcut_table_from_list(shortcuts, timesteps, reps, order="descending"):
+    """Recorded per-forward (w_c, b_c) pairs -> step-indexed table.  order='descending': iteration k is
+    step T-k (sampler); 'ascending': iteration k is step k+1 (likelihood loop)."""
+    n_feat = shortcuts[0][0].numel()
+    tab = torch.zeros(timesteps + 1, reps, 2, n_feat)
+    for k in range(timesteps):
+        i = timesteps - k if order == "descending" else k + 1
+        for r in range(reps):
+            w, b = shortcuts[k * reps + r]
+            tab[i, r, 0], tab[i, r, 1] = w.view(-1), b.view(-1)
+    return tab
+
+
+def snapshot_steps(timesteps, save_rate=20):
+    return [i for i in range(timesteps, 0, -1) if i % save_rate == 0 or i == timesteps or i < 8]
+
+
+# --------------------------------------------------------------------------- elementwise API
+def perturb_input(x, t, noise, ab_t):
+    """sqrt(ab_t[t]) * x + (1 - ab_t[t]) * noise  (train_diffusion_paper.py:320-321; not sqrt(1-ab_t))."""
+    dev = ab_t.device
+    x = x.to(dev, torch.float32).contiguous()
+    noise = noise.to(dev, torch.float32).contiguous()
+    out = torch.empty_like(x)
+    ca, cb = ab_t.sqrt().contiguous(), (1 - ab_t).contiguous()
+    if torch.is_tensor(t) and t.numel() > 1:
+        L.perturb(x, out, ca, cb, noise=noise, t_idx=t.to(dev, torch.int64).contiguous())
+    else:
+        L.perturb(x, out, ca, cb, noise=noise, t_shared=int(t))
+    return out
+
+
+def denoise_add_noise(x, t, pred_noise, z=None, b_t=None, a_t=None, ab_t=None):
+    """(x - pred_noise*(1-a_t)/sqrt(1-ab_t))/sqrt(a_t) + sqrt(b_t)*z  (sample_power_spectra.py:64-69)."""
+    dev = b_t.device
+    out = x.to(dev, torch.float32).clone().contiguous()
+    eps = pred_noise.to(dev, torch.float32).contiguous()
+    if z is None:
+        z = torch.randn_like(out)
+    elif not torch.is_tensor(z):
+        z = torch.full_like(out, float(z))
+    t = int(t)
+    # the kernel zeroes z at step 1 (the sampler's convention); apply the explicit z through a 2-step table
+    coef = _coef_table(b_t, a_t, ab_t)
+    tab = torch.stack([coef[t], coef[t], coef[t]], 0).contiguous()
+    L.ddpm_step(out, eps, tab, 2, reps=1, step=2, z=z.to(dev, torch.float32).contiguous(), z_iter_stride=0)
+    return out
+
+
+# --------------------------------------------------------------------------- sampler
+class _SamplerRun:
+    """Device state of one sampling run + the captured one-step CUDA graph."""
+
+    def __init__(self, model, x_T, params, guide_w, timesteps, sched, *, z_all=None, shortcut_tab=None,
+                 save_rate=20, seed=None, use_graph=True, snapshots=True):
+        dev = model._check_supported()
+        if model.training:
+            raise L.CdmError("sampling needs eval mode (BatchNorm running statistics): call model.eval()")
+        self.model, self.T, self.dev = model, timesteps, dev
+        b_t, a_t, ab_t = (s.to(dev, torch.float32) for s in sched)
+        B = x_T.shape[0]
+        self.B = B
+        self.cfg = bool(guide_w > 0 and params is not None)
+        self.reps = 2 if self.cfg else 1
+        self.guide_w = float(guide_w)
+        hw = model.h * model.h
+        self.x = x_T.detach().to(dev, torch.float32).reshape(B, 1, model.h, model.h).clone().contiguous()
+        c = torch.zeros(B, model.n_cfeat, device=dev) if params is None else params.to(dev, torch.float32)
+        c_all = torch.cat([c, torch.zeros_like(c)], 0) if self.cfg else c
+        self.cemb1, self.cemb2 = model.contextembed1(c_all.contiguous()), model.contextembed2(c_all.contiguous())
+        self.temb1, self.temb2 = _time_table(model, timesteps, dev)
+        if shortcut_tab is None:
+            shortcut_tab = draw_shortcut_table(timesteps, self.reps, model.n_feat)
+        assert tuple(shortcut_tab.shape) == (timesteps + 1, self.reps, 2, model.n_feat)
+        self.sc_tab = shortcut_tab.to(dev, torch.float32).contiguous()
+        self.coef = _coef_table(b_t, a_t, ab_t)
+        self.step = torch.full((1,), timesteps, device=dev, dtype=torch.int32)
+        self.snap_steps = snapshot_steps(timesteps, save_rate) if snapshots else []
+        if self.snap_steps:
+            slot = torch.full((timesteps + 1,), -1, dtype=torch.int32)
+            for k, i in enumerate(self.snap_steps):
+                slot[i] = k
+            self.snap_slot = slot.to(dev)
+            self.snap = torch.empty(len(self.snap_steps), B, 1, model.h, model.h, device=dev)
+        else:
+            self.snap_slot, self.snap = None, None
+        if z_all is not None:
+            self.z = z_all.to(dev, torch.float32).reshape(timesteps, B * hw).contiguous()
+            self.z_stride = B * hw
+        else:
+            self.z, self.z_stride = None, 0
+        self.seed = int(seed) if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        self.graph = None
+        self.use_graph = use_graph
+
+    def _one_step(self):
+        m = self.model
+        eps = m.forward_eval_into(self.x.view(self.B, m.h, m.h), self.sc_tab, self.cemb1, self.temb1, self.cemb2,
+                                  self.temb2, 1, reps=self.reps, step_ptr=self.step)
+        L.ddpm_step(self.x, eps, self.coef, self.T, reps=self.reps, guide_w=self.guide_w, step_ptr=self.step,
+                    z=self.z, z_iter_stride=self.z_stride, seed=self.seed, snap=self.snap, snap_slot=self.snap_slot)
+        L.step_advance(self.step, -1)
+
+    def capture(self):
+        """Warm up once on scratch state (sets kernel attributes, fills caches), then capture one step."""
+        x_keep = self.x.clone()
+        self._one_step()
+        torch.cuda.synchronize()
+        self.x.copy_(x_keep)
+        self.step.fill_(self.T)
+        if self.use_graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._one_step()
+            self.x.copy_(x_keep)
+            self.step.fill_(self.T)
+            self.graph = g
+        torch.cuda.synchronize()
+
+    def run(self, n_steps=None):
+        n_steps = self.T if n_steps is None else n_steps
+        for _ in range(n_steps):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._one_step()
+
+    def intermediate(self):
+        if self.snap is None:
+            return np.zeros((0,) + tuple(self.x.shape), np.float32)
+        return self.snap.cpu().numpy()
+
+
+def _sample(model, x_T, params, guide_w, timesteps, sched, **kw):
+    run = _SamplerRun(model, x_T, params, guide_w, timesteps, sched, **kw)
+    run.capture()
+    t0 = time.time()
+    run.run()
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    return run.x, run.intermediate(), dt
+
+
+@torch.no_grad()
+def sample_ddpm(model, n_sample=1, size=64, device=None, params=None, guide_w=0.0, timesteps=1000, b_t=None,
+                a_t=None, ab_t=None, **kw):
+    """Pure-function sampler of code/sample_power_spectra.py:71-110 -> x [n,1,size,size]."""
+    dev = model._check_supported() if device is None else torch.device(device)
+    x = torch.randn(n_sample, 1, size, size)  # CPU generator, as the reference (:79)
+    if params is None:
+        params = torch.rand(n_sample, 6)  # :83 (hard-coded 6 in the reference's pure-function form)
+    x, _, _ = _sample(model, x.to(dev), params.to(dev), guide_w, timesteps, (b_t, a_t, ab_t), snapshots=False, **kw)
+    return x
+
+
+class DDPM:
+    """The closures of code/train_diffusion_paper.py bound to one model + schedule."""
+
+    def __init__(self, nn_model, timesteps, beta1=1e-4, beta2=0.02, device=None):
+        self.nn_model = nn_model
+        self.timesteps = timesteps
+        self.device = torch.device(device) if device is not None else nn_model.out[3].weight.device
+        self.b_t, self.a_t, self.ab_t = make_schedule(timesteps, beta1, beta2, self.device)
+        self.n_cfeat = nn_model.n_cfeat
+
+    @property
+    def sched(self):
+        return self.b_t, self.a_t, self.ab_t
+
+    def perturb_input(self, x, t, noise):
+        return perturb_input(x, t, noise, self.ab_t)
+
+    def denoise_add_noise(self, x, t, pred_noise, z=None):
+        return denoise_add_noise(x, t, pred_noise, z, self.b_t, self.a_t, self.ab_t)
+
+    @torch.no_grad()
+    def sample_ddpm(self, n_sample=1, size=64, device=None, params=None, guide_w=0.0, **kw):
+        """train_diffusion_paper.py:555-623 -> (x, intermediate[n_snap,B,1,64,64], sampling_time, timestep_times)."""
+        t0 = time.time()
+        x = torch.randn(n_sample, 1, size, size)  # :578
+        if params is None:
+            params = torch.rand(n_sample, self.n_cfeat)  # :580-582
+        x, inter, dt = _sample(self.nn_model, x.to(self.device), params.to(self.device), guide_w, self.timesteps,
+                               self.sched, **kw)
+        return x, inter, time.time() - t0, [dt / self.timesteps] * self.timesteps
+
+    @torch.no_grad()
+    def sample_ddpm_from_noise(self, noise_images, params=None, save_rate=20, guide_w=0.0, **kw):
+        """train_diffusion_paper.py:625-686: params=None -> unconditional (c=None -> zeros), no CFG."""
+        t0 = time.time()
+        x, inter, dt = _sample(self.nn_model, noise_images.clone().to(self.device), params, guide_w, self.timesteps,
+                               self.sched, save_rate=save_rate, **kw)
+        return x, inter, time.time() - t0, [dt / self.timesteps] * self.timesteps
+
+    def calculate_likelihood(self, dataloader, **kw):
+        return calculate_likelihood(self.nn_model, dataloader, self.timesteps, self.device, self.ab_t, self.b_t,
+                                    self.a_t, **kw)
+
+    def calculate_elbo_and_bpd(self, dataloader, **kw):
+        return calculate_elbo_and_bpd(self.nn_model, dataloader, self.timesteps, self.device, self.ab_t, self.b_t,
+                                      self.a_t, **kw)
+
+
+# --------------------------------------------------------------------------- likelihood / ELBO
+class _EvalLoop:
+    """perturb -> U-Net -> per-sample MSE accumulate for one (x, param) batch at a device-resident step t."""
+
+    def __init__(self, model, x, param, timesteps, sched, cb_kind, weight_tab, *, shortcut_tab=None, seed=0):
+        dev = model._check_supported()
+        if model.training:
+            raise L.CdmError("likelihood / ELBO evaluation needs eval mode: call model.eval()")
+        self.model, self.T, self.dev = model, timesteps, dev
+        b_t, a_t, ab_t = (s.to(dev, torch.float32) for s in sched)
+        self.B = x.shape[0]
+        self.x = x.detach().to(dev, torch.float32).reshape(self.B, 1, model.h, model.h).contiguous()
+        c = torch.zeros(self.B, model.n_cfeat, device=dev) if param is None else param.to(dev, torch.float32)
+        self.cemb1, self.cemb2 = model.contextembed1(c.contiguous()), model.contextembed2(c.contiguous())
+        self.temb1, self.temb2 = _time_table(model, timesteps, dev)
+        self.ca = ab_t.sqrt().contiguous()
+        self.cb = ((1 - ab_t) if cb_kind == "one_minus" else torch.sqrt(1 - ab_t)).contiguous()
+        self.weight = weight_tab.to(dev, torch.float32).contiguous()
+        if shortcut_tab is None:
+            shortcut_tab = torch.zeros(timesteps + 1, 1, 2, model.n_feat)
+            for i in range(1, timesteps + 1):
+                shortcut_tab[i, 0, 0].uniform_(-1, 1)
+                shortcut_tab[i, 0, 1].uniform_(-1, 1)
+        self.sc_tab = shortcut_tab.to(dev, torch.float32).contiguous()
+        self.step = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.xt = torch.empty_like(self.x)
+        self.noise = torch.empty_like(self.x)
+        self.acc = torch.zeros(self.B, device=dev)
+        self.mse = torch.zeros(self.B, device=dev)
+        self.seed = seed
+        self.graph = None
+
+    def one(self, noise=None):
+        m = self.model
+        if noise is not None:
+            self.noise.copy_(noise.reshape(self.noise.shape))
+            L.perturb(self.x, self.xt, self.ca, self.cb, noise=self.noise, step_ptr=self.step)
+        else:
+            L.perturb(self.x, self.xt, self.ca, self.cb, step_ptr=self.step, seed=self.seed, noise_out=self.noise)
+        eps = m.forward_eval_into(self.xt.view(self.B, m.h, m.h), self.sc_tab, self.cemb1, self.temb1, self.cemb2,
+                                  self.temb2, 1, reps=1, step_ptr=self.step)
+        L.mse_accum(eps, self.noise, weight_tab=self.weight, step_ptr=self.step, mse_out=self.mse, acc=self.acc)
+
+    def sweep_all(self):
+        """t = 1..T with in-kernel noise, one captured graph replayed T times."""
+        self.step.fill_(1)
+        self.one()
+        torch.cuda.synchronize()
+        self.acc.zero_()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.one()
+            L.step_advance(self.step, 1)
+        self.acc.zero_()
+        self.step.fill_(1)
+        for _ in range(self.T):
+            g.replay()
+        return self.acc
+
+
+@torch.no_grad()
+def calculate_likelihood(model, dataloader, timesteps, device, ab_t, b_t, a_t, *, noises=None, shortcuts=None,
+                         seed=0):
+    """Mean over the dataset of sum_{t=1..T} mse_t / (2 b_t)  (train_diffusion_paper.py:142-183).
+    noises / shortcuts: optional per-batch lists of recorded draws (tests); default: in-kernel Philox noise
+    and shortcut draws from the global CPU generator."""
+    model.eval()
+    total_nll, num_samples = 0.0, 0
+    w = 1.0 / (2 * b_t.float())
+    for bi, (x, param) in enumerate(dataloader):
+        sc = None
+        if shortcuts is not None:
+            sc = shortcut_table_from_list(shortcuts[bi], timesteps, 1, order="ascending")
+        loop = _EvalLoop(model, x, param, timesteps, (b_t, a_t, ab_t), "one_minus", w, shortcut_tab=sc,
+                         seed=seed + 7919 * bi)
+        if noises is None:
+            acc = loop.sweep_all()
+        else:
+            for t in range(1, timesteps + 1):
+                loop.step.fill_(t)
+                loop.one(noises[bi][t - 1].to(loop.dev))
+            acc = loop.acc
+        total_nll += acc.sum().item()
+        num_samples += x.shape[0]
+    return total_nll / num_samples
+
+
+@torch.no_grad()
+def calculate_elbo_and_bpd(model, dataloader, timesteps, device, ab_t, b_t, a_t, *, noises=None, shortcuts=None,
+                           seed=0):
+    """Dataloader ELBO/BPD of train_diffusion_paper.py:77-139: 10 timesteps linspace(1,T,10).long(),
+    x_t = sqrt(ab) x + sqrt(1-ab) noise, weight 0.5 b_t/(1-ab_t), t<=1 skipped, /10."""
+    model.eval()
+    total, num = 0.0, 0
+    w = 0.5 * (b_t.float() / (1.0 - ab_t.float())) / 10.0
+    w = torch.where(torch.arange(timesteps + 1, device=w.device) > 1, w, torch.zeros_like(w))
+    ts = [int(v) for v in torch.linspace(1, timesteps, 10).long()]
+    for bi, (x, param) in enumerate(dataloader):
+        sc = None
+        if shortcuts is not None:
+            sc = torch.zeros(timesteps + 1, 1, 2, model.n_feat)
+            for k, t in enumerate(ts):  # later duplicates of t (tiny T) overwrite: replay needs distinct t
+                sc[t, 0, 0], sc[t, 0, 1] = shortcuts[bi][k][0].view(-1), shortcuts[bi][k][1].view(-1)
+        loop = _EvalLoop(model, x, param, timesteps, (b_t, a_t, ab_t), "sqrt", w, shortcut_tab=sc,
+                         seed=seed + 104729 * bi)
+        for k, t in enumerate(ts):
+            loop.step.fill_(t)
+            loop.seed = seed + 104729 * bi + 31 * k
+            loop.one(None if noises is None else noises[bi][k].to(loop.dev))
+        total += loop.acc.sum().item()
+        num += x.shape[0]
+    avg = total / num
+    return avg, avg / (64 * 64 * np.log(2))
+
+
+@torch.no_grad()
+def calculate_elbo_and_bpd_batch(x, pred_noise, noise, t, b_t, a_t, ab_t, dims):
+    """Per-batch ELBO/BPD of train_diffusion_elbo.py:74-105 -> (0-d tensor, 0-d tensor)."""
+    dev = ab_t.device
+    pred = pred_noise.detach().to(dev, torch.float32).contiguous()
+    tgt = noise.detach().to(dev, torch.float32).contiguous()
+    B = pred.shape[0]
+    w = (0.5 * (1.0 / (1.0 - ab_t.float()) - 1.0)).contiguous()
+    acc = torch.zeros(B, device=dev)
+    L.mse_accum(pred, tgt, weight_tab=w, t_idx=t.to(dev, torch.int64).contiguous(), acc=acc)
+    elbo = acc.mean()
+    return elbo, elbo / (dims * np.log(2))

@@ -1,0 +1,295 @@
+"""Drop-in ContextUnet for the reference's `ContextUnet.py` / `diffusion_utilities.py`.
+
+Same constructor, attribute names, parameter shapes and `state_dict` keys as the
+reference (ContextUnet.py:5-40, code/diffusion_utilities.py:13-145), so weights
+move both ways with `load_state_dict`.  The nn.Conv2d / BatchNorm2d / ... children
+are parameter containers only: `forward` never calls them.  All arithmetic runs in
+the sm_100a kernels behind include/cdm_b200.h; on a CPU tensor / non-sm_100 device
+`forward` raises (there is no fallback path).
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+BN_EPS = 1e-5
+GN_EPS = 1e-5
+
+
+class ResidualConvBlock(nn.Module):
+    """Parameter layout of diffusion_utilities.py:13-37 (Conv3x3-BN-ReLU twice)."""
+
+    def __init__(self, in_channels, out_channels, is_res=False):
+        super().__init__()
+        self.same_channels = in_channels == out_channels
+        self.is_res = is_res
+        self.conv1 = nn.Sequential(nn.Conv2d(in_channels, out_channels, 3, 1, 1), nn.BatchNorm2d(out_channels),
+                                   nn.ReLU())
+        self.conv2 = nn.Sequential(nn.Conv2d(out_channels, out_channels, 3, 1, 1), nn.BatchNorm2d(out_channels),
+                                   nn.ReLU())
+
+    def get_out_channels(self):
+        return self.conv2[0].out_channels
+
+
+class UnetUp(nn.Module):
+    """diffusion_utilities.py:79-92."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.model = nn.Sequential(nn.ConvTranspose2d(in_channels, out_channels, 2, 2),
+                                   ResidualConvBlock(out_channels, out_channels),
+                                   ResidualConvBlock(out_channels, out_channels))
+
+
+class UnetDown(nn.Module):
+    """diffusion_utilities.py:103-112."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.model = nn.Sequential(ResidualConvBlock(in_channels, out_channels),
+                                   ResidualConvBlock(out_channels, out_channels), nn.MaxPool2d(2))
+
+
+class EmbedFC(nn.Module):
+    """diffusion_utilities.py:118-145."""
+
+    def __init__(self, input_dim, emb_dim):
+        super().__init__()
+        self.input_dim = input_dim
+        self.model = nn.Sequential(nn.Linear(input_dim, emb_dim), nn.GELU(), nn.Linear(emb_dim, emb_dim))
+
+    def forward(self, x):
+        p = self.model[0].weight
+        x = x.to(p.device).reshape(-1, self.input_dim).float().contiguous()
+        out = torch.empty(x.shape[0], self.model[2].weight.shape[0], device=p.device, dtype=torch.float32)
+        return L.embed_fc(x, self.model[0].weight.detach().contiguous(), self.model[0].bias.detach().contiguous(),
+                          self.model[2].weight.detach().contiguous(), self.model[2].bias.detach().contiguous(), out)
+
+
+def _fold_bn(conv, bn):
+    """Eval-mode BatchNorm folded into a per-channel scale/shift of the conv accumulator."""
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    shift = bn.bias.detach().float() + (conv.bias.detach().float() - bn.running_mean.detach().float()) * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+def _pack_conv3(conv):
+    """OIHW fp32 -> [cout][kh][kw][cin] bf16 (K-major rows for the implicit GEMM)."""
+    return conv.weight.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def _pack_convT(convt):
+    """ConvTranspose2d IOHW -> GEMM B operand [(kh*k+kw)*cout + co][ci] bf16."""
+    w = convt.weight.detach()
+    ci, co, kh, kw = w.shape
+    return w.permute(2, 3, 1, 0).reshape(kh * kw * co, ci).contiguous().to(torch.bfloat16)
+
+
+class _Workspace:
+    """Activation buffers (NHWC bf16) for `n` images in flight (n = reps * batch)."""
+
+    def __init__(self, batch, reps, nf, h, dev):
+        n = batch * reps
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        f32 = dict(device=dev, dtype=torch.float32)
+        h2, h4 = h // 2, h // 4
+        self.n, self.batch, self.reps = n, batch, reps
+        self.x0 = torch.empty(n, h, h, nf, **bf)
+        self.p64 = torch.empty(n, h, h, nf, **bf)
+        self.q64 = torch.empty(n, h, h, nf, **bf)
+        self.a1 = self.q64[:batch]  # init_conv.conv1 output, dead before q64 is first written
+        self.d1 = torch.empty(n, h2, h2, nf, **bf)
+        self.p32w = torch.empty(n, h2, h2, 2 * nf, **bf)
+        self.q32w = torch.empty(n, h2, h2, 2 * nf, **bf)
+        # the nf-wide h/2 buffers of up1 alias the (dead by then) 2nf-wide ones of down2
+        self.p32 = self.p32w.view(-1)[: n * h2 * h2 * nf].view(n, h2, h2, nf)
+        self.q32 = self.q32w.view(-1)[: n * h2 * h2 * nf].view(n, h2, h2, nf)
+        self.u1f = torch.empty(n, h2, h2, nf, **bf)
+        self.d2 = torch.empty(n, h4, h4, 2 * nf, **bf)
+        self.hidden = torch.empty(n, 2 * nf, **bf)
+        self.u0raw = torch.empty(n, h4 * h4, 2 * nf, **bf)
+        self.u0f = torch.empty(n, h4 * h4, 2 * nf, **bf)
+        self.gn_partial = torch.empty(n, (h // 16) * (h // 16) * 8, 8, 2, **f32)
+        self.gn_mr = torch.empty(n, 8, 2, **f32)
+        self.eps = torch.empty(n, 1, h, h, **f32)
+
+
+class ContextUnet(nn.Module):
+    """ContextUnet(in_channels=1, n_feat=128, n_cfeat, height=64) — ContextUnet.py:5-60."""
+
+    def __init__(self, in_channels, n_feat=128, n_cfeat=10, height=64):
+        super().__init__()
+        self.in_channels = in_channels
+        self.n_feat = n_feat
+        self.n_cfeat = n_cfeat
+        self.h = height
+        # construction order == reference (ContextUnet.py:14-40): seeded init gives identical weights
+        self.init_conv = ResidualConvBlock(in_channels, n_feat, is_res=True)
+        self.down1 = UnetDown(n_feat, n_feat)
+        self.down2 = UnetDown(n_feat, 2 * n_feat)
+        self.to_vec = nn.Sequential(nn.AvgPool2d((self.h // 4)), nn.GELU())
+        self.timeembed1 = EmbedFC(1, 2 * n_feat)
+        self.timeembed2 = EmbedFC(1, n_feat)
+        self.contextembed1 = EmbedFC(n_cfeat, 2 * n_feat)
+        self.contextembed2 = EmbedFC(n_cfeat, n_feat)
+        self.up0 = nn.Sequential(nn.ConvTranspose2d(2 * n_feat, 2 * n_feat, self.h // 4, self.h // 4),
+                                 nn.GroupNorm(8, 2 * n_feat), nn.ReLU())
+        self.up1 = UnetUp(4 * n_feat, n_feat)
+        self.up2 = UnetUp(2 * n_feat, n_feat)
+        self.out = nn.Sequential(nn.Conv2d(2 * n_feat, n_feat, 3, 1, 1), nn.GroupNorm(8, n_feat), nn.ReLU(),
+                                 nn.Conv2d(n_feat, self.in_channels, 3, 1, 1))
+        self._packed = None
+        self._packed_key = None
+        self._ws = {}
+        self.conv_mode = L.CONV_MODE_SHIFT18
+
+    # ------------------------------------------------------------------ weights
+    def _check_supported(self):
+        if self.in_channels != 1 or self.n_feat != 128 or self.h != 64:
+            raise L.CdmError("the sm_100a kernels are specialised for in_channels=1, n_feat=128, height=64 "
+                             "(the configuration BASELINE.json names)")
+        dev = self.out[3].weight.device
+        if dev.type != "cuda":
+            raise L.CdmError("ContextUnet parameters are on the CPU: the hot path has no CPU fallback; "
+                             "move the module to an sm_100 device with .to('cuda')")
+        return dev
+
+    def _key(self):
+        return tuple((id(t), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def invalidate(self):
+        """Drop packed (bf16, BN-folded) weights; called automatically when parameters change."""
+        self._packed, self._packed_key = None, None
+
+    def packed(self):
+        """BF16 K-major weights + folded eval-BatchNorm vectors, rebuilt when any parameter/buffer changed."""
+        key = self._key()
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        P = {}
+        rcbs = {"init_conv": self.init_conv, "down1.0": self.down1.model[0], "down1.1": self.down1.model[1],
+                "down2.0": self.down2.model[0], "down2.1": self.down2.model[1],
+                "up1.1": self.up1.model[1], "up1.2": self.up1.model[2],
+                "up2.1": self.up2.model[1], "up2.2": self.up2.model[2]}
+        for name, blk in rcbs.items():
+            for cname, seq in (("c1", blk.conv1), ("c2", blk.conv2)):
+                scale, shift = _fold_bn(seq[0], seq[1])
+                if name == "init_conv" and cname == "c1":
+                    w = seq[0].weight.detach().float().reshape(self.n_feat, 9).t().contiguous()  # [9][cout]
+                else:
+                    w = _pack_conv3(seq[0])
+                P[f"{name}.{cname}"] = (w, scale, shift)
+        dev = self.out[3].weight.device
+        P["up0.w"] = _pack_convT(self.up0[0])
+        P["up0.b"] = self.up0[0].bias.detach().float().contiguous()
+        P["up0.gn"] = (self.up0[1].weight.detach().float().contiguous(), self.up0[1].bias.detach().float().contiguous())
+        for nm, mod in (("up1", self.up1), ("up2", self.up2)):
+            P[nm + ".w"] = _pack_convT(mod.model[0])
+            P[nm + ".b"] = mod.model[0].bias.detach().float().contiguous()
+        P["out0"] = (_pack_conv3(self.out[0]), torch.ones(self.n_feat, device=dev),
+                     self.out[0].bias.detach().float().contiguous())
+        P["out.gn"] = (self.out[1].weight.detach().float().contiguous(), self.out[1].bias.detach().float().contiguous())
+        P["out3.w"] = self.out[3].weight.detach().float()[0].permute(1, 2, 0).reshape(9, self.n_feat).contiguous()
+        P["out3.b"] = self.out[3].bias.detach().float().contiguous()
+        self._packed, self._packed_key = P, key
+        return P
+
+    def workspace(self, batch, reps):
+        k = (batch, reps)
+        if k not in self._ws:
+            if len(self._ws) > 4:
+                self._ws.clear()
+            self._ws[k] = _Workspace(batch, reps, self.n_feat, self.h, self.out[3].weight.device)
+        return self._ws[k]
+
+    # ------------------------------------------------------------------ embeddings
+    def embed(self, t, c):
+        """The four EmbedFC outputs (ContextUnet.py:51-54): cemb1[B,2nf], temb1[nt,2nf], cemb2[B,nf], temb2[nt,nf]."""
+        return self.contextembed1(c), self.timeembed1(t), self.contextembed2(c), self.timeembed2(t)
+
+    # ------------------------------------------------------------------ eval forward
+    def forward_eval_into(self, x, sc_tab, cemb1, temb1, cemb2, temb2, temb_rows, *, reps=1, step_ptr=None):
+        """Eval-mode forward of `reps` passes that share x (reps=2: the conditional and unconditional
+        classifier-free-guidance passes).  x fp32 [B,64,64]; sc_tab fp32 [steps][reps][2][128];
+        cemb* fp32 [reps*B,C]; temb* fp32 [steps][temb_rows][C] (row picked by *step_ptr).
+        Returns the workspace's eps buffer, fp32 [reps*B,1,64,64] (overwritten by the next call)."""
+        P = self.packed()
+        B = x.shape[0]
+        ws = self.workspace(B, reps)
+        n, h, nf, mode = ws.n, self.h, self.n_feat, self.conv_mode
+        R, POOL, FILM, SC, GN = L.EPI_RELU, L.EPI_POOL, L.EPI_FILM, L.EPI_SHORTCUT, L.EPI_GNSTATS
+
+        def conv(src, name, out, flags=R, **kw):
+            w, s, b = P[name]
+            return L.conv3x3(src, w, s, b, out, flags=flags, mode=mode, **kw)
+
+        w, s, b = P["init_conv.c1"]
+        L.conv_in(x, w, s, b, ws.a1)
+        conv(ws.a1, "init_conv.c2", ws.x0, R | SC, sc_x=x, sc_tab=sc_tab, sc_reps=reps, step_ptr=step_ptr)
+        conv(ws.x0, "down1.0.c1", ws.p64)
+        conv(ws.p64, "down1.0.c2", ws.q64)
+        conv(ws.q64, "down1.1.c1", ws.p64)
+        conv(ws.p64, "down1.1.c2", ws.d1, R | POOL)
+        conv(ws.d1, "down2.0.c1", ws.p32w)
+        conv(ws.p32w, "down2.0.c2", ws.q32w)
+        conv(ws.q32w, "down2.1.c1", ws.p32w)
+        conv(ws.p32w, "down2.1.c2", ws.d2, R | POOL)
+        h4 = h // 4
+        L.avgpool_gelu(ws.d2.view(n, h4 * h4, 2 * nf), ws.hidden)
+        L.gemm(ws.hidden, P["up0.w"], P["up0.b"], ws.u0raw, shift_mod=2 * nf)
+        g, bt = P["up0.gn"]
+        L.gn_relu_film(ws.u0raw, g, bt, ws.u0f, groups=8, eps=GN_EPS, film_scale=cemb1, film_shift=temb1,
+                       film_rows=temb_rows, step_ptr=step_ptr)
+        L.gemm(ws.u0f.view(n * h4 * h4, 2 * nf), P["up1.w"], P["up1.b"], ws.p32,
+               a1=ws.d2.view(n * h4 * h4, 2 * nf), out_mode=1, H=h4, W=h4, shift_mod=nf)
+        conv(ws.p32, "up1.1.c1", ws.q32)
+        conv(ws.q32, "up1.1.c2", ws.p32)
+        conv(ws.p32, "up1.2.c1", ws.q32)
+        conv(ws.q32, "up1.2.c2", ws.u1f, R | FILM, film_scale=cemb2, film_shift=temb2, film_shift_rows=temb_rows,
+             step_ptr=step_ptr)
+        h2 = h // 2
+        L.gemm(ws.u1f.view(n * h2 * h2, nf), P["up2.w"], P["up2.b"], ws.p64, a1=ws.d1.view(n * h2 * h2, nf),
+               out_mode=1, H=h2, W=h2, shift_mod=nf)
+        conv(ws.p64, "up2.1.c1", ws.q64)
+        conv(ws.q64, "up2.1.c2", ws.p64)
+        conv(ws.p64, "up2.2.c1", ws.q64)
+        conv(ws.q64, "up2.2.c2", ws.p64)
+        conv(ws.p64, "out0", ws.q64, GN, src1=ws.x0, gn_partial=ws.gn_partial)
+        L.gn_finalize(ws.gn_partial, float((nf // 8) * h * h), ws.gn_mr, GN_EPS)
+        g, bt = P["out.gn"]
+        L.conv_out(ws.q64, ws.gn_mr, g, bt, P["out3.w"], P["out3.b"], ws.eps.view(n, h, h))
+        return ws.eps
+
+    def draw_shortcut(self):
+        """The reference builds `nn.Conv2d(C_in, n_feat, 1)` afresh on every forward
+        (diffusion_utilities.py:54): random, unregistered, drawn from the global CPU generator.
+        Constructing the same layer consumes the generator identically."""
+        sc = nn.Conv2d(self.in_channels, self.n_feat, kernel_size=1, stride=1, padding=0)
+        return torch.cat([sc.weight.detach().view(-1), sc.bias.detach().view(-1)])  # [2*n_feat]: w_c then b_c
+
+    def forward(self, x, t, c=None, shortcut=None):
+        """ContextUnet.forward (ContextUnet.py:42-60).  x [B,1,64,64]; t numel 1 or B; c [B,n_cfeat] or None.
+        `shortcut` ([2*n_feat] = w_c,b_c) overrides the per-call random 1x1 shortcut (tests / replay)."""
+        dev = self._check_supported()
+        if self.training:
+            from .train import forward_train
+            return forward_train(self, x, t, c, shortcut)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and x.requires_grad:
+            raise L.CdmError("eval-mode forward does not build an autograd graph; call .train() for training")
+        B = x.shape[0]
+        x3 = x.detach().to(dev, torch.float32).reshape(B, self.h, self.h).contiguous()
+        if c is None:
+            c = torch.zeros(B, self.n_cfeat, device=dev)  # ContextUnet.py:48-49
+        t = torch.as_tensor(t).to(dev, torch.float32).reshape(-1, 1)
+        if t.shape[0] not in (1, B):
+            raise L.CdmError(f"t must have 1 or {B} elements, got {t.shape[0]}")
+        cemb1, temb1, cemb2, temb2 = self.embed(t, c.to(dev, torch.float32))
+        sc = self.draw_shortcut() if shortcut is None else shortcut
+        sc_tab = sc.detach().to(dev, torch.float32).reshape(1, 1, 2, self.n_feat).contiguous()
+        eps = self.forward_eval_into(x3, sc_tab, cemb1, temb1, cemb2, temb2, t.shape[0], reps=1)
+        return eps.clone()
+
+    def train(self, mode=True):
+        self.invalidate()
+        return super().train(mode)

@@ -1,9 +1,11 @@
-"""Import shim: the package directory is `camels-diffusion-model_b200/` (a hyphen is
-not a valid Python identifier), so this module exposes it as the importable
-package `camels_diffusion_model_b200`."""
+"""Import shim: the package directory is `camels-diffusion-model_b200/` (a hyphen is not a valid
+Python identifier), so this module loads it as the importable package `camels_diffusion_model_b200`."""
+import importlib.util as _ilu
 import os as _os
+import sys as _sys
 
-__path__ = [_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "camels-diffusion-model_b200")]
-__file__ = _os.path.join(__path__[0], "__init__.py")
-with open(__file__) as _fh:
-    exec(compile(_fh.read(), __file__, "exec"))
+_dir = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "camels-diffusion-model_b200")
+_spec = _ilu.spec_from_file_location(__name__, _os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = _ilu.module_from_spec(_spec)
+_sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)
