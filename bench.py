@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native ContextUnet / DDPM hot path.
+
+Metric (BASELINE.json): classifier-free-guided DDPM samples/sec at 64x64, 1500 timesteps.
+Workload at every N: BASELINE config 2 — global batch 1024 samples, 6 context parameters, guide_w > 0
+(two U-Net passes per step, run as one 2B-image batch), batch-sharded contiguously over the N GPUs
+with no data-path communication (strong scaling).  A "step" is one reverse-diffusion step of the whole
+batch (2 forwards + CFG mix + x_{t-1} update), captured as a CUDA graph; samples/s = batch / (1500 * s/step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §measurement for every key.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TIMESTEPS = 1500
+NCF = 6
+GFLOP_PER_IMAGE_FWD = 19.1785  # conv + transposed-conv MACs x 2 per image per forward
+CONV64_FLOP_PER_IMAGE = 2.0 * 64 * 64 * 128 * 9 * 128  # one 3x3 128->128 conv at 64x64
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1024, help="global number of samples (BASELINE config 2: 1024)")
+    ap.add_argument("--guide-w", type=float, default=2.0)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-steps", type=int, default=8, help="steps of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--breakdown", default="", help="write the per-kernel CUDA-event breakdown of one step here")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return dict(tf_sustained=d.get("bf16_tflops_sustained", 1368.9), tf_burst=d.get("bf16_tflops", 1663.0),
+                    hbm=d.get("hbm_gbs", 6548.2), src="measured (MEASURED_PEAKS.json)")
+    return dict(tf_sustained=1400.0, tf_burst=1590.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        return False
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_steps(steps, warmup, batch=4, guide_w=2.0):
+    """The reference algorithm (oracle port, fp32, torch CPU kernels, all host threads) on a bounded sample
+    of the workload: `batch` samples, CFG (two forwards per step).  Returns (ms_per_step, cores)."""
+    import torch
+    from oracle import contextunet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.init_state_dict(0, n_cfeat=NCF)
+    sched = O.make_schedule(TIMESTEPS)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, 1, 64, 64, generator=g)
+    params = torch.rand(batch, NCF, generator=g)
+    times = []
+    with torch.no_grad():
+        for k in range(warmup + steps):
+            i = TIMESTEPS - k
+            t0 = time.perf_counter()
+            z = torch.randn(x.shape, generator=g)
+            t = torch.tensor([i / TIMESTEPS])
+            e_c = O.unet_forward(sd, x, t, params, O.draw_shortcut(128, g), n_cfeat=NCF)
+            e_u = O.unet_forward(sd, x, t, torch.zeros_like(params), O.draw_shortcut(128, g), n_cfeat=NCF)
+            eps = e_u + guide_w * (e_c - e_u)
+            x = O.denoise_add_noise(x, i, eps, z, *sched)
+            if k >= warmup:
+                times.append(time.perf_counter() - t0)
+    return 1e3 * sum(times) / len(times), cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 4
+    ms, cores = cpu_reference_steps(args.steps, args.warmup, batch=batch, guide_w=args.guide_w)
+    val = batch / (ms / 1e3 * TIMESTEPS)
+    sample = (f"{batch} samples x {args.steps} CFG steps of {TIMESTEPS} (2 forwards/step), fp32, oracle port of the "
+              f"reference loop on {cores} host threads; samples/s extrapolated to 1500 steps")
+    print(json.dumps({
+        "impl": "reference", "metric": "cfg_ddpm_samples_per_sec_64x64_1500steps", "value": val,
+        "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2 (CFG sampling, 6 params, 1500 timesteps), bounded CPU sample",
+                   "batch": batch, "timesteps": TIMESTEPS, "guide_w": args.guide_w},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# --------------------------------------------------------------------------- B200 arm
+KERNELS_PER_STEP = 28  # 26 per (2B-batched) forward + ddpm_step + step_advance
+
+
+def kernel_breakdown(run):
+    """One eager step with a CUDA event pair around every C-ABI launch (same stream as the launches)."""
+    import torch
+    from camels_diffusion_model_b200 import _lib as L
+    names = ["conv3x3", "gemm", "conv_in", "conv_out", "embed_fc", "avgpool_gelu", "gn_relu_film", "gn_finalize",
+             "ddpm_step", "step_advance"]
+    recs, orig = [], {}
+    for nme in names:
+        fn = getattr(L, nme)
+        orig[nme] = fn
+
+        def wrap(*a, _fn=fn, _n=nme, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = _fn(*a, **k)
+            e1.record()
+            desc = _n
+            if _n == "conv3x3":
+                src, w = a[0], a[1]
+                desc = f"conv3x3 {tuple(src.shape)} cin{w.shape[3]}->cout{w.shape[0]} flags{k.get('flags', 1)}"
+            elif _n == "gemm":
+                desc = f"gemm M{a[0].shape[0]} K{a[1].shape[1]} N{a[1].shape[0]}"
+            recs.append((desc, e0, e1))
+            return r
+        setattr(L, nme, wrap)
+    try:
+        run._one_step()
+        torch.cuda.synchronize()
+    finally:
+        for nme, fn in orig.items():
+            setattr(L, nme, fn)
+    return [(d, e0.elapsed_time(e1)) for d, e0, e1 in recs]
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import camels_diffusion_model_b200 as cdm
+    from camels_diffusion_model_b200 import diffusion as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert args.batch % world == 0, "global batch must divide over the ranks"
+    B = args.batch // world  # contiguous shard [rank*B, (rank+1)*B) of the sample batch
+
+    torch.manual_seed(0)  # identical weights and shortcut table on every rank
+    model = cdm.ContextUnet(1, 128, NCF, 64).to(dev).eval()
+    sched = D.make_schedule(TIMESTEPS, device=dev)
+    sc_tab = D.draw_shortcut_table(TIMESTEPS, 2, 128)
+    g = torch.Generator().manual_seed(1)
+    x_T_all = torch.randn(args.batch, 1, 64, 64, generator=g)
+    params_all = torch.rand(args.batch, NCF, generator=g)
+    x_T = x_T_all[rank * B:(rank + 1) * B].pin_memory()
+    params = params_all[rank * B:(rank + 1) * B].pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: inputs in HBM, z from the in-kernel Philox generator
+    run = D._SamplerRun(model, x_T.to(dev), params.to(dev), args.guide_w, TIMESTEPS, sched, shortcut_tab=sc_tab,
+                        seed=1234 + rank, snapshots=True)
+    run.capture()
+    run.run(args.warmup)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        run.run(args.steps)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = args.batch / (ms_max / 1e3 * TIMESTEPS)
+    finite = bool(torch.isfinite(run.x).all())
+
+    # ---- end to end through the public API with HOST buffers: pinned x_T / params / per-step z in, x out
+    e2e = None
+    if not args.no_e2e:
+        z_host = torch.randn(args.steps, B, 1, 64, 64, generator=g).pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        run2 = D._SamplerRun(model, x_T.to(dev, non_blocking=True), params.to(dev, non_blocking=True), args.guide_w,
+                             TIMESTEPS, sched, shortcut_tab=sc_tab, seed=1, snapshots=True)
+        run2.z = torch.empty(B * 4096, device=dev)
+        run2.z_stride = 0
+        run2.capture()
+        barrier()
+        t_setup = time.perf_counter() - t0
+        d2h = 0
+        t1 = time.perf_counter()
+        for k in range(args.steps):
+            run2.z.copy_(z_host[k].view(-1), non_blocking=True)  # this step's noise: pinned host -> device
+            run2.graph.replay()
+            int(run2.step.item())  # device -> host read of the step's result (step counter) every step
+            d2h += 4
+        x_host = run2.x.cpu()  # final samples back on the host
+        inter = run2.intermediate()
+        d2h += x_host.numel() * 4 + inter.size * 4
+        barrier()
+        dt = time.perf_counter() - t1
+        tt = torch.tensor([dt], device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_e2e = 1e3 * float(tt.item()) / args.steps
+        h2d_step = B * 4096 * 4 + (x_T.numel() * 4 + params.numel() * 4 + sc_tab.numel() * 4) / args.steps
+        e2e = {"value": args.batch / (ms_e2e / 1e3 * TIMESTEPS), "unit": "samples/s",
+               "h2d_bytes_per_step": int(h2d_step) * world, "d2h_bytes_per_step": int(d2h / args.steps) * world,
+               "ms_per_step": ms_e2e, "setup_s": t_setup,
+               "note": "public sampler path with pinned host x_T/params/per-step z in and x + snapshots out; "
+                       "graph capture/setup reported separately in setup_s"}
+
+    # ---- roofline of the dominant kernel (3x3 128->128 conv at 64x64: 9 of 26 launches, ~57% of the FLOPs)
+    pk = peaks()
+    bd = kernel_breakdown(run)
+    step_ms = sum(v for _, v in bd)
+    conv64 = [v for d, v in bd if d.startswith("conv3x3") and "64, 64, 128) cin128->cout128" in d]
+    n_img = 2 * B
+    conv_ms = sum(conv64) / max(len(conv64), 1)
+    achieved = CONV64_FLOP_PER_IMAGE * n_img / (conv_ms * 1e-3) / 1e12
+    conv_all_ms = sum(v for d, v in bd if d.startswith("conv3x3") or d.startswith("gemm"))
+    roofline = {"bound": "tensor", "kernel": "conv3x3_kernel<SHIFT18> 128->128 @64x64", "achieved": achieved,
+                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
+                "frac_of_burst_peak": achieved / pk["tf_burst"], "peak_source": pk["src"] + ", sustained bf16",
+                "traffic": None, "launch_ms": conv_ms, "launches_per_step": len(conv64),
+                "share_of_step": sum(conv64) / step_ms, "tensor_kernels_share_of_step": conv_all_ms / step_ms,
+                "step_tflops": GFLOP_PER_IMAGE_FWD * 1e9 * n_img / (ms_max * 1e-3) / 1e12}
+    if args.breakdown and rank == 0:
+        with open(args.breakdown, "w") as fh:
+            for d, v in bd:
+                fh.write(f"{v:9.4f} ms  {d}\n")
+            fh.write(f"{step_ms:9.4f} ms  TOTAL (eager, one CFG step, {n_img} images)\n")
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cms, cores = cpu_reference_steps(args.cpu_steps, 1, batch=4, guide_w=args.guide_w)
+        cpu = {"value": 4 / (cms / 1e3 * TIMESTEPS), "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"4 samples x {args.cpu_steps} CFG steps (2 fp32 forwards/step) of the oracle port on "
+                         f"{cores} host threads, extrapolated to {TIMESTEPS} steps"}
+    if rank == 0:
+        out = {
+            "metric": "cfg_ddpm_samples_per_sec_64x64_1500steps", "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE config 2: CFG sampling, ContextUnet n_feat=128 n_cfeat=6 64x64, "
+                                   "global batch 1024 sharded contiguously over the GPUs, 1500 timesteps, "
+                                   "random-init weights", "global_batch": args.batch, "per_gpu_batch": B,
+                       "images_per_forward_per_gpu": 2 * B, "timesteps": TIMESTEPS, "guide_w": args.guide_w,
+                       "parallelism": f"batch-shard x{world}, no collective",
+                       "l2_policy": "inputs larger than L2 (activation working set >> 126 MB per step)"},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": KERNELS_PER_STEP * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "finite": finite,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

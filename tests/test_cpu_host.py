@@ -1,0 +1,112 @@
+"""CPU-only checks: the C-ABI library builds/loads and exports every symbol the header declares; host
+logic (schedule tables, shortcut replay order, snapshot schedule, weight packing); loud failure without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import contextunet_oracle as O
+from tests._util import NCF, ROOT, T, load, raw_sd
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from camels_diffusion_model_b200 import _lib
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(lib):
+    with open(os.path.join(ROOT, "include", "cdm_b200.h")) as fh:
+        hdr = fh.read()
+    declared = set(re.findall(r"\b(cdm_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    handle = lib.lib()
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in cdm_b200.h but not exported by libcdm_b200.so"
+    assert declared == set(lib.EXPORTS)
+    assert handle.cdm_version() >= 100
+
+
+def test_no_gpu_fails_loudly(lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert lib.lib().cdm_device_ok() != 0
+    assert b"no CPU path" in lib.lib().cdm_last_error() or lib.lib().cdm_last_error()
+    import camels_diffusion_model_b200 as cdm
+    m = cdm.ContextUnet(1, 128, NCF, 64).eval()
+    with pytest.raises(cdm.CdmError):
+        m(torch.zeros(1, 1, 64, 64), torch.tensor([0.5]))
+
+
+def test_module_matches_reference_state_dict_and_seeded_init():
+    import camels_diffusion_model_b200 as cdm
+    torch.manual_seed(0)
+    m = cdm.ContextUnet(1, 128, NCF, 64)
+    sd = raw_sd()
+    msd = m.state_dict()
+    assert list(msd) == list(sd) and len(msd) == 156
+    assert all(torch.equal(msd[k], sd[k]) for k in sd)
+    assert sum(p.numel() for p in m.parameters()) == 21626881
+    m1 = cdm.ContextUnet(1, 128, 1, 64)
+    assert sum(p.numel() for p in m1.parameters()) == 21624961
+
+
+def test_shortcut_draw_order_matches_conv2d_construction():
+    import camels_diffusion_model_b200 as cdm
+    from camels_diffusion_model_b200 import diffusion as D
+    m = cdm.ContextUnet(1, 128, NCF, 64)
+    torch.manual_seed(7)
+    ref = []
+    for _ in range(6):  # T=3 steps x 2 forwards, the order the reference's CFG loop constructs them
+        conv = torch.nn.Conv2d(1, 128, kernel_size=1)
+        ref.append(torch.cat([conv.weight.detach().view(-1), conv.bias.detach()]))
+    torch.manual_seed(7)
+    tab = D.draw_shortcut_table(3, 2)
+    k = 0
+    for i in (3, 2, 1):
+        for r in range(2):
+            assert torch.equal(tab[i, r].reshape(-1), ref[k])
+            k += 1
+    torch.manual_seed(7)
+    assert torch.equal(m.draw_shortcut(), ref[0])
+    lst = [(v[:128], v[128:]) for v in ref]
+    assert torch.equal(D.shortcut_table_from_list(lst, 3, 2), tab)
+
+
+def test_schedule_coef_and_snapshot_tables():
+    from camels_diffusion_model_b200 import diffusion as D
+    g = load("sampler.npz")
+    Tn = int(g["T"])
+    b_t, a_t, ab_t = D.make_schedule(Tn, device="cpu")
+    assert np.array_equal(ab_t.numpy(), g["sched/ab_t"]) and np.array_equal(b_t.numpy(), g["sched/b_t"])
+    coef = D._coef_table(b_t, a_t, ab_t)
+    i = 7
+    x, e, z = T(g["ew/x"]), T(g["ew/eps"]), T(g["ew/z"])
+    assert np.array_equal(((x - e * coef[i, 0]) / coef[i, 1] + coef[i, 2] * z).numpy(), g["ew/denoise_t7"])
+    assert D.snapshot_steps(1500) == O.snapshot_steps(1500) and len(D.snapshot_steps(1500)) == 82
+    assert D.snapshot_steps(12) == [12, 7, 6, 5, 4, 3, 2, 1]
+
+
+def test_weight_packing_layouts():
+    from camels_diffusion_model_b200 import unet as U
+    conv = torch.nn.Conv2d(4, 3, 3, 1, 1)
+    w = U._pack_conv3(conv).float()
+    assert w.shape == (3, 3, 3, 4)
+    assert torch.allclose(w[1, 2, 0, 3], conv.weight[1, 3, 2, 0].detach().to(torch.bfloat16).float())
+    ct = torch.nn.ConvTranspose2d(5, 3, 2, 2)
+    b = U._pack_convT(ct).float()
+    assert b.shape == (12, 5)
+    assert torch.allclose(b[(1 * 2 + 0) * 3 + 2, 4], ct.weight[4, 2, 1, 0].detach().to(torch.bfloat16).float())
+    bn = torch.nn.BatchNorm2d(3).eval()
+    bn.running_mean.uniform_(-1, 1), bn.running_var.uniform_(0.5, 2), bn.weight.data.uniform_(0.5, 2), bn.bias.data.uniform_(-1, 1)
+    c2 = torch.nn.Conv2d(4, 3, 3, 1, 1)
+    scale, shift = U._fold_bn(c2, bn)
+    x = torch.randn(2, 4, 8, 8)
+    ref = bn(c2(x))
+    got = torch.nn.functional.conv2d(x, c2.weight) * 1  # noqa
+    got = torch.nn.functional.conv2d(x, c2.weight, None, padding=1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    assert torch.allclose(got, ref, atol=1e-5)
