@@ -254,8 +254,9 @@ def run_b200(args):
             int(run2.step.item())  # device -> host read of the step's result (step counter) every step
             d2h += 4
         x_host = run2.x.cpu()  # final samples back on the host
-        inter = run2.intermediate()
-        d2h += x_host.numel() * 4 + inter.size * 4
+        n_snap = sum(1 for i in run2.snap_steps if i > TIMESTEPS - args.steps)  # snapshots taken in these steps
+        inter = run2.snap[:n_snap].cpu()
+        d2h += x_host.numel() * 4 + inter.numel() * 4
         barrier()
         dt = time.perf_counter() - t1
         tt = torch.tensor([dt], device=dev)

@@ -191,7 +191,8 @@ extern "C" int cdm_gemm(const cdm_gemm_args* a, void* stream) {
   CDM_CHECK_ARG(a->a0 && a->bw && a->shift && a->out);
   CDM_CHECK_ARG(a->k0 > 0 && a->k0 % 64 == 0 && a->k1 >= 0 && a->k1 % 64 == 0);
   CDM_CHECK_ARG((a->k1 == 0) == (a->a1 == nullptr));
-  CDM_CHECK_ARG(a->M > 0 && a->N > 0 && a->N % 128 == 0 && a->shift_mod > 0);
+  CDM_CHECK_ARG(a->M > 0 && a->N > 0 && a->N % 128 == 0 && a->shift_mod > 0 && a->shift_mod % 128 == 0);
+  if (a->out_mode == 1) CDM_CHECK_ARG((a->H & (a->H - 1)) == 0 && (a->W & (a->W - 1)) == 0);
   CDM_CHECK_ARG(a->out_mode == 0 || (a->out_mode == 1 && a->N == 512 && a->H > 0 && a->W > 0 &&
                                      a->M % (a->H * a->W) == 0));
   int rc = check_device();
@@ -235,6 +236,8 @@ extern "C" int cdm_gemm(const cdm_gemm_args* a, void* stream) {
   p.out_mode = a->out_mode;
   p.H = a->H;
   p.W = a->W;
+  for (int v = a->H; v > 1; v >>= 1) ++p.h_shift;
+  for (int v = a->W; v > 1; v >>= 1) ++p.w_shift;
   p.out = reinterpret_cast<bf16*>(a->out);
   constexpr int smem = gemm_smem_bytes();
   static bool attr_set = false;

@@ -412,7 +412,7 @@ struct GemmKParams {
   int m_tiles, n_tiles, n_units;
   const float* shift;
   int shift_mod;
-  int out_mode, H, W;
+  int out_mode, H, W, h_shift, w_shift;
   bf16* out;
 };
 constexpr int kGemmStages = 5;
@@ -513,6 +513,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       mbar_wait(&t_full[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128);
+      const float* shift = p.shift + (n_tile * 128) % p.shift_mod;  // shift_mod is a multiple of 128
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         uint32_t v[32];
@@ -520,8 +521,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         tmem_wait_ld();
         float f[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          f[i] = __uint_as_float(v[i]) + __ldg(p.shift + (n_tile * 128 + cc * 32 + i) % p.shift_mod);
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + __ldg(shift + cc * 32 + i);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int un = cc * 4 + j;
@@ -541,7 +541,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           if (p.out_mode == 0) {
             g = p.out + (size_t)m * p.N + n_tile * 128;
           } else {
-            const int w = m % p.W, h = (m / p.W) % p.H, img = m / (p.W * p.H);
+            // H, W are powers of two (checked on the host): shifts instead of integer division
+            const int w = m & (p.W - 1), h = (m >> p.w_shift) & (p.H - 1), img = m >> (p.w_shift + p.h_shift);
             const int kh = n_tile >> 1, kw = n_tile & 1;
             g = p.out + (((size_t)img * 2 * p.H + 2 * h + kh) * (2 * p.W) + 2 * w + kw) * 128;
           }

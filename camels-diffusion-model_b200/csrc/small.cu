@@ -49,125 +49,142 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 
 // ------------------------------------------------------------------ conv_in
 // Conv2d(1, C, 3, 1, 1) + folded BatchNorm + ReLU.  K = 9: CUDA cores, bound by the
-// bf16 NHWC write (256 B / pixel).  One thread = one pixel x 8 channels.
+// bf16 NHWC write (256 B / pixel).  A thread owns 8 output channels (its 72 weights
+// live in registers) and walks pixels; 16 threads cover one pixel's 128 channels,
+// so every store instruction of a warp writes 512 contiguous bytes.
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, int n_img, int H, int W, int C,
                                                       const float* __restrict__ wgt, const float* __restrict__ scale,
                                                       const float* __restrict__ shift, int relu,
                                                       bf16* __restrict__ out) {
-  extern __shared__ float s_par[];  // [9][C] weights, [C] scale, [C] shift
-  float* s_w = s_par;
-  float* s_scale = s_w + 9 * C;
-  float* s_shift = s_scale + C;
-  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i] = wgt[i];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    s_scale[i] = scale[i];
-    s_shift[i] = shift[i];
+  const int groups = C >> 3;              // threads per pixel
+  const int ppb = blockDim.x / groups;    // pixels per block iteration
+  const int cg = threadIdx.x % groups, psub = threadIdx.x / groups;
+  float wr[9][8], sc[8], sh[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[t][j] = __ldg(wgt + t * C + cg * 8 + j);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(scale + cg * 8 + j);
+    sh[j] = __ldg(shift + cg * 8 + j);
   }
-  __syncthreads();
-  const int groups = C >> 3;
-  const size_t total = (size_t)n_img * H * W * groups;
-  for (size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(gid % groups);
-    const size_t p = gid / groups;
-    const int w = (int)(p % W), h = (int)((p / W) % H);
-    const size_t n = p / ((size_t)W * H);
-    float xin[9];
+  const int n_rows = n_img * H;
+  for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const int h = row % H;
+    const float* xr = x + (size_t)row * W;
+    bf16* orow = out + (size_t)row * W * C;
+    for (int w = psub; w < W; w += ppb) {
+      float xin[9];
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ih = h + kh - 1;
+        const bool okh = ih >= 0 && ih < H;
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int ih = h + kh - 1, iw = w + kw - 1;
-        xin[kh * 3 + kw] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(x + (n * H + ih) * W + iw) : 0.f;
+        for (int kw = 0; kw < 3; ++kw) {
+          const int iw = w + kw - 1;
+          xin[kh * 3 + kw] = (okh && iw >= 0 && iw < W) ? __ldg(xr + (kh - 1) * W + iw) : 0.f;
+        }
       }
-    float acc[8];
+      float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const float4 w0 = *reinterpret_cast<const float4*>(s_w + t * C + cg * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(s_w + t * C + cg * 8 + 4);
-      acc[0] = fmaf(xin[t], w0.x, acc[0]);
-      acc[1] = fmaf(xin[t], w0.y, acc[1]);
-      acc[2] = fmaf(xin[t], w0.z, acc[2]);
-      acc[3] = fmaf(xin[t], w0.w, acc[3]);
-      acc[4] = fmaf(xin[t], w1.x, acc[4]);
-      acc[5] = fmaf(xin[t], w1.y, acc[5]);
-      acc[6] = fmaf(xin[t], w1.z, acc[6]);
-      acc[7] = fmaf(xin[t], w1.w, acc[7]);
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xin[t], wr[t][j], acc[j]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float y = fmaf(acc[j], sc[j], sh[j]);
+        acc[j] = relu ? fmaxf(y, 0.f) : y;
+      }
+      *reinterpret_cast<uint4*>(orow + (size_t)w * C + cg * 8) = pack8(acc);
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float y = fmaf(acc[j], s_scale[cg * 8 + j], s_shift[cg * 8 + j]);
-      acc[j] = relu ? fmaxf(y, 0.f) : y;
-    }
-    *reinterpret_cast<uint4*>(out + p * C + cg * 8) = pack8(acc);
   }
 }
 
 // ----------------------------------------------------------------- conv_out
-// GroupNorm(8, 128) + ReLU applied on load, then Conv2d(128, 1, 3, 1, 1): N = 1, so
-// CUDA cores.  One warp walks a 16-pixel row segment; lane l owns channels 4l..4l+3.
+// GroupNorm(8, 128) + ReLU applied once per input element while staging a halo tile in
+// shared memory (bf16, 16-byte units XOR-swizzled by pixel so that a warp of consecutive
+// pixels reads conflict-free), then Conv2d(128, 1, 3, 1, 1) on CUDA cores (N = 1): one
+// thread per output pixel, 1152 fp32 FMAs each.  Tile = ROWS x 64 outputs.
+constexpr int kCoRows = 4, kCoW = 64, kCoC = 128;
+constexpr int kCoTilePx = (kCoRows + 2) * (kCoW + 2);
+constexpr int kCoSmem = kCoTilePx * kCoC * 2 + 9 * kCoC * 4 + 2 * kCoC * 4;
+
 __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ src, int n_img, int H, int W,
                                                        const float* __restrict__ mean_rstd,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ wgt, const float* __restrict__ bias,
                                                        float* __restrict__ out) {
-  constexpr int C = 128, SEG = 16;
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int segs_per_row = W / SEG;
-  const size_t n_items = (size_t)n_img * H * segs_per_row;
-  float wr[9][4];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const float4 w4 = *reinterpret_cast<const float4*>(wgt + t * C + lane * 4);
-    wr[t][0] = w4.x;
-    wr[t][1] = w4.y;
-    wr[t][2] = w4.z;
-    wr[t][3] = w4.w;
-  }
-  const float4 g4 = *reinterpret_cast<const float4*>(gamma + lane * 4);
-  const float4 b4 = *reinterpret_cast<const float4*>(beta + lane * 4);
+  extern __shared__ __align__(16) uint8_t co_smem[];
+  uint8_t* s_tile = co_smem;
+  float* s_w = reinterpret_cast<float*>(co_smem + kCoTilePx * kCoC * 2);  // [9][128]
+  float* s_a = s_w + 9 * kCoC;                                            // [128] rstd*gamma
+  float* s_b = s_a + kCoC;                                                // [128] beta - mean*rstd*gamma
+  const uint32_t tile_u32 = smem_u32(s_tile);
+  for (int i = threadIdx.x; i < 9 * kCoC; i += blockDim.x) s_w[i] = wgt[i];
   const float bias0 = __ldg(bias);
-  for (size_t item = (size_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < n_items;
-       item += (size_t)gridDim.x * warps_per_block) {
-    const int seg = (int)(item % segs_per_row);
-    const int h = (int)((item / segs_per_row) % H);
-    const size_t n = item / ((size_t)segs_per_row * H);
-    const int grp = lane >> 2;  // 16 channels per group, 4 per lane
-    const float mean = __ldg(mean_rstd + (n * 8 + grp) * 2), rstd = __ldg(mean_rstd + (n * 8 + grp) * 2 + 1);
-    float a[4], b[4];
-    a[0] = rstd * g4.x;
-    a[1] = rstd * g4.y;
-    a[2] = rstd * g4.z;
-    a[3] = rstd * g4.w;
-    b[0] = b4.x - mean * a[0];
-    b[1] = b4.y - mean * a[1];
-    b[2] = b4.z - mean * a[2];
-    b[3] = b4.w - mean * a[3];
-    for (int w = seg * SEG; w < seg * SEG + SEG; ++w) {
-      float acc = 0.f;
+  const int tiles_x = W / kCoW, tiles_y = H / kCoRows;
+  const int n_tiles = n_img * tiles_y * tiles_x;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
+    __syncthreads();  // previous tile fully consumed (also covers s_w on the first pass)
+    if (threadIdx.x < kCoC) {
+      const int c = threadIdx.x, g = c >> 4;
+      const float mean = __ldg(mean_rstd + ((size_t)n * 8 + g) * 2), rstd = __ldg(mean_rstd + ((size_t)n * 8 + g) * 2 + 1);
+      const float a = rstd * __ldg(gamma + c);
+      s_a[c] = a;
+      s_b[c] = __ldg(beta + c) - mean * a;
+    }
+    __syncthreads();
+    const int h0 = ty * kCoRows - 1, w0 = tx * kCoW - 1;
+    for (int u = threadIdx.x; u < kCoTilePx * 16; u += blockDim.x) {
+      const int px = u >> 4, un = u & 15;
+      const int pr = px / (kCoW + 2), pc = px - pr * (kCoW + 2);
+      const int ih = h0 + pr, iw = w0 + pc;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);  // zero padding is applied AFTER GroupNorm+ReLU, as nn.Conv2d does
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src + (((size_t)n * H + ih) * W + iw) * kCoC + un * 8));
+        float f[8];
+        unpack8(raw, f);
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const int ih = h + kh - 1;
-        if (ih < 0 || ih >= H) continue;
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], s_a[un * 8 + j], s_b[un * 8 + j]), 0.f);
+        v = pack8(f);
+      }
+      st_shared_v4(tile_u32 + px * 256 + ((un ^ (px & 7)) << 4), v.x, v.y, v.z, v.w);
+    }
+    __syncthreads();
+    const int r = threadIdx.x >> 6, c = threadIdx.x & 63;
+    float acc = 0.f;
+#pragma unroll 1
+    for (int un = 0; un < 16; ++un) {
+      float wr[9][8];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float4 w0v = *reinterpret_cast<const float4*>(s_w + t * kCoC + un * 8);
+        const float4 w1v = *reinterpret_cast<const float4*>(s_w + t * kCoC + un * 8 + 4);
+        wr[t][0] = w0v.x; wr[t][1] = w0v.y; wr[t][2] = w0v.z; wr[t][3] = w0v.w;
+        wr[t][4] = w1v.x; wr[t][5] = w1v.y; wr[t][6] = w1v.z; wr[t][7] = w1v.w;
+      }
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const int iw = w + kw - 1;
-          if (iw < 0 || iw >= W) continue;
-          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(src + ((n * H + ih) * W + iw) * C + lane * 4));
-          const float2 v01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-          const float2 v23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+          const int px = (r + kh) * (kCoW + 2) + c + kw;
+          const uint4 v = ld_shared_v4(tile_u32 + px * 256 + ((un ^ (px & 7)) << 4));
           const int t = kh * 3 + kw;
-          acc = fmaf(fmaxf(fmaf(v01.x, a[0], b[0]), 0.f), wr[t][0], acc);
-          acc = fmaf(fmaxf(fmaf(v01.y, a[1], b[1]), 0.f), wr[t][1], acc);
-          acc = fmaf(fmaxf(fmaf(v23.x, a[2], b[2]), 0.f), wr[t][2], acc);
-          acc = fmaf(fmaxf(fmaf(v23.y, a[3], b[3]), 0.f), wr[t][3], acc);
+          acc = fmaf(__uint_as_float(v.x << 16), wr[t][0], acc);
+          acc = fmaf(__uint_as_float(v.x & 0xffff0000u), wr[t][1], acc);
+          acc = fmaf(__uint_as_float(v.y << 16), wr[t][2], acc);
+          acc = fmaf(__uint_as_float(v.y & 0xffff0000u), wr[t][3], acc);
+          acc = fmaf(__uint_as_float(v.z << 16), wr[t][4], acc);
+          acc = fmaf(__uint_as_float(v.z & 0xffff0000u), wr[t][5], acc);
+          acc = fmaf(__uint_as_float(v.w << 16), wr[t][6], acc);
+          acc = fmaf(__uint_as_float(v.w & 0xffff0000u), wr[t][7], acc);
         }
-      }
-      acc = warp_sum(acc);
-      if (lane == 0) out[(n * H + h) * W + w] = acc + bias0;
     }
+    out[((size_t)n * H + ty * kCoRows + r) * W + tx * kCoW + c] = acc + bias0;
   }
 }
 
@@ -436,9 +453,9 @@ extern "C" int cdm_conv_in(const cdm_conv_in_args* a, void* stream) {
   CDM_CHECK_ARG(a->n_img > 0 && a->H > 0 && a->W > 0 && a->cout > 0 && a->cout % 8 == 0 && a->cout <= 512);
   int rc = check_device();
   if (rc) return rc;
-  const size_t total = (size_t)a->n_img * a->H * a->W * (a->cout / 8);
-  const int smem = 11 * a->cout * (int)sizeof(float);
-  conv_in_kernel<<<grid_for(total, 256), 256, smem, (cudaStream_t)stream>>>(
+  CDM_CHECK_ARG(256 % (a->cout / 8) == 0);
+  const int rows = a->n_img * a->H;
+  conv_in_kernel<<<rows < 148 * 8 ? rows : 148 * 8, 256, 0, (cudaStream_t)stream>>>(
       a->x, a->n_img, a->H, a->W, a->cout, a->weight, a->scale, a->shift, a->relu, (bf16*)a->out);
   CDM_CHECK_LAUNCH();
   return CDM_OK;
@@ -446,11 +463,16 @@ extern "C" int cdm_conv_in(const cdm_conv_in_args* a, void* stream) {
 
 extern "C" int cdm_conv_out(const cdm_conv_out_args* a, void* stream) {
   CDM_CHECK_ARG(a && a->src && a->mean_rstd && a->gamma && a->beta && a->weight && a->bias && a->out);
-  CDM_CHECK_ARG(a->n_img > 0 && a->H > 0 && a->W > 0 && a->W % 16 == 0 && a->C == 128);
+  CDM_CHECK_ARG(a->n_img > 0 && a->H > 0 && a->W > 0 && a->W % kCoW == 0 && a->H % kCoRows == 0 && a->C == kCoC);
   int rc = check_device();
   if (rc) return rc;
-  const size_t items = (size_t)a->n_img * a->H * (a->W / 16);
-  conv_out_kernel<<<grid_for(items, 8), 256, 0, (cudaStream_t)stream>>>(
+  static bool attr_set = false;
+  if (!attr_set) {
+    CDM_CHECK_CUDA(cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCoSmem));
+    attr_set = true;
+  }
+  const int tiles = a->n_img * (a->H / kCoRows) * (a->W / kCoW);
+  conv_out_kernel<<<tiles < 148 * 2 ? tiles : 148 * 2, 256, kCoSmem, (cudaStream_t)stream>>>(
       (const bf16*)a->src, a->n_img, a->H, a->W, a->mean_rstd, a->gamma, a->beta, a->weight, a->bias, a->out);
   CDM_CHECK_LAUNCH();
   return CDM_OK;
