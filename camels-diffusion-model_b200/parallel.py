@@ -1,0 +1,72 @@
+"""One process per GPU (torch.distributed over NCCL/NVLink for the plumbing).
+
+Sampling, likelihood and ELBO evaluation shard the batch contiguously over the ranks and need NO
+data-path collective (independent samples / maps); only the per-forward shortcut table has to
+be identical on every rank, and results are gathered once at the end.  Training is data-parallel: gradient
+all-reduce + cross-rank BatchNorm statistics (see train.py).
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n_total, rank, world_size):
+    """Contiguous shard [start, end) of n_total items; the first n_total % world ranks get one extra item."""
+    base, rem = divmod(n_total, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def broadcast_from_rank0(t, device=None):
+    """Make `t` (e.g. the shortcut table drawn from rank 0's CPU generator) identical on every rank."""
+    rank, ws = world()
+    if ws == 1:
+        return t
+    backend = dist.get_backend()
+    buf = t.to(device) if (backend == "nccl" and device is not None) else t.clone()
+    dist.broadcast(buf, src=0)
+    return buf.to(t.device)
+
+
+def gather_shards(local, n_total, dim=0):
+    """All-gather ragged contiguous shards back into the full batch (every rank gets the result)."""
+    rank, ws = world()
+    if ws == 1:
+        return local
+    sizes = [shard_range(n_total, r, ws) for r in range(ws)]
+    max_n = max(e - s for s, e in sizes)
+    pad_shape = list(local.shape)
+    pad_shape[dim] = max_n
+    padded = local.new_zeros(pad_shape)
+    padded.narrow(dim, 0, local.shape[dim]).copy_(local)
+    outs = [torch.empty_like(padded) for _ in range(ws)]
+    dist.all_gather(outs, padded)
+    return torch.cat([o.narrow(dim, 0, e - s) for o, (s, e) in zip(outs, sizes)], dim)
+
+
+def sample_sharded(sample_fn, x_T_all, params_all, shortcut_tab, gather=True, device=None):
+    """Batch-sharded sampling: rank r runs `sample_fn(x_T_shard, params_shard, shortcut_tab)` on its contiguous
+    shard.  `shortcut_tab` is taken from rank 0.  Returns the gathered [n_total, ...] samples (or the local shard)."""
+    rank, ws = world()
+    n = x_T_all.shape[0]
+    s, e = shard_range(n, rank, ws)
+    tab = broadcast_from_rank0(shortcut_tab, device)
+    prm = None if params_all is None else params_all[s:e]
+    local = sample_fn(x_T_all[s:e], prm, tab)
+    return gather_shards(local, n) if gather else local
+
+
+def reduce_mean_scalar(total, count, device=None):
+    """Dataset-level mean of per-rank (sum, count) pairs — the single scalar exchange of the sharded NLL / ELBO."""
+    rank, ws = world()
+    if ws == 1:
+        return total / max(count, 1)
+    t = torch.tensor([float(total), float(count)], dtype=torch.float64,
+                     device=device if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(t)
+    return float(t[0] / t[1])

@@ -1,0 +1,62 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: contiguous ragged sharding, rank-identical
+shortcut table, gather, scalar reduction.  The GPU sampler is replaced by a deterministic stub."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, ws, port, n_total, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    from camels_diffusion_model_b200 import parallel as P
+    torch.manual_seed(100 + rank)  # ranks deliberately start with different CPU generators
+    tab = torch.rand(5, 2, 2, 128)
+    g = torch.Generator().manual_seed(0)
+    x_all = torch.randn(n_total, 1, 8, 8, generator=g)
+    p_all = torch.rand(n_total, 6, generator=g)
+    seen = {}
+
+    def stub(x, prm, t):
+        seen["tab"] = t.clone()
+        seen["n"] = x.shape[0]
+        return x * 2 + prm.sum(1).view(-1, 1, 1, 1) + t[1, 0, 0, 0]
+
+    out = P.sample_sharded(stub, x_all, p_all, tab)
+    tab0 = P.broadcast_from_rank0(tab)
+    mean = P.reduce_mean_scalar(float(rank + 1) * 10, seen["n"])
+    ret[rank] = dict(out=out, tab=seen["tab"], tab0=tab0, n=seen["n"], mean=mean, x=x_all, p=p_all)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [8, 7])
+def test_sharded_sampling_gloo(n_total):
+    ws = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(ws, _free_port(), n_total, ret), nprocs=ws, join=True)
+    r0, r1 = ret[0], ret[1]
+    assert torch.equal(r0["tab"], r1["tab"]) and torch.equal(r0["tab0"], r1["tab0"])  # rank-identical shortcuts
+    assert r0["n"] + r1["n"] == n_total and r0["n"] >= r1["n"]
+    expect = r0["x"] * 2 + r0["p"].sum(1).view(-1, 1, 1, 1) + r0["tab"][1, 0, 0, 0]
+    assert torch.equal(r0["out"], expect) and torch.equal(r1["out"], expect)
+    assert abs(r0["mean"] - 30.0 / n_total) < 1e-12 and r0["mean"] == r1["mean"]
+
+
+def test_shard_range_covers_everything():
+    from camels_diffusion_model_b200.parallel import shard_range
+    for n in (0, 1, 7, 8, 1024, 1025):
+        for ws in (1, 2, 4, 8):
+            spans = [shard_range(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(ws - 1))
+            assert max(e - s for s, e in spans) - min(e - s for s, e in spans) <= 1

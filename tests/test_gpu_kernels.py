@@ -167,7 +167,7 @@ def test_conv_out_groupnorm_fused(L):
     out = torch.empty(n, 64, 64, device="cuda")
     L.conv_out(src, mr, gamma, beta, w[0].permute(1, 2, 0).reshape(9, 128).contiguous(), bias, out)
     ref = F.conv2d(F.relu(F.group_norm(xs, 8, gamma, beta, 1e-5)), w, bias, padding=1)[:, 0]
-    assert rel_l2(out, ref) < 1e-4
+    assert rel_l2(out, ref) < BF16_TOL  # the normalised activation is staged in shared memory as bf16
 
 
 @pytest.mark.parametrize("din,emb,rows", [(1, 256, 1), (6, 128, 37), (3, 256, 1501)])
