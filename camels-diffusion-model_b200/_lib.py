@@ -54,7 +54,8 @@ class ConvOutArgs(C.Structure):
 class GnReluFilmArgs(C.Structure):
     _fields_ = [("src", C.c_void_p), ("n_img", C.c_int), ("P", C.c_int), ("C", C.c_int), ("groups", C.c_int),
                 ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float), ("film_scale", C.c_void_p),
-                ("film_shift", C.c_void_p), ("film_rows", C.c_int), ("step_ptr", C.c_void_p), ("out", C.c_void_p)]
+                ("film_shift", C.c_void_p), ("film_rows", C.c_int), ("step_ptr", C.c_void_p), ("out", C.c_void_p),
+                ("mean_rstd_out", C.c_void_p)]
 
 
 class DdpmStepArgs(C.Structure):
@@ -102,6 +103,10 @@ EXPORTS = [
     "cdm_conv3x3", "cdm_gemm", "cdm_probe_tma_l2",
     "cdm_conv_in", "cdm_conv_out", "cdm_embed_fc", "cdm_avgpool_gelu", "cdm_gn_relu_film", "cdm_gn_finalize",
     "cdm_ddpm_step", "cdm_step_advance", "cdm_perturb", "cdm_mse_accum",
+    "cdm_gemm_tn", "cdm_chan_reduce", "cdm_bn_finalize", "cdm_bn_apply", "cdm_bn_bwd_apply", "cdm_maxpool2_fwd",
+    "cdm_maxpool2_bwd", "cdm_add_bf16", "cdm_space_to_depth", "cdm_film_bwd", "cdm_gn_bwd", "cdm_rows_sum",
+    "cdm_avgpool_gelu_train", "cdm_avgpool_gelu_bwd", "cdm_outer_wgrad", "cdm_embed_bwd", "cdm_mse_grad",
+    "cdm_adam_step",
 ]
 
 
@@ -196,13 +201,14 @@ def avgpool_gelu(src, out):
 
 
 def gn_relu_film(src, gamma, beta, out, *, groups=8, eps=1e-5, film_scale=None, film_shift=None, film_rows=1,
-                 step_ptr=None):
+                 step_ptr=None, mean_rstd_out=None):
     """src/out bf16 [n,P,C]."""
     a = GnReluFilmArgs()
     a.src, (a.n_img, a.P, a.C) = ptr(src), src.shape
     a.groups, a.gamma, a.beta, a.eps = groups, ptr(gamma), ptr(beta), eps
     a.film_scale, a.film_shift, a.film_rows, a.step_ptr, a.out = (ptr(film_scale), ptr(film_shift), film_rows,
                                                                   ptr(step_ptr), ptr(out))
+    a.mean_rstd_out = ptr(mean_rstd_out)
     check(lib().cdm_gn_relu_film(C.byref(a), stream_ptr()), "cdm_gn_relu_film")
     return out
 
@@ -249,3 +255,154 @@ def mse_accum(pred, target, *, weight_tab=None, t_idx=None, t_shared=0, step_ptr
     a.weight_tab, a.t_idx, a.t_shared, a.step_ptr = ptr(weight_tab), ptr(t_idx), t_shared, ptr(step_ptr)
     a.mse_out, a.acc = ptr(mse_out), ptr(acc)
     check(lib().cdm_mse_accum(C.byref(a), stream_ptr()), "cdm_mse_accum")
+
+
+# ----------------------------------------------------------------------------- training path
+VP, I, F, LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+
+class GemmTnArgs(C.Structure):
+    _fields_ = [("a", VP), ("a_c", I), ("b", VP), ("b_c", I), ("n_img", I), ("H", I), ("W", I), ("taps", I),
+                ("m_off", I), ("M", I), ("n_off", I), ("N", I), ("c", VP), ("ldc", I), ("tap_stride", I),
+                ("k_split", I)]
+
+
+class ChanReduceArgs(C.Structure):
+    _fields_ = [("a", VP), ("lda", I), ("z", VP), ("ldz", I), ("scale", VP), ("shift", VP), ("mean", VP),
+                ("rstd", VP), ("relu", I), ("mode", I), ("P", LL), ("C", I), ("workspace", VP),
+                ("workspace_blocks", I), ("out", VP)]
+
+
+class BnApplyArgs(C.Structure):
+    _fields_ = [("z", VP), ("P", LL), ("C", I), ("relu", I), ("scale", VP), ("shift", VP), ("y", VP), ("sc_x", VP),
+                ("sc_w", VP), ("sc_b", VP), ("film_scale", VP), ("film_shift", VP), ("film_rows", I),
+                ("px_per_img", I), ("yf", VP)]
+
+
+class BnBwdArgs(C.Structure):
+    _fields_ = [("dy", VP), ("lddy", I), ("z", VP), ("P", LL), ("C", I), ("relu", I), ("scale", VP), ("shift", VP),
+                ("mean", VP), ("rstd", VP), ("sums", VP), ("count", F), ("dz", VP)]
+
+
+class GnBwdArgs(C.Structure):
+    _fields_ = [("x", VP), ("dyf", VP), ("lddyf", I), ("n_img", I), ("P", I), ("C", I), ("groups", I),
+                ("mean_rstd", VP), ("gamma", VP), ("beta", VP), ("film_scale", VP), ("dx", VP), ("dgamma_nc", VP),
+                ("dbeta_nc", VP), ("dfs", VP), ("dfb", VP)]
+
+
+class OuterWgradArgs(C.Structure):
+    _fields_ = [("s", VP), ("v", VP), ("n_img", I), ("H", I), ("W", I), ("C", I), ("flip", I), ("mean_rstd", VP),
+                ("gamma", VP), ("beta", VP), ("workspace", VP), ("workspace_blocks", I), ("out", VP)]
+
+
+class EmbedBwdArgs(C.Structure):
+    _fields_ = [("inp", VP), ("rows", I), ("din", I), ("emb", I), ("w1", VP), ("b1", VP), ("w2", VP), ("dout", VP),
+                ("pre", VP), ("h", VP), ("dpre", VP), ("dw1", VP), ("db1", VP), ("dw2", VP), ("db2", VP)]
+
+
+def rawptr(t):
+    """data_ptr of a (possibly channel-sliced) device tensor view."""
+    return None if t is None else t.data_ptr()
+
+
+def gemm_tn(a, b, c, *, n_img, H, W, a_c, b_c, M, N, ldc, m_off=0, n_off=0, taps=1, tap_stride=0, k_split=0):
+    g = GemmTnArgs(rawptr(a), a_c, rawptr(b), b_c, n_img, H, W, taps, m_off, M, n_off, N, rawptr(c), ldc, tap_stride,
+                   k_split)
+    check(lib().cdm_gemm_tn(C.byref(g), stream_ptr()), "cdm_gemm_tn")
+
+
+def chan_reduce(a, lda, P, Cn, out, ws, *, mode=0, z=None, ldz=0, scale=None, shift=None, mean=None, rstd=None,
+                relu=1):
+    g = ChanReduceArgs(rawptr(a), lda, rawptr(z), ldz, rawptr(scale), rawptr(shift), rawptr(mean), rawptr(rstd),
+                       relu, mode, P, Cn, rawptr(ws), ws.numel() // (2 * Cn), rawptr(out))
+    check(lib().cdm_chan_reduce(C.byref(g), stream_ptr()), "cdm_chan_reduce")
+
+
+def bn_finalize(sums, Cn, count, gamma, beta, eps, momentum, rm, rv, scale, shift, mean, rstd):
+    check(lib().cdm_bn_finalize(VP(rawptr(sums)), Cn, F(count), VP(rawptr(gamma)), VP(rawptr(beta)), F(eps),
+                                F(momentum), VP(rawptr(rm)), VP(rawptr(rv)), VP(rawptr(scale)), VP(rawptr(shift)),
+                                VP(rawptr(mean)), VP(rawptr(rstd)), stream_ptr()), "cdm_bn_finalize")
+
+
+def bn_apply(z, P, Cn, scale, shift, y, *, relu=1, sc_x=None, sc_w=None, sc_b=None, film_scale=None, film_shift=None,
+             film_rows=1, px_per_img=1, yf=None):
+    g = BnApplyArgs(rawptr(z), P, Cn, relu, rawptr(scale), rawptr(shift), rawptr(y), rawptr(sc_x), rawptr(sc_w),
+                    rawptr(sc_b), rawptr(film_scale), rawptr(film_shift), film_rows, px_per_img, rawptr(yf))
+    check(lib().cdm_bn_apply(C.byref(g), stream_ptr()), "cdm_bn_apply")
+
+
+def bn_bwd_apply(dy, lddy, z, P, Cn, scale, shift, mean, rstd, sums, count, dz, relu=1):
+    g = BnBwdArgs(rawptr(dy), lddy, rawptr(z), P, Cn, relu, rawptr(scale), rawptr(shift), rawptr(mean), rawptr(rstd),
+                  rawptr(sums), count, rawptr(dz))
+    check(lib().cdm_bn_bwd_apply(C.byref(g), stream_ptr()), "cdm_bn_bwd_apply")
+
+
+def maxpool2_fwd(y, out):
+    n, H, W, Cn = y.shape
+    check(lib().cdm_maxpool2_fwd(VP(rawptr(y)), n, H, W, Cn, VP(rawptr(out)), stream_ptr()), "cdm_maxpool2_fwd")
+
+
+def maxpool2_bwd(dpool, lddp, y, dy):
+    n, H, W, Cn = y.shape
+    check(lib().cdm_maxpool2_bwd(VP(rawptr(dpool)), lddp, VP(rawptr(y)), n, H, W, Cn, VP(rawptr(dy)), stream_ptr()),
+          "cdm_maxpool2_bwd")
+
+
+def add_bf16(a, lda, b, ldb, P, Cn):
+    check(lib().cdm_add_bf16(VP(rawptr(a)), lda, VP(rawptr(b)), ldb, LL(P), Cn, stream_ptr()), "cdm_add_bf16")
+
+
+def space_to_depth(dv, out):
+    n, H2, W2, Cn = dv.shape
+    check(lib().cdm_space_to_depth(VP(rawptr(dv)), n, H2 // 2, W2 // 2, Cn, VP(rawptr(out)), stream_ptr()),
+          "cdm_space_to_depth")
+
+
+def film_bwd(dyf, lddyf, y, n_img, px, Cn, fs, dy, dfs, dfb):
+    check(lib().cdm_film_bwd(VP(rawptr(dyf)), lddyf, VP(rawptr(y)), n_img, px, Cn, VP(rawptr(fs)), VP(rawptr(dy)),
+                             VP(rawptr(dfs)), VP(rawptr(dfb)), stream_ptr()), "cdm_film_bwd")
+
+
+def gn_bwd(x, dyf, lddyf, n_img, P, Cn, groups, mean_rstd, gamma, beta, dx, dgamma_nc, dbeta_nc, *, film_scale=None,
+           dfs=None, dfb=None):
+    g = GnBwdArgs(rawptr(x), rawptr(dyf), lddyf, n_img, P, Cn, groups, rawptr(mean_rstd), rawptr(gamma), rawptr(beta),
+                  rawptr(film_scale), rawptr(dx), rawptr(dgamma_nc), rawptr(dbeta_nc), rawptr(dfs), rawptr(dfb))
+    check(lib().cdm_gn_bwd(C.byref(g), stream_ptr()), "cdm_gn_bwd")
+
+
+def rows_sum(inp, rows, Cn, out):
+    check(lib().cdm_rows_sum(VP(rawptr(inp)), rows, Cn, VP(rawptr(out)), stream_ptr()), "cdm_rows_sum")
+
+
+def avgpool_gelu_train(src, pre, out):
+    n, P, Cn = src.shape
+    check(lib().cdm_avgpool_gelu_train(VP(rawptr(src)), n, P, Cn, VP(rawptr(pre)), VP(rawptr(out)), stream_ptr()),
+          "cdm_avgpool_gelu_train")
+
+
+def avgpool_gelu_bwd(pre, dh, n, P, Cn, dx):
+    check(lib().cdm_avgpool_gelu_bwd(VP(rawptr(pre)), VP(rawptr(dh)), n, P, Cn, VP(rawptr(dx)), stream_ptr()),
+          "cdm_avgpool_gelu_bwd")
+
+
+def outer_wgrad(s, v, n_img, H, W, Cn, out, ws, *, flip=0, mean_rstd=None, gamma=None, beta=None):
+    g = OuterWgradArgs(rawptr(s), rawptr(v), n_img, H, W, Cn, flip, rawptr(mean_rstd), rawptr(gamma), rawptr(beta),
+                       rawptr(ws), ws.numel() // (9 * Cn), rawptr(out))
+    check(lib().cdm_outer_wgrad(C.byref(g), stream_ptr()), "cdm_outer_wgrad")
+
+
+def embed_bwd(inp, w1, b1, w2, dout, pre, h, dpre, dw1, db1, dw2, db2):
+    rows, din = inp.shape
+    g = EmbedBwdArgs(rawptr(inp), rows, din, w2.shape[0], rawptr(w1), rawptr(b1), rawptr(w2), rawptr(dout),
+                     rawptr(pre), rawptr(h), rawptr(dpre), rawptr(dw1), rawptr(db1), rawptr(dw2), rawptr(db2))
+    check(lib().cdm_embed_bwd(C.byref(g), stream_ptr()), "cdm_embed_bwd")
+
+
+def mse_grad(pred, target, inv_count, dpred, partial, loss_sum):
+    check(lib().cdm_mse_grad(VP(rawptr(pred)), VP(rawptr(target)), LL(pred.numel()), F(inv_count), VP(rawptr(dpred)),
+                             VP(rawptr(partial)), partial.numel(), VP(rawptr(loss_sum)), stream_ptr()), "cdm_mse_grad")
+
+
+def adam_step(table, n_tensors, max_numel, lr, beta1, beta2, eps, step):
+    check(lib().cdm_adam_step(VP(rawptr(table)), n_tensors, LL(max_numel), F(lr), F(beta1), F(beta2), F(eps), step,
+                              stream_ptr()), "cdm_adam_step")

@@ -251,6 +251,74 @@ extern "C" int cdm_gemm(const cdm_gemm_args* a, void* stream) {
   return CDM_OK;
 }
 
+extern "C" int cdm_gemm_tn(const cdm_gemm_tn_args* a, void* stream) {
+  CDM_CHECK_ARG(a != nullptr && a->a && a->b && a->c);
+  CDM_CHECK_ARG(a->n_img > 0 && a->H > 0 && a->W > 0 && (a->taps == 1 || a->taps == 9));
+  CDM_CHECK_ARG(a->a_c % 64 == 0 && a->b_c % 64 == 0 && a->M > 0 && a->N > 0 && a->M % 128 == 0 && a->N % 128 == 0);
+  CDM_CHECK_ARG(a->m_off >= 0 && a->m_off % 64 == 0 && a->m_off + a->M <= a->a_c);
+  CDM_CHECK_ARG(a->n_off >= 0 && a->n_off % 64 == 0 && a->n_off + a->N <= a->b_c);
+  CDM_CHECK_ARG(a->ldc > 0);
+  int rc = check_device();
+  if (rc) return rc;
+  // a K block is 128 rows: [rows] mode (H == 1, n_img == 1) takes 128 consecutive rows (ragged tail zero-filled
+  // by TMA); image mode takes a bw x bh pixel rectangle so that a tap shift is a coordinate offset
+  int bw = 128, bh = 1;
+  if (a->H > 1 || a->n_img > 1) {
+    bw = a->W;
+    CDM_CHECK_ARG(bw <= 128 && 128 % bw == 0);
+    bh = 128 / bw;
+    CDM_CHECK_ARG(a->H % bh == 0);
+  } else {
+    CDM_CHECK_ARG(a->taps == 1);
+  }
+  CUtensorMap mA, mB;
+  {
+    uint64_t dims[4] = {(uint64_t)a->a_c, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
+    uint64_t str[3] = {(uint64_t)a->a_c * 2, (uint64_t)a->W * a->a_c * 2, (uint64_t)a->H * a->W * a->a_c * 2};
+    uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
+    rc = make_tmap_bf16(&mA, a->a, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)a->b_c, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
+    uint64_t str[3] = {(uint64_t)a->b_c * 2, (uint64_t)a->W * a->b_c * 2, (uint64_t)a->H * a->W * a->b_c * 2};
+    uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
+    rc = make_tmap_bf16(&mB, a->b, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  GemmTnKParams p;
+  memset(&p, 0, sizeof(p));
+  p.m_tiles = a->M / 128;
+  p.n_tiles = a->N / 128;
+  p.taps = a->taps;
+  p.bw = bw;
+  p.bh = bh;
+  p.tiles_x = (a->W + bw - 1) / bw;
+  p.tiles_y = (a->H + bh - 1) / bh;
+  p.k_blocks = p.tiles_x * p.tiles_y * a->n_img;
+  const int base_units = p.taps * p.m_tiles * p.n_tiles;
+  int ks = a->k_split > 0 ? a->k_split : (2 * num_sms() + base_units - 1) / base_units;
+  if (ks > p.k_blocks) ks = p.k_blocks;
+  if (ks < 1) ks = 1;
+  p.k_split = ks;
+  p.n_units = base_units * ks;
+  p.a_off = a->m_off;
+  p.b_off = a->n_off;
+  p.C = a->c;
+  p.ldc = a->ldc;
+  p.tap_stride = a->tap_stride;
+  constexpr int smem = gemm_tn_smem_bytes();
+  static bool attr_set = false;
+  if (!attr_set) {
+    CDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
+  gemm_tn_kernel<<<grid, kConvThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(mA, mB, p);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
 extern "C" int cdm_probe_tma_l2(const void* buf, int n_rows, int iters, void* stream) {
   CDM_CHECK_ARG(buf && n_rows >= 128 && n_rows % 128 == 0 && iters > 0);
   int rc = check_device();

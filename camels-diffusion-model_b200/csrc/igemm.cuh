@@ -561,6 +561,145 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
 }
 
 // --------------------------------------------------------------------------
+// gemm_tn: C[m][n] (+)= sum_k A[k][m] * B[k][n]  — both operands "MN-major": the reduction
+// index k is the ROW (a pixel / a sample), the output indices are the contiguous channels.
+// This is every weight gradient of the network (conv3x3 wgrad per tap with a pixel-shifted B,
+// transposed-conv wgrad, up0 wgrad).  A K block is 128 rows = one TMA box {64 ch, bw, bh, 1}
+// per 64-channel half (the same NHWC bytes the forward reads as a K-major A operand, here
+// described to the tensor core as MN-major).  Split-K over CTAs, fp32 atomics into C.
+// --------------------------------------------------------------------------
+struct GemmTnKParams {
+  int m_tiles, n_tiles, taps, k_split;
+  int k_blocks;                 // total 128-row K blocks
+  int bw, bh;                   // box extent in w / h (bw * bh == 128)
+  int tiles_x, tiles_y;         // K block index -> (img, ty, tx)
+  int n_units;
+  int a_off, b_off;             // first channel of the A / B windows
+  float* C;
+  int ldc, tap_stride;
+};
+constexpr int kTnStages = 3;
+constexpr int kTnStageBytes = 4 * 16384;
+constexpr int gemm_tn_smem_bytes() { return kTnStages * kTnStageBytes + 256 + 1024; }
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const GemmTnKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTnStages * kTnStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = full + kTnStages;
+  uint64_t* t_full = empty + kTnStages;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTnStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int kb_per_slice = (p.k_blocks + p.k_split - 1) / p.k_split;
+  // unit -> (slice, tap, m_tile, n_tile); slice slowest so that concurrently running CTAs share K blocks in L2
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    int st = 0;
+    uint32_t ph = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int n_tile = u % p.n_tiles, m_tile = (u / p.n_tiles) % p.m_tiles;
+      const int tap = (u / (p.n_tiles * p.m_tiles)) % p.taps, slice = u / (p.n_tiles * p.m_tiles * p.taps);
+      const int dh = p.taps == 9 ? tap / 3 - 1 : 0, dw = p.taps == 9 ? tap % 3 - 1 : 0;
+      const int kb0 = slice * kb_per_slice, kb1 = min(p.k_blocks, kb0 + kb_per_slice);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int tx = kb % p.tiles_x, ty = (kb / p.tiles_x) % p.tiles_y, img = kb / (p.tiles_x * p.tiles_y);
+        mbar_wait(&empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&full[st], kTnStageBytes);
+        uint8_t* sp = smem + st * kTnStageBytes;
+        const int ca = p.a_off + m_tile * 128, cb = p.b_off + n_tile * 128;
+        tma_load_4d(sp, &mapA, &full[st], ca, tx * p.bw, ty * p.bh, img);
+        tma_load_4d(sp + 16384, &mapA, &full[st], ca + 64, tx * p.bw, ty * p.bh, img);
+        tma_load_4d(sp + 32768, &mapB, &full[st], cb, tx * p.bw + dw, ty * p.bh + dh, img);
+        tma_load_4d(sp + 49152, &mapB, &full[st], cb + 64, tx * p.bw + dw, ty * p.bh + dh, img);
+        if (++st == kTnStages) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = umma_idesc_bf16_mn(128, 128);
+    int st = 0, it = 0;
+    uint32_t ph = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
+      const int slice = u / (p.n_tiles * p.m_tiles * p.taps);
+      const int kb0 = slice * kb_per_slice, kb1 = min(p.k_blocks, kb0 + kb_per_slice);
+      const int buf = it & 1;
+      mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + st * kTnStageBytes), b_base = a_base + 32768;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)  // 16 K rows (two 8-row swizzle atoms) per instruction
+          umma_bf16(tmem_base + buf * 128, umma_desc_sw128_mn(a_base + ks * 2048, 16384, 1024),
+                    umma_desc_sw128_mn(b_base + ks * 2048, 16384, 1024), idesc, (kb == kb0 && ks == 0) ? 0u : 1u);
+        umma_commit(&empty[st]);
+        if (++st == kTnStages) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+      umma_commit(&t_full[buf]);
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    int it = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
+      const int n_tile = u % p.n_tiles, m_tile = (u / p.n_tiles) % p.m_tiles;
+      const int tap = (u / (p.n_tiles * p.m_tiles)) % p.taps, slice = u / (p.n_tiles * p.m_tiles * p.taps);
+      const int kb0 = slice * kb_per_slice, kb1 = min(p.k_blocks, kb0 + kb_per_slice);
+      const int buf = it & 1;
+      mbar_wait(&t_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      if (kb1 > kb0) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128);
+        float* crow = p.C + (size_t)(m_tile * 128 + q * 32 + lane) * p.ldc + tap * p.tap_stride + n_tile * 128;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t v[32];
+          tmem_ld_x32(taddr + cc * 32, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(crow + cc * 32 + i, __uint_as_float(v[i]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
+// --------------------------------------------------------------------------
 // probe: how fast can TMA refill shared memory from L2?  Each CTA streams
 // 16 KB boxes (128 rows x 128 B) of an L2-resident [n_rows][64] bf16 buffer.
 // --------------------------------------------------------------------------

@@ -138,6 +138,21 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t sbo
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// Same with both operands MN-major (bit 15 = A major, bit 16 = B major).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(uint32_t M, uint32_t N) {
+  return umma_idesc_bf16(M, N) | (1u << 15) | (1u << 16);
+}
+// MN-major operand, 128-byte swizzle: each K row holds 64 contiguous MN elements (128 B); 8-row
+// K groups are `sbo_bytes` apart, 64-element MN blocks `lbo_bytes` apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1u << 46;
+  d |= (uint64_t)2u << 61;
+  return d;
+}
 
 // ------------------------------------------------------------------ helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -231,7 +231,8 @@ __global__ void __launch_bounds__(256) gn_relu_film_kernel(const bf16* __restric
                                                            const float* __restrict__ beta, float eps,
                                                            const float* __restrict__ film_scale,
                                                            const float* __restrict__ film_shift, int film_rows,
-                                                           const int* __restrict__ step_ptr, bf16* __restrict__ out) {
+                                                           const int* __restrict__ step_ptr, bf16* __restrict__ out,
+                                                           float* __restrict__ mean_rstd_out) {
   __shared__ float red[32];
   const int n = blockIdx.x / groups, g = blockIdx.x % groups;
   const int cpg = C / groups;      // multiple of 8
@@ -257,6 +258,10 @@ __global__ void __launch_bounds__(256) gn_relu_film_kernel(const bf16* __restric
     for (int j = 0; j < 8; ++j) q = fmaf(f[j] - mean, f[j] - mean, q);
   }
   const float rstd = rsqrtf(block_sum(q, red) / cnt + eps);
+  if (mean_rstd_out && threadIdx.x == 0) {
+    mean_rstd_out[((size_t)n * groups + g) * 2] = mean;
+    mean_rstd_out[((size_t)n * groups + g) * 2 + 1] = rstd;
+  }
   const int step = step_ptr ? *step_ptr : 0;
   const float* fs = film_scale ? film_scale + (size_t)n * C + g * cpg : nullptr;
   const float* fb =
@@ -506,7 +511,7 @@ extern "C" int cdm_gn_relu_film(const cdm_gn_relu_film_args* a, void* stream) {
   if (rc) return rc;
   gn_relu_film_kernel<<<a->n_img * a->groups, 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)a->src, a->P, a->C, a->groups, a->gamma, a->beta, a->eps, a->film_scale, a->film_shift,
-      a->film_rows, a->step_ptr, (bf16*)a->out);
+      a->film_rows, a->step_ptr, (bf16*)a->out, a->mean_rstd_out);
   CDM_CHECK_LAUNCH();
   return CDM_OK;
 }

@@ -1,0 +1,902 @@
+// Training-path kernels that are not dense contractions: train-mode BatchNorm (statistics,
+// normalise, backward), MaxPool forward/backward, FiLM / GroupNorm / to_vec / EmbedFC backward,
+// the K=9 / N=1 convolutions' weight gradients, space-to-depth for the transposed-conv backward,
+// the MSE loss gradient and a fused multi-tensor Adam.  Activations and their gradients are
+// NHWC bf16 (pixel stride `ld`, so channel slices of wider tensors can be used in place);
+// every statistic, reduction and parameter gradient is fp32.  Reductions are two-stage with a
+// fixed order (deterministic); nothing here uses atomics on global memory.
+#include <math.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace cdm {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float t_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float t_block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = t_warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+__device__ __forceinline__ void t_unpack8(const uint4& v, float* f) {
+  f[0] = __uint_as_float(v.x << 16);
+  f[1] = __uint_as_float(v.x & 0xffff0000u);
+  f[2] = __uint_as_float(v.y << 16);
+  f[3] = __uint_as_float(v.y & 0xffff0000u);
+  f[4] = __uint_as_float(v.z << 16);
+  f[5] = __uint_as_float(v.z & 0xffff0000u);
+  f[6] = __uint_as_float(v.w << 16);
+  f[7] = __uint_as_float(v.w & 0xffff0000u);
+}
+__device__ __forceinline__ uint4 t_pack8(const float* f) {
+  uint4 v;
+  v.x = pack_bf16x2(f[0], f[1]);
+  v.y = pack_bf16x2(f[2], f[3]);
+  v.z = pack_bf16x2(f[4], f[5]);
+  v.w = pack_bf16x2(f[6], f[7]);
+  return v;
+}
+__device__ __forceinline__ uint4 ld8(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * expf(-0.5f * x * x);
+}
+
+// ---------------------------------------------------------------- channel reductions
+// mode 0: s0 = sum z, s1 = sum z^2                      (BatchNorm batch statistics)
+// mode 1: g = dy * [z*scale+shift > 0 if relu]; xhat = (z-mean)*rstd; s0 = sum g, s1 = sum g*xhat
+// mode 2: s0 = sum a, s1 = 0                            (bias gradients)
+// partial[block][2][C]; chan_reduce_final sums the blocks in order.
+struct ChanReduceP {
+  const bf16* a;   // z (mode 0), dy (mode 1, 2)
+  int lda;
+  const bf16* z;   // mode 1
+  int ldz;
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* rstd;
+  int relu, mode;
+  long long P;
+  int C;
+  float* partial;
+};
+__global__ void __launch_bounds__(256) chan_reduce_kernel(const ChanReduceP p) {
+  __shared__ float red[2][256][8];
+  const int groups = p.C >> 3, rows = 256 / groups;
+  const int cg = threadIdx.x % groups, pr = threadIdx.x / groups;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
+  float sc[8], sh[8], mu[8], rs[8];
+  if (p.mode == 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = p.scale[cg * 8 + j];
+      sh[j] = p.shift[cg * 8 + j];
+      mu[j] = p.mean[cg * 8 + j];
+      rs[j] = p.rstd[cg * 8 + j];
+    }
+  }
+  for (long long r = (long long)blockIdx.x * rows + pr; r < p.P; r += (long long)gridDim.x * rows) {
+    float a[8];
+    t_unpack8(ld8(p.a + r * p.lda + cg * 8), a);
+    if (p.mode == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s0[j] += a[j];
+        s1[j] = fmaf(a[j], a[j], s1[j]);
+      }
+    } else if (p.mode == 1) {
+      float z[8];
+      t_unpack8(ld8(p.z + r * p.ldz + cg * 8), z);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g = (!p.relu || fmaf(z[j], sc[j], sh[j]) > 0.f) ? a[j] : 0.f;
+        s0[j] += g;
+        s1[j] = fmaf(g, (z[j] - mu[j]) * rs[j], s1[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s0[j] += a[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][threadIdx.x][j] = s0[j];
+    red[1][threadIdx.x][j] = s1[j];
+  }
+  __syncthreads();
+  if (pr == 0) {
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = 0.f;
+        for (int q = 0; q < rows; ++q) t += red[k][q * groups + cg][j];
+        p.partial[((size_t)blockIdx.x * 2 + k) * p.C + cg * 8 + j] = t;
+      }
+  }
+}
+__global__ void chan_reduce_final_kernel(const float* __restrict__ partial, int n_blocks, int C2,
+                                         float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C2) return;
+  float t = 0.f;
+  for (int b = 0; b < n_blocks; ++b) t += partial[(size_t)b * C2 + i];
+  out[i] = t;
+}
+
+// BatchNorm2d train-mode finalisation from (possibly all-reduced) sums over `count` elements.
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, int C, float count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ rstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = sums[c] / count;
+  const float var = fmaxf(sums[C + c] / count - mean * mean, 0.f);  // biased, used for normalisation
+  const float rstd = rsqrtf(var + eps);
+  const float sc = gamma[c] * rstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  mean_out[c] = mean;
+  rstd_out[c] = rstd;
+  if (running_mean) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * (count / fmaxf(count - 1.f, 1.f));
+  }
+}
+
+// y = act(z*scale+shift) [+ w_c*x + b_c] ; optional second output yf = fs[n]*y + fb[n|0].
+struct BnApplyP {
+  const bf16* z;
+  long long P;
+  int C, relu;
+  const float* scale;
+  const float* shift;
+  bf16* y;
+  const float* sc_x;  // fp32 [P] or null
+  const float* sc_w;
+  const float* sc_b;
+  const float* fs;  // film scale [n][C] or null
+  const float* fb;  // film shift [rows][C]
+  int fb_rows, px_per_img;
+  bf16* yf;
+};
+__global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyP p) {
+  const int groups = p.C >> 3;
+  const long long total = p.P * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % groups);
+    const long long r = i / groups;
+    float f[8];
+    t_unpack8(ld8(p.z + r * p.C + cg * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = fmaf(f[j], p.scale[cg * 8 + j], p.shift[cg * 8 + j]);
+      f[j] = p.relu ? fmaxf(y, 0.f) : y;
+    }
+    if (p.sc_x) {
+      const float xv = p.sc_x[r];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += fmaf(p.sc_w[cg * 8 + j], xv, p.sc_b[cg * 8 + j]);
+    }
+    *reinterpret_cast<uint4*>(p.y + r * p.C + cg * 8) = t_pack8(f);
+    if (p.fs) {
+      const long long n = r / p.px_per_img;
+      const float* fs = p.fs + n * p.C + cg * 8;
+      const float* fb = p.fb + (p.fb_rows == 1 ? 0 : n) * p.C + cg * 8;
+      // FiLM acts on the bf16-rounded y the next layer's backward sees
+      float g[8];
+      t_unpack8(t_pack8(f), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = fmaf(fs[j], g[j], fb[j]);
+      *reinterpret_cast<uint4*>(p.yf + r * p.C + cg * 8) = t_pack8(g);
+    }
+  }
+}
+
+// dz = scale * (g - S0/N - xhat * S1/N),  g = dy * relu-mask  (scale = gamma * rstd).
+struct BnBwdP {
+  const bf16* dy;
+  int lddy;
+  const bf16* z;
+  long long P;
+  int C, relu;
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* rstd;
+  const float* sums;  // [2][C] (all-reduced)
+  float count;
+  bf16* dz;
+};
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdP p) {
+  const int groups = p.C >> 3;
+  const long long total = p.P * groups;
+  const float inv = 1.f / p.count;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % groups);
+    const long long r = i / groups;
+    float d[8], z[8];
+    t_unpack8(ld8(p.dy + r * p.lddy + cg * 8), d);
+    t_unpack8(ld8(p.z + r * p.C + cg * 8), z);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      const float g = (!p.relu || fmaf(z[j], p.scale[c], p.shift[c]) > 0.f) ? d[j] : 0.f;
+      const float xh = (z[j] - p.mean[c]) * p.rstd[c];
+      d[j] = p.scale[c] * (g - p.sums[c] * inv - xh * p.sums[p.C + c] * inv);
+    }
+    *reinterpret_cast<uint4*>(p.dz + r * p.C + cg * 8) = t_pack8(d);
+  }
+}
+
+// ---------------------------------------------------------------- MaxPool2d(2)
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const bf16* __restrict__ y, int n_img, int H, int W, int C,
+                                                           bf16* __restrict__ out) {
+  const int groups = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)n_img * Ho * Wo * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % groups);
+    long long r = i / groups;
+    const int wo = (int)(r % Wo);
+    r /= Wo;
+    const int ho = (int)(r % Ho);
+    const long long n = r / Ho;
+    const bf16* b = y + (((n * H + 2 * ho) * W) + 2 * wo) * C + cg * 8;
+    const uint4 v0 = ld8(b), v1 = ld8(b + C), v2 = ld8(b + (size_t)W * C), v3 = ld8(b + (size_t)W * C + C);
+    uint4 m;
+    m.x = bf16x2_max(bf16x2_max(v0.x, v1.x), bf16x2_max(v2.x, v3.x));
+    m.y = bf16x2_max(bf16x2_max(v0.y, v1.y), bf16x2_max(v2.y, v3.y));
+    m.z = bf16x2_max(bf16x2_max(v0.z, v1.z), bf16x2_max(v2.z, v3.z));
+    m.w = bf16x2_max(bf16x2_max(v0.w, v1.w), bf16x2_max(v2.w, v3.w));
+    *reinterpret_cast<uint4*>(out + (((n * Ho + ho) * Wo) + wo) * C + cg * 8) = m;
+  }
+}
+// dy[px] = dpool if px is the FIRST maximum of its 2x2 window (torch's tie rule), else 0.
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const bf16* __restrict__ dpool, int lddp,
+                                                           const bf16* __restrict__ y, int n_img, int H, int W, int C,
+                                                           bf16* __restrict__ dy) {
+  const int groups = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)n_img * Ho * Wo * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % groups);
+    long long r = i / groups;
+    const int wo = (int)(r % Wo);
+    r /= Wo;
+    const int ho = (int)(r % Ho);
+    const long long n = r / Ho;
+    const size_t base = ((((size_t)n * H + 2 * ho) * W) + 2 * wo) * C + cg * 8;
+    const size_t off[4] = {0, (size_t)C, (size_t)W * C, (size_t)W * C + C};
+    float v[4][8], g[8], o[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) t_unpack8(ld8(y + base + off[q]), v[q]);
+    t_unpack8(ld8(dpool + (((size_t)n * Ho + ho) * Wo + wo) * lddp + cg * 8), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float m = fmaxf(fmaxf(v[0][j], v[1][j]), fmaxf(v[2][j], v[3][j]));
+      bool taken = false;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool hit = !taken && v[q][j] == m;
+        o[q][j] = hit ? g[j] : 0.f;
+        taken = taken || hit;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(dy + base + off[q]) = t_pack8(o[q]);
+  }
+}
+
+// a[r][c] += b[r][c]   (gradient accumulation at the skip connections)
+__global__ void __launch_bounds__(256) add_bf16_kernel(bf16* __restrict__ a, int lda, const bf16* __restrict__ b,
+                                                       int ldb, long long P, int C) {
+  const int groups = C >> 3;
+  const long long total = P * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % groups);
+    const long long r = i / groups;
+    float x[8], y[8];
+    t_unpack8(ld8(a + r * lda + cg * 8), x);
+    t_unpack8(ld8(b + r * ldb + cg * 8), y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+    *reinterpret_cast<uint4*>(a + r * lda + cg * 8) = t_pack8(x);
+  }
+}
+
+// dv [n][2H][2W][C] -> s2d [n][H][W][(kh,kw,c)]  (A operand of the transposed-conv dgrad / wgrad GEMMs)
+__global__ void __launch_bounds__(256) space_to_depth_kernel(const bf16* __restrict__ dv, int n_img, int H, int W,
+                                                             int C, bf16* __restrict__ out) {
+  const int groups = C >> 3;
+  const long long total = (long long)n_img * H * W * 4 * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % groups);
+    long long r = i / groups;
+    const int k = (int)(r & 3);
+    r >>= 2;
+    const int w = (int)(r % W);
+    r /= W;
+    const int h = (int)(r % H);
+    const long long n = r / H;
+    const uint4 v = ld8(dv + (((n * 2 * H + 2 * h + (k >> 1)) * (2 * W)) + 2 * w + (k & 1)) * C + cg * 8);
+    *reinterpret_cast<uint4*>(out + (((n * H + h) * W + w) * 4 + k) * C + cg * 8) = v;
+  }
+}
+
+// ---------------------------------------------------------------- FiLM backward
+// yf = fs[n][c]*y + fb: dy = fs*dyf; dfs[n][c] = sum_px dyf*y; dfb[n][c] = sum_px dyf.  One block per image.
+__global__ void __launch_bounds__(256) film_bwd_kernel(const bf16* __restrict__ dyf, int lddyf,
+                                                       const bf16* __restrict__ y, int px, int C,
+                                                       const float* __restrict__ fs, bf16* __restrict__ dy,
+                                                       float* __restrict__ dfs, float* __restrict__ dfb) {
+  __shared__ float red[2][256][8];
+  const size_t n = blockIdx.x;
+  const int groups = C >> 3, rows = 256 / groups;
+  const int cg = threadIdx.x % groups, pr = threadIdx.x / groups;
+  float a0[8], a1[8], s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a0[j] = a1[j] = 0.f;
+    s[j] = fs[n * C + cg * 8 + j];
+  }
+  for (int r = pr; r < px; r += rows) {
+    float d[8], v[8];
+    t_unpack8(ld8(dyf + (n * px + r) * lddyf + cg * 8), d);
+    t_unpack8(ld8(y + (n * px + r) * C + cg * 8), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a0[j] = fmaf(d[j], v[j], a0[j]);
+      a1[j] += d[j];
+      d[j] *= s[j];
+    }
+    *reinterpret_cast<uint4*>(dy + (n * px + r) * C + cg * 8) = t_pack8(d);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][threadIdx.x][j] = a0[j];
+    red[1][threadIdx.x][j] = a1[j];
+  }
+  __syncthreads();
+  if (pr == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t0 = 0.f, t1 = 0.f;
+      for (int q = 0; q < rows; ++q) {
+        t0 += red[0][q * groups + cg][j];
+        t1 += red[1][q * groups + cg][j];
+      }
+      dfs[n * C + cg * 8 + j] = t0;
+      dfb[n * C + cg * 8 + j] = t1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- GroupNorm (+ReLU, +FiLM) backward
+// forward: h = (x-mean)*rstd; y = relu(h*gamma+beta); yf = fs*y + fb (FiLM optional).
+// One block per (image, group).  Outputs dx (bf16) and per-(image, channel) dgamma/dbeta/dfs/dfb.
+struct GnBwdP {
+  const bf16* x;
+  const bf16* dyf;
+  int lddyf;
+  int P, C, groups;
+  const float* mean_rstd;
+  const float* gamma;
+  const float* beta;
+  const float* fs;
+  bf16* dx;
+  float* dgamma_nc;
+  float* dbeta_nc;
+  float* dfs;
+  float* dfb;
+};
+__global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdP p) {
+  __shared__ float red[32];
+  __shared__ float chan[4][32];  // dgamma, dbeta, dfs, dfb per channel of the group (cpg <= 32)
+  const int n = blockIdx.x / p.groups, g = blockIdx.x % p.groups;
+  const int cpg = p.C / p.groups, vpp = cpg / 8, n_vec = p.P * vpp;
+  const float mean = p.mean_rstd[((size_t)n * p.groups + g) * 2], rstd = p.mean_rstd[((size_t)n * p.groups + g) * 2 + 1];
+  if (threadIdx.x < 128) chan[threadIdx.x >> 5][threadIdx.x & 31] = 0.f;
+  __syncthreads();
+  const bf16* xb = p.x + (size_t)n * p.P * p.C + g * cpg;
+  const bf16* db = p.dyf + (size_t)n * p.P * p.lddyf + g * cpg;
+  // a thread always visits the same 8 channels (blockDim.x is a multiple of vpp)
+  const int v = threadIdx.x % vpp;
+  float ga[8], be[8], fsv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ga[j] = p.gamma[g * cpg + v * 8 + j];
+    be[j] = p.beta[g * cpg + v * 8 + j];
+    fsv[j] = p.fs ? p.fs[(size_t)n * p.C + g * cpg + v * 8 + j] : 1.f;
+  }
+  float S1 = 0.f, S2 = 0.f, dg[8], dbt[8], dfs[8], dfb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dg[j] = dbt[j] = dfs[j] = dfb[j] = 0.f;
+  for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
+    const int px = i / vpp;
+    float x[8], d[8];
+    t_unpack8(ld8(xb + (size_t)px * p.C + v * 8), x);
+    t_unpack8(ld8(db + (size_t)px * p.lddyf + v * 8), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float h = (x[j] - mean) * rstd;
+      const float pre = fmaf(h, ga[j], be[j]);
+      const float y = fmaxf(pre, 0.f);
+      dfs[j] = fmaf(d[j], y, dfs[j]);
+      dfb[j] += d[j];
+      const float dyv = pre > 0.f ? d[j] * fsv[j] : 0.f;
+      dg[j] = fmaf(dyv, h, dg[j]);
+      dbt[j] += dyv;
+      const float dh = dyv * ga[j];
+      S1 += dh;
+      S2 = fmaf(dh, h, S2);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&chan[0][v * 8 + j], dg[j]);
+    atomicAdd(&chan[1][v * 8 + j], dbt[j]);
+    atomicAdd(&chan[2][v * 8 + j], dfs[j]);
+    atomicAdd(&chan[3][v * 8 + j], dfb[j]);
+  }
+  const float M = (float)(p.P * cpg);
+  const float s1 = t_block_sum(S1, red) / M;
+  const float s2 = t_block_sum(S2, red) / M;
+  if (threadIdx.x < cpg) {
+    const size_t o = (size_t)n * p.C + g * cpg + threadIdx.x;
+    p.dgamma_nc[o] = chan[0][threadIdx.x];
+    p.dbeta_nc[o] = chan[1][threadIdx.x];
+    if (p.dfs) {
+      p.dfs[o] = chan[2][threadIdx.x];
+      p.dfb[o] = chan[3][threadIdx.x];
+    }
+  }
+  bf16* ob = p.dx + (size_t)n * p.P * p.C + g * cpg;
+  for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
+    const int px = i / vpp;
+    float x[8], d[8];
+    t_unpack8(ld8(xb + (size_t)px * p.C + v * 8), x);
+    t_unpack8(ld8(db + (size_t)px * p.lddyf + v * 8), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float h = (x[j] - mean) * rstd;
+      const float dh = fmaf(h, ga[j], be[j]) > 0.f ? d[j] * fsv[j] * ga[j] : 0.f;
+      d[j] = rstd * (dh - s1 - h * s2);
+    }
+    *reinterpret_cast<uint4*>(ob + (size_t)px * p.C + v * 8) = t_pack8(d);
+  }
+}
+
+// out[c] = sum_n in[n][c]  (sum the per-image partials over the batch; tiny)
+__global__ void rows_sum_kernel(const float* __restrict__ in, int rows, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t = 0.f;
+  for (int r = 0; r < rows; ++r) t += in[(size_t)r * C + c];
+  out[c] = t;
+}
+
+// d_d2[n][px][c] += gelu'(pre[n][c]) * dh[n][c] / P    (to_vec backward)
+__global__ void __launch_bounds__(256) avgpool_gelu_bwd_kernel(const float* __restrict__ pre,
+                                                               const float* __restrict__ dh, int P, int C,
+                                                               bf16* __restrict__ dx) {
+  const size_t n = blockIdx.x;
+  const int groups = C >> 3;
+  for (int i = threadIdx.x; i < P * groups; i += blockDim.x) {
+    const int cg = i % groups, px = i / groups;
+    float d[8];
+    t_unpack8(ld8(dx + (n * P + px) * C + cg * 8), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      d[j] += gelu_grad(pre[n * C + c]) * dh[n * C + c] / (float)P;
+    }
+    *reinterpret_cast<uint4*>(dx + (n * P + px) * C + cg * 8) = t_pack8(d);
+  }
+}
+__global__ void __launch_bounds__(256) avgpool_pre_kernel(const bf16* __restrict__ src, int P, int C,
+                                                          float* __restrict__ pre, bf16* __restrict__ out) {
+  const size_t n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int px = 0; px < P; ++px) s += __bfloat162float(src[(n * P + px) * C + c]);
+    s /= (float)P;
+    pre[n * C + c] = s;
+    out[n * C + c] = __float2bfloat16(gelu_f(s));
+  }
+}
+
+// ---------------------------------------------------------------- K=9 / N=1 convolution weight gradients
+// dW[tap][c] = sum_px s[px + d(tap)] * v[px][c],  d(tap) = (kh-1, kw-1) (flip = 0) or its negative (flip = 1).
+//  * conv_in  wgrad: s = x (network input),   v = dz1,                      flip = 0
+//  * conv_out wgrad: s = d eps,               v = relu(GroupNorm(o)) on load, flip = 1
+// partial[block][9][C] -> chan_reduce_final.
+struct OuterWgradP {
+  const float* s;
+  const bf16* v;
+  int n_img, H, W, C, flip;
+  const float* mean_rstd;  // non-null: apply GroupNorm(8)+ReLU to v on load
+  const float* gamma;
+  const float* beta;
+  float* partial;
+};
+__global__ void __launch_bounds__(256) outer_wgrad_kernel(const OuterWgradP p) {
+  __shared__ float red[256][8];
+  const int groups = p.C >> 3, rows = 256 / groups;
+  const int cg = threadIdx.x % groups, pr = threadIdx.x / groups;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  const long long P = (long long)p.n_img * p.H * p.W;
+  const int cpg = p.C / 8;
+  for (long long r = (long long)blockIdx.x * rows + pr; r < P; r += (long long)gridDim.x * rows) {
+    const int w = (int)(r % p.W), h = (int)((r / p.W) % p.H);
+    const long long n = r / ((long long)p.W * p.H);
+    float v[8];
+    t_unpack8(ld8(p.v + r * p.C + cg * 8), v);
+    if (p.mean_rstd) {
+      const int g = (cg * 8) / cpg;
+      const float mean = p.mean_rstd[(n * 8 + g) * 2], rstd = p.mean_rstd[(n * 8 + g) * 2 + 1];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        v[j] = fmaxf(fmaf((v[j] - mean) * rstd, p.gamma[cg * 8 + j], p.beta[cg * 8 + j]), 0.f);
+    }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int dh = p.flip ? 1 - kh : kh - 1, dw = p.flip ? 1 - kw : kw - 1;
+        const int hh = h + dh, ww = w + dw;
+        const float sv = (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) ? __ldg(p.s + (n * p.H + hh) * p.W + ww) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[kh * 3 + kw][j] = fmaf(sv, v[j], acc[kh * 3 + kw][j]);
+      }
+  }
+  for (int t = 0; t < 9; ++t) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[t][j];
+    __syncthreads();
+    if (pr == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float s = 0.f;
+        for (int q = 0; q < rows; ++q) s += red[q * groups + cg][j];
+        p.partial[((size_t)blockIdx.x * 9 + t) * p.C + cg * 8 + j] = s;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- EmbedFC backward (tiny)
+// forward: pre = W1 v + b1, h = gelu(pre), out = W2 h + b2.
+__global__ void __launch_bounds__(256) embed_hidden_kernel(const float* __restrict__ in, int din,
+                                                           const float* __restrict__ w1, const float* __restrict__ b1,
+                                                           int emb, float* __restrict__ pre, float* __restrict__ h) {
+  const size_t r = blockIdx.x;
+  for (int j = threadIdx.x; j < emb; j += blockDim.x) {
+    float s = b1[j];
+    for (int i = 0; i < din; ++i) s = fmaf(w1[j * din + i], in[r * din + i], s);
+    pre[r * emb + j] = s;
+    h[r * emb + j] = gelu_f(s);
+  }
+}
+// block j: dW2[j][k] = sum_r dout[r][j] h[r][k]; db2[j] = sum_r dout[r][j]
+__global__ void __launch_bounds__(256) embed_bwd_w2_kernel(const float* __restrict__ dout, const float* __restrict__ h,
+                                                           int rows, int emb, float* __restrict__ dw2,
+                                                           float* __restrict__ db2) {
+  const int j = blockIdx.x;
+  for (int k = threadIdx.x; k < emb; k += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s = fmaf(dout[(size_t)r * emb + j], h[(size_t)r * emb + k], s);
+    dw2[(size_t)j * emb + k] = s;
+  }
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += dout[(size_t)r * emb + j];
+    db2[j] = s;
+  }
+}
+// block r: dpre[r][k] = gelu'(pre[r][k]) * sum_j dout[r][j] W2[j][k]
+__global__ void __launch_bounds__(256) embed_bwd_hidden_kernel(const float* __restrict__ dout,
+                                                               const float* __restrict__ w2,
+                                                               const float* __restrict__ pre, int emb,
+                                                               float* __restrict__ dpre) {
+  extern __shared__ float s_d[];
+  const size_t r = blockIdx.x;
+  for (int j = threadIdx.x; j < emb; j += blockDim.x) s_d[j] = dout[r * emb + j];
+  __syncthreads();
+  for (int k = threadIdx.x; k < emb; k += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < emb; ++j) s = fmaf(s_d[j], w2[(size_t)j * emb + k], s);
+    dpre[r * emb + k] = s * gelu_grad(pre[r * emb + k]);
+  }
+}
+// thread (k): dW1[k][i] = sum_r dpre[r][k] in[r][i]; db1[k] = sum_r dpre[r][k]
+__global__ void embed_bwd_w1_kernel(const float* __restrict__ dpre, const float* __restrict__ in, int rows, int din,
+                                    int emb, float* __restrict__ dw1, float* __restrict__ db1) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= emb) return;
+  float sb = 0.f;
+  for (int r = 0; r < rows; ++r) sb += dpre[(size_t)r * emb + k];
+  db1[k] = sb;
+  for (int i = 0; i < din; ++i) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s = fmaf(dpre[(size_t)r * emb + k], in[(size_t)r * din + i], s);
+    dw1[(size_t)k * din + i] = s;
+  }
+}
+
+// ---------------------------------------------------------------- loss + Adam
+// F.mse_loss(pred, noise) (mean over all elements): partial sums of (pred-noise)^2 per block and
+// d pred = 2 (pred - noise) * inv_count (inv_count = 1 / GLOBAL element count in data-parallel runs).
+__global__ void __launch_bounds__(256) mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                                                       long long n4, float inv_count, float* __restrict__ dpred,
+                                                       float* __restrict__ partial) {
+  __shared__ float red[32];
+  float q = 0.f;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += (long long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(pred)[v], b = reinterpret_cast<const float4*>(tgt)[v];
+    float4 d = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+    q += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+    const float s = 2.f * inv_count;
+    reinterpret_cast<float4*>(dpred)[v] = make_float4(d.x * s, d.y * s, d.z * s, d.w * s);
+  }
+  const float t = t_block_sum(q, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+// torch.optim.Adam defaults (no weight decay, no amsgrad), all tensors in one launch.
+struct AdamTensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  long long n;
+};
+__global__ void __launch_bounds__(256) adam_kernel(const AdamTensor* __restrict__ tab, int n_tensors, float lr,
+                                                   float beta1, float beta2, float eps, float bc1, float bc2) {
+  // grid.y = tensor, grid.x strides over its elements
+  const AdamTensor t = tab[blockIdx.y];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < t.n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = t.g[i];
+    const float m = beta1 * t.m[i] + (1.f - beta1) * g;
+    const float v = beta2 * t.v[i] + (1.f - beta2) * g * g;
+    t.m[i] = m;
+    t.v[i] = v;
+    // torch: denom = sqrt(v)/sqrt(bc2) + eps; p -= (lr/bc1) * m / denom
+    const float denom = sqrtf(v) / sqrtf(bc2) + eps;
+    t.p[i] -= (lr / bc1) * (m / denom);
+  }
+}
+
+static int grid1d(long long work, int block = 256, int cap = 148 * 8) {
+  long long g = (work + block - 1) / block;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace cdm
+
+using namespace cdm;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int cdm_chan_reduce(const cdm_chan_reduce_args* a, void* stream) {
+  CDM_CHECK_ARG(a && a->a && a->out && a->workspace && a->P > 0 && a->C > 0 && a->C % 8 == 0 && 256 % (a->C / 8) == 0);
+  CDM_CHECK_ARG(a->mode >= 0 && a->mode <= 2 && a->lda >= a->C);
+  if (a->mode == 1) CDM_CHECK_ARG(a->z && a->scale && a->shift && a->mean && a->rstd && a->ldz >= a->C);
+  int rc = check_device();
+  if (rc) return rc;
+  const int rows = 256 / (a->C / 8);
+  int blocks = (int)((a->P + rows * 8 - 1) / (rows * 8));
+  if (blocks > a->workspace_blocks) blocks = a->workspace_blocks;
+  if (blocks < 1) blocks = 1;
+  ChanReduceP p{(const bf16*)a->a, a->lda, (const bf16*)a->z, a->ldz, a->scale, a->shift, a->mean, a->rstd,
+                a->relu, a->mode, a->P, a->C, a->workspace};
+  chan_reduce_kernel<<<blocks, 256, 0, ST(stream)>>>(p);
+  CDM_CHECK_LAUNCH();
+  chan_reduce_final_kernel<<<(2 * a->C + 127) / 128, 128, 0, ST(stream)>>>(a->workspace, blocks, 2 * a->C, a->out);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
+extern "C" int cdm_bn_finalize(const float* sums, int C, float count, const float* gamma, const float* beta, float eps,
+                               float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                               float* mean, float* rstd, void* stream) {
+  CDM_CHECK_ARG(sums && gamma && beta && scale && shift && mean && rstd && C > 0 && count > 0);
+  CDM_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr));
+  int rc = check_device();
+  if (rc) return rc;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sums, C, count, gamma, beta, eps, momentum, running_mean,
+                                                             running_var, scale, shift, mean, rstd);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
+extern "C" int cdm_bn_apply(const cdm_bn_apply_args* a, void* stream) {
+  CDM_CHECK_ARG(a && a->z && a->scale && a->shift && a->y && a->P > 0 && a->C % 8 == 0);
+  CDM_CHECK_ARG(!a->sc_x || (a->sc_w && a->sc_b));
+  CDM_CHECK_ARG(!a->film_scale || (a->film_shift && a->yf && a->px_per_img > 0 && a->film_rows >= 1));
+  int rc = check_device();
+  if (rc) return rc;
+  BnApplyP p{(const bf16*)a->z, a->P, a->C, a->relu, a->scale, a->shift, (bf16*)a->y, a->sc_x, a->sc_w, a->sc_b,
+             a->film_scale, a->film_shift, a->film_rows, a->px_per_img, (bf16*)a->yf};
+  bn_apply_kernel<<<grid1d(a->P * (a->C / 8)), 256, 0, ST(stream)>>>(p);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
+extern "C" int cdm_bn_bwd_apply(const cdm_bn_bwd_args* a, void* stream) {
+  CDM_CHECK_ARG(a && a->dy && a->z && a->scale && a->shift && a->mean && a->rstd && a->sums && a->dz);
+  CDM_CHECK_ARG(a->P > 0 && a->C % 8 == 0 && a->lddy >= a->C && a->count > 0);
+  int rc = check_device();
+  if (rc) return rc;
+  BnBwdP p{(const bf16*)a->dy, a->lddy, (const bf16*)a->z, a->P, a->C, a->relu, a->scale, a->shift, a->mean, a->rstd,
+           a->sums, a->count, (bf16*)a->dz};
+  bn_bwd_apply_kernel<<<grid1d(a->P * (a->C / 8)), 256, 0, ST(stream)>>>(p);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
+extern "C" int cdm_maxpool2_fwd(const void* y, int n_img, int H, int W, int C, void* out, void* stream) {
+  CDM_CHECK_ARG(y && out && n_img > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0);
+  int rc = check_device();
+  if (rc) return rc;
+  maxpool2_fwd_kernel<<<grid1d((long long)n_img * (H / 2) * (W / 2) * (C / 8)), 256, 0, ST(stream)>>>(
+      (const bf16*)y, n_img, H, W, C, (bf16*)out);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+extern "C" int cdm_maxpool2_bwd(const void* dpool, int lddp, const void* y, int n_img, int H, int W, int C, void* dy,
+                                void* stream) {
+  CDM_CHECK_ARG(dpool && y && dy && n_img > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && lddp >= C);
+  int rc = check_device();
+  if (rc) return rc;
+  maxpool2_bwd_kernel<<<grid1d((long long)n_img * (H / 2) * (W / 2) * (C / 8)), 256, 0, ST(stream)>>>(
+      (const bf16*)dpool, lddp, (const bf16*)y, n_img, H, W, C, (bf16*)dy);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+extern "C" int cdm_add_bf16(void* a, int lda, const void* b, int ldb, long long P, int C, void* stream) {
+  CDM_CHECK_ARG(a && b && P > 0 && C % 8 == 0 && lda >= C && ldb >= C);
+  int rc = check_device();
+  if (rc) return rc;
+  add_bf16_kernel<<<grid1d(P * (C / 8)), 256, 0, ST(stream)>>>((bf16*)a, lda, (const bf16*)b, ldb, P, C);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+extern "C" int cdm_space_to_depth(const void* dv, int n_img, int H, int W, int C, void* out, void* stream) {
+  CDM_CHECK_ARG(dv && out && n_img > 0 && H > 0 && W > 0 && C % 8 == 0);
+  int rc = check_device();
+  if (rc) return rc;
+  space_to_depth_kernel<<<grid1d((long long)n_img * H * W * 4 * (C / 8)), 256, 0, ST(stream)>>>(
+      (const bf16*)dv, n_img, H, W, C, (bf16*)out);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+extern "C" int cdm_film_bwd(const void* dyf, int lddyf, const void* y, int n_img, int px, int C, const float* fs,
+                            void* dy, float* dfs, float* dfb, void* stream) {
+  CDM_CHECK_ARG(dyf && y && fs && dy && dfs && dfb && n_img > 0 && px > 0 && C % 8 == 0 && 256 % (C / 8) == 0);
+  int rc = check_device();
+  if (rc) return rc;
+  film_bwd_kernel<<<n_img, 256, 0, ST(stream)>>>((const bf16*)dyf, lddyf, (const bf16*)y, px, C, fs, (bf16*)dy, dfs,
+                                                 dfb);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+extern "C" int cdm_gn_bwd(const cdm_gn_bwd_args* a, void* stream) {
+  CDM_CHECK_ARG(a && a->x && a->dyf && a->mean_rstd && a->gamma && a->beta && a->dx && a->dgamma_nc && a->dbeta_nc);
+  CDM_CHECK_ARG(a->n_img > 0 && a->P > 0 && a->groups > 0 && a->C % a->groups == 0);
+  const int cpg = a->C / a->groups;
+  CDM_CHECK_ARG(cpg % 8 == 0 && cpg <= 32 && 256 % (cpg / 8) == 0 && a->lddyf >= a->C);
+  CDM_CHECK_ARG((a->film_scale == nullptr) == (a->dfs == nullptr) && (a->dfs == nullptr) == (a->dfb == nullptr));
+  int rc = check_device();
+  if (rc) return rc;
+  GnBwdP p{(const bf16*)a->x, (const bf16*)a->dyf, a->lddyf, a->P, a->C, a->groups, a->mean_rstd, a->gamma, a->beta,
+           a->film_scale, (bf16*)a->dx, a->dgamma_nc, a->dbeta_nc, a->dfs, a->dfb};
+  gn_bwd_kernel<<<a->n_img * a->groups, 256, 0, ST(stream)>>>(p);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+extern "C" int cdm_rows_sum(const float* in, int rows, int C, float* out, void* stream) {
+  CDM_CHECK_ARG(in && out && rows > 0 && C > 0);
+  int rc = check_device();
+  if (rc) return rc;
+  rows_sum_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(in, rows, C, out);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+extern "C" int cdm_avgpool_gelu_train(const void* src, int n_img, int P, int C, float* pre, void* out, void* stream) {
+  CDM_CHECK_ARG(src && pre && out && n_img > 0 && P > 0 && C > 0);
+  int rc = check_device();
+  if (rc) return rc;
+  avgpool_pre_kernel<<<n_img, 256, 0, ST(stream)>>>((const bf16*)src, P, C, pre, (bf16*)out);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+extern "C" int cdm_avgpool_gelu_bwd(const float* pre, const float* dh, int n_img, int P, int C, void* dx,
+                                    void* stream) {
+  CDM_CHECK_ARG(pre && dh && dx && n_img > 0 && P > 0 && C % 8 == 0);
+  int rc = check_device();
+  if (rc) return rc;
+  avgpool_gelu_bwd_kernel<<<n_img, 256, 0, ST(stream)>>>(pre, dh, P, C, (bf16*)dx);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+extern "C" int cdm_outer_wgrad(const cdm_outer_wgrad_args* a, void* stream) {
+  CDM_CHECK_ARG(a && a->s && a->v && a->out && a->workspace && a->n_img > 0 && a->H > 0 && a->W > 0);
+  CDM_CHECK_ARG(a->C % 8 == 0 && 256 % (a->C / 8) == 0);
+  CDM_CHECK_ARG(!a->mean_rstd || (a->gamma && a->beta));
+  int rc = check_device();
+  if (rc) return rc;
+  const int rows = 256 / (a->C / 8);
+  const long long P = (long long)a->n_img * a->H * a->W;
+  int blocks = (int)((P + rows * 16 - 1) / (rows * 16));
+  if (blocks > a->workspace_blocks) blocks = a->workspace_blocks;
+  if (blocks < 1) blocks = 1;
+  OuterWgradP p{a->s, (const bf16*)a->v, a->n_img, a->H, a->W, a->C, a->flip, a->mean_rstd, a->gamma, a->beta,
+                a->workspace};
+  outer_wgrad_kernel<<<blocks, 256, 0, ST(stream)>>>(p);
+  CDM_CHECK_LAUNCH();
+  chan_reduce_final_kernel<<<(9 * a->C + 127) / 128, 128, 0, ST(stream)>>>(a->workspace, blocks, 9 * a->C, a->out);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+extern "C" int cdm_embed_bwd(const cdm_embed_bwd_args* a, void* stream) {
+  CDM_CHECK_ARG(a && a->in && a->w1 && a->b1 && a->w2 && a->dout && a->pre && a->h && a->dpre);
+  CDM_CHECK_ARG(a->dw1 && a->db1 && a->dw2 && a->db2 && a->rows > 0 && a->din > 0 && a->emb > 0 && a->emb <= 4096);
+  int rc = check_device();
+  if (rc) return rc;
+  embed_hidden_kernel<<<a->rows, 256, 0, ST(stream)>>>(a->in, a->din, a->w1, a->b1, a->emb, a->pre, a->h);
+  CDM_CHECK_LAUNCH();
+  embed_bwd_w2_kernel<<<a->emb, 256, 0, ST(stream)>>>(a->dout, a->h, a->rows, a->emb, a->dw2, a->db2);
+  CDM_CHECK_LAUNCH();
+  embed_bwd_hidden_kernel<<<a->rows, 256, a->emb * sizeof(float), ST(stream)>>>(a->dout, a->w2, a->pre, a->emb,
+                                                                               a->dpre);
+  CDM_CHECK_LAUNCH();
+  embed_bwd_w1_kernel<<<(a->emb + 127) / 128, 128, 0, ST(stream)>>>(a->dpre, a->in, a->rows, a->din, a->emb, a->dw1,
+                                                                   a->db1);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+extern "C" int cdm_mse_grad(const float* pred, const float* target, long long n, float inv_count, float* dpred,
+                            float* partial, int partial_blocks, float* loss_sum, void* stream) {
+  CDM_CHECK_ARG(pred && target && dpred && partial && loss_sum && n > 0 && n % 4 == 0 && partial_blocks > 0);
+  int rc = check_device();
+  if (rc) return rc;
+  int blocks = grid1d(n / 4);
+  if (blocks > partial_blocks) blocks = partial_blocks;
+  mse_grad_kernel<<<blocks, 256, 0, ST(stream)>>>(pred, target, n / 4, inv_count, dpred, partial);
+  CDM_CHECK_LAUNCH();
+  chan_reduce_final_kernel<<<1, 32, 0, ST(stream)>>>(partial, blocks, 1, loss_sum);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+extern "C" int cdm_adam_step(const void* table, int n_tensors, long long max_numel, float lr, float beta1, float beta2,
+                             float eps, int step, void* stream) {
+  CDM_CHECK_ARG(table && n_tensors > 0 && max_numel > 0 && step >= 1);
+  int rc = check_device();
+  if (rc) return rc;
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  int gx = (int)((max_numel + 256 * 8 - 1) / (256 * 8));
+  if (gx > 512) gx = 512;
+  if (gx < 1) gx = 1;
+  adam_kernel<<<dim3(gx, n_tensors), 256, 0, ST(stream)>>>((const AdamTensor*)table, n_tensors, lr, beta1, beta2, eps,
+                                                          bc1, bc2);
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}

@@ -1,7 +1,442 @@
-"""Training path (train-mode BatchNorm forward, backward, Adam) — see DESIGN.md."""
+"""Training path of ContextUnet: train-mode BatchNorm forward, full backward and a fused Adam, all through
+the sm_100a kernels behind include/cdm_b200.h.
+
+Mirrors the reference training step (code/train_diffusion_paper.py:349-366):
+    pred = nn_model(x_pert, t / timesteps, param); loss = F.mse_loss(pred, noise); loss.backward(); optim.step()
+`ContextUnet.forward` in `.train()` mode returns `pred` attached to autograd through `_UnetFn`, whose backward runs
+the hand-written backward pass and hands every parameter its gradient, so `loss.backward()` and any torch optimizer
+work unchanged; `FusedAdam` is the in-house optimizer (one multi-tensor kernel).
+
+Data parallelism (one process per GPU): if torch.distributed is initialised, BatchNorm batch statistics and their
+backward sums are all-reduced across ranks (count = global N*H*W, so results match the single-device reference at
+the same global batch) and parameter gradients are all-reduced once, as one flat buffer, at the end of backward.
+
+Tensor-core work: forward convs and data gradients (a conv with flipped / transposed weights) use cdm_conv3x3 /
+cdm_gemm; every weight gradient is cdm_gemm_tn (MN-major operands straight from the NHWC activations).
+"""
+import torch
+import torch.distributed as dist
+
 from . import _lib as L
 
+BN_EPS, GN_EPS, BN_MOMENTUM = 1e-5, 1e-5, 0.1
 
-def forward_train(model, x, t, c, shortcut):
-    raise L.CdmError("train-mode forward is not built yet in this revision: call model.eval() "
-                     "(sampling / likelihood / ELBO paths are available)")
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return 1
+
+
+def _allreduce(t):
+    if _world() > 1:
+        dist.all_reduce(t)
+    return t
+
+
+class _Ctx:
+    """Saved tensors of one training forward."""
+    pass
+
+
+def _bf(*shape, dev):
+    return torch.empty(*shape, device=dev, dtype=torch.bfloat16)
+
+
+def _f32(*shape, dev, zero=False):
+    return (torch.zeros if zero else torch.empty)(*shape, device=dev, dtype=torch.float32)
+
+
+def _rcb_list(m):
+    return [("init_conv", m.init_conv), ("down1.0", m.down1.model[0]), ("down1.1", m.down1.model[1]),
+            ("down2.0", m.down2.model[0]), ("down2.1", m.down2.model[1]), ("up1.1", m.up1.model[1]),
+            ("up1.2", m.up1.model[2]), ("up2.1", m.up2.model[1]), ("up2.2", m.up2.model[2])]
+
+
+def _pack_train(m):
+    """bf16 operand packs for this step (weights change every optimizer step): forward and data-gradient forms."""
+    P = {}
+    for name, blk in _rcb_list(m):
+        for cn, seq in (("c1", blk.conv1), ("c2", blk.conv2)):
+            w = seq[0].weight.detach()
+            key = f"{name}.{cn}"
+            if w.shape[1] == 1:
+                P[key + ".f"] = w.float().reshape(w.shape[0], 9).t().contiguous()  # [9][cout] fp32
+            else:
+                P[key + ".f"] = w.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)  # [co][kh][kw][ci]
+                P[key + ".d"] = w.flip(2, 3).permute(1, 2, 3, 0).contiguous().to(torch.bfloat16)  # [ci][kh][kw][co]
+    w = m.out[0].weight.detach()
+    P["out0.f"] = w.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    P["out0.d"] = w.flip(2, 3).permute(1, 2, 3, 0).contiguous().to(torch.bfloat16)  # [256][3][3][128]
+    w3 = m.out[3].weight.detach().float()[0].permute(1, 2, 0).reshape(9, -1)  # [tap][c]
+    P["out3.f"] = w3.contiguous()
+    P["out3.d"] = w3.flip(0).contiguous()  # flipped taps: dgrad of a 1-output-channel conv
+    for nm, mod in (("up0", m.up0[0]), ("up1", m.up1.model[0]), ("up2", m.up2.model[0])):
+        w = mod.weight.detach()  # IOHW
+        ci, co, kh, kw = w.shape
+        P[nm + ".f"] = w.permute(2, 3, 1, 0).reshape(kh * kw * co, ci).contiguous().to(torch.bfloat16)
+        P[nm + ".d"] = w.permute(0, 2, 3, 1).reshape(ci, kh * kw * co).contiguous().to(torch.bfloat16)
+    return P
+
+
+class _Layer:
+    """One Conv3x3 + train-mode BatchNorm + ReLU, with everything its backward needs."""
+    __slots__ = ("name", "conv", "bn", "x_in", "z", "y", "scale", "shift", "mean", "rstd", "count", "H", "cin", "cout")
+
+
+def _conv_bn_relu(S, P, name, seq, src, n, H, *, first=False, **apply_kw):
+    """z = conv(src)+bias; batch statistics (all-reduced over ranks); y = relu(bn(z)) [+ extras]."""
+    dev = S.dev
+    conv, bn = seq[0], seq[1]
+    cout = conv.out_channels
+    z = _bf(n, H, H, cout, dev=dev)
+    bias = conv.bias.detach().float().contiguous()
+    if first:
+        L.conv_in(src, P[name + ".f"], S.ones[:cout], bias, z, relu=False)
+    else:
+        L.conv3x3(src, P[name + ".f"], S.ones[:cout], bias, z, flags=0, mode=S.mode)
+    Pn = n * H * H
+    sums = _f32(2, cout, dev=dev)
+    L.chan_reduce(z, cout, Pn, cout, sums, S.ws, mode=0)
+    _allreduce(sums)
+    count = float(Pn * _world())
+    ly = _Layer()
+    ly.name, ly.conv, ly.bn, ly.x_in, ly.z, ly.count, ly.H = name, conv, bn, src, z, count, H
+    ly.cin, ly.cout = conv.in_channels, cout
+    ly.scale, ly.shift, ly.mean, ly.rstd = (_f32(cout, dev=dev) for _ in range(4))
+    L.bn_finalize(sums, cout, count, bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum, bn.running_mean,
+                  bn.running_var, ly.scale, ly.shift, ly.mean, ly.rstd)
+    bn.num_batches_tracked += 1
+    y = _bf(n, H, H, cout, dev=dev)
+    L.bn_apply(z, Pn, cout, ly.scale, ly.shift, y, relu=1, **apply_kw)
+    ly.y = y
+    S.layers[name] = ly
+    return y
+
+
+def forward_train(model, x, t, c, shortcut=None):
+    dev = model._check_supported()
+    params = [p for p in model.parameters()]
+    return _UnetFn.apply(model, x, t, c, shortcut, *params)
+
+
+class _UnetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, t, c, shortcut, *params):
+        dev = model._check_supported()
+        m = model
+        nf, h, n = m.n_feat, m.h, x.shape[0]
+        S = _Ctx()
+        S.dev, S.mode, S.layers, S.n = dev, m.conv_mode, {}, n
+        S.ones = torch.ones(256, device=dev)
+        S.zeros = torch.zeros(65536, device=dev)
+        S.ws = _f32(148 * 8, 9 * 256, dev=dev)  # reduction workspace (partials)
+        P = _pack_train(m)
+        S.P = P
+        x3 = x.detach().to(dev, torch.float32).reshape(n, h, h).contiguous()
+        if c is None:
+            c = torch.zeros(n, m.n_cfeat, device=dev)
+        c = c.detach().to(dev, torch.float32).contiguous()
+        tt = torch.as_tensor(t).detach().to(dev, torch.float32).reshape(-1, 1).contiguous()
+        if tt.shape[0] not in (1, n):
+            raise L.CdmError(f"t must have 1 or {n} elements")
+        S.x, S.c, S.t = x3, c, tt
+        sc = (m.draw_shortcut() if shortcut is None else shortcut).detach().to(dev, torch.float32).contiguous()
+        S.cemb1, S.temb1, S.cemb2, S.temb2 = m.embed(tt, c)
+        trows = tt.shape[0]
+        # ---- init_conv (ContextUnet.py:43): conv1, conv2, + fresh 1x1 shortcut
+        y1 = _conv_bn_relu(S, P, "init_conv.c1", m.init_conv.conv1, x3, n, h, first=True)
+        x0 = _conv_bn_relu(S, P, "init_conv.c2", m.init_conv.conv2, y1, n, h, sc_x=x3, sc_w=sc[:nf], sc_b=sc[nf:])
+        # ---- down1 / down2 (RCB, RCB, MaxPool2d)
+        a = x0
+        for nm, blk in (("down1.0", m.down1.model[0]), ("down1.1", m.down1.model[1])):
+            a = _conv_bn_relu(S, P, nm + ".c1", blk.conv1, a, n, h)
+            a = _conv_bn_relu(S, P, nm + ".c2", blk.conv2, a, n, h)
+        d1 = _bf(n, h // 2, h // 2, nf, dev=dev)
+        L.maxpool2_fwd(a, d1)
+        a = d1
+        for nm, blk in (("down2.0", m.down2.model[0]), ("down2.1", m.down2.model[1])):
+            a = _conv_bn_relu(S, P, nm + ".c1", blk.conv1, a, n, h // 2)
+            a = _conv_bn_relu(S, P, nm + ".c2", blk.conv2, a, n, h // 2)
+        h4 = h // 4
+        d2 = _bf(n, h4, h4, 2 * nf, dev=dev)
+        L.maxpool2_fwd(a, d2)
+        # ---- to_vec, up0 (+GroupNorm, ReLU, FiLM)
+        S.hid_pre = _f32(n, 2 * nf, dev=dev)
+        hidden = _bf(n, 2 * nf, dev=dev)
+        L.avgpool_gelu_train(d2.view(n, h4 * h4, 2 * nf), S.hid_pre, hidden)
+        u0raw = _bf(n, h4 * h4, 2 * nf, dev=dev)
+        L.gemm(hidden, P["up0.f"], m.up0[0].bias.detach().float().contiguous(), u0raw, shift_mod=2 * nf)
+        u0f = _bf(n, h4 * h4, 2 * nf, dev=dev)
+        S.gn0_mr = _f32(n, 8, 2, dev=dev)
+        L.gn_relu_film(u0raw, m.up0[1].weight.detach(), m.up0[1].bias.detach(), u0f, groups=8, eps=GN_EPS,
+                       film_scale=S.cemb1, film_shift=S.temb1.view(1, trows, 2 * nf), film_rows=trows,
+                       mean_rstd_out=S.gn0_mr)
+        # ---- up1
+        v1 = _bf(n, h // 2, h // 2, nf, dev=dev)
+        L.gemm(u0f.view(n * h4 * h4, 2 * nf), P["up1.f"], m.up1.model[0].bias.detach().float().contiguous(), v1,
+               a1=d2.view(n * h4 * h4, 2 * nf), out_mode=1, H=h4, W=h4, shift_mod=nf)
+        a = _conv_bn_relu(S, P, "up1.1.c1", m.up1.model[1].conv1, v1, n, h // 2)
+        a = _conv_bn_relu(S, P, "up1.1.c2", m.up1.model[1].conv2, a, n, h // 2)
+        a = _conv_bn_relu(S, P, "up1.2.c1", m.up1.model[2].conv1, a, n, h // 2)
+        u1f = _bf(n, h // 2, h // 2, nf, dev=dev)
+        u1 = _conv_bn_relu(S, P, "up1.2.c2", m.up1.model[2].conv2, a, n, h // 2, film_scale=S.cemb2,
+                           film_shift=S.temb2, film_rows=trows, px_per_img=(h // 2) ** 2, yf=u1f)
+        # ---- up2
+        h2 = h // 2
+        v2 = _bf(n, h, h, nf, dev=dev)
+        L.gemm(u1f.view(n * h2 * h2, nf), P["up2.f"], m.up2.model[0].bias.detach().float().contiguous(), v2,
+               a1=d1.view(n * h2 * h2, nf), out_mode=1, H=h2, W=h2, shift_mod=nf)
+        a = _conv_bn_relu(S, P, "up2.1.c1", m.up2.model[1].conv1, v2, n, h)
+        a = _conv_bn_relu(S, P, "up2.1.c2", m.up2.model[1].conv2, a, n, h)
+        a = _conv_bn_relu(S, P, "up2.2.c1", m.up2.model[2].conv1, a, n, h)
+        u2 = _conv_bn_relu(S, P, "up2.2.c2", m.up2.model[2].conv2, a, n, h)
+        # ---- out: conv(cat(u2, x0)) -> GroupNorm -> ReLU -> conv
+        o = _bf(n, h, h, nf, dev=dev)
+        gnp = _f32(n, (h // 16) ** 2 * 8, 8, 2, dev=dev)
+        L.conv3x3(u2, P["out0.f"], S.ones[:nf], m.out[0].bias.detach().float().contiguous(), o, src1=x0,
+                  flags=L.EPI_GNSTATS, gn_partial=gnp, mode=S.mode)
+        S.gn1_mr = _f32(n, 8, 2, dev=dev)
+        L.gn_finalize(gnp, float((nf // 8) * h * h), S.gn1_mr, GN_EPS)
+        eps = _f32(n, 1, h, h, dev=dev)
+        L.conv_out(o, S.gn1_mr, m.out[1].weight.detach(), m.out[1].bias.detach(), P["out3.f"],
+                   m.out[3].bias.detach().float().contiguous(), eps.view(n, h, h))
+        S.x0, S.d1, S.d2, S.hidden, S.u0raw, S.u0f, S.u1, S.u1f, S.u2, S.o = x0, d1, d2, hidden, u0raw, u0f, u1, u1f, u2, o
+        S.pool1_in, S.pool2_in = S.layers["down1.1.c2"].y, S.layers["down2.1.c2"].y
+        ctx.S, ctx.model = S, m
+        ctx.names = [nme for nme, _ in m.named_parameters()]
+        return eps
+
+    @staticmethod
+    def backward(ctx, deps):
+        S, m = ctx.S, ctx.model
+        dev, P, n, nf, h = S.dev, S.P, S.n, m.n_feat, m.h
+        G = {}  # parameter name -> gradient (torch layout, fp32)
+        bn_affine = set()
+        deps = deps.detach().to(dev, torch.float32).contiguous().view(n, h, h)
+
+        def conv_wgrad(dz, srcs, cout):
+            cin = sum(s.shape[3] for s in srcs)
+            dw = _f32(cout, 9 * cin, dev=dev, zero=True)
+            off = 0
+            Hh = dz.shape[1]
+            for s in srcs:
+                L.gemm_tn(dz, s, dw.view(-1)[off:], n_img=n, H=Hh, W=Hh, a_c=cout, b_c=s.shape[3], M=cout,
+                          N=s.shape[3], ldc=9 * cin, taps=9, tap_stride=cin)
+                off += s.shape[3]
+            return dw.view(cout, 3, 3, cin).permute(0, 3, 1, 2).contiguous()
+
+        def cbr_bwd(name, prefix, dy, lddy, need_dx=True):
+            ly = S.layers[name]
+            Pn, C = n * ly.H * ly.H, ly.cout
+            sums = _f32(2, C, dev=dev)
+            L.chan_reduce(dy, lddy, Pn, C, sums, S.ws, mode=1, z=ly.z, ldz=C, scale=ly.scale, shift=ly.shift,
+                          mean=ly.mean, rstd=ly.rstd, relu=1)
+            _allreduce(sums)
+            G[prefix + ".1.weight"], G[prefix + ".1.bias"] = sums[1].clone(), sums[0].clone()
+            bn_affine.update((prefix + ".1.weight", prefix + ".1.bias"))
+            dz = _bf(n, ly.H, ly.H, C, dev=dev)
+            L.bn_bwd_apply(dy, lddy, ly.z, Pn, C, ly.scale, ly.shift, ly.mean, ly.rstd, sums, ly.count, dz, relu=1)
+            G[prefix + ".0.bias"] = torch.zeros(C, device=dev)  # a bias in front of train-mode BN has zero gradient
+            if ly.cin == 1:
+                w9 = _f32(9, C, dev=dev)
+                L.outer_wgrad(ly.x_in, dz, n, ly.H, ly.H, C, w9, S.ws, flip=0)
+                G[prefix + ".0.weight"] = w9.t().reshape(C, 1, 3, 3).contiguous()
+                return None
+            G[prefix + ".0.weight"] = conv_wgrad(dz, [ly.x_in], C)
+            if not need_dx:
+                return None
+            dx = _bf(n, ly.H, ly.H, ly.cin, dev=dev)
+            L.conv3x3(dz, P[name + ".d"], S.ones[:ly.cin], S.zeros[:ly.cin], dx, flags=0, mode=S.mode)
+            return dx
+
+        def rcb_bwd(name, prefix, dy, lddy):
+            d = cbr_bwd(name + ".c2", prefix + ".conv2", dy, lddy)
+            return cbr_bwd(name + ".c1", prefix + ".conv1", d, d.shape[3])
+
+        def convT_bwd(nm, prefix, dv, srcs):
+            """ConvTranspose2d(cin, 128, 2, 2) backward: dv [n,2H,2W,128]; srcs = the two K-split inputs."""
+            Hh = dv.shape[1] // 2
+            Mrows = n * Hh * Hh
+            s2d = _bf(Mrows, 4 * nf, dev=dev)
+            L.space_to_depth(dv, s2d)
+            sums = _f32(2, nf, dev=dev)
+            L.chan_reduce(dv, nf, Mrows * 4, nf, sums, S.ws, mode=2)
+            G[prefix + ".bias"] = sums[0].clone()
+            cin = sum(s.shape[-1] for s in srcs)
+            da = _bf(Mrows, cin, dev=dev)
+            L.gemm(s2d, P[nm + ".d"], S.zeros[:cin], da, shift_mod=cin)
+            dw = _f32(cin, 4 * nf, dev=dev, zero=True)
+            off = 0
+            for s in srcs:
+                cs = s.shape[-1]
+                L.gemm_tn(s, s2d, dw[off:], n_img=1, H=1, W=Mrows, a_c=cs, b_c=4 * nf, M=cs, N=4 * nf, ldc=4 * nf)
+                off += cs
+            G[prefix + ".weight"] = dw.view(cin, 2, 2, nf).permute(0, 3, 1, 2).contiguous()
+            return da
+
+        def embed_bwd(mod, prefix, inp, dout):
+            rows, emb = inp.shape[0], mod.model[2].weight.shape[0]
+            w1, b1, w2 = (mod.model[0].weight.detach().contiguous(), mod.model[0].bias.detach().contiguous(),
+                          mod.model[2].weight.detach().contiguous())
+            pre, hh, dpre = (_f32(rows, emb, dev=dev) for _ in range(3))
+            dw1, db1, dw2, db2 = _f32(emb, inp.shape[1], dev=dev), _f32(emb, dev=dev), _f32(emb, emb, dev=dev), _f32(emb, dev=dev)
+            L.embed_bwd(inp, w1, b1, w2, dout.contiguous(), pre, hh, dpre, dw1, db1, dw2, db2)
+            G[prefix + ".model.0.weight"], G[prefix + ".model.0.bias"] = dw1, db1
+            G[prefix + ".model.2.weight"], G[prefix + ".model.2.bias"] = dw2, db2
+
+        # ---- out.3 (Conv 128->1), out.1 (GroupNorm) + ReLU
+        G["out.3.bias"] = deps.sum().reshape(1)
+        w9 = _f32(9, nf, dev=dev)
+        L.outer_wgrad(deps, S.o, n, h, h, nf, w9, S.ws, flip=1, mean_rstd=S.gn1_mr, gamma=m.out[1].weight.detach(),
+                      beta=m.out[1].bias.detach())
+        G["out.3.weight"] = w9.view(3, 3, nf).permute(2, 0, 1).reshape(1, nf, 3, 3).contiguous()
+        d_a = _bf(n, h, h, nf, dev=dev)
+        L.conv_in(deps, P["out3.d"], S.ones[:nf], S.zeros[:nf], d_a, relu=False)
+        do = _bf(n, h, h, nf, dev=dev)
+        dg_nc, db_nc = _f32(n, nf, dev=dev), _f32(n, nf, dev=dev)
+        L.gn_bwd(S.o, d_a, nf, n, h * h, nf, 8, S.gn1_mr, m.out[1].weight.detach(), m.out[1].bias.detach(), do, dg_nc,
+                 db_nc)
+        G["out.1.weight"], G["out.1.bias"] = _f32(nf, dev=dev), _f32(nf, dev=dev)
+        L.rows_sum(dg_nc, n, nf, G["out.1.weight"])
+        L.rows_sum(db_nc, n, nf, G["out.1.bias"])
+        # ---- out.0 (Conv 256->128 on cat(u2, x0))
+        sums = _f32(2, nf, dev=dev)
+        L.chan_reduce(do, nf, n * h * h, nf, sums, S.ws, mode=2)
+        G["out.0.bias"] = sums[0].clone()
+        G["out.0.weight"] = conv_wgrad(do, [S.u2, S.x0], nf)
+        d_cat = _bf(n, h, h, 2 * nf, dev=dev)
+        L.conv3x3(do, P["out0.d"], S.ones[:2 * nf], S.zeros[:2 * nf], d_cat, flags=0, mode=S.mode)
+        # ---- up2
+        d = rcb_bwd("up2.2", "up2.model.2", d_cat, 2 * nf)  # channels [0,128) of d_cat
+        d_v2 = rcb_bwd("up2.1", "up2.model.1", d, nf)
+        h2 = h // 2
+        da2 = convT_bwd("up2", "up2.model.0", d_v2, [S.u1f.view(-1, nf), S.d1.view(-1, nf)])  # [n*32*32, 256]
+        # FiLM2: u1f = cemb2*u1 + temb2
+        d_u1 = _bf(n, h2, h2, nf, dev=dev)
+        dcemb2, dtemb2 = _f32(n, nf, dev=dev), _f32(n, nf, dev=dev)
+        L.film_bwd(da2, 2 * nf, S.u1, n, h2 * h2, nf, S.cemb2, d_u1, dcemb2, dtemb2)
+        # ---- up1
+        d = rcb_bwd("up1.2", "up1.model.2", d_u1, nf)
+        d_v1 = rcb_bwd("up1.1", "up1.model.1", d, nf)
+        h4 = h // 4
+        da1 = convT_bwd("up1", "up1.model.0", d_v1, [S.u0f.view(-1, 2 * nf), S.d2.view(-1, 2 * nf)])  # [n*256, 512]
+        # ---- up0: GroupNorm + ReLU + FiLM backward, then the [B,256]x[256,65536] GEMM
+        d_u0raw = _bf(n, h4 * h4, 2 * nf, dev=dev)
+        dg_nc, db_nc = _f32(n, 2 * nf, dev=dev), _f32(n, 2 * nf, dev=dev)
+        dcemb1, dtemb1 = _f32(n, 2 * nf, dev=dev), _f32(n, 2 * nf, dev=dev)
+        L.gn_bwd(S.u0raw, da1, 4 * nf, n, h4 * h4, 2 * nf, 8, S.gn0_mr, m.up0[1].weight.detach(),
+                 m.up0[1].bias.detach(), d_u0raw, dg_nc, db_nc, film_scale=S.cemb1, dfs=dcemb1, dfb=dtemb1)
+        G["up0.1.weight"], G["up0.1.bias"] = _f32(2 * nf, dev=dev), _f32(2 * nf, dev=dev)
+        L.rows_sum(dg_nc, n, 2 * nf, G["up0.1.weight"])
+        L.rows_sum(db_nc, n, 2 * nf, G["up0.1.bias"])
+        sums = _f32(2, 2 * nf, dev=dev)
+        L.chan_reduce(d_u0raw, 2 * nf, n * h4 * h4, 2 * nf, sums, S.ws, mode=2)
+        G["up0.0.bias"] = sums[0].clone()
+        K0 = h4 * h4 * 2 * nf
+        d_hid = _bf(n, 2 * nf, dev=dev)
+        L.gemm(d_u0raw.view(n, K0), P["up0.d"], S.zeros[:2 * nf], d_hid, shift_mod=2 * nf)
+        dw0 = _f32(2 * nf, K0, dev=dev, zero=True)
+        L.gemm_tn(S.hidden, d_u0raw, dw0, n_img=1, H=1, W=n, a_c=2 * nf, b_c=K0, M=2 * nf, N=K0, ldc=K0)
+        G["up0.0.weight"] = dw0.view(2 * nf, h4, h4, 2 * nf).permute(0, 3, 1, 2).contiguous()
+        # ---- to_vec backward joins the skip gradient of d2
+        d_d2 = da1[:, 2 * nf:].contiguous().view(n, h4, h4, 2 * nf)
+        L.avgpool_gelu_bwd(S.hid_pre, d_hid.float().contiguous(), n, h4 * h4, 2 * nf, d_d2)
+        # ---- down2
+        dy = _bf(n, h2, h2, 2 * nf, dev=dev)
+        L.maxpool2_bwd(d_d2, 2 * nf, S.pool2_in, dy)
+        d = rcb_bwd("down2.1", "down2.model.1", dy, 2 * nf)
+        d_d1 = rcb_bwd("down2.0", "down2.model.0", d, 2 * nf)
+        L.add_bf16(d_d1, nf, da2[:, nf:], 2 * nf, n * h2 * h2, nf)
+        # ---- down1
+        dy = _bf(n, h, h, nf, dev=dev)
+        L.maxpool2_bwd(d_d1, nf, S.pool1_in, dy)
+        d = rcb_bwd("down1.1", "down1.model.1", dy, nf)
+        d_x0 = rcb_bwd("down1.0", "down1.model.0", d, nf)
+        L.add_bf16(d_x0, nf, d_cat.view(-1, 2 * nf)[:, nf:], 2 * nf, n * h * h, nf)
+        # ---- init_conv: x0 = y2 + shortcut(x) (the shortcut is not a parameter)
+        d_y1 = cbr_bwd("init_conv.c2", "init_conv.conv2", d_x0, nf)
+        cbr_bwd("init_conv.c1", "init_conv.conv1", d_y1, nf)
+        # ---- embeddings
+        trows = S.t.shape[0]
+        embed_bwd(m.contextembed1, "contextembed1", S.c, dcemb1)
+        embed_bwd(m.contextembed2, "contextembed2", S.c, dcemb2)
+        embed_bwd(m.timeembed1, "timeembed1", S.t, dtemb1 if trows == n else dtemb1.sum(0, keepdim=True))
+        embed_bwd(m.timeembed2, "timeembed2", S.t, dtemb2 if trows == n else dtemb2.sum(0, keepdim=True))
+        # ---- data parallel: one flat all-reduce, then the 1/world of the global-batch mean
+        W = _world()
+        if W > 1:
+            names = [k for k in ctx.names if k not in bn_affine]
+            flat = torch.cat([G[k].reshape(-1) for k in names])
+            dist.all_reduce(flat)
+            o = 0
+            for k in names:
+                cnt = G[k].numel()
+                G[k] = flat[o:o + cnt].view_as(G[k])
+                o += cnt
+            for k in ctx.names:
+                G[k] = G[k] / W
+        ctx.S = None
+        return (None, None, None, None, None) + tuple(G[k].view_as(p) for k, p in zip(ctx.names, m.parameters()))
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(params, lr) defaults (betas 0.9/0.999, eps 1e-8, no weight decay) — the optimiser of
+    code/train_diffusion_paper.py:318 — as ONE multi-tensor kernel launch per step."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self._tab, self._key, self._step = None, None, 0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        assert closure is None
+        self._step += 1
+        for gi, group in enumerate(self.param_groups):
+            ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            for p in ps:
+                st = self.state[p]
+                if not st:
+                    st["exp_avg"], st["exp_avg_sq"] = torch.zeros_like(p), torch.zeros_like(p)
+            grads = [p.grad.contiguous() for p in ps]
+            key = tuple((p.data_ptr(), g.data_ptr()) for p, g in zip(ps, grads))
+            if self._tab is None or self._key != (gi, key):
+                rows = [[p.data_ptr(), g.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
+                         self.state[p]["exp_avg_sq"].data_ptr(), p.numel()] for p, g in zip(ps, grads)]
+                self._tab = torch.tensor(rows, dtype=torch.int64).to(ps[0].device)
+                self._key = (gi, key)
+            self._grads_keepalive = grads
+            b1, b2 = group["betas"]
+            L.adam_step(self._tab, len(ps), max(p.numel() for p in ps), group["lr"], b1, b2, group["eps"], self._step)
+
+
+def training_step(model, optim, x, param, timesteps, ab_t, *, noise=None, t=None, shortcut=None):
+    """The loop body of code/train_diffusion_paper.py:350-364 on device: noise, t, perturb_input, forward, MSE,
+    backward, optimizer step.  Returns the (local) loss as a 0-d tensor; `loss.item()` is left to the caller."""
+    dev = model._check_supported()
+    n = x.shape[0]
+    x = x.to(dev, torch.float32).contiguous()
+    if t is None:
+        t = torch.randint(1, timesteps + 1, (n,))
+    t = t.to(dev)
+    x_pert = torch.empty_like(x)
+    ca, cb = ab_t.sqrt().contiguous(), (1 - ab_t).contiguous()
+    if noise is None:
+        noise = torch.empty_like(x)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        L.perturb(x, x_pert, ca, cb, t_idx=t.to(torch.int64).contiguous(), seed=seed, noise_out=noise)
+    else:
+        noise = noise.to(dev, torch.float32).contiguous()
+        L.perturb(x, x_pert, ca, cb, noise=noise, t_idx=t.to(torch.int64).contiguous())
+    optim.zero_grad(set_to_none=True)
+    pred = model(x_pert, t / timesteps, param, shortcut=shortcut)
+    # F.mse_loss + its gradient in one kernel; the backward pass starts from d pred directly
+    dpred = torch.empty_like(pred)
+    partial = torch.empty(148 * 8, device=dev)
+    loss_sum = torch.empty(1, device=dev)
+    L.mse_grad(pred.detach(), noise, 1.0 / pred.numel(), dpred, partial, loss_sum)
+    pred.backward(dpred)
+    optim.step()
+    return loss_sum[0] / pred.numel()

@@ -155,6 +155,7 @@ typedef struct {
   int film_rows;           /* 1 or n_img */
   const int* step_ptr;     /* device int32 row selector, NULL = 0 */
   void* out;               /* bf16 [n_img][P][C] */
+  float* mean_rstd_out;    /* optional fp32 [n_img][groups][2] (kept for the backward pass) */
 } cdm_gn_relu_film_args;
 int cdm_gn_relu_film(const cdm_gn_relu_film_args* a, void* stream);
 
@@ -217,6 +218,132 @@ typedef struct {
   float* acc;     /* fp32 [n] or NULL */
 } cdm_mse_accum_args;
 int cdm_mse_accum(const cdm_mse_accum_args* a, void* stream);
+
+/* ======================= training path (code/train_diffusion_paper.py:349-366) =======================
+ * Activations / activation gradients: NHWC bf16 with a pixel stride `ld*` (elements) so channel slices of
+ * wider tensors are usable in place.  Statistics and parameter gradients: fp32.  All reductions are
+ * two-stage with a fixed order (deterministic). */
+
+/* Per-channel reductions over P rows -> out[2][C]:
+ *   mode 0: sum z, sum z^2                       (train-mode nn.BatchNorm2d batch statistics)
+ *   mode 1: sum g, sum g*xhat, g = dy*[relu mask] (BatchNorm2d + ReLU backward)
+ *   mode 2: sum a, 0                             (bias gradients)
+ * workspace: fp32 [workspace_blocks][2][C]. */
+typedef struct {
+  const void* a; int lda;
+  const void* z; int ldz;
+  const float* scale; const float* shift; const float* mean; const float* rstd;
+  int relu, mode;
+  long long P; int C;
+  float* workspace; int workspace_blocks;
+  float* out;
+} cdm_chan_reduce_args;
+int cdm_chan_reduce(const cdm_chan_reduce_args* a, void* stream);
+
+/* sums[2][C] (after the optional cross-rank all-reduce) -> scale = gamma*rstd, shift = beta - mean*scale,
+ * mean, rstd; running_mean/var updated with `momentum` and the UNBIASED variance (torch semantics). */
+int cdm_bn_finalize(const float* sums, int C, float count, const float* gamma, const float* beta, float eps,
+                    float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                    float* mean, float* rstd, void* stream);
+
+/* y = act(z*scale+shift) [+ w_c*x + b_c (init_conv shortcut)]; optional yf = film_scale[n]*y + film_shift[n|0]. */
+typedef struct {
+  const void* z; long long P; int C, relu;
+  const float* scale; const float* shift;
+  void* y;
+  const float* sc_x; const float* sc_w; const float* sc_b;
+  const float* film_scale; const float* film_shift; int film_rows, px_per_img;
+  void* yf;
+} cdm_bn_apply_args;
+int cdm_bn_apply(const cdm_bn_apply_args* a, void* stream);
+
+/* dz = scale*(g - S0/N - xhat*S1/N) with sums = {S0[C], S1[C]} from cdm_chan_reduce mode 1. */
+typedef struct {
+  const void* dy; int lddy;
+  const void* z; long long P; int C, relu;
+  const float* scale; const float* shift; const float* mean; const float* rstd;
+  const float* sums; float count;
+  void* dz;
+} cdm_bn_bwd_args;
+int cdm_bn_bwd_apply(const cdm_bn_bwd_args* a, void* stream);
+
+/* nn.MaxPool2d(2) forward / backward (first-maximum tie rule, as torch). */
+int cdm_maxpool2_fwd(const void* y, int n_img, int H, int W, int C, void* out, void* stream);
+int cdm_maxpool2_bwd(const void* dpool, int lddp, const void* y, int n_img, int H, int W, int C, void* dy,
+                     void* stream);
+/* a += b (gradient accumulation at skip connections). */
+int cdm_add_bf16(void* a, int lda, const void* b, int ldb, long long P, int C, void* stream);
+/* dv[n][2H][2W][C] -> [n][H][W][(kh,kw,c)]: A operand of the ConvTranspose2d(2,2) dgrad / wgrad GEMMs. */
+int cdm_space_to_depth(const void* dv, int n_img, int H, int W, int C, void* out, void* stream);
+/* FiLM backward: dy = fs*dyf; dfs[n][c] = sum_px dyf*y; dfb[n][c] = sum_px dyf. */
+int cdm_film_bwd(const void* dyf, int lddyf, const void* y, int n_img, int px, int C, const float* fs, void* dy,
+                 float* dfs, float* dfb, void* stream);
+
+/* nn.GroupNorm + ReLU (+FiLM) backward; per-(image, channel) parameter-gradient partials. */
+typedef struct {
+  const void* x; const void* dyf; int lddyf;
+  int n_img, P, C, groups;
+  const float* mean_rstd; const float* gamma; const float* beta;
+  const float* film_scale;
+  void* dx;
+  float* dgamma_nc; float* dbeta_nc; float* dfs; float* dfb;
+} cdm_gn_bwd_args;
+int cdm_gn_bwd(const cdm_gn_bwd_args* a, void* stream);
+int cdm_rows_sum(const float* in, int rows, int C, float* out, void* stream);
+
+/* to_vec forward that also keeps the pre-GELU mean, and its backward (accumulates into dx). */
+int cdm_avgpool_gelu_train(const void* src, int n_img, int P, int C, float* pre, void* out, void* stream);
+int cdm_avgpool_gelu_bwd(const float* pre, const float* dh, int n_img, int P, int C, void* dx, void* stream);
+
+/* Weight gradient of the K=9 (1->C) and N=1 (C->1) convolutions: out[tap][c] = sum_px s[px+d(tap)]*v[px][c];
+ * flip=1 negates d(tap); mean_rstd != NULL applies GroupNorm(8)+ReLU to v on load. workspace fp32 [blocks][9][C]. */
+typedef struct {
+  const float* s; const void* v;
+  int n_img, H, W, C, flip;
+  const float* mean_rstd; const float* gamma; const float* beta;
+  float* workspace; int workspace_blocks;
+  float* out;
+} cdm_outer_wgrad_args;
+int cdm_outer_wgrad(const cdm_outer_wgrad_args* a, void* stream);
+
+/* EmbedFC backward (recomputes the hidden layer): scratch pre/h/dpre are fp32 [rows][emb]. */
+typedef struct {
+  const float* in; int rows, din, emb;
+  const float* w1; const float* b1; const float* w2;
+  const float* dout;
+  float* pre; float* h; float* dpre;
+  float* dw1; float* db1; float* dw2; float* db2;
+} cdm_embed_bwd_args;
+int cdm_embed_bwd(const cdm_embed_bwd_args* a, void* stream);
+
+/* F.mse_loss(pred, target) summed (loss_sum[0] = sum of squares) and d pred = 2 (pred-target) * inv_count. */
+int cdm_mse_grad(const float* pred, const float* target, long long n, float inv_count, float* dpred, float* partial,
+                 int partial_blocks, float* loss_sum, void* stream);
+/* torch.optim.Adam defaults over a device table of {p, g, m, v, n} (5 x 8 bytes per tensor). */
+int cdm_adam_step(const void* table, int n_tensors, long long max_numel, float lr, float beta1, float beta2, float eps,
+                  int step, void* stream);
+
+/* Weight-gradient GEMM  C[m][tap*tap_stride + n] += sum_px A[px][m_off+m] * B[px + (kh-1,kw-1)][n_off+n]
+ * with both operands read straight from NHWC bf16 activations (the reduction index is the pixel, the
+ * channels are contiguous: tensor-core "MN-major" operands), fp32 accumulate, split-K with fp32 atomics:
+ * the caller zero-fills C.  taps = 9 is the 3x3 convolution wgrad (what autograd / cuDNN computes for
+ * nn.Conv2d in loss.backward(), code/train_diffusion_paper.py:363): A = dL/d(conv output), B = conv input,
+ * C = dW as [cout][3][3][cin].  taps = 1 with H = n_img = 1, W = rows is a plain A^T B (transposed-conv and
+ * up0 wgrad).  M, N multiples of 128; channel windows let A / B be slices of wider tensors. */
+typedef struct {
+  const void* a; /* bf16 [n_img][H][W][a_c] */
+  int a_c;
+  const void* b; /* bf16 [n_img][H][W][b_c] */
+  int b_c;
+  int n_img, H, W;
+  int taps;
+  int m_off, M;
+  int n_off, N;
+  float* c;
+  int ldc, tap_stride;
+  int k_split; /* 0 = choose so that ~2 CTAs per SM have work */
+} cdm_gemm_tn_args;
+int cdm_gemm_tn(const cdm_gemm_tn_args* a, void* stream);
 
 /* Measurement probe: every CTA streams `tile_bytes` TMA tiles from an
  * L2-resident buffer into a shared-memory ring; returns nothing, caller times it. */

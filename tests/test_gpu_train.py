@@ -1,0 +1,335 @@
+"""GPU parity of the training path: every backward / statistics kernel against torch autograd on the same
+inputs, then one whole training step (forward in train mode, loss, all 102 parameter gradients, BatchNorm
+running statistics, Adam update) against the reference vectors and the CPU oracle.
+
+Tolerances: activations and their gradients are bf16 between layers, so tensor-valued comparisons use 1e-2
+relative L2 (kernel level) and 5e-2 for end-to-end parameter gradients through ~40 bf16 layers; fp32
+reductions use 1e-4."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import contextunet_oracle as O
+from tests._util import NCF, T, cal_sd, load, rel_l2, split_shortcut
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from camels_diffusion_model_b200 import _lib
+    return _lib
+
+
+def _g(seed):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+def _ws():
+    return torch.empty(148 * 8, 9 * 256, device="cuda")
+
+
+@pytest.mark.parametrize("rows,M,N", [(300, 128, 256), (32, 256, 512), (1024, 128, 128)])
+def test_gemm_tn_rows(L, rows, M, N):
+    g = _g(0)
+    a = torch.randn(rows, M, device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn(rows, N, device="cuda", generator=g).to(torch.bfloat16)
+    c = torch.zeros(M, N, device="cuda")
+    L.gemm_tn(a, b, c, n_img=1, H=1, W=rows, a_c=M, b_c=N, M=M, N=N, ldc=N)
+    assert rel_l2(c, a.float().t() @ b.float()) < 1e-5
+
+
+def test_gemm_tn_channel_windows(L):
+    g = _g(1)
+    rows = 500
+    a = torch.randn(rows, 256, device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn(rows, 384, device="cuda", generator=g).to(torch.bfloat16)
+    c = torch.zeros(128, 700, device="cuda")
+    L.gemm_tn(a, b, c.view(-1)[44:], n_img=1, H=1, W=rows, a_c=256, b_c=384, M=128, N=256, ldc=700, m_off=128,
+              n_off=64)
+    ref = a[:, 128:].float().t() @ b[:, 64:320].float()
+    assert rel_l2(c[:, 44:300], ref) < 1e-5 and float(c[:, :44].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n,H,cin,cout", [(3, 64, 128, 128), (2, 32, 256, 256), (5, 32, 128, 256), (2, 16, 128, 128)])
+def test_gemm_tn_is_conv3x3_wgrad(L, n, H, cin, cout):
+    g = _g(2)
+    x = torch.randn(n, H, H, cin, device="cuda", generator=g).to(torch.bfloat16)
+    dz = torch.randn(n, H, H, cout, device="cuda", generator=g).to(torch.bfloat16)
+    dw = torch.zeros(cout, 9 * cin, device="cuda")
+    L.gemm_tn(dz, x, dw, n_img=n, H=H, W=H, a_c=cout, b_c=cin, M=cout, N=cin, ldc=9 * cin, taps=9, tap_stride=cin)
+    w = torch.zeros(cout, cin, 3, 3, device="cuda", requires_grad=True)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, padding=1)
+    y.backward(dz.float().permute(0, 3, 1, 2))
+    assert rel_l2(dw.view(cout, 3, 3, cin).permute(0, 3, 1, 2), w.grad) < 1e-4
+
+
+def test_conv_dgrad_is_conv_with_flipped_weights(L):
+    g = _g(3)
+    n, H, cin, cout = 2, 32, 128, 256
+    w = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / 30).to(torch.bfloat16)
+    dz = torch.randn(n, H, H, cout, device="cuda", generator=g).to(torch.bfloat16)
+    wd = w.flip(2, 3).permute(1, 2, 3, 0).contiguous()
+    dx = torch.empty(n, H, H, cin, device="cuda", dtype=torch.bfloat16)
+    L.conv3x3(dz, wd, torch.ones(cin, device="cuda"), torch.zeros(cin, device="cuda"), dx, flags=0)
+    x = torch.zeros(n, cin, H, H, device="cuda", requires_grad=True)
+    F.conv2d(x, w.float(), padding=1).backward(dz.float().permute(0, 3, 1, 2))
+    assert rel_l2(dx.float(), x.grad.permute(0, 2, 3, 1)) < 4e-3
+
+
+@pytest.mark.parametrize("C", [128, 256])
+def test_batchnorm_train_forward_backward(L, C):
+    g = _g(4)
+    n, H = 3, 32
+    P = n * H * H
+    z = (torch.randn(n, H, H, C, device="cuda", generator=g) * 1.5 + 0.3).to(torch.bfloat16)
+    dy = torch.randn(n, H, H, 2 * C, device="cuda", generator=g).to(torch.bfloat16)  # use a channel slice (ld = 2C)
+    gamma = torch.rand(C, device="cuda", generator=g) + 0.5
+    beta = torch.randn(C, device="cuda", generator=g) * 0.3
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    sums = torch.empty(2, C, device="cuda")
+    L.chan_reduce(z, C, P, C, sums, _ws(), mode=0)
+    zf = z.float().view(P, C)
+    assert rel_l2(sums[0], zf.sum(0)) < 1e-5 and rel_l2(sums[1], (zf * zf).sum(0)) < 1e-5
+    scale, shift, mean, rstd = (torch.empty(C, device="cuda") for _ in range(4))
+    L.bn_finalize(sums, C, float(P), gamma, beta, 1e-5, 0.1, rm, rv, scale, shift, mean, rstd)
+    bn = torch.nn.BatchNorm2d(C).cuda().train()
+    bn.weight.data.copy_(gamma), bn.bias.data.copy_(beta)
+    zt = z.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    yt = F.relu(bn(zt))
+    assert rel_l2(rm, bn.running_mean) < 1e-4 and rel_l2(rv, bn.running_var) < 1e-4
+    y = torch.empty(n, H, H, C, device="cuda", dtype=torch.bfloat16)
+    L.bn_apply(z, P, C, scale, shift, y, relu=1)
+    assert rel_l2(y.float(), yt.permute(0, 2, 3, 1)) < 4e-3
+    dys = dy[..., C // 2:C // 2 + C]
+    yt.backward(dys.float().permute(0, 3, 1, 2))
+    bs = torch.empty(2, C, device="cuda")
+    L.chan_reduce(dys, 2 * C, P, C, bs, _ws(), mode=1, z=z, ldz=C, scale=scale, shift=shift, mean=mean, rstd=rstd)
+    assert rel_l2(bs[0], bn.bias.grad) < 1e-3 and rel_l2(bs[1], bn.weight.grad) < 1e-3
+    dz = torch.empty(n, H, H, C, device="cuda", dtype=torch.bfloat16)
+    L.bn_bwd_apply(dys, 2 * C, z, P, C, scale, shift, mean, rstd, bs, float(P), dz)
+    assert rel_l2(dz.float(), zt.grad.permute(0, 2, 3, 1)) < 6e-3
+
+
+def test_bn_apply_shortcut_and_film(L):
+    g = _g(5)
+    n, H, C = 2, 16, 128
+    P = n * H * H
+    z = torch.randn(n, H, H, C, device="cuda", generator=g).to(torch.bfloat16)
+    scale, shift = torch.rand(C, device="cuda", generator=g) + 0.5, torch.randn(C, device="cuda", generator=g)
+    xs = torch.randn(n, H, H, device="cuda", generator=g)
+    w, b = torch.randn(C, device="cuda", generator=g), torch.randn(C, device="cuda", generator=g)
+    y = torch.empty_like(z)
+    L.bn_apply(z, P, C, scale, shift, y, sc_x=xs, sc_w=w, sc_b=b)
+    ref = F.relu(z.float() * scale + shift) + xs.unsqueeze(-1) * w + b
+    assert rel_l2(y.float(), ref) < 4e-3
+    fs, fb = torch.randn(n, C, device="cuda", generator=g), torch.randn(n, C, device="cuda", generator=g)
+    yf = torch.empty_like(z)
+    L.bn_apply(z, P, C, scale, shift, y, film_scale=fs, film_shift=fb, film_rows=n, px_per_img=H * H, yf=yf)
+    ref2 = F.relu(z.float() * scale + shift) * fs.view(n, 1, 1, C) + fb.view(n, 1, 1, C)
+    assert rel_l2(yf.float(), ref2) < 6e-3
+
+
+def test_maxpool_forward_backward(L):
+    g = _g(6)
+    n, H, C = 3, 32, 256
+    y = F.relu(torch.randn(n, H, H, C, device="cuda", generator=g)).to(torch.bfloat16)  # many exact ties at 0
+    out = torch.empty(n, H // 2, H // 2, C, device="cuda", dtype=torch.bfloat16)
+    L.maxpool2_fwd(y, out)
+    yt = y.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    pt = F.max_pool2d(yt, 2)
+    assert torch.equal(out.float(), pt.permute(0, 2, 3, 1))
+    dp = torch.randn(n, H // 2, H // 2, C, device="cuda", generator=g).to(torch.bfloat16)
+    pt.backward(dp.float().permute(0, 3, 1, 2))
+    dy = torch.empty_like(y)
+    L.maxpool2_bwd(dp, C, y, dy)
+    assert torch.equal(dy.float(), yt.grad.permute(0, 2, 3, 1))
+
+
+def test_space_to_depth_add_film_bwd(L):
+    g = _g(7)
+    n, H, C = 2, 16, 128
+    dv = torch.randn(n, 2 * H, 2 * H, C, device="cuda", generator=g).to(torch.bfloat16)
+    out = torch.empty(n * H * H, 4 * C, device="cuda", dtype=torch.bfloat16)
+    L.space_to_depth(dv, out)
+    ref = dv.view(n, H, 2, H, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(n * H * H, 4 * C)
+    assert torch.equal(out, ref)
+    a = torch.randn(50, 128, device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn(50, 256, device="cuda", generator=g).to(torch.bfloat16)
+    a0 = a.clone()
+    L.add_bf16(a, 128, b[:, 128:], 256, 50, 128)
+    assert rel_l2(a.float(), a0.float() + b[:, 128:].float()) < 4e-3
+    px = H * H
+    dyf = torch.randn(n, px, 2 * C, device="cuda", generator=g).to(torch.bfloat16)
+    y = torch.randn(n, px, C, device="cuda", generator=g).to(torch.bfloat16)
+    fs = torch.randn(n, C, device="cuda", generator=g)
+    dy = torch.empty_like(y)
+    dfs, dfb = torch.empty(n, C, device="cuda"), torch.empty(n, C, device="cuda")
+    L.film_bwd(dyf, 2 * C, y, n, px, C, fs, dy, dfs, dfb)
+    d = dyf[..., :C].float()
+    assert rel_l2(dy.float(), d * fs.view(n, 1, C)) < 4e-3
+    assert rel_l2(dfs, (d * y.float()).sum(1)) < 1e-5 and rel_l2(dfb, d.sum(1)) < 1e-5
+
+
+@pytest.mark.parametrize("P,C,film", [(256, 256, True), (4096, 128, False)])
+def test_groupnorm_relu_film_backward(L, P, C, film):
+    g = _g(8)
+    n = 3
+    x = (torch.randn(n, P, C, device="cuda", generator=g) * 2 + 0.5).to(torch.bfloat16)
+    dyf = torch.randn(n, P, C, device="cuda", generator=g).to(torch.bfloat16)
+    gamma = (torch.rand(C, device="cuda", generator=g) + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, device="cuda", generator=g) * 0.3).requires_grad_(True)
+    fs = torch.randn(n, C, device="cuda", generator=g).requires_grad_(True)
+    fb = torch.randn(n, C, device="cuda", generator=g).requires_grad_(True)
+    xt = x.float().permute(0, 2, 1).clone().requires_grad_(True)
+    y = F.relu(F.group_norm(xt, 8, gamma, beta, 1e-5))
+    yf = y * fs.view(n, C, 1) + fb.view(n, C, 1) if film else y
+    yf.backward(dyf.float().permute(0, 2, 1))
+    gs = x.float().view(n, P, 8, C // 8).permute(0, 2, 1, 3).reshape(n, 8, -1)
+    mr = torch.stack([gs.mean(2), torch.rsqrt(gs.var(2, unbiased=False) + 1e-5)], -1).contiguous()
+    dx = torch.empty_like(x)
+    dg, db = torch.empty(n, C, device="cuda"), torch.empty(n, C, device="cuda")
+    dfs, dfb = (torch.empty(n, C, device="cuda"), torch.empty(n, C, device="cuda")) if film else (None, None)
+    L.gn_bwd(x, dyf, C, n, P, C, 8, mr, gamma.detach(), beta.detach(), dx, dg, db,
+             film_scale=fs.detach() if film else None, dfs=dfs, dfb=dfb)
+    assert rel_l2(dx.float(), xt.grad.permute(0, 2, 1)) < 6e-3
+    assert rel_l2(dg.sum(0), gamma.grad) < 1e-4 and rel_l2(db.sum(0), beta.grad) < 1e-4
+    if film:
+        assert rel_l2(dfs, fs.grad) < 1e-4 and rel_l2(dfb, fb.grad) < 1e-4
+    out = torch.empty(C, device="cuda")
+    L.rows_sum(dg, n, C, out)
+    assert rel_l2(out, dg.sum(0)) < 1e-6
+
+
+def test_outer_wgrad_first_and_last_conv(L):
+    g = _g(9)
+    n, H, C = 3, 64, 128
+    x = torch.randn(n, H, H, device="cuda", generator=g)
+    dz = torch.randn(n, H, H, C, device="cuda", generator=g).to(torch.bfloat16)
+    w9 = torch.empty(9, C, device="cuda")
+    L.outer_wgrad(x, dz, n, H, H, C, w9, _ws(), flip=0)
+    w = torch.zeros(C, 1, 3, 3, device="cuda", requires_grad=True)
+    F.conv2d(x.unsqueeze(1), w, padding=1).backward(dz.float().permute(0, 3, 1, 2))
+    assert rel_l2(w9.t().reshape(C, 1, 3, 3), w.grad) < 1e-4
+    # last conv: weight gradient with GroupNorm+ReLU applied on load, and the data gradient via conv_in
+    o = (torch.randn(n, H, H, C, device="cuda", generator=g) * 2).to(torch.bfloat16)
+    gamma, beta = torch.rand(C, device="cuda", generator=g) + 0.5, torch.randn(C, device="cuda", generator=g) * 0.2
+    deps = torch.randn(n, H, H, device="cuda", generator=g)
+    ot = o.float().permute(0, 3, 1, 2)
+    gs = ot.reshape(n, 8, -1)
+    mr = torch.stack([gs.mean(2), torch.rsqrt(gs.var(2, unbiased=False) + 1e-5)], -1).contiguous()
+    a = F.relu(F.group_norm(ot, 8, gamma, beta, 1e-5)).detach().requires_grad_(True)
+    w3 = (torch.randn(1, C, 3, 3, device="cuda", generator=g) / 30).requires_grad_(True)
+    F.conv2d(a, w3, padding=1).backward(deps.unsqueeze(1))
+    L.outer_wgrad(deps, o, n, H, H, C, w9, _ws(), flip=1, mean_rstd=mr, gamma=gamma, beta=beta)
+    assert rel_l2(w9.view(3, 3, C).permute(2, 0, 1).reshape(1, C, 3, 3), w3.grad) < 1e-4
+    d_a = torch.empty(n, H, H, C, device="cuda", dtype=torch.bfloat16)
+    w3t = w3.detach()[0].permute(1, 2, 0).reshape(9, C)
+    L.conv_in(deps, w3t.flip(0).contiguous(), torch.ones(C, device="cuda"), torch.zeros(C, device="cuda"), d_a,
+              relu=False)
+    assert rel_l2(d_a.float(), a.grad.permute(0, 2, 3, 1)) < 4e-3
+
+
+def test_embed_backward_loss_and_adam(L):
+    g = _g(10)
+    rows, din, emb = 37, 6, 256
+    lin1, lin2 = torch.nn.Linear(din, emb).cuda(), torch.nn.Linear(emb, emb).cuda()
+    inp = torch.rand(rows, din, device="cuda", generator=g)
+    dout = torch.randn(rows, emb, device="cuda", generator=g)
+    lin2(F.gelu(lin1(inp))).backward(dout)
+    pre, h, dpre = (torch.empty(rows, emb, device="cuda") for _ in range(3))
+    dw1, db1 = torch.empty(emb, din, device="cuda"), torch.empty(emb, device="cuda")
+    dw2, db2 = torch.empty(emb, emb, device="cuda"), torch.empty(emb, device="cuda")
+    L.embed_bwd(inp, lin1.weight.detach(), lin1.bias.detach(), lin2.weight.detach(), dout, pre, h, dpre, dw1, db1,
+                dw2, db2)
+    for got, ref in ((dw1, lin1.weight.grad), (db1, lin1.bias.grad), (dw2, lin2.weight.grad), (db2, lin2.bias.grad)):
+        assert rel_l2(got, ref) < 1e-4
+    pred = torch.randn(5, 1, 64, 64, device="cuda", generator=g).requires_grad_(True)
+    tgt = torch.randn(5, 1, 64, 64, device="cuda", generator=g)
+    loss = F.mse_loss(pred, tgt)
+    loss.backward()
+    dpred, part, ls = torch.empty_like(tgt), torch.empty(148 * 8, device="cuda"), torch.empty(1, device="cuda")
+    L.mse_grad(pred.detach(), tgt, 1.0 / pred.numel(), dpred, part, ls)
+    assert rel_l2(dpred, pred.grad) < 1e-6 and abs(float(ls) / pred.numel() - float(loss)) < 1e-5 * float(loss)
+    # fused Adam == torch.optim.Adam over three steps
+    from camels_diffusion_model_b200.train import FusedAdam
+    ps = [torch.randn(s, device="cuda", generator=g) for s in ((300,), (17, 5), (4, 3, 3, 3))]
+    a = [p.clone().requires_grad_(True) for p in ps]
+    b = [p.clone().requires_grad_(True) for p in ps]
+    oa, ob = torch.optim.Adam(a, lr=1e-3), FusedAdam(b, lr=1e-3)
+    for _ in range(3):
+        for x, y in zip(a, b):
+            gr = torch.randn(x.shape, device="cuda", generator=g)
+            x.grad, y.grad = gr.clone(), gr.clone()
+        oa.step(), ob.step()
+    for x, y in zip(a, b):
+        assert torch.allclose(x, y, rtol=1e-5, atol=1e-7)
+
+
+def test_training_step_vs_reference_vectors():
+    """One step of code/train_diffusion_paper.py:349-366 at batch 4: loss / pred vs the reference run stored in
+    train_step.npz, every gradient vs the CPU oracle's autograd, BN running stats and the Adam update."""
+    import camels_diffusion_model_b200 as cdm
+    from camels_diffusion_model_b200.train import FusedAdam
+    g = load("train_step.npz")
+    sd = cal_sd()
+    model = cdm.ContextUnet(1, 128, NCF, 64)
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    b_t, a_t, ab_t = cdm.make_schedule(1500)
+    x, param, noise, t = T(g["x"]), T(g["param"]), T(g["noise"]), T(g["t"])
+    optim = FusedAdam(model.parameters(), lr=float(g["lr"]))
+    x_pert = cdm.perturb_input(x, t, noise, ab_t)
+    pred = model(x_pert, (t / 1500).cuda(), param.cuda(), shortcut=T(g["shortcut"]))
+    err = rel_l2(pred, g["pred_noise"])
+    print(f"train-mode pred rel-L2 vs reference = {err:.3e}")
+    assert err < 2e-2
+    loss = F.mse_loss(pred, noise.cuda())
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 2e-2
+    loss.backward()
+    _, _, ab_cpu = O.make_schedule(1500)
+    _, grads, _ = O.train_step(sd, x, param, t, noise, split_shortcut(g["shortcut"]), 1500, ab_cpu, n_cfeat=NCF)
+    worst, big = 0.0, []
+    for name, p in model.named_parameters():
+        ref = grads[name]
+        if float(ref.norm()) < 1e-6:
+            assert float(p.grad.norm()) < 1e-5, name
+            continue
+        e = rel_l2(p.grad, ref)
+        worst = max(worst, e)
+        if e > 5e-2:
+            big.append((name, round(e, 4)))
+    print(f"worst parameter-gradient rel-L2 vs oracle autograd = {worst:.3e}")
+    assert not big, big
+    for k in g.files:
+        if k.startswith("bn/") and "running" in k:
+            got = dict(model.named_buffers())[k[3:]]
+            assert rel_l2(got, g[k]) < 1e-2, k
+    before = {n_: p.detach().clone() for n_, p in model.named_parameters()}
+    optim.step()
+    name = "out.3.weight"
+    p1, _, _ = O.adam_step(before[name].cpu(), dict(model.named_parameters())[name].grad.cpu(),
+                           torch.zeros_like(before[name].cpu()), torch.zeros_like(before[name].cpu()), 1, float(g["lr"]))
+    assert torch.allclose(dict(model.named_parameters())[name].detach().cpu(), p1, rtol=0, atol=1e-7)
+    assert int(model.init_conv.conv1[1].num_batches_tracked) == int(sd["init_conv.conv1.1.num_batches_tracked"]) + 1
+
+
+def test_training_step_api_reduces_loss():
+    import camels_diffusion_model_b200 as cdm
+    from camels_diffusion_model_b200.train import FusedAdam, training_step
+    torch.manual_seed(0)
+    model = cdm.ContextUnet(1, 128, NCF, 64).cuda().train()
+    b_t, a_t, ab_t = cdm.make_schedule(1500)
+    optim = FusedAdam(model.parameters(), lr=1e-4)
+    gen = torch.Generator().manual_seed(0)
+    x = torch.rand(8, 1, 64, 64, generator=gen)
+    param = torch.rand(8, NCF, generator=gen)
+    noise = torch.randn(8, 1, 64, 64, generator=gen)
+    t = torch.randint(1, 1501, (8,), generator=gen)
+    sc = torch.rand(256, generator=gen) * 2 - 1
+    losses = [float(training_step(model, optim, x, param, 1500, ab_t, noise=noise, t=t, shortcut=sc)) for _ in range(6)]
+    print("losses", [round(v, 4) for v in losses])
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
