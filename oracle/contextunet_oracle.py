@@ -45,6 +45,14 @@ def draw_shortcut(n_out=128, generator=None):
 
 
 # --------------------------------------------------------------------------- blocks
+def _rb(v, on):
+    """bf16 rounding with a straight-through gradient.  `emulate_bf16=True` places it exactly where the
+    sm_100a path stores bf16 (tensor-core weights, every conv / norm output), so that a test can separate
+    rounding noise (ReLU masks flipping near zero) from real backward-pass errors.  Off by default: the
+    oracle proper is the reference's fp32 arithmetic."""
+    return v + (v.to(torch.bfloat16).float() - v).detach() if on else v
+
+
 def _bn(x, sd, prefix, training, stats_out=None):
     """nn.BatchNorm2d (diffusion_utilities.py:28,35): eval = running stats; train = batch stats
     (biased var for normalisation; running stats get momentum 0.1 and the unbiased var)."""
@@ -62,15 +70,17 @@ def _bn(x, sd, prefix, training, stats_out=None):
         + b.view(1, -1, 1, 1)
 
 
-def _cbr(x, sd, prefix, training, stats_out):
+def _cbr(x, sd, prefix, training, stats_out, rb=False, round_out=True):
     """Conv3x3(s1,p1) -> BatchNorm2d -> ReLU (diffusion_utilities.py:26-37; G2: ReLU, not GELU)."""
-    y = F.conv2d(x, sd[prefix + ".0.weight"], sd[prefix + ".0.bias"], padding=1)
-    return F.relu(_bn(y, sd, prefix + ".1", training, stats_out))
+    w = sd[prefix + ".0.weight"]
+    y = _rb(F.conv2d(x, _rb(w, rb and w.shape[1] > 1), sd[prefix + ".0.bias"], padding=1), rb)
+    return _rb(F.relu(_bn(y, sd, prefix + ".1", training, stats_out)), rb and round_out)
 
 
-def _rcb(x, sd, prefix, training, stats_out):
+def _rcb(x, sd, prefix, training, stats_out, rb=False):
     """ResidualConvBlock with is_res=False (diffusion_utilities.py:62-65)."""
-    return _cbr(_cbr(x, sd, prefix + ".conv1", training, stats_out), sd, prefix + ".conv2", training, stats_out)
+    return _cbr(_cbr(x, sd, prefix + ".conv1", training, stats_out, rb), sd, prefix + ".conv2", training, stats_out,
+                rb)
 
 
 def _embed(v, sd, prefix, in_dim):
@@ -81,7 +91,7 @@ def _embed(v, sd, prefix, in_dim):
 
 
 def unet_forward(sd, x, t, c, shortcut, *, n_feat=128, n_cfeat=6, height=64, training=False, stats_out=None,
-                 taps=None):
+                 taps=None, emulate_bf16=False):
     """ContextUnet.forward (ContextUnet.py:42-60) on a state_dict `sd`.
 
     shortcut = (w_c[n_feat], b_c[n_feat]) — the fresh 1x1 conv of this call (G1).
@@ -90,16 +100,17 @@ def unet_forward(sd, x, t, c, shortcut, *, n_feat=128, n_cfeat=6, height=64, tra
     """
     B = x.shape[0]
     w_c, b_c = shortcut
+    rb = emulate_bf16
     # init_conv: is_res=True, in!=out channels -> conv2(conv1(x)) + fresh 1x1 conv(x), no /1.414
-    x1 = _cbr(x, sd, "init_conv.conv1", training, stats_out)
-    x2 = _cbr(x1, sd, "init_conv.conv2", training, stats_out)
-    x0 = x2 + (x * w_c.view(1, -1, 1, 1) + b_c.view(1, -1, 1, 1))
+    x1 = _cbr(x, sd, "init_conv.conv1", training, stats_out, rb)
+    x2 = _cbr(x1, sd, "init_conv.conv2", training, stats_out, rb, round_out=False)
+    x0 = _rb(x2 + (x * w_c.view(1, -1, 1, 1) + b_c.view(1, -1, 1, 1)), rb)
     # UnetDown = RCB, RCB, MaxPool2d(2)  (diffusion_utilities.py:109)
-    d1 = F.max_pool2d(_rcb(_rcb(x0, sd, "down1.model.0", training, stats_out), sd, "down1.model.1", training,
-                           stats_out), 2)
-    d2 = F.max_pool2d(_rcb(_rcb(d1, sd, "down2.model.0", training, stats_out), sd, "down2.model.1", training,
-                           stats_out), 2)
-    hidden = F.gelu(F.avg_pool2d(d2, height // 4))  # to_vec (ContextUnet.py:17)
+    d1 = F.max_pool2d(_rcb(_rcb(x0, sd, "down1.model.0", training, stats_out, rb), sd, "down1.model.1", training,
+                           stats_out, rb), 2)
+    d2 = F.max_pool2d(_rcb(_rcb(d1, sd, "down2.model.0", training, stats_out, rb), sd, "down2.model.1", training,
+                           stats_out, rb), 2)
+    hidden = _rb(F.gelu(F.avg_pool2d(d2, height // 4)), rb)  # to_vec (ContextUnet.py:17)
     if c is None:
         c = torch.zeros(B, n_cfeat)
     cemb1 = _embed(c, sd, "contextembed1", n_cfeat).view(-1, 2 * n_feat, 1, 1)
@@ -107,20 +118,22 @@ def unet_forward(sd, x, t, c, shortcut, *, n_feat=128, n_cfeat=6, height=64, tra
     cemb2 = _embed(c, sd, "contextembed2", n_cfeat).view(-1, n_feat, 1, 1)
     temb2 = _embed(t, sd, "timeembed2", 1).view(-1, n_feat, 1, 1)
     # up0: ConvT(k=s=h/4) on a 1x1 map == GEMM; GroupNorm(8); ReLU  (ContextUnet.py:26-30)
-    u0 = torch.einsum("ni,iokl->nokl", hidden.view(B, -1), sd["up0.0.weight"]) + sd["up0.0.bias"].view(1, -1, 1, 1)
-    u0 = F.relu(F.group_norm(u0, 8, sd["up0.1.weight"], sd["up0.1.bias"], GN_EPS))
+    u0 = torch.einsum("ni,iokl->nokl", hidden.view(B, -1), _rb(sd["up0.0.weight"], rb)) \
+        + sd["up0.0.bias"].view(1, -1, 1, 1)
+    u0 = F.relu(F.group_norm(_rb(u0, rb), 8, sd["up0.1.weight"], sd["up0.1.bias"], GN_EPS))
 
     def unet_up(a, skip, prefix):
         # UnetUp: cat(x, skip) -> ConvT 2x2 s2 -> RCB, RCB  (diffusion_utilities.py:86-100)
         z = torch.cat((a, skip), 1)
-        v = F.conv_transpose2d(z, sd[prefix + ".model.0.weight"], sd[prefix + ".model.0.bias"], stride=2)
-        return _rcb(_rcb(v, sd, prefix + ".model.1", training, stats_out), sd, prefix + ".model.2", training,
-                    stats_out)
+        v = _rb(F.conv_transpose2d(z, _rb(sd[prefix + ".model.0.weight"], rb), sd[prefix + ".model.0.bias"],
+                                   stride=2), rb)
+        return _rcb(_rcb(v, sd, prefix + ".model.1", training, stats_out, rb), sd, prefix + ".model.2", training,
+                    stats_out, rb)
 
-    u1 = unet_up(cemb1 * u0 + temb1, d2, "up1")
-    u2 = unet_up(cemb2 * u1 + temb2, d1, "up2")
-    o = F.conv2d(torch.cat((u2, x0), 1), sd["out.0.weight"], sd["out.0.bias"], padding=1)
-    o = F.relu(F.group_norm(o, 8, sd["out.1.weight"], sd["out.1.bias"], GN_EPS))
+    u1 = unet_up(_rb(cemb1 * u0 + temb1, rb), d2, "up1")
+    u2 = unet_up(_rb(cemb2 * u1 + temb2, rb), d1, "up2")
+    o = _rb(F.conv2d(torch.cat((u2, x0), 1), _rb(sd["out.0.weight"], rb), sd["out.0.bias"], padding=1), rb)
+    o = _rb(F.relu(F.group_norm(o, 8, sd["out.1.weight"], sd["out.1.bias"], GN_EPS)), rb)
     eps = F.conv2d(o, sd["out.3.weight"], sd["out.3.bias"], padding=1)
     if taps is not None:
         taps.update(x1=x1, x0=x0, d1=d1, d2=d2, hidden=hidden, cemb1=cemb1, temb1=temb1, cemb2=cemb2, temb2=temb2,
@@ -211,7 +224,7 @@ def elbo_paper_batch(sd, x, param, timesteps, sched, noises, shortcuts, *, n_cfe
     return out
 
 
-def train_step(sd, x, param, t, noise, shortcut, timesteps, ab_t, *, n_cfeat=6):
+def train_step(sd, x, param, t, noise, shortcut, timesteps, ab_t, *, n_cfeat=6, emulate_bf16=False):
     """Loss + gradients of one training step (train_diffusion_paper.py:351-363), train-mode BN.
     Returns (loss, grads{name: tensor}, bn_batch_stats{prefix: (mean, unbiased_var)})."""
     params = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "running" not in k)
@@ -219,7 +232,7 @@ def train_step(sd, x, param, t, noise, shortcut, timesteps, ab_t, *, n_cfeat=6):
     x_pert = perturb_input(x, t, noise, ab_t)
     stats = {}
     pred = unet_forward(params, x_pert, t / timesteps, param, shortcut, n_cfeat=n_cfeat, training=True,
-                        stats_out=stats)
+                        stats_out=stats, emulate_bf16=emulate_bf16)
     loss = F.mse_loss(pred, noise)
     names = [k for k, v in params.items() if v.requires_grad]
     grads = torch.autograd.grad(loss, [params[k] for k in names])

@@ -291,18 +291,27 @@ def test_training_step_vs_reference_vectors():
     assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 2e-2
     loss.backward()
     _, _, ab_cpu = O.make_schedule(1500)
-    _, grads, _ = O.train_step(sd, x, param, t, noise, split_shortcut(g["shortcut"]), 1500, ab_cpu, n_cfeat=NCF)
-    worst, big = 0.0, []
+    sc = split_shortcut(g["shortcut"])
+    # (a) against the reference's fp32 arithmetic: bf16 activations flip ReLU masks of near-zero pre-activations,
+    #     which perturbs gradients by ~sqrt(flipped fraction) per layer (noise, not bias): direction and norm hold.
+    _, g32, _ = O.train_step(sd, x, param, t, noise, sc, 1500, ab_cpu, n_cfeat=NCF)
+    # (b) against the same fp32 autograd with bf16 rounding emulated at the points where the device path stores
+    #     bf16 (same masks): this is the sharp check of the hand-written backward pass.
+    _, g16, _ = O.train_step(sd, x, param, t, noise, sc, 1500, ab_cpu, n_cfeat=NCF, emulate_bf16=True)
+    worst32, worst16, big = 1.0, 0.0, []
     for name, p in model.named_parameters():
-        ref = grads[name]
-        if float(ref.norm()) < 1e-6:
-            assert float(p.grad.norm()) < 1e-5, name
+        r32, r16, got = g32[name].flatten().double(), g16[name].flatten().double(), p.grad.flatten().double().cpu()
+        if float(r32.norm()) < 1e-6:  # conv bias in front of train-mode BatchNorm: exactly zero
+            assert float(got.norm()) < 1e-5, name
             continue
-        e = rel_l2(p.grad, ref)
-        worst = max(worst, e)
-        if e > 5e-2:
+        cos = float(torch.dot(got, r32) / (got.norm() * r32.norm()))
+        worst32 = min(worst32, cos)
+        assert cos > 0.8 and abs(float(got.norm() / r32.norm()) - 1) < 0.15, (name, cos)
+        e = rel_l2(got, r16)
+        worst16 = max(worst16, e)
+        if e > 4e-2:
             big.append((name, round(e, 4)))
-    print(f"worst parameter-gradient rel-L2 vs oracle autograd = {worst:.3e}")
+    print(f"parameter gradients: min cosine vs fp32 oracle {worst32:.4f}; worst rel-L2 vs bf16-emulating oracle {worst16:.3e}")
     assert not big, big
     for k in g.files:
         if k.startswith("bn/") and "running" in k:
