@@ -1,0 +1,84 @@
+"""Data-parallel training check (run under torchrun on >= 2 GPUs):
+the 2-rank step on a sharded global batch (cross-rank BatchNorm statistics + gradient all-reduce) must reproduce
+the single-process step on the whole batch.   torchrun --nproc-per-node 2 tools/dp_check.py
+Also times a training step (BASELINE config 3: global batch 256) and prints img/s."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+import camels_diffusion_model_b200 as cdm
+from camels_diffusion_model_b200 import train as TR
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+NCF, T = 6, 1500
+torch.manual_seed(0)
+ref_model = cdm.ContextUnet(1, 128, NCF, 64)
+g = torch.Generator().manual_seed(1)
+for k, v in ref_model.state_dict().items():            # non-trivial norm layers
+    if k.endswith(".1.weight") and v.dim() == 1: v.uniform_(0.5, 1.5, generator=g)
+    if k.endswith(".1.bias") and v.dim() == 1: v.normal_(0, 0.2, generator=g)
+sd = {k: v.clone() for k, v in ref_model.state_dict().items()}
+b_t, a_t, ab_t = cdm.make_schedule(T, device=dev)
+B = 4 * world
+x, prm = torch.rand(B, 1, 64, 64, generator=g), torch.rand(B, NCF, generator=g)
+noise, t = torch.randn(B, 1, 64, 64, generator=g), torch.randint(1, T + 1, (B,), generator=g)
+sc = torch.rand(256, generator=g) * 2 - 1
+
+
+def step(xs, ps, ns, ts, dp):
+    TR.DATA_PARALLEL = dp
+    m = cdm.ContextUnet(1, 128, NCF, 64)
+    m.load_state_dict(sd)
+    m = m.to(dev).train()
+    xp = cdm.perturb_input(xs, ts, ns, ab_t)
+    pred = m(xp, (ts / T).to(dev), ps.to(dev), shortcut=sc)
+    loss = F.mse_loss(pred, ns.to(dev))
+    loss.backward()
+    return m, float(loss)
+
+s, e = rank * 4, rank * 4 + 4
+m_dp, loss_dp = step(x[s:e], prm[s:e], noise[s:e], t[s:e], True)
+m_1, loss_1 = step(x, prm, noise, t, False)
+worst = 0.0
+for (n1, p1), (n2, p2) in zip(m_1.named_parameters(), m_dp.named_parameters()):
+    if float(p1.grad.norm()) < 1e-7: continue
+    err = float((p1.grad - p2.grad).norm() / p1.grad.norm())
+    worst = max(worst, err)
+bn_err = max(float((b1 - b2).abs().max()) for (k, b1), (_, b2) in zip(m_1.named_buffers(), m_dp.named_buffers())
+             if "running" in k)
+lt = torch.tensor([loss_dp], device=dev)
+dist.all_reduce(lt)
+if rank == 0:
+    print(f"DP-CHECK world={world}: worst grad rel-L2 (sharded vs single-process) {worst:.3e}; "
+          f"max |running-stat diff| {bn_err:.3e}; mean rank loss {float(lt) / world:.6f} vs global {loss_1:.6f}")
+
+# ---- throughput of a training step, BASELINE config 3: global batch 256
+TR.DATA_PARALLEL = True
+GB = 256
+per = GB // world
+model = cdm.ContextUnet(1, 128, NCF, 64)
+model.load_state_dict(sd)
+model = model.to(dev).train()
+opt = TR.FusedAdam(model.parameters(), lr=1e-5)
+xb, pb = torch.rand(per, 1, 64, 64, generator=g).to(dev), torch.rand(per, NCF, generator=g).to(dev)
+for _ in range(3):
+    TR.training_step(model, opt, xb, pb, T, ab_t, shortcut=sc)
+torch.cuda.synchronize(); dist.barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+K = 10
+e0.record()
+for _ in range(K):
+    loss = TR.training_step(model, opt, xb, pb, T, ab_t, shortcut=sc)
+e1.record(); torch.cuda.synchronize()
+ms = torch.tensor([e0.elapsed_time(e1) / K], device=dev)
+dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+if rank == 0:
+    tf = 3 * 19.1785e9 * GB / (float(ms) * 1e-3) / 1e12
+    print(f"TRAIN-BENCH world={world} global_batch={GB}: {float(ms):.2f} ms/step, {GB / float(ms) * 1e3:.0f} img/s, "
+          f"{tf:.0f} TFLOP/s aggregate (3x forward FLOPs), loss {float(loss):.4f}")
+dist.destroy_process_group()
