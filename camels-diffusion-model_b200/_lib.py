@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcdm_b200.so")
 
 EPI_RELU, EPI_SHORTCUT, EPI_POOL, EPI_FILM, EPI_GNSTATS = 1, 2, 4, 8, 16
-CONV_MODE_COPIES, CONV_MODE_SHIFT24, CONV_MODE_SHIFT18 = 0, 1, 2
+CONV_MODE_COPIES, CONV_MODE_SHIFT24, CONV_MODE_SHIFT18, CONV_MODE_SWAPPED = 0, 1, 2, 3
 
 
 class CdmError(RuntimeError):

@@ -119,7 +119,7 @@ extern "C" int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream) {
   CDM_CHECK_ARG((a->c1 == 0) == (a->src1 == nullptr));
   CDM_CHECK_ARG(a->n_img > 0 && a->H >= 16 && a->W >= 16 && a->H % 16 == 0 && a->W % 16 == 0);
   CDM_CHECK_ARG(a->cout > 0 && a->cout % 128 == 0 && a->cout <= 256);
-  CDM_CHECK_ARG(a->mode >= 0 && a->mode <= 2);
+  CDM_CHECK_ARG(a->mode >= 0 && a->mode <= 3);
   if (a->flags & CDM_EPI_SHORTCUT)
     CDM_CHECK_ARG(a->sc_x && a->sc_tab && a->sc_reps >= 1);
   if (a->flags & CDM_EPI_FILM) CDM_CHECK_ARG(a->film_scale && a->film_shift && a->film_shift_rows >= 1);
@@ -127,20 +127,23 @@ extern "C" int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream) {
   int rc = check_device();
   if (rc) return rc;
 
-  static const int pitch_of_mode[3] = {16, 24, 18};
-  const uint32_t pitch = pitch_of_mode[a->mode];
+  // MODE 3 (swapped operands, 8 px x 32 row patches) needs H % 32 == 0; otherwise fall back to SHIFT18
+  const int mode = (a->mode == 3 && (a->H % 32 != 0 || a->W % 8 != 0)) ? 2 : a->mode;
+  static const int pitch_of_mode[4] = {16, 24, 18, 10};
+  const uint32_t pitch = pitch_of_mode[mode];
+  const uint32_t box_rows = mode == 3 ? 34 : 18;
   CUtensorMap mA0, mA1, mB;
   {
     uint64_t dims[4] = {(uint64_t)a->c0, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
     uint64_t str[3] = {(uint64_t)a->c0 * 2, (uint64_t)a->W * a->c0 * 2, (uint64_t)a->H * a->W * a->c0 * 2};
-    uint32_t box[4] = {64, pitch, 18, 1};
+    uint32_t box[4] = {64, pitch, box_rows, 1};
     rc = make_tmap_bf16(&mA0, a->src0, 4, dims, str, box);
     if (rc) return rc;
   }
   if (a->src1) {
     uint64_t dims[4] = {(uint64_t)a->c1, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
     uint64_t str[3] = {(uint64_t)a->c1 * 2, (uint64_t)a->W * a->c1 * 2, (uint64_t)a->H * a->W * a->c1 * 2};
-    uint32_t box[4] = {64, pitch, 18, 1};
+    uint32_t box[4] = {64, pitch, box_rows, 1};
     rc = make_tmap_bf16(&mA1, a->src1, 4, dims, str, box);
     if (rc) return rc;
   } else {
@@ -179,7 +182,20 @@ extern "C" int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream) {
   p.step_ptr = a->step_ptr;
   p.gn_partial = a->gn_partial;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (a->mode) {
+  if (mode == 3) {
+    p.n_units = a->n_img * (a->W / 8) * (a->H / 32) * p.n_tiles;
+    constexpr int smem = conv_sw_smem_bytes();
+    static bool attr_set = false;
+    if (!attr_set) {
+      CDM_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set = true;
+    }
+    const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
+    conv3x3_sw_kernel<<<grid, kConvThreads, smem, st>>>(mA0, mA1, mB, p);
+    CDM_CHECK_LAUNCH();
+    return CDM_OK;
+  }
+  switch (mode) {
     case 0: return launch_conv<0>(mA0, mA1, mB, p, st);
     case 1: return launch_conv<1>(mA0, mA1, mB, p, st);
     default: return launch_conv<2>(mA0, mA1, mB, p, st);

@@ -7,6 +7,8 @@ are parameter containers only: `forward` never calls them.  All arithmetic runs 
 the sm_100a kernels behind include/cdm_b200.h; on a CPU tensor / non-sm_100 device
 `forward` raises (there is no fallback path).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -142,7 +144,7 @@ class ContextUnet(nn.Module):
         self._packed = None
         self._packed_key = None
         self._ws = {}
-        self.conv_mode = L.CONV_MODE_SHIFT18
+        self.conv_mode = int(os.environ.get("CDM_CONV_MODE", L.CONV_MODE_SHIFT18))
 
     # ------------------------------------------------------------------ weights
     def _check_supported(self):

@@ -48,6 +48,7 @@ int cdm_device_ok(void);
 #define CDM_CONV_MODE_COPIES 0  /* three kw-shifted TMA copies, aligned views  */
 #define CDM_CONV_MODE_SHIFT24 1 /* one halo tile, pitch 24, row-shifted views  */
 #define CDM_CONV_MODE_SHIFT18 2 /* one halo tile, pitch 18, row-shifted views  */
+#define CDM_CONV_MODE_SWAPPED 3 /* weights = M operand, 256 pixels = N operand (M128 N256 K16); H % 32 == 0 */
 
 /* 3x3, stride 1, pad 1 convolution as tcgen05 implicit GEMM.
  * Replaces nn.Conv2d(+BatchNorm2d eval +ReLU) of ResidualConvBlock

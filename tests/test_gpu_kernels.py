@@ -36,7 +36,7 @@ def _conv_inputs(n, H, cin, cout, seed=0):
     return x, w, scale, shift
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("n,H,c0,c1,cout", [(3, 32, 128, 0, 128), (2, 64, 64, 64, 256), (1, 16, 256, 0, 128)])
 def test_conv3x3_modes(L, mode, n, H, c0, c1, cout):
     x, w, scale, shift = _conv_inputs(n, H, c0 + c1, cout)
@@ -46,27 +46,30 @@ def test_conv3x3_modes(L, mode, n, H, c0, c1, cout):
     assert rel_l2(out.float(), _conv_ref(x, w, scale, shift).clamp_min(0)) < BF16_TOL
 
 
-def test_conv3x3_many_units_persistent(L):
+@pytest.mark.parametrize("mode", [2, 3])
+def test_conv3x3_many_units_persistent(L, mode):
     """More work units than SMs x 2: exercises the persistent loop, ring wrap-around and TMEM double buffering."""
     x, w, scale, shift = _conv_inputs(40, 64, 128, 128, seed=3)
     out = torch.empty(40, 64, 64, 128, device="cuda", dtype=torch.bfloat16)
-    L.conv3x3(x, w, scale, shift, out)
+    L.conv3x3(x, w, scale, shift, out, mode=mode)
     assert rel_l2(out.float(), _conv_ref(x, w, scale, shift).clamp_min(0)) < BF16_TOL
     out2 = torch.empty_like(out)
-    L.conv3x3(x, w, scale, shift, out2)
+    L.conv3x3(x, w, scale, shift, out2, mode=mode)
     assert torch.equal(out, out2), "conv3x3 must be deterministic"
 
 
-def test_conv3x3_pool(L):
+@pytest.mark.parametrize("mode", [2, 3])
+def test_conv3x3_pool(L, mode):
     x, w, scale, shift = _conv_inputs(4, 32, 128, 256, seed=1)
     out = torch.empty(4, 16, 16, 256, device="cuda", dtype=torch.bfloat16)
-    L.conv3x3(x, w, scale, shift, out, flags=L.EPI_RELU | L.EPI_POOL)
+    L.conv3x3(x, w, scale, shift, out, flags=L.EPI_RELU | L.EPI_POOL, mode=mode)
     ref = F.max_pool2d(_conv_ref(x, w, scale, shift).clamp_min(0).permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
     assert rel_l2(out.float(), ref) < BF16_TOL
 
 
+@pytest.mark.parametrize("mode", [2, 3])
 @pytest.mark.parametrize("rows", [1, 4])
-def test_conv3x3_film(L, rows):
+def test_conv3x3_film(L, rows, mode):
     n, cout = 4, 128
     x, w, scale, shift = _conv_inputs(n, 32, 128, cout, seed=2)
     fs = torch.randn(n, cout, device="cuda")
@@ -74,14 +77,15 @@ def test_conv3x3_film(L, rows):
     step = torch.tensor([2], device="cuda", dtype=torch.int32)
     out = torch.empty(n, 32, 32, cout, device="cuda", dtype=torch.bfloat16)
     L.conv3x3(x, w, scale, shift, out, flags=L.EPI_RELU | L.EPI_FILM, film_scale=fs, film_shift=fsh,
-              film_shift_rows=rows, step_ptr=step)
+              film_shift_rows=rows, step_ptr=step, mode=mode)
     sh = fsh[2].expand(n, cout) if rows == 1 else fsh[2]
     ref = _conv_ref(x, w, scale, shift).clamp_min(0) * fs.view(n, 1, 1, cout) + sh.reshape(n, 1, 1, cout)
     assert rel_l2(out.float(), ref) < BF16_TOL
 
 
+@pytest.mark.parametrize("mode", [2, 3])
 @pytest.mark.parametrize("reps", [1, 2])
-def test_conv3x3_shortcut_fanout(L, reps):
+def test_conv3x3_shortcut_fanout(L, reps, mode):
     n, H, cout = 3, 64, 128
     x, w, scale, shift = _conv_inputs(n, H, 128, cout, seed=4)
     xs = torch.randn(n, H, H, device="cuda")
@@ -89,20 +93,21 @@ def test_conv3x3_shortcut_fanout(L, reps):
     step = torch.tensor([3], device="cuda", dtype=torch.int32)
     out = torch.empty(reps * n, H, H, cout, device="cuda", dtype=torch.bfloat16)
     L.conv3x3(x, w, scale, shift, out, flags=L.EPI_RELU | L.EPI_SHORTCUT, sc_x=xs, sc_tab=tab, sc_reps=reps,
-              step_ptr=step)
+              step_ptr=step, mode=mode)
     base = _conv_ref(x, w, scale, shift).clamp_min(0)
     for r in range(reps):
         ref = base + xs.view(n, H, H, 1) * tab[3, r, 0].view(1, 1, 1, cout) + tab[3, r, 1].view(1, 1, 1, cout)
         assert rel_l2(out[r * n:(r + 1) * n].float(), ref) < BF16_TOL
 
 
-def test_conv3x3_gnstats(L):
+@pytest.mark.parametrize("mode", [2, 3])
+def test_conv3x3_gnstats(L, mode):
     n, H = 3, 64
     x, w, scale, shift = _conv_inputs(n, H, 256, 128, seed=5)
-    part = torch.zeros(n, (H // 16) ** 2 * 8, 8, 2, device="cuda")
+    part = torch.full((n, (H // 16) ** 2 * 8, 8, 2), float("nan"), device="cuda")  # every slot must be written
     out = torch.empty(n, H, H, 128, device="cuda", dtype=torch.bfloat16)
     L.conv3x3(x[..., :128].contiguous(), w, scale, shift, out, src1=x[..., 128:].contiguous(), flags=L.EPI_GNSTATS,
-              gn_partial=part)
+              gn_partial=part, mode=mode)
     ref = _conv_ref(x, w, scale, shift)
     assert rel_l2(out.float(), ref) < BF16_TOL
     mr = torch.empty(n, 8, 2, device="cuda")

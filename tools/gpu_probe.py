@@ -218,6 +218,12 @@ CASES = {
     "perf_m1": lambda: case_perf("perf_m1", 1),
     "perf_m2": lambda: case_perf("perf_m2", 2),
     "perf_m0_c256": lambda: case_perf("perf_m0_c256", 0, n=256, H=32, cin=256, cout=256),
+    "perf_m3": lambda: case_perf("perf_m3", 3, n=1024),
+    "perf_m2_big": lambda: case_perf("perf_m2_big", 2, n=1024),
+    "perf_m3_c256": lambda: case_perf("perf_m3_c256", 3, n=1024, H=32, cin=256, cout=256),
+    "perf_m2_c256": lambda: case_perf("perf_m2_c256", 2, n=1024, H=32, cin=256, cout=256),
+    "perf_m3_out0": lambda: case_perf("perf_m3_out0", 3, n=1024, H=64, cin=256, cout=128),
+    "perf_m2_out0": lambda: case_perf("perf_m2_out0", 2, n=1024, H=64, cin=256, cout=128),
     "probe_l2": lambda: case_probe_l2("probe_l2"),
 }
 
