@@ -129,7 +129,7 @@ def stream_ptr():
 
 def conv3x3(src0, weight, scale, shift, out, *, src1=None, flags=EPI_RELU, sc_x=None, sc_tab=None, sc_reps=1,
             film_scale=None, film_shift=None, film_shift_rows=1, step_ptr=None, gn_partial=None,
-            mode=CONV_MODE_SHIFT18):
+            mode=CONV_MODE_SWAPPED):
     """src*: bf16 [n,H,W,c]; weight bf16 [cout,3,3,cin]; out bf16 NHWC. See cdm_conv3x3 in cdm_b200.h."""
     n, H, W, c0 = src0.shape
     a = Conv3x3Args()

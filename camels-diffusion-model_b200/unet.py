@@ -144,7 +144,7 @@ class ContextUnet(nn.Module):
         self._packed = None
         self._packed_key = None
         self._ws = {}
-        self.conv_mode = int(os.environ.get("CDM_CONV_MODE", L.CONV_MODE_SHIFT18))
+        self.conv_mode = int(os.environ.get("CDM_CONV_MODE", L.CONV_MODE_SWAPPED))
 
     # ------------------------------------------------------------------ weights
     def _check_supported(self):
