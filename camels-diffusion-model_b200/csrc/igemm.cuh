@@ -413,9 +413,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 // Halo tile: TMA box {64 ch, 10, 34, 1}, pitch 10 (SBO 1280 B), tap (kh,kw) = start row kh*10 + kw.
 // --------------------------------------------------------------------------
 constexpr int kSwPitch = 10, kSwRows = 34, kSwABytes = kSwRows * kSwPitch * 128, kSwAStride = 44032, kSwNA = 3;
-constexpr int conv_sw_smem_bytes() { return kSwNA * kSwAStride + kNB * kBBytes + 2 * 8192 + 2 * 256 * 4 + 256 + 1024; }
-
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+constexpr int conv_sw_smem_bytes() { return kSwNA * kSwAStride + kNB * kBBytes + 2 * 256 * 4 + 256 + 1024; }
 
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -424,8 +422,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smemA = smem;  // pixel halo tiles
   uint8_t* smemB = smemA + kSwNA * kSwAStride;  // weight tiles
-  uint8_t* smemStage = smemB + kNB * kBBytes;
-  float* s_scale = reinterpret_cast<float*>(smemStage + 2 * 8192);
+  float* s_scale = reinterpret_cast<float*>(smemB + kNB * kBBytes);
   float* s_shift = s_scale + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
   uint64_t* a_full = bars;
@@ -547,10 +544,9 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const int q = warp - 4;
     const int et = threadIdx.x - 128;  // 0..127 among the epilogue threads
     const int co_l = q * 32 + lane;    // this thread's channel inside the 128-wide tile
-    const uint32_t stg0 = smem_u32(smemStage);
     const int step = p.step_ptr ? *p.step_ptr : 0;
     const bool pool = p.flags & CDM_EPI_POOL;
-    int it = 0, sbuf = 0;
+    int it = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
       const int buf = it & 1;
       const int img = u / units_per_img;
@@ -607,45 +603,40 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               gq = fmaf(f[i], f[i], gq);
             }
           }
-          const uint32_t stg = stg0 + sbuf * 8192 + co_l * 2;
+          // NHWC store without shared memory: lanes 2k / 2k+1 own channels co, co+1.  One shuffle per pixel
+          // pair gives the even lane both channels of pixel i and the odd lane both channels of pixel i+1, so a
+          // warp instruction writes 2 x 64 contiguous bytes (full sectors) as 32-bit bf16x2 words.
+          const int odd = lane & 1;
           if (!pool) {
+            bf16* gbase = p.out + (((size_t)oimg * p.H + oh0 + 4 * c8) * p.W + ow0) * p.cout + n_tile * 128 +
+                          (co_l & ~1);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const __nv_bfloat16 h = __float2bfloat16(f[i]);
-              asm volatile("st.shared.b16 [%0], %1;" ::"r"(stg + i * 256), "h"(*reinterpret_cast<const uint16_t*>(&h))
-                           : "memory");
+            for (int i = 0; i < 32; i += 2) {
+              const float recv = __shfl_xor_sync(0xffffffffu, odd ? f[i] : f[i + 1], 1);
+              const uint32_t w = odd ? pack_bf16x2(recv, f[i + 1]) : pack_bf16x2(f[i], recv);
+              const int px = i + odd;  // rows 4*c8 + (px >> 3), column px & 7
+              *reinterpret_cast<uint32_t*>(gbase + ((size_t)(px >> 3) * p.W + (px & 7)) * p.cout) = w;
             }
           } else {
+            float m[8];
 #pragma unroll
             for (int pr = 0; pr < 2; ++pr)
 #pragma unroll
               for (int pj = 0; pj < 4; ++pj) {
                 const int i00 = (2 * pr) * 8 + 2 * pj;
-                const float m = fmaxf(fmaxf(f[i00], f[i00 + 1]), fmaxf(f[i00 + 8], f[i00 + 9]));
-                const __nv_bfloat16 h = __float2bfloat16(m);
-                asm volatile("st.shared.b16 [%0], %1;" ::"r"(stg + (pr * 4 + pj) * 256),
-                             "h"(*reinterpret_cast<const uint16_t*>(&h))
-                             : "memory");
+                m[pr * 4 + pj] = fmaxf(fmaxf(f[i00], f[i00 + 1]), fmaxf(f[i00 + 8], f[i00 + 9]));
               }
-          }
-          epi_bar_sync();
-          // cooperative copy-out of [n_px][128 ch] bf16: 16 lanes x 16 B = one pixel's 256 bytes
-          const int n_px = pool ? 8 : 32;
-          for (int un = et; un < n_px * 16; un += 128) {
-            const int px = un >> 4, part = un & 15;
-            const uint4 val = ld_shared_v4(stg0 + sbuf * 8192 + px * 256 + part * 16);
-            bf16* g;
-            if (!pool) {
-              const int r = 4 * c8 + (px >> 3), jx = px & 7;
-              g = p.out + (((size_t)oimg * p.H + oh0 + r) * p.W + ow0 + jx) * p.cout + n_tile * 128;
-            } else {
-              const int r = 2 * c8 + (px >> 2), jx = px & 3;
-              g = p.out + (((size_t)oimg * (p.H >> 1) + (oh0 >> 1) + r) * (p.W >> 1) + (ow0 >> 1) + jx) * p.cout +
-                  n_tile * 128;
+            const int Ho = p.H >> 1, Wo = p.W >> 1;
+            bf16* gbase = p.out + (((size_t)oimg * Ho + (oh0 >> 1) + 2 * c8) * Wo + (ow0 >> 1)) * p.cout +
+                          n_tile * 128 + (co_l & ~1);
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              const float recv = __shfl_xor_sync(0xffffffffu, odd ? m[i] : m[i + 1], 1);
+              const uint32_t w = odd ? pack_bf16x2(recv, m[i + 1]) : pack_bf16x2(m[i], recv);
+              const int px = i + odd;  // pooled row 2*c8 + (px >> 2), pooled column px & 3
+              *reinterpret_cast<uint32_t*>(gbase + ((size_t)(px >> 2) * Wo + (px & 3)) * p.cout) = w;
             }
-            reinterpret_cast<uint4*>(g)[part] = val;
           }
-          sbuf ^= 1;
         }
         if (p.flags & CDM_EPI_GNSTATS) {
           // 16 channels per group = 16 consecutive lanes
