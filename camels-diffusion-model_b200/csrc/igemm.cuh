@@ -577,6 +577,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         float gs = 0.f, gq = 0.f;
 #pragma unroll 1
         for (int c8 = 0; c8 < 8; ++c8) {  // 32 pixels: patch rows 4*c8 .. 4*c8+3, 8 px each
+          if (p.flags & (1 << 29)) continue;  // probe: no epilogue work at all
           uint32_t v[32];
           tmem_ld_x32(taddr + c8 * 32, v);
           tmem_wait_ld();
@@ -607,6 +608,13 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           // pair gives the even lane both channels of pixel i and the odd lane both channels of pixel i+1, so a
           // warp instruction writes 2 x 64 contiguous bytes (full sectors) as 32-bit bf16x2 words.
           const int odd = lane & 1;
+          if (p.flags & (1 << 30)) {  // probe: everything but the global stores
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc += f[i];
+            if (acc == 123.456f) p.out[0] = __float2bfloat16(acc);
+            continue;
+          }
           if (!pool) {
             bf16* gbase = p.out + (((size_t)oimg * p.H + oh0 + 4 * c8) * p.W + ow0) * p.cout + n_tile * 128 +
                           (co_l & ~1);
@@ -776,42 +784,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128);
       const float* shift = p.shift + (n_tile * 128) % p.shift_mod;  // shift_mod is a multiple of 128
+      // this thread's output row: 128 contiguous bf16 (256 B) written straight from registers
+      const int m = m_tile * 128 + q * 32 + lane;
+      bf16* g = nullptr;
+      if (m < p.M) {
+        if (p.out_mode == 0) {
+          g = p.out + (size_t)m * p.N + n_tile * 128;
+        } else {
+          // H, W are powers of two (checked on the host): shifts instead of integer division
+          const int w = m & (p.W - 1), h = (m >> p.w_shift) & (p.H - 1), img = m >> (p.w_shift + p.h_shift);
+          const int kh = n_tile >> 1, kw = n_tile & 1;
+          g = p.out + (((size_t)img * 2 * p.H + 2 * h + kh) * (2 * p.W) + 2 * w + kw) * 128;
+        }
+      }
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         uint32_t v[32];
         tmem_ld_x32(taddr + cc * 32, v);
         tmem_wait_ld();
-        float f[32];
+        if (g) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + __ldg(shift + cc * 32 + i);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int un = cc * 4 + j;
-          st_shared_v4(stg + lane * 256 + ((un ^ (lane & 7)) << 4), pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]),
-                       pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]), pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]),
-                       pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]));
-        }
-      }
-      __syncwarp();
-#pragma unroll 4
-      for (int i2 = 0; i2 < 16; ++i2) {
-        const int rw = 2 * i2 + (lane >> 4), un = lane & 15;
-        const int m = m_tile * 128 + q * 32 + rw;
-        if (m < p.M) {
-          const uint4 val = ld_shared_v4(stg + rw * 256 + ((un ^ (rw & 7)) << 4));
-          bf16* g;
-          if (p.out_mode == 0) {
-            g = p.out + (size_t)m * p.N + n_tile * 128;
-          } else {
-            // H, W are powers of two (checked on the host): shifts instead of integer division
-            const int w = m & (p.W - 1), h = (m >> p.w_shift) & (p.H - 1), img = m >> (p.w_shift + p.h_shift);
-            const int kh = n_tile >> 1, kw = n_tile & 1;
-            g = p.out + (((size_t)img * 2 * p.H + 2 * h + kh) * (2 * p.W) + 2 * w + kw) * 128;
+          for (int j = 0; j < 4; ++j) {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift + cc * 32 + j * 8));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(shift + cc * 32 + j * 8 + 4));
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[j * 8 + 0]) + s0.x, __uint_as_float(v[j * 8 + 1]) + s0.y);
+            o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]) + s0.z, __uint_as_float(v[j * 8 + 3]) + s0.w);
+            o.z = pack_bf16x2(__uint_as_float(v[j * 8 + 4]) + s1.x, __uint_as_float(v[j * 8 + 5]) + s1.y);
+            o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]) + s1.z, __uint_as_float(v[j * 8 + 7]) + s1.w);
+            reinterpret_cast<uint4*>(g)[cc * 4 + j] = o;
           }
-          reinterpret_cast<uint4*>(g)[un] = val;
         }
       }
-      __syncwarp();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[buf]);

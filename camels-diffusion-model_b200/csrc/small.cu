@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ 
     }
     __syncthreads();
     const int r = threadIdx.x >> 6, c = threadIdx.x & 63;
-    float acc = 0.f;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;  // four chains: the FMAs are not latency bound
 #pragma unroll 1
     for (int un = 0; un < 16; ++un) {
       float wr[9][8];
@@ -174,17 +174,17 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ 
           const int px = (r + kh) * (kCoW + 2) + c + kw;
           const uint4 v = ld_shared_v4(tile_u32 + px * 256 + ((un ^ (px & 7)) << 4));
           const int t = kh * 3 + kw;
-          acc = fmaf(__uint_as_float(v.x << 16), wr[t][0], acc);
-          acc = fmaf(__uint_as_float(v.x & 0xffff0000u), wr[t][1], acc);
-          acc = fmaf(__uint_as_float(v.y << 16), wr[t][2], acc);
-          acc = fmaf(__uint_as_float(v.y & 0xffff0000u), wr[t][3], acc);
-          acc = fmaf(__uint_as_float(v.z << 16), wr[t][4], acc);
-          acc = fmaf(__uint_as_float(v.z & 0xffff0000u), wr[t][5], acc);
-          acc = fmaf(__uint_as_float(v.w << 16), wr[t][6], acc);
-          acc = fmaf(__uint_as_float(v.w & 0xffff0000u), wr[t][7], acc);
+          acc0 = fmaf(__uint_as_float(v.x << 16), wr[t][0], acc0);
+          acc1 = fmaf(__uint_as_float(v.x & 0xffff0000u), wr[t][1], acc1);
+          acc2 = fmaf(__uint_as_float(v.y << 16), wr[t][2], acc2);
+          acc3 = fmaf(__uint_as_float(v.y & 0xffff0000u), wr[t][3], acc3);
+          acc0 = fmaf(__uint_as_float(v.z << 16), wr[t][4], acc0);
+          acc1 = fmaf(__uint_as_float(v.z & 0xffff0000u), wr[t][5], acc1);
+          acc2 = fmaf(__uint_as_float(v.w << 16), wr[t][6], acc2);
+          acc3 = fmaf(__uint_as_float(v.w & 0xffff0000u), wr[t][7], acc3);
         }
     }
-    out[((size_t)n * H + ty * kCoRows + r) * W + tx * kCoW + c] = acc + bias0;
+    out[((size_t)n * H + ty * kCoRows + r) * W + tx * kCoW + c] = ((acc0 + acc1) + (acc2 + acc3)) + bias0;
   }
 }
 

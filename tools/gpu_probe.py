@@ -137,7 +137,7 @@ def case_gemm(name, M, k0, k1, N, out_mode=0, H=0, W=0):
     return diag(name, out.float(), r)
 
 
-def case_perf(name, mode, n=256, H=64, cin=128, cout=128):
+def case_perf(name, mode, n=256, H=64, cin=128, cout=128, flags=1):
     import torch
     L = _load()
     dev = "cuda"
@@ -147,13 +147,13 @@ def case_perf(name, mode, n=256, H=64, cin=128, cout=128):
     shift = torch.zeros(cout, device=dev)
     out = torch.empty(n, H, H, cout, device=dev, dtype=torch.bfloat16)
     for _ in range(3):
-        L.conv3x3(x, w, scale, shift, out, mode=mode)
+        L.conv3x3(x, w, scale, shift, out, mode=mode, flags=flags)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     iters = 10
     e0.record()
     for _ in range(iters):
-        L.conv3x3(x, w, scale, shift, out, mode=mode)
+        L.conv3x3(x, w, scale, shift, out, mode=mode, flags=flags)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
@@ -219,6 +219,8 @@ CASES = {
     "perf_m2": lambda: case_perf("perf_m2", 2),
     "perf_m0_c256": lambda: case_perf("perf_m0_c256", 0, n=256, H=32, cin=256, cout=256),
     "perf_m3": lambda: case_perf("perf_m3", 3, n=1024),
+    "perf_m3_nostore": lambda: case_perf("perf_m3_nostore", 3, n=1024, flags=1 | (1 << 30)),
+    "perf_m3_noepi": lambda: case_perf("perf_m3_noepi", 3, n=1024, flags=1 | (1 << 29)),
     "perf_m2_big": lambda: case_perf("perf_m2_big", 2, n=1024),
     "perf_m3_c256": lambda: case_perf("perf_m3_c256", 3, n=1024, H=32, cin=256, cout=256),
     "perf_m2_c256": lambda: case_perf("perf_m2_c256", 2, n=1024, H=32, cin=256, cout=256),
