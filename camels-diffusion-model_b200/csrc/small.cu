@@ -74,31 +74,41 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
     const int h = row % H;
     const float* xr = x + (size_t)row * W;
     bf16* orow = out + (size_t)row * W * C;
-    for (int w = psub; w < W; w += ppb) {
-      float xin[9];
+    for (int w = psub; w < W; w += 2 * ppb) {
+      // two pixels per iteration: all 18 input loads are issued before the first FMA
+      float xin[2][9];
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const int ih = h + kh - 1;
-        const bool okh = ih >= 0 && ih < H;
+      for (int q = 0; q < 2; ++q) {
+        const int wq = w + q * ppb;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int iw = w + kw - 1;
-          xin[kh * 3 + kw] = (okh && iw >= 0 && iw < W) ? __ldg(xr + (kh - 1) * W + iw) : 0.f;
+        for (int kh = 0; kh < 3; ++kh) {
+          const int ih = h + kh - 1;
+          const bool okh = ih >= 0 && ih < H && wq < W;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int iw = wq + kw - 1;
+            xin[q][kh * 3 + kw] = (okh && iw >= 0 && iw < W) ? __ldg(xr + (kh - 1) * W + iw) : 0.f;
+          }
         }
       }
-      float acc[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int q = 0; q < 2; ++q) {
+        const int wq = w + q * ppb;
+        if (wq >= W) break;
+        float acc[8];
 #pragma unroll
-      for (int t = 0; t < 9; ++t)
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xin[t], wr[t][j], acc[j]);
+        for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float y = fmaf(acc[j], sc[j], sh[j]);
-        acc[j] = relu ? fmaxf(y, 0.f) : y;
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(xin[q][t], wr[t][j], acc[j]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float y = fmaf(acc[j], sc[j], sh[j]);
+          acc[j] = relu ? fmaxf(y, 0.f) : y;
+        }
+        *reinterpret_cast<uint4*>(orow + (size_t)wq * C + cg * 8) = pack8(acc);
       }
-      *reinterpret_cast<uint4*>(orow + (size_t)w * C + cg * 8) = pack8(acc);
     }
   }
 }
@@ -139,20 +149,37 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ 
     }
     __syncthreads();
     const int h0 = ty * kCoRows - 1, w0 = tx * kCoW - 1;
-    for (int u = threadIdx.x; u < kCoTilePx * 16; u += blockDim.x) {
-      const int px = u >> 4, un = u & 15;
-      const int pr = px / (kCoW + 2), pc = px - pr * (kCoW + 2);
-      const int ih = h0 + pr, iw = w0 + pc;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);  // zero padding is applied AFTER GroupNorm+ReLU, as nn.Conv2d does
-      if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src + (((size_t)n * H + ih) * W + iw) * kCoC + un * 8));
-        float f[8];
-        unpack8(raw, f);
+    // stage the halo tile: 5 independent 16-byte global loads in flight per thread before any is consumed
+    constexpr int kBatch = 5;
+    for (int base = 0; base < kCoTilePx * 16; base += kBatch * 256) {
+      uint4 raw[kBatch];
+      int pxs[kBatch], uns[kBatch];
+      bool inb[kBatch];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], s_a[un * 8 + j], s_b[un * 8 + j]), 0.f);
-        v = pack8(f);
+      for (int j = 0; j < kBatch; ++j) {
+        const int u = base + j * 256 + threadIdx.x;
+        const int px = u >> 4, un = u & 15;
+        const int pr = px / (kCoW + 2), pc = px - pr * (kCoW + 2);
+        const int ih = h0 + pr, iw = w0 + pc;
+        pxs[j] = px;
+        uns[j] = un;
+        inb[j] = u < kCoTilePx * 16 && ih >= 0 && ih < H && iw >= 0 && iw < W;
+        raw[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (inb[j]) raw[j] = __ldg(reinterpret_cast<const uint4*>(src + (((size_t)n * H + ih) * W + iw) * kCoC + un * 8));
       }
-      st_shared_v4(tile_u32 + px * 256 + ((un ^ (px & 7)) << 4), v.x, v.y, v.z, v.w);
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        if (base + j * 256 + (int)threadIdx.x >= kCoTilePx * 16) continue;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);  // zero padding is applied AFTER GroupNorm+ReLU, as nn.Conv2d does
+        if (inb[j]) {
+          float f[8];
+          unpack8(raw[j], f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], s_a[uns[j] * 8 + k], s_b[uns[j] * 8 + k]), 0.f);
+          v = pack8(f);
+        }
+        st_shared_v4(tile_u32 + pxs[j] * 256 + ((uns[j] ^ (pxs[j] & 7)) << 4), v.x, v.y, v.z, v.w);
+      }
     }
     __syncthreads();
     const int r = threadIdx.x >> 6, c = threadIdx.x & 63;

@@ -33,6 +33,53 @@ class ResidualConvBlock(nn.Module):
     def get_out_channels(self):
         return self.conv2[0].out_channels
 
+    def _run_nhwc(self, a, pool=False, shortcut=None):
+        """Eval-mode block on an NHWC bf16 tensor (or fp32 [n,H,W] if in_channels == 1)."""
+        if self.training:
+            raise L.CdmError("stand-alone blocks run in eval mode; training goes through ContextUnet.forward")
+        dev = self.conv1[0].weight.device
+        cout = self.conv2[0].out_channels
+        s1, b1 = _fold_bn(self.conv1[0], self.conv1[1])
+        s2, b2 = _fold_bn(self.conv2[0], self.conv2[1])
+        if self.conv1[0].in_channels == 1:
+            n, H, W = a.shape
+            y1 = torch.empty(n, H, W, cout, device=dev, dtype=torch.bfloat16)
+            L.conv_in(a, self.conv1[0].weight.detach().float().reshape(cout, 9).t().contiguous(), s1, b1, y1)
+        else:
+            n, H, W, _ = a.shape
+            y1 = torch.empty(n, H, W, cout, device=dev, dtype=torch.bfloat16)
+            L.conv3x3(a, _pack_conv3(self.conv1[0]), s1, b1, y1)
+        Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+        y2 = torch.empty(n, Ho, Wo, cout, device=dev, dtype=torch.bfloat16)
+        kw = {}
+        flags = L.EPI_RELU | (L.EPI_POOL if pool else 0)
+        if shortcut is not None:  # is_res with in_channels != out_channels: the fresh random 1x1 conv (G1)
+            flags |= L.EPI_SHORTCUT
+            kw = dict(sc_x=a, sc_tab=shortcut.to(dev, torch.float32).reshape(1, 1, 2, cout).contiguous(), sc_reps=1)
+        L.conv3x3(y1, _pack_conv3(self.conv2[0]), s2, b2, y2, flags=flags, **kw)
+        return y2
+
+    def forward(self, x, shortcut=None):
+        """diffusion_utilities.py:39-65, eval mode, NCHW fp32 in / out."""
+        dev = self.conv1[0].weight.device
+        if dev.type != "cuda":
+            raise L.CdmError("no CPU path: move the block to an sm_100 device")
+        x = x.detach().to(dev, torch.float32)
+        cin, cout = self.conv1[0].in_channels, self.conv2[0].out_channels
+        a = x[:, 0].contiguous() if cin == 1 else x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        sc = None
+        if self.is_res and not self.same_channels:
+            if cin != 1:
+                raise L.CdmError("the fresh 1x1 shortcut is only built for in_channels == 1 (init_conv)")
+            if shortcut is None:
+                conv = nn.Conv2d(cin, cout, kernel_size=1)  # consumes the global CPU generator like the reference
+                shortcut = torch.cat([conv.weight.detach().view(-1), conv.bias.detach().view(-1)])
+            sc = shortcut
+        y = self._run_nhwc(a, shortcut=sc)
+        if self.is_res and self.same_channels:
+            L.add_bf16(y, cout, a, cout, y.shape[0] * y.shape[1] * y.shape[2], cout)
+        return y.float().permute(0, 3, 1, 2).contiguous()
+
 
 class UnetUp(nn.Module):
     """diffusion_utilities.py:79-92."""
@@ -43,6 +90,24 @@ class UnetUp(nn.Module):
                                    ResidualConvBlock(out_channels, out_channels),
                                    ResidualConvBlock(out_channels, out_channels))
 
+    def forward(self, x, skip):
+        """cat(x, skip) -> ConvTranspose2d(2,2) -> RCB -> RCB (diffusion_utilities.py:94-100), eval, NCHW fp32."""
+        ct = self.model[0]
+        dev = ct.weight.device
+        if dev.type != "cuda":
+            raise L.CdmError("no CPU path: move the block to an sm_100 device")
+        n, c0, H, W = x.shape
+        a0 = x.detach().to(dev, torch.float32).permute(0, 2, 3, 1).reshape(n * H * W, c0).contiguous().to(torch.bfloat16)
+        a1 = skip.detach().to(dev, torch.float32).permute(0, 2, 3, 1).reshape(n * H * W, -1).contiguous().to(torch.bfloat16)
+        cout = ct.out_channels
+        if cout != 128 or (H & (H - 1)) or (W & (W - 1)):
+            raise L.CdmError("UnetUp kernel path is specialised for 128 output channels and power-of-two maps")
+        v = torch.empty(n, 2 * H, 2 * W, cout, device=dev, dtype=torch.bfloat16)
+        L.gemm(a0, _pack_convT(ct), ct.bias.detach().float().contiguous(), v, a1=a1, out_mode=1, H=H, W=W,
+               shift_mod=cout)
+        y = self.model[2]._run_nhwc(self.model[1]._run_nhwc(v))
+        return y.float().permute(0, 3, 1, 2).contiguous()
+
 
 class UnetDown(nn.Module):
     """diffusion_utilities.py:103-112."""
@@ -51,6 +116,15 @@ class UnetDown(nn.Module):
         super().__init__()
         self.model = nn.Sequential(ResidualConvBlock(in_channels, out_channels),
                                    ResidualConvBlock(out_channels, out_channels), nn.MaxPool2d(2))
+
+    def forward(self, x):
+        """RCB -> RCB -> MaxPool2d(2) (diffusion_utilities.py:114-116), eval mode, NCHW fp32 in / out."""
+        dev = self.model[0].conv1[0].weight.device
+        if dev.type != "cuda":
+            raise L.CdmError("no CPU path: move the block to an sm_100 device")
+        a = x.detach().to(dev, torch.float32).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        y = self.model[1]._run_nhwc(self.model[0]._run_nhwc(a), pool=True)
+        return y.float().permute(0, 3, 1, 2).contiguous()
 
 
 class EmbedFC(nn.Module):

@@ -207,3 +207,82 @@ def test_likelihood_graph_sweep_runs(models):
     torch.manual_seed(0)
     b = cdm.calculate_likelihood(m, [(maps, prm)], Tn, "cuda", ab_t, b_t, a_t, seed=5)
     assert np.isfinite(a) and a > 0 and a == b
+
+
+def test_blocks_standalone_forward():
+    """ResidualConvBlock / UnetDown / UnetUp / EmbedFC forward on their own (eval) vs torch.nn.functional."""
+    import torch.nn.functional as F
+    import camels_diffusion_model_b200 as cdm
+    torch.manual_seed(3)
+
+    def randomise(mod):
+        for m_ in mod.modules():
+            if isinstance(m_, torch.nn.BatchNorm2d):
+                m_.running_mean.normal_(0, 0.2), m_.running_var.uniform_(0.5, 1.5)
+                m_.weight.data.uniform_(0.5, 1.5), m_.bias.data.normal_(0, 0.2)
+        return mod.cuda().eval()
+
+    def cbr(seq, x):
+        return F.relu(F.batch_norm(F.conv2d(x, seq[0].weight, seq[0].bias, padding=1), seq[1].running_mean,
+                                   seq[1].running_var, seq[1].weight, seq[1].bias, False, 0.0, 1e-5))
+
+    def rcb(blk, x):
+        return cbr(blk.conv2, cbr(blk.conv1, x))
+
+    g = torch.Generator().manual_seed(0)
+    down = randomise(cdm.UnetDown(128, 256))
+    x = torch.randn(2, 128, 32, 32, generator=g).cuda()
+    with torch.no_grad():
+        ref = F.max_pool2d(rcb(down.model[1], rcb(down.model[0], x)), 2)
+    assert rel_l2(down(x), ref) < 1e-2
+    up = randomise(cdm.UnetUp(256, 128))
+    xa, sk = torch.randn(2, 128, 32, 32, generator=g).cuda(), torch.randn(2, 128, 32, 32, generator=g).cuda()
+    with torch.no_grad():
+        v = F.conv_transpose2d(torch.cat((xa, sk), 1), up.model[0].weight, up.model[0].bias, stride=2)
+        ref = rcb(up.model[2], rcb(up.model[1], v))
+    assert rel_l2(up(xa, sk), ref) < 1e-2
+    init = randomise(cdm.ResidualConvBlock(1, 128, is_res=True))
+    x1 = torch.randn(3, 1, 64, 64, generator=g).cuda()
+    sc = torch.rand(256, generator=g) * 2 - 1
+    with torch.no_grad():
+        ref = rcb(init, x1) + x1 * sc[:128].cuda().view(1, -1, 1, 1) + sc[128:].cuda().view(1, -1, 1, 1)
+    assert rel_l2(init(x1, shortcut=sc), ref) < 1e-2
+    same = randomise(cdm.ResidualConvBlock(128, 128, is_res=True))
+    with torch.no_grad():
+        ref = x[:, :, :32, :32] + rcb(same, x)
+    assert rel_l2(same(x), ref) < 1e-2
+
+
+@pytest.mark.parametrize("ncf", [1, 3])
+def test_other_context_widths(ncf):
+    """BASELINE config 4: n_cfeat 1..6 only changes the first EmbedFC layer of the two context embeddings."""
+    import camels_diffusion_model_b200 as cdm
+    sd = O.init_state_dict(5, n_cfeat=ncf)
+    m = cdm.ContextUnet(1, 128, ncf, 64)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(1)
+    x, c = torch.randn(2, 1, 64, 64, generator=g), torch.rand(2, ncf, generator=g)
+    sc = torch.rand(256, generator=g) * 2 - 1
+    t = torch.tensor([0.25])
+    with torch.no_grad():
+        ref = O.unet_forward(sd, x, t, c, (sc[:128], sc[128:]), n_cfeat=ncf)
+    assert rel_l2(m(x.cuda(), t.cuda(), c.cuda(), shortcut=sc), ref) < EPS_TOL_RAW
+
+
+def test_drivers_grid_guidance_sensitivity(models):
+    import camels_diffusion_model_b200 as cdm
+    from camels_diffusion_model_b200 import drivers as DR
+    ddpm = cdm.DDPM(models["raw"], timesteps=6)
+    base = torch.rand(NCF, generator=torch.Generator().manual_seed(0))
+    ctx = DR.parameter_grid_contexts(base, NCF)
+    assert ctx.shape == (25, NCF) and torch.equal(ctx[:, 2:], base[2:].expand(25, NCF - 2))
+    assert torch.equal(ctx[:, 0], torch.linspace(0, 1, 5).repeat_interleave(5))
+    assert torch.equal(ctx[:, 1], torch.linspace(0, 1, 5).repeat(5))
+    assert DR.parameter_grid_contexts(base[:1], 1).shape == (25, 1)
+    x, inter, dt, c2 = DR.sample_parameter_grid(ddpm, base)
+    assert x.shape == (25, 1, 64, 64) and torch.isfinite(x).all()
+    sweep = DR.guidance_sweep(ddpm, base, strengths=(0.0, 2.0), n_sample=3)
+    assert set(sweep) == {0.0, 2.0} and sweep[2.0][0].shape == (3, 1, 64, 64)
+    xs, cs, _ = DR.parameter_sensitivity(ddpm, base, batched=True)
+    assert xs.shape == (NCF * 5, 1, 64, 64) and cs.shape == (NCF * 5, NCF)
