@@ -238,6 +238,38 @@ extern "C" int cdm_gemm(const cdm_gemm_args* a, void* stream) {
     rc = make_tmap_bf16(&mB, a->bw, 2, dims, str, box);
     if (rc) return rc;
   }
+  // small N (transposed convolutions): keep the weight tiles resident, stream A once per weight group
+  const int n_tiles_total = a->N / 128;
+  const int n_res = K <= 256 ? 2 : (K <= 512 ? 1 : 0);
+  if (n_res > 0 && n_tiles_total <= 4 && n_tiles_total % n_res == 0 && a->M >= 128 * 64) {
+    GemmBresKParams q;
+    memset(&q, 0, sizeof(q));
+    q.M = a->M;
+    q.N = a->N;
+    q.chunks0 = a->k0 / 64;
+    q.chunks = K / 64;
+    q.m_tiles = (a->M + 127) / 128;
+    q.n_res = n_res;
+    q.n_groups = n_tiles_total / n_res;
+    q.shift = a->shift;
+    q.shift_mod = a->shift_mod;
+    q.out_mode = a->out_mode;
+    q.H = a->H;
+    q.W = a->W;
+    for (int v = a->H; v > 1; v >>= 1) ++q.h_shift;
+    for (int v = a->W; v > 1; v >>= 1) ++q.w_shift;
+    q.out = reinterpret_cast<bf16*>(a->out);
+    constexpr int smem_b = gemm_bres_smem_bytes();
+    static bool attr_b = false;
+    if (!attr_b) {
+      CDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
+      attr_b = true;
+    }
+    const int grid_b = (num_sms() / q.n_groups) * q.n_groups;
+    gemm_bres_kernel<<<grid_b, kConvThreads, smem_b, reinterpret_cast<cudaStream_t>(stream)>>>(mA0, mA1, mB, q);
+    CDM_CHECK_LAUNCH();
+    return CDM_OK;
+  }
   GemmKParams p;
   memset(&p, 0, sizeof(p));
   p.M = a->M;

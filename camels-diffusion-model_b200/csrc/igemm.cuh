@@ -827,6 +827,168 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
 }
 
 // --------------------------------------------------------------------------
+// gemm_bres: same contraction as gemm_kernel for SMALL N (the 2x2 transposed convolutions: N = 512,
+// K = 256 / 512).  The weight rows a CTA needs (n_res 128-row tiles, all of K: 128 KB) are loaded once and
+// stay resident in shared memory; the CTA then streams A row tiles through a 4-stage ring and issues
+// n_res accumulations per stage, so L2->smem traffic per output tile drops from 2*K*256 B to K*256/n_res B
+// and the kernel sits at the DRAM roofline of its output instead of the L2 refill rate.
+// CTA b serves weight group b % n_groups and the row tiles b / n_groups, + gridDim.x / n_groups, ...
+// --------------------------------------------------------------------------
+struct GemmBresKParams {
+  int M, N;
+  int chunks0, chunks;
+  int m_tiles, n_res, n_groups;
+  const float* shift;
+  int shift_mod;
+  int out_mode, H, W, h_shift, w_shift;
+  bf16* out;
+};
+constexpr int kBresStages = 4;
+constexpr int gemm_bres_smem_bytes() { return 131072 + kBresStages * 16384 + 256 + 1024; }
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                 const __grid_constant__ CUtensorMap mapB, const GemmBresKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smemW = smem;            // [n_res][chunks][128 rows][64 ch]
+  uint8_t* smemA = smem + 131072;   // ring of [128 rows][64 ch]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemA + kBresStages * 16384);
+  uint64_t* full = bars;
+  uint64_t* empty = full + kBresStages;
+  uint64_t* t_full = empty + kBresStages;
+  uint64_t* t_empty = t_full + 2;
+  uint64_t* w_ready = t_empty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_ready + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kBresStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 4);
+    }
+    mbar_init(w_ready, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int group = blockIdx.x % p.n_groups, first = blockIdx.x / p.n_groups, stride = gridDim.x / p.n_groups;
+  const int n_tile0 = group * p.n_res;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0);
+    tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapB);
+    mbar_arrive_expect_tx(w_ready, (uint32_t)(p.n_res * p.chunks * 16384));
+    for (int nt = 0; nt < p.n_res; ++nt)
+      for (int ch = 0; ch < p.chunks; ++ch)
+        tma_load_2d(smemW + (nt * p.chunks + ch) * 16384, &mapB, w_ready, ch * 64, (n_tile0 + nt) * 128);
+    int st = 0;
+    uint32_t ph = 0;
+    for (int mt = first; mt < p.m_tiles; mt += stride)
+      for (int ch = 0; ch < p.chunks; ++ch) {
+        const CUtensorMap* m = ch < p.chunks0 ? &mapA0 : &mapA1;
+        const int c_off = (ch < p.chunks0 ? ch : ch - p.chunks0) * 64;
+        mbar_wait(&empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&full[st], 16384);
+        tma_load_2d(smemA + st * 16384, m, &full[st], c_off, mt * 128);
+        if (++st == kBresStages) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+    mbar_wait(w_ready, 0);
+    tc_fence_after();
+    const uint32_t w_base = smem_u32(smemW);
+    int st = 0, it = 0;
+    uint32_t ph = 0;
+    for (int mt = first; mt < p.m_tiles; mt += stride, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int ch = 0; ch < p.chunks; ++ch) {
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smemA + st * 16384);
+        for (int nt = 0; nt < p.n_res; ++nt) {
+          const uint32_t b_base = w_base + (uint32_t)((nt * p.chunks + ch) * 16384);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + (uint32_t)((buf * p.n_res + nt) * 128), umma_desc_sw128(a_base + k * 32, 1024),
+                      umma_desc_sw128(b_base + k * 32, 1024), idesc, (ch == 0 && k == 0) ? 0u : 1u);
+        }
+        umma_commit(&empty[st]);
+        if (++st == kBresStages) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+      umma_commit(&t_full[buf]);
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    int it = 0;
+    for (int mt = first; mt < p.m_tiles; mt += stride, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&t_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const int m = mt * 128 + q * 32 + lane;
+      for (int nt = 0; nt < p.n_res; ++nt) {
+        const int n_tile = n_tile0 + nt;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.n_res + nt) * 128);
+        const float* shift = p.shift + (n_tile * 128) % p.shift_mod;
+        bf16* g = nullptr;
+        if (m < p.M) {
+          if (p.out_mode == 0) {
+            g = p.out + (size_t)m * p.N + n_tile * 128;
+          } else {
+            const int w = m & (p.W - 1), h = (m >> p.w_shift) & (p.H - 1), img = m >> (p.w_shift + p.h_shift);
+            const int kh = n_tile >> 1, kw = n_tile & 1;
+            g = p.out + (((size_t)img * 2 * p.H + 2 * h + kh) * (2 * p.W) + 2 * w + kw) * 128;
+          }
+        }
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t v[32];
+          tmem_ld_x32(taddr + cc * 32, v);
+          tmem_wait_ld();
+          if (g) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift + cc * 32 + j * 8));
+              const float4 s1 = __ldg(reinterpret_cast<const float4*>(shift + cc * 32 + j * 8 + 4));
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(v[j * 8 + 0]) + s0.x, __uint_as_float(v[j * 8 + 1]) + s0.y);
+              o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]) + s0.z, __uint_as_float(v[j * 8 + 3]) + s0.w);
+              o.z = pack_bf16x2(__uint_as_float(v[j * 8 + 4]) + s1.x, __uint_as_float(v[j * 8 + 5]) + s1.y);
+              o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]) + s1.z, __uint_as_float(v[j * 8 + 7]) + s1.w);
+              reinterpret_cast<uint4*>(g)[cc * 4 + j] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// --------------------------------------------------------------------------
 // gemm_tn: C[m][n] (+)= sum_k A[k][m] * B[k][n]  — both operands "MN-major": the reduction
 // index k is the ROW (a pixel / a sample), the output indices are the contiguous channels.
 // This is every weight gradient of the network (conv3x3 wgrad per tap with a pixel-shifted B,

@@ -146,6 +146,29 @@ def test_gemm_pixel_shuffle_is_conv_transpose(L):
     assert rel_l2(out.float(), ref) < BF16_TOL
 
 
+@pytest.mark.parametrize("n,H,c0,c1", [(8, 32, 128, 128), (40, 16, 256, 256), (9, 32, 256, 0)])
+def test_gemm_resident_weights_path(L, n, H, c0, c1):
+    """M >= 8192 rows and N = 512 take gemm_bres_kernel (weight tiles resident in shared memory)."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a = torch.randn(n, H, H, c0 + c1, device="cuda", generator=g).to(torch.bfloat16)
+    wt = (torch.randn(c0 + c1, 128, 2, 2, device="cuda", generator=g) / 20.0).to(torch.bfloat16)
+    bias = torch.randn(128, device="cuda", generator=g)
+    bw = wt.permute(2, 3, 1, 0).reshape(512, c0 + c1).contiguous()
+    out = torch.full((n, 2 * H, 2 * H, 128), float("nan"), device="cuda").to(torch.bfloat16)
+    L.gemm(a[..., :c0].reshape(-1, c0).contiguous(), bw, bias, out,
+           a1=a[..., c0:].reshape(-1, c1).contiguous() if c1 else None, out_mode=1, H=H, W=H, shift_mod=128)
+    ref = F.conv_transpose2d(a.float().permute(0, 3, 1, 2), wt.float(), bias, stride=2).permute(0, 2, 3, 1)
+    assert rel_l2(out.float(), ref) < BF16_TOL
+    # plain row-major output, ragged M, N = 256
+    M = 128 * 64 + 37
+    a2 = torch.randn(M, 512, device="cuda", generator=g).to(torch.bfloat16)
+    b2 = (torch.randn(256, 512, device="cuda", generator=g) / 22.0).to(torch.bfloat16)
+    sh = torch.randn(256, device="cuda", generator=g)
+    o2 = torch.full((M, 256), float("nan"), device="cuda").to(torch.bfloat16)
+    L.gemm(a2, b2, sh, o2)
+    assert rel_l2(o2.float(), a2.float() @ b2.float().t() + sh) < BF16_TOL
+
+
 def test_conv_in(L):
     g = torch.Generator(device="cuda").manual_seed(2)
     x = torch.randn(5, 64, 64, device="cuda", generator=g)
