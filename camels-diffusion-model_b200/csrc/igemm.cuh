@@ -844,7 +844,7 @@ struct GemmBresKParams {
   bf16* out;
 };
 constexpr int kBresStages = 4;
-constexpr int gemm_bres_smem_bytes() { return 131072 + kBresStages * 16384 + 256 + 1024; }
+constexpr int gemm_bres_smem_bytes() { return 131072 + kBresStages * 16384 + 256 + 1024 + 1024; }
 
 __global__ void __launch_bounds__(kConvThreads, 1)
 gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -860,7 +860,10 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint64_t* t_empty = t_full + 2;
   uint64_t* w_ready = t_empty + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_ready + 1);
+  float* s_shift = reinterpret_cast<float*>(tmem_ptr + 2);  // [n_res][128]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < p.n_res * 128; i += blockDim.x)
+    s_shift[i] = p.shift[(((blockIdx.x % p.n_groups) * p.n_res) * 128 + i) % p.shift_mod];
   if (threadIdx.x == 0) {
     for (int i = 0; i < kBresStages; ++i) {
       mbar_init(&full[i], 1);
@@ -947,7 +950,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       for (int nt = 0; nt < p.n_res; ++nt) {
         const int n_tile = n_tile0 + nt;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.n_res + nt) * 128);
-        const float* shift = p.shift + (n_tile * 128) % p.shift_mod;
+        const float* shift = s_shift + nt * 128;  // shared memory: broadcast reads, no global-load latency
         bf16* g = nullptr;
         if (m < p.M) {
           if (p.out_mode == 0) {
@@ -966,8 +969,8 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           if (g) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift + cc * 32 + j * 8));
-              const float4 s1 = __ldg(reinterpret_cast<const float4*>(shift + cc * 32 + j * 8 + 4));
+              const float4 s0 = *reinterpret_cast<const float4*>(shift + cc * 32 + j * 8);
+              const float4 s1 = *reinterpret_cast<const float4*>(shift + cc * 32 + j * 8 + 4);
               uint4 o;
               o.x = pack_bf16x2(__uint_as_float(v[j * 8 + 0]) + s0.x, __uint_as_float(v[j * 8 + 1]) + s0.y);
               o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]) + s0.z, __uint_as_float(v[j * 8 + 3]) + s0.w);
