@@ -279,7 +279,7 @@ def run_b200(args):
     conv_ms = sum(conv64) / max(len(conv64), 1)
     achieved = CONV64_FLOP_PER_IMAGE * n_img / (conv_ms * 1e-3) / 1e12
     conv_all_ms = sum(v for d, v in bd if d.startswith("conv3x3") or d.startswith("gemm"))
-    roofline = {"bound": "tensor", "kernel": "conv3x3_kernel<SHIFT18> 128->128 @64x64", "achieved": achieved,
+    roofline = {"bound": "tensor", "kernel": "conv3x3_sw_kernel (M128 N256 K16) 128->128 @64x64", "achieved": achieved,
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
                 "frac_of_burst_peak": achieved / pk["tf_burst"], "peak_source": pk["src"] + ", sustained bf16",
                 "traffic": None, "launch_ms": conv_ms, "launches_per_step": len(conv64),
