@@ -286,3 +286,34 @@ def test_drivers_grid_guidance_sensitivity(models):
     assert set(sweep) == {0.0, 2.0} and sweep[2.0][0].shape == (3, 1, 64, 64)
     xs, cs, _ = DR.parameter_sensitivity(ddpm, base, batched=True)
     assert xs.shape == (NCF * 5, 1, 64, 64) and cs.shape == (NCF * 5, NCF)
+
+
+@pytest.mark.parametrize("B", [1, 3, 28])
+def test_ragged_batch_sizes(models, B):
+    """The reference's DataLoader has no drop_last (13500 % 32 = 28) and the sensitivity sweeps run batch 1."""
+    m = models["cal"]
+    sd = cal_sd()
+    g = torch.Generator().manual_seed(B)
+    x, c = torch.randn(B, 1, 64, 64, generator=g), torch.rand(B, NCF, generator=g)
+    t = torch.rand(B, generator=g)
+    sc = torch.rand(256, generator=g) * 2 - 1
+    eps = m(x.cuda(), t.cuda(), c.cuda(), shortcut=sc)
+    nref = min(B, 3)  # the CPU oracle on a few images is enough: images are independent in eval mode
+    with torch.no_grad():
+        ref = O.unet_forward(sd, x[:nref], t[:nref], c[:nref], split_shortcut(sc), n_cfeat=NCF)
+    assert eps.shape == (B, 1, 64, 64) and torch.isfinite(eps).all()
+    assert rel_l2(eps[:nref], ref) < EPS_TOL_CAL
+
+
+def test_empty_and_bad_inputs_raise(models):
+    import camels_diffusion_model_b200 as cdm
+    m = models["raw"]
+    with pytest.raises(cdm.CdmError):
+        m(torch.zeros(2, 1, 64, 64).cuda(), torch.rand(3).cuda(), torch.zeros(2, NCF).cuda())  # t: numel 1 or B
+    with pytest.raises((cdm.CdmError, RuntimeError)):
+        m(torch.zeros(0, 1, 64, 64).cuda(), torch.rand(1).cuda())
+    cpu_model = cdm.ContextUnet(1, 128, NCF, 64).eval()
+    with pytest.raises(cdm.CdmError):
+        cpu_model(torch.zeros(1, 1, 64, 64), torch.tensor([0.5]))
+    with pytest.raises(cdm.CdmError):
+        cdm.ContextUnet(1, 64, NCF, 64).cuda().eval()(torch.zeros(1, 1, 64, 64).cuda(), torch.tensor([0.5]).cuda())
