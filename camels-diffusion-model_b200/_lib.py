@@ -403,6 +403,6 @@ def mse_grad(pred, target, inv_count, dpred, partial, loss_sum):
                              VP(rawptr(partial)), partial.numel(), VP(rawptr(loss_sum)), stream_ptr()), "cdm_mse_grad")
 
 
-def adam_step(table, n_tensors, max_numel, lr, beta1, beta2, eps, step):
+def adam_step(table, n_tensors, max_numel, lr, beta1, beta2, eps, step, lr_dev=None, step_dev=None):
     check(lib().cdm_adam_step(VP(rawptr(table)), n_tensors, LL(max_numel), F(lr), F(beta1), F(beta2), F(eps), step,
-                              stream_ptr()), "cdm_adam_step")
+                              VP(rawptr(lr_dev)), VP(rawptr(step_dev)), stream_ptr()), "cdm_adam_step")

@@ -670,8 +670,16 @@ struct AdamTensor {
   long long n;
 };
 __global__ void __launch_bounds__(256) adam_kernel(const AdamTensor* __restrict__ tab, int n_tensors, float lr,
-                                                   float beta1, float beta2, float eps, float bc1, float bc2) {
+                                                   float beta1, float beta2, float eps, float bc1, float bc2,
+                                                   const float* __restrict__ lr_dev,
+                                                   const int* __restrict__ step_dev) {
   // grid.y = tensor, grid.x strides over its elements
+  if (lr_dev) lr = *lr_dev;  // device-resident hyper-parameters: the launch can be replayed from a CUDA graph
+  if (step_dev) {
+    const float st = (float)*step_dev;
+    bc1 = 1.f - powf(beta1, st);
+    bc2 = 1.f - powf(beta2, st);
+  }
   const AdamTensor t = tab[blockIdx.y];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < t.n; i += (long long)gridDim.x * blockDim.x) {
     const float g = t.g[i];
@@ -887,16 +895,16 @@ extern "C" int cdm_mse_grad(const float* pred, const float* target, long long n,
   return CDM_OK;
 }
 extern "C" int cdm_adam_step(const void* table, int n_tensors, long long max_numel, float lr, float beta1, float beta2,
-                             float eps, int step, void* stream) {
-  CDM_CHECK_ARG(table && n_tensors > 0 && max_numel > 0 && step >= 1);
+                             float eps, int step, const float* lr_dev, const int* step_dev, void* stream) {
+  CDM_CHECK_ARG(table && n_tensors > 0 && max_numel > 0 && (step >= 1 || step_dev));
   int rc = check_device();
   if (rc) return rc;
-  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  const float bc1 = 1.f - powf(beta1, (float)(step < 1 ? 1 : step)), bc2 = 1.f - powf(beta2, (float)(step < 1 ? 1 : step));
   int gx = (int)((max_numel + 256 * 8 - 1) / (256 * 8));
   if (gx > 512) gx = 512;
   if (gx < 1) gx = 1;
   adam_kernel<<<dim3(gx, n_tensors), 256, 0, ST(stream)>>>((const AdamTensor*)table, n_tensors, lr, beta1, beta2, eps,
-                                                          bc1, bc2);
+                                                          bc1, bc2, lr_dev, step_dev);
   CDM_CHECK_LAUNCH();
   return CDM_OK;
 }

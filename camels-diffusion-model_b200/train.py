@@ -441,3 +441,96 @@ def training_step(model, optim, x, param, timesteps, ab_t, *, noise=None, t=None
     pred.backward(dpred)
     optim.step()
     return loss_sum[0] / pred.numel()
+
+
+class GraphedTrainStep:
+    """The whole training step (in-kernel noise + perturb_input, train-mode forward, MSE + gradient, backward, cross-rank
+    reductions, Adam) captured ONCE as a CUDA graph and replayed: ~400 kernel launches become one graph launch, which is
+    what bounds the step at 32 images per GPU (BASELINE config 3).  Per step the host only copies the batch, the
+    timesteps `t` and the fresh shortcut draw (both from torch's CPU generator, like the reference) into static buffers.
+    Learning rate and Adam's step count live on the device so the captured launch stays valid across epochs."""
+
+    def __init__(self, model, batch, timesteps, ab_t, lr, betas=(0.9, 0.999), eps=1e-8, seed=0, warmup=2,
+                 use_graph=True):
+        dev = model._check_supported()
+        self.model, self.T, self.dev, self.B = model, timesteps, dev, batch
+        h, ncf = model.h, model.n_cfeat
+        self.x = torch.zeros(batch, 1, h, h, device=dev)
+        self.param = torch.zeros(batch, ncf, device=dev)
+        self.t = torch.ones(batch, device=dev, dtype=torch.int64)
+        self.sc = torch.zeros(2 * model.n_feat, device=dev)
+        self.ca, self.cb = ab_t.to(dev).sqrt().contiguous(), (1 - ab_t.to(dev)).contiguous()
+        self.noise, self.x_pert = torch.empty_like(self.x), torch.empty_like(self.x)
+        self.dpred = torch.empty_like(self.x)
+        self.partial, self.loss_sum = torch.empty(148 * 8, device=dev), torch.zeros(1, device=dev)
+        self.lr = torch.full((1,), float(lr), device=dev)
+        self.count = torch.zeros(1, device=dev, dtype=torch.int32)  # Adam step == Philox stream offset
+        self.betas, self.eps, self.seed = betas, eps, seed
+        self.params = [p for p in model.parameters()]
+        for p in self.params:
+            p.grad = torch.zeros_like(p)
+        self.m = [torch.zeros_like(p) for p in self.params]
+        self.v = [torch.zeros_like(p) for p in self.params]
+        rows = [[p.data_ptr(), p.grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()]
+                for p, m, v in zip(self.params, self.m, self.v)]
+        self.table = torch.tensor(rows, dtype=torch.int64).to(dev)
+        self.max_numel = max(p.numel() for p in self.params)
+        self.graph = None
+        if not use_graph:
+            return
+        # warm-up (kernel attributes, allocator) with lr = 0 so parameters do not move; BatchNorm buffers and the
+        # optimizer state it touches are restored afterwards, so the first real step starts from a clean state
+        saved = [b.detach().clone() for b in model.buffers()]
+        self.lr.zero_()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step()
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for b, sv in zip(model.buffers(), saved):
+                b.copy_(sv)
+        self.reset_optimizer()
+        self.lr.fill_(float(lr))
+
+    def _step(self):
+        m = self.model
+        L.step_advance(self.count, 1)
+        L.perturb(self.x, self.x_pert, self.ca, self.cb, t_idx=self.t, step_ptr=self.count, seed=self.seed,
+                  noise_out=self.noise)
+        ctx = _Ctx()
+        pred = _UnetFn.forward(ctx, m, self.x_pert, self.t / self.T, self.param, self.sc, *self.params)
+        L.mse_grad(pred, self.noise, 1.0 / pred.numel(), self.dpred, self.partial, self.loss_sum)
+        grads = _UnetFn.backward(ctx, self.dpred)[5:]
+        for p, g in zip(self.params, grads):
+            p.grad.copy_(g)
+        b1, b2 = self.betas
+        L.adam_step(self.table, len(self.params), self.max_numel, 0.0, b1, b2, self.eps, 0, lr_dev=self.lr,
+                    step_dev=self.count)
+
+    def set_lr(self, lr):
+        self.lr.fill_(float(lr))
+
+    def reset_optimizer(self):
+        for t in self.m + self.v:
+            t.zero_()
+        self.count.zero_()
+
+    def __call__(self, x, param, t=None, shortcut=None):
+        """One optimisation step; returns the mean-squared-error loss as a 0-d device tensor (no host sync)."""
+        m = self.model
+        self.x.copy_(x.reshape(self.x.shape), non_blocking=True)
+        self.param.copy_(param, non_blocking=True)
+        self.t.copy_(torch.randint(1, self.T + 1, (self.B,)) if t is None else t, non_blocking=True)
+        self.sc.copy_(m.draw_shortcut() if shortcut is None else shortcut, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step()
+        return self.loss_sum[0] / self.x.numel()

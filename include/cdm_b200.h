@@ -320,9 +320,10 @@ int cdm_embed_bwd(const cdm_embed_bwd_args* a, void* stream);
 /* F.mse_loss(pred, target) summed (loss_sum[0] = sum of squares) and d pred = 2 (pred-target) * inv_count. */
 int cdm_mse_grad(const float* pred, const float* target, long long n, float inv_count, float* dpred, float* partial,
                  int partial_blocks, float* loss_sum, void* stream);
-/* torch.optim.Adam defaults over a device table of {p, g, m, v, n} (5 x 8 bytes per tensor). */
+/* torch.optim.Adam defaults over a device table of {p, g, m, v, n} (5 x 8 bytes per tensor).  lr_dev / step_dev
+ * (device scalars, optional) override lr / step so that the launch can be replayed from a CUDA graph. */
 int cdm_adam_step(const void* table, int n_tensors, long long max_numel, float lr, float beta1, float beta2, float eps,
-                  int step, void* stream);
+                  int step, const float* lr_dev, const int* step_dev, void* stream);
 
 /* Weight-gradient GEMM  C[m][tap*tap_stride + n] += sum_px A[px][m_off+m] * B[px + (kh-1,kw-1)][n_off+n]
  * with both operands read straight from NHWC bf16 activations (the reduction index is the pixel, the

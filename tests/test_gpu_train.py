@@ -344,3 +344,32 @@ def test_training_step_api_reduces_loss():
     losses = [float(training_step(model, optim, x, param, 1500, ab_t, noise=noise, t=t, shortcut=sc)) for _ in range(6)]
     print("losses", [round(v, 4) for v in losses])
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_graphed_training_step_equals_eager():
+    """The CUDA-graph-captured step replays exactly the eager kernel sequence: same losses, same parameters
+    (up to the fp32 atomics order of the split-K weight gradients) after three optimisation steps."""
+    import camels_diffusion_model_b200 as cdm
+    from camels_diffusion_model_b200.train import GraphedTrainStep
+    b_t, a_t, ab_t = cdm.make_schedule(1500)
+    gen = torch.Generator().manual_seed(0)
+    B = 6
+    xs = [torch.rand(B, 1, 64, 64, generator=gen) for _ in range(3)]
+    ps = [torch.rand(B, NCF, generator=gen) for _ in range(3)]
+    ts = [torch.randint(1, 1501, (B,), generator=gen) for _ in range(3)]
+    scs = [torch.rand(256, generator=gen) * 2 - 1 for _ in range(3)]
+    results = []
+    for use_graph in (True, False):
+        torch.manual_seed(0)
+        model = cdm.ContextUnet(1, 128, NCF, 64).cuda().train()
+        step = GraphedTrainStep(model, B, 1500, ab_t, lr=1e-4, seed=7, use_graph=use_graph)
+        losses = [float(step(xs[i], ps[i], t=ts[i], shortcut=scs[i])) for i in range(3)]
+        results.append((losses, {k: v.detach().clone() for k, v in model.state_dict().items()}))
+    (l_g, sd_g), (l_e, sd_e) = results
+    print("graph losses", l_g, "eager losses", l_e)
+    assert all(np.isfinite(l_g)) and max(abs(a - b) / b for a, b in zip(l_g, l_e)) < 1e-3
+    assert int(sd_g["init_conv.conv1.1.num_batches_tracked"]) == 3 == int(sd_e["init_conv.conv1.1.num_batches_tracked"])
+    for k in ("out.3.weight", "out.0.weight", "up2.model.2.conv2.1.weight", "out.1.weight"):
+        assert rel_l2(sd_g[k], sd_e[k]) < 1e-4, k
+    for k in ("out.0.weight", "init_conv.conv1.0.weight"):   # parameters did move
+        assert not torch.equal(sd_g[k].cpu(), O.init_state_dict(0, n_cfeat=NCF)[k])

@@ -71,4 +71,22 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 out["cfg3_train_step_B256_1gpu"] = {"ms_per_step": round(ms, 2), "img_per_s": round(256 / ms * 1e3, 1),
                                     "tflops_3x_forward": round(3 * 19.1785e9 * 256 / (ms * 1e-3) / 1e12, 1)}
+for B in (256, 32):
+    torch.manual_seed(0)
+    model = cdm.ContextUnet(1, 128, NCF, 64).to(dev).train()
+    gstep = TR.GraphedTrainStep(model, B, T, sched[2], lr=1e-5)
+    xb, pb = torch.rand(B, 1, 64, 64, generator=g).to(dev), torch.rand(B, NCF, generator=g).to(dev)
+    tb = torch.randint(1, T + 1, (B,), generator=g).to(dev)
+    for _ in range(3): gstep(xb, pb, t=tb, shortcut=sc)
+    torch.cuda.synchronize()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(10): loss = gstep(xb, pb, t=tb, shortcut=sc)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    out[f"cfg3_train_step_graph_B{B}_1gpu"] = {"ms_per_step": round(ms, 2), "img_per_s": round(B / ms * 1e3, 1),
+                                               "tflops_3x_forward": round(3 * 19.1785e9 * B / (ms * 1e-3) / 1e12, 1),
+                                               "loss": round(float(loss), 4)}
+    del gstep, model
+    torch.cuda.empty_cache()
 print(json.dumps(out, indent=1))
