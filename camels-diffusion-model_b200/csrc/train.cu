@@ -176,22 +176,30 @@ struct BnApplyP {
   bf16* yf;
 };
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyP p) {
-  const int groups = p.C >> 3;
+  const int groups = p.C >> 3;  // 16 or 32: divides blockDim.x, so a thread keeps the same 8 channels
   const long long total = p.P * groups;
+  const int cg = (int)(threadIdx.x % groups);
+  float sc[8], sh[8], sw[8], sb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = p.scale[cg * 8 + j];
+    sh[j] = p.shift[cg * 8 + j];
+    sw[j] = p.sc_x ? p.sc_w[cg * 8 + j] : 0.f;
+    sb[j] = p.sc_x ? p.sc_b[cg * 8 + j] : 0.f;
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % groups);
     const long long r = i / groups;
     float f[8];
     t_unpack8(ld8(p.z + r * p.C + cg * 8), f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float y = fmaf(f[j], p.scale[cg * 8 + j], p.shift[cg * 8 + j]);
+      float y = fmaf(f[j], sc[j], sh[j]);
       f[j] = p.relu ? fmaxf(y, 0.f) : y;
     }
     if (p.sc_x) {
       const float xv = p.sc_x[r];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += fmaf(p.sc_w[cg * 8 + j], xv, p.sc_b[cg * 8 + j]);
+      for (int j = 0; j < 8; ++j) f[j] += fmaf(sw[j], xv, sb[j]);
     }
     *reinterpret_cast<uint4*>(p.y + r * p.C + cg * 8) = t_pack8(f);
     if (p.fs) {
@@ -224,21 +232,31 @@ struct BnBwdP {
   bf16* dz;
 };
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdP p) {
-  const int groups = p.C >> 3;
+  const int groups = p.C >> 3;  // divides blockDim.x: a thread keeps the same 8 channels
   const long long total = p.P * groups;
   const float inv = 1.f / p.count;
+  const int cg = (int)(threadIdx.x % groups);
+  float sc[8], sh[8], mu[8], rs[8], m0[8], m1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    sc[j] = p.scale[c];
+    sh[j] = p.shift[c];
+    mu[j] = p.mean[c];
+    rs[j] = p.rstd[c];
+    m0[j] = p.sums[c] * inv;
+    m1[j] = p.sums[p.C + c] * inv;
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % groups);
     const long long r = i / groups;
     float d[8], z[8];
     t_unpack8(ld8(p.dy + r * p.lddy + cg * 8), d);
     t_unpack8(ld8(p.z + r * p.C + cg * 8), z);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = cg * 8 + j;
-      const float g = (!p.relu || fmaf(z[j], p.scale[c], p.shift[c]) > 0.f) ? d[j] : 0.f;
-      const float xh = (z[j] - p.mean[c]) * p.rstd[c];
-      d[j] = p.scale[c] * (g - p.sums[c] * inv - xh * p.sums[p.C + c] * inv);
+      const float g = (!p.relu || fmaf(z[j], sc[j], sh[j]) > 0.f) ? d[j] : 0.f;
+      const float xh = (z[j] - mu[j]) * rs[j];
+      d[j] = sc[j] * (g - m0[j] - xh * m1[j]);
     }
     *reinterpret_cast<uint4*>(p.dz + r * p.C + cg * 8) = t_pack8(d);
   }
@@ -711,6 +729,7 @@ extern "C" int cdm_chan_reduce(const cdm_chan_reduce_args* a, void* stream) {
   if (rc) return rc;
   const int rows = 256 / (a->C / 8);
   int blocks = (int)((a->P + rows * 8 - 1) / (rows * 8));
+  if (blocks > 148 * 4) blocks = 148 * 4;  // the fixed-order final pass walks the partials serially: keep them few
   if (blocks > a->workspace_blocks) blocks = a->workspace_blocks;
   if (blocks < 1) blocks = 1;
   ChanReduceP p{(const bf16*)a->a, a->lda, (const bf16*)a->z, a->ldz, a->scale, a->shift, a->mean, a->rstd,
@@ -736,7 +755,7 @@ extern "C" int cdm_bn_finalize(const float* sums, int C, float count, const floa
 }
 
 extern "C" int cdm_bn_apply(const cdm_bn_apply_args* a, void* stream) {
-  CDM_CHECK_ARG(a && a->z && a->scale && a->shift && a->y && a->P > 0 && a->C % 8 == 0);
+  CDM_CHECK_ARG(a && a->z && a->scale && a->shift && a->y && a->P > 0 && a->C % 8 == 0 && 256 % (a->C / 8) == 0);
   CDM_CHECK_ARG(!a->sc_x || (a->sc_w && a->sc_b));
   CDM_CHECK_ARG(!a->film_scale || (a->film_shift && a->yf && a->px_per_img > 0 && a->film_rows >= 1));
   int rc = check_device();
@@ -750,7 +769,7 @@ extern "C" int cdm_bn_apply(const cdm_bn_apply_args* a, void* stream) {
 
 extern "C" int cdm_bn_bwd_apply(const cdm_bn_bwd_args* a, void* stream) {
   CDM_CHECK_ARG(a && a->dy && a->z && a->scale && a->shift && a->mean && a->rstd && a->sums && a->dz);
-  CDM_CHECK_ARG(a->P > 0 && a->C % 8 == 0 && a->lddy >= a->C && a->count > 0);
+  CDM_CHECK_ARG(a->P > 0 && a->C % 8 == 0 && 256 % (a->C / 8) == 0 && a->lddy >= a->C && a->count > 0);
   int rc = check_device();
   if (rc) return rc;
   BnBwdP p{(const bf16*)a->dy, a->lddy, (const bf16*)a->z, a->P, a->C, a->relu, a->scale, a->shift, a->mean, a->rstd,
@@ -854,6 +873,7 @@ extern "C" int cdm_outer_wgrad(const cdm_outer_wgrad_args* a, void* stream) {
   const int rows = 256 / (a->C / 8);
   const long long P = (long long)a->n_img * a->H * a->W;
   int blocks = (int)((P + rows * 16 - 1) / (rows * 16));
+  if (blocks > 148 * 2) blocks = 148 * 2;
   if (blocks > a->workspace_blocks) blocks = a->workspace_blocks;
   if (blocks < 1) blocks = 1;
   OuterWgradP p{a->s, (const bf16*)a->v, a->n_img, a->H, a->W, a->C, a->flip, a->mean_rstd, a->gamma, a->beta,
