@@ -89,27 +89,44 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const ChanReduceP p) {
       rs[j] = p.rstd[cg * 8 + j];
     }
   }
-  for (long long r = (long long)blockIdx.x * rows + pr; r < p.P; r += (long long)gridDim.x * rows) {
-    float a[8];
-    t_unpack8(ld8(p.a + r * p.lda + cg * 8), a);
-    if (p.mode == 0) {
+  // 4 rows per iteration with all loads issued first (the loop is latency bound otherwise)
+  const long long stride = (long long)gridDim.x * rows;
+  for (long long r0 = (long long)blockIdx.x * rows + pr; r0 < p.P; r0 += 4 * stride) {
+    uint4 ra[4], rz[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s0[j] += a[j];
-        s1[j] = fmaf(a[j], a[j], s1[j]);
+    for (int u = 0; u < 4; ++u) {
+      const long long r = r0 + u * stride;
+      ra[u] = make_uint4(0u, 0u, 0u, 0u);
+      rz[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (r < p.P) {
+        ra[u] = ld8(p.a + r * p.lda + cg * 8);
+        if (p.mode == 1) rz[u] = ld8(p.z + r * p.ldz + cg * 8);
       }
-    } else if (p.mode == 1) {
-      float z[8];
-      t_unpack8(ld8(p.z + r * p.ldz + cg * 8), z);
+    }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float g = (!p.relu || fmaf(z[j], sc[j], sh[j]) > 0.f) ? a[j] : 0.f;
-        s0[j] += g;
-        s1[j] = fmaf(g, (z[j] - mu[j]) * rs[j], s1[j]);
+    for (int u = 0; u < 4; ++u) {
+      if (r0 + u * stride >= p.P) break;
+      float a[8];
+      t_unpack8(ra[u], a);
+      if (p.mode == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s0[j] += a[j];
+          s1[j] = fmaf(a[j], a[j], s1[j]);
+        }
+      } else if (p.mode == 1) {
+        float z[8];
+        t_unpack8(rz[u], z);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float g = (!p.relu || fmaf(z[j], sc[j], sh[j]) > 0.f) ? a[j] : 0.f;
+          s0[j] += g;
+          s1[j] = fmaf(g, (z[j] - mu[j]) * rs[j], s1[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s0[j] += a[j];
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s0[j] += a[j];
     }
   }
 #pragma unroll
@@ -128,13 +145,15 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const ChanReduceP p) {
       }
   }
 }
+// One warp per output: lane l sums partials l, l+32, ... in order, then a fixed-order shuffle tree (deterministic).
 __global__ void chan_reduce_final_kernel(const float* __restrict__ partial, int n_blocks, int C2,
                                          float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= C2) return;
   float t = 0.f;
-  for (int b = 0; b < n_blocks; ++b) t += partial[(size_t)b * C2 + i];
-  out[i] = t;
+  for (int b = lane; b < n_blocks; b += 32) t += partial[(size_t)b * C2 + i];
+  t = t_warp_sum(t);
+  if (lane == 0) out[i] = t;
 }
 
 // BatchNorm2d train-mode finalisation from (possibly all-reduced) sums over `count` elements.
@@ -736,7 +755,7 @@ extern "C" int cdm_chan_reduce(const cdm_chan_reduce_args* a, void* stream) {
                 a->relu, a->mode, a->P, a->C, a->workspace};
   chan_reduce_kernel<<<blocks, 256, 0, ST(stream)>>>(p);
   CDM_CHECK_LAUNCH();
-  chan_reduce_final_kernel<<<(2 * a->C + 127) / 128, 128, 0, ST(stream)>>>(a->workspace, blocks, 2 * a->C, a->out);
+  chan_reduce_final_kernel<<<(2 * a->C * 32 + 255) / 256, 256, 0, ST(stream)>>>(a->workspace, blocks, 2 * a->C, a->out);
   CDM_CHECK_LAUNCH();
   return CDM_OK;
 }
@@ -880,7 +899,7 @@ extern "C" int cdm_outer_wgrad(const cdm_outer_wgrad_args* a, void* stream) {
                 a->workspace};
   outer_wgrad_kernel<<<blocks, 256, 0, ST(stream)>>>(p);
   CDM_CHECK_LAUNCH();
-  chan_reduce_final_kernel<<<(9 * a->C + 127) / 128, 128, 0, ST(stream)>>>(a->workspace, blocks, 9 * a->C, a->out);
+  chan_reduce_final_kernel<<<(9 * a->C * 32 + 255) / 256, 256, 0, ST(stream)>>>(a->workspace, blocks, 9 * a->C, a->out);
   CDM_CHECK_LAUNCH();
   return CDM_OK;
 }
