@@ -191,7 +191,7 @@ extern "C" int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream) {
       attr_set = true;
     }
     const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
-    conv3x3_sw_kernel<<<grid, kConvThreads, smem, st>>>(mA0, mA1, mB, p);
+    conv3x3_sw_kernel<<<grid, kSwThreads, smem, st>>>(mA0, mA1, mB, p);
     CDM_CHECK_LAUNCH();
     return CDM_OK;
   }

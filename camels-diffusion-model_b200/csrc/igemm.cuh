@@ -413,9 +413,10 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 // Halo tile: TMA box {64 ch, 10, 34, 1}, pitch 10 (SBO 1280 B), tap (kh,kw) = start row kh*10 + kw.
 // --------------------------------------------------------------------------
 constexpr int kSwPitch = 10, kSwRows = 34, kSwABytes = kSwRows * kSwPitch * 128, kSwAStride = 44032, kSwNA = 3;
+constexpr int kSwEpiWarps = 8, kSwThreads = 128 + 32 * kSwEpiWarps;
 constexpr int conv_sw_smem_bytes() { return kSwNA * kSwAStride + kNB * kBBytes + 2 * 256 * 4 + 256 + 1024; }
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kSwThreads, 1)
 conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapB, const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -448,7 +449,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&t_full[i], 1);
-      mbar_init(&t_empty[i], 4);
+      mbar_init(&t_empty[i], kSwEpiWarps);
     }
     fence_barrier_init();
   }
@@ -541,8 +542,9 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       umma_commit(&t_full[buf]);
     }
   } else if (warp >= 4) {
-    const int q = warp - 4;
-    const int et = threadIdx.x - 128;  // 0..127 among the epilogue threads
+    // 8 epilogue warps: TMEM lane quadrant q = warp % 4 (hardware rule), column half = (warp - 4) / 4
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int et = threadIdx.x - 128;  // 0..255 among the epilogue threads
     const int co_l = q * 32 + lane;    // this thread's channel inside the 128-wide tile
     const int step = p.step_ptr ? *p.step_ptr : 0;
     const bool pool = p.flags & CDM_EPI_POOL;
@@ -576,7 +578,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         const int oimg = rep * p.n_img + img;
         float gs = 0.f, gq = 0.f;
 #pragma unroll 1
-        for (int c8 = 0; c8 < 8; ++c8) {  // 32 pixels: patch rows 4*c8 .. 4*c8+3, 8 px each
+        for (int c8 = half * 4; c8 < half * 4 + 4; ++c8) {  // 32 pixels: patch rows 4*c8 .. 4*c8+3, 8 px each
           if (p.flags & (1 << 29)) continue;  // probe: no epilogue work at all
           uint32_t v[32];
           tmem_ld_x32(taddr + c8 * 32, v);
@@ -653,14 +655,14 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             gs += __shfl_xor_sync(0xffffffffu, gs, o);
             gq += __shfl_xor_sync(0xffffffffu, gq, o);
           }
-          const int slots = (p.H >> 4) * (p.W >> 4) * 8;  // API layout; this mode fills 8 slots per patch
-          float* dst = p.gn_partial + ((size_t)oimg * slots + (size_t)s * 8) * 16;
+          const int slots = (p.H >> 4) * (p.W >> 4) * 8;  // API layout; this mode owns 8 slots per patch:
+          float* dst = p.gn_partial + ((size_t)oimg * slots + (size_t)s * 8) * 16;  // slot `half` + six zero slots
           if ((lane & 15) == 0) {
             const int g = q * 2 + (lane >> 4);
-            dst[g * 2] = gs;
-            dst[g * 2 + 1] = gq;
+            dst[half * 16 + g * 2] = gs;
+            dst[half * 16 + g * 2 + 1] = gq;
           }
-          for (int z = et; z < 7 * 16; z += 128) dst[16 + z] = 0.f;
+          for (int z = et; z < 6 * 16; z += 256) dst[32 + z] = 0.f;
         }
       }
       tc_fence_before();
