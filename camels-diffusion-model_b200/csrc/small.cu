@@ -114,104 +114,136 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
 }
 
 // ----------------------------------------------------------------- conv_out
-// GroupNorm(8, 128) + ReLU applied once per input element while staging a halo tile in
-// shared memory (bf16, 16-byte units XOR-swizzled by pixel so that a warp of consecutive
-// pixels reads conflict-free), then Conv2d(128, 1, 3, 1, 1) on CUDA cores (N = 1): one
-// thread per output pixel, 1152 fp32 FMAs each.  Tile = ROWS x 64 outputs.
-constexpr int kCoRows = 4, kCoW = 64, kCoC = 128;
-constexpr int kCoTilePx = (kCoRows + 2) * (kCoW + 2);
-constexpr int kCoSmem = kCoTilePx * kCoC * 2 + 9 * kCoC * 4 + 2 * kCoC * 4;
+// out.1-out.3: GroupNorm(8,128) + ReLU on load, then Conv2d(128, 1, 3, 1, 1).  N = 1 would waste a
+// tcgen05 tile, but the nine taps are a perfectly good N: per INPUT pixel p the kernel computes the nine
+// dot products d[p][tap] = sum_c relu(gn(x[p][c])) * w[tap][c] as one [pixels x 128] x [128 x 16] bf16
+// mma.sync GEMM (9 of 16 columns used), parks them in shared memory as nine fp32 planes, and the output is
+// the 9-point stencil out(y,x) = bias + sum_{kh,kw} d[(y+kh-1, x+kw-1)][kh*3+kw] (zero outside the image =
+// nn.Conv2d's padding, applied after GroupNorm+ReLU).  The activations go global -> registers -> tensor core:
+// every element is used once, so there is no shared-memory staging of the 1 MiB/image input.  The K
+// (channel) order of an MMA is free as long as A and B agree, so a thread loads 8 CONSECUTIVE channels
+// (one 16-byte LDG) of pixel rows g and g+8 and hands them to two k-steps: a warp-level load covers
+// 8 pixels x 64 contiguous bytes.  HBM-bound: 1 MiB in + 16 KiB out per image.
+constexpr int kCoC = 128;
 
-__global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ src, int n_img, int H, int W,
-                                                       const float* __restrict__ mean_rstd,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       const float* __restrict__ wgt, const float* __restrict__ bias,
-                                                       float* __restrict__ out) {
-  extern __shared__ __align__(16) uint8_t co_smem[];
-  uint8_t* s_tile = co_smem;
-  float* s_w = reinterpret_cast<float*>(co_smem + kCoTilePx * kCoC * 2);  // [9][128]
-  float* s_a = s_w + 9 * kCoC;                                            // [128] rstd*gamma
-  float* s_b = s_a + kCoC;                                                // [128] beta - mean*rstd*gamma
-  const uint32_t tile_u32 = smem_u32(s_tile);
-  for (int i = threadIdx.x; i < 9 * kCoC; i += blockDim.x) s_w[i] = wgt[i];
+__device__ __forceinline__ void mma_bf16_m16n8k16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                  uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// relu(a * x + b) on 8 bf16 channels, re-packed to bf16x2 (the one rounding of this layer's input).
+__device__ __forceinline__ uint4 gn_relu8(const uint4& v, const float4& a0, const float4& a1, const float4& b0,
+                                          const float4& b1) {
+  uint4 r;
+  r.x = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v.x << 16), a0.x, b0.x), 0.f),
+                    fmaxf(fmaf(__uint_as_float(v.x & 0xffff0000u), a0.y, b0.y), 0.f));
+  r.y = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v.y << 16), a0.z, b0.z), 0.f),
+                    fmaxf(fmaf(__uint_as_float(v.y & 0xffff0000u), a0.w, b0.w), 0.f));
+  r.z = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v.z << 16), a1.x, b1.x), 0.f),
+                    fmaxf(fmaf(__uint_as_float(v.z & 0xffff0000u), a1.y, b1.y), 0.f));
+  r.w = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v.w << 16), a1.z, b1.z), 0.f),
+                    fmaxf(fmaf(__uint_as_float(v.w & 0xffff0000u), a1.w, b1.w), 0.f));
+  return r;
+}
+
+// Plane stride (floats) of the d[tap] planes: (R+2) x (W+2) padded so that stride % 16 == 4, which makes the
+// accumulator stores of a warp (4 planes x 8 consecutive pixels) hit 32 different banks.
+static __host__ __device__ inline int co_plane_stride(int R, int W) {
+  int ps = (R + 2) * (W + 2);
+  while ((ps & 15) != 4) ++ps;
+  return ps;
+}
+
+template <int R>
+__global__ void __launch_bounds__(256, 2) conv_out_mma_kernel(const bf16* __restrict__ src, int n_img, int H, int W,
+                                                              const float* __restrict__ mean_rstd,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta,
+                                                              const float* __restrict__ wgt,
+                                                              const float* __restrict__ bias, float* __restrict__ out) {
+  extern __shared__ __align__(16) float co_smem[];
+  const int PW = W + 2, PS = co_plane_stride(R, W);
+  float* s_d = co_smem;          // [9][PS]: plane row 0 <-> image row ty*R-1, column 0 <-> image column -1
+  float* s_a = s_d + 9 * PS;     // [128] rstd * gamma
+  float* s_b = s_a + kCoC;       // [128] beta - mean * rstd * gamma
+  const int tiles_y = H / R;
+  const int n = blockIdx.x / tiles_y, ty = blockIdx.x % tiles_y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  if (threadIdx.x < kCoC) {
+    const int c = threadIdx.x, grp = c >> 4;
+    const float mean = __ldg(mean_rstd + ((size_t)n * 8 + grp) * 2), rstd = __ldg(mean_rstd + ((size_t)n * 8 + grp) * 2 + 1);
+    const float a = rstd * __ldg(gamma + c);
+    s_a[c] = a;
+    s_b[c] = __ldg(beta + c) - mean * a;
+  }
+  for (int i = threadIdx.x; i < 9 * (R + 2) * 2; i += blockDim.x) {  // the two x-halo columns of every plane row
+    const int plane = i / ((R + 2) * 2), rem = i - plane * (R + 2) * 2;
+    s_d[plane * PS + (rem >> 1) * PW + ((rem & 1) ? W + 1 : 0)] = 0.f;
+  }
+  // B fragments (weights), bf16, in the permuted channel order: k-step 2q+h, fragment columns {2t,2t+1} and
+  // {2t+8,2t+9} <-> channels 32q + 8t + 4h + {0,1} and + {2,3}.  n-tile 0 = taps 0..7, n-tile 1 = tap 8 (g == 0).
+  uint32_t bw0[8][2], bw1[8][2];
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const int ch = 32 * (ks >> 1) + 8 * t + 4 * (ks & 1);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wgt + g * kCoC + ch));
+    bw0[ks][0] = pack_bf16x2(w0.x, w0.y);
+    bw0[ks][1] = pack_bf16x2(w0.z, w0.w);
+    float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g == 0) w1 = __ldg(reinterpret_cast<const float4*>(wgt + 8 * kCoC + ch));
+    bw1[ks][0] = pack_bf16x2(w1.x, w1.y);
+    bw1[ks][1] = pack_bf16x2(w1.z, w1.w);
+  }
+  __syncthreads();
+  const int mtx = W >> 4, n_mt = (R + 2) * mtx;
+  const float4* sa4 = reinterpret_cast<const float4*>(s_a);
+  const float4* sb4 = reinterpret_cast<const float4*>(s_b);
+  for (int mt = warp; mt < n_mt; mt += 8) {
+    const int pr = mt / mtx, mx = mt - pr * mtx;
+    const int ih = ty * R - 1 + pr;
+    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ih >= 0 && ih < H) {  // warp-uniform; rows outside the image contribute zeros (the conv padding)
+      const bf16* p0 = src + ((((size_t)n * H + ih) * W + mx * 16 + g) * kCoC + 8 * t);
+      uint4 v0[4], v1[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v0[q] = __ldg(reinterpret_cast<const uint4*>(p0 + 32 * q));
+        v1[q] = __ldg(reinterpret_cast<const uint4*>(p0 + 8 * kCoC + 32 * q));
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 a0 = sa4[8 * q + 2 * t], a1 = sa4[8 * q + 2 * t + 1];
+        const float4 b0 = sb4[8 * q + 2 * t], b1 = sb4[8 * q + 2 * t + 1];
+        const uint4 r0 = gn_relu8(v0[q], a0, a1, b0, b1), r1 = gn_relu8(v1[q], a0, a1, b0, b1);
+        mma_bf16_m16n8k16(acc0, r0.x, r1.x, r0.y, r1.y, bw0[2 * q][0], bw0[2 * q][1]);
+        mma_bf16_m16n8k16(acc1, r0.x, r1.x, r0.y, r1.y, bw1[2 * q][0], bw1[2 * q][1]);
+        mma_bf16_m16n8k16(acc0, r0.z, r1.z, r0.w, r1.w, bw0[2 * q + 1][0], bw0[2 * q + 1][1]);
+        mma_bf16_m16n8k16(acc1, r0.z, r1.z, r0.w, r1.w, bw1[2 * q + 1][0], bw1[2 * q + 1][1]);
+      }
+    }
+    float* d0 = s_d + pr * PW + mx * 16 + g + 1;
+    d0[(2 * t) * PS] = acc0[0];
+    d0[(2 * t + 1) * PS] = acc0[1];
+    d0[(2 * t) * PS + 8] = acc0[2];
+    d0[(2 * t + 1) * PS + 8] = acc0[3];
+    if (t == 0) {
+      d0[8 * PS] = acc1[0];
+      d0[8 * PS + 8] = acc1[2];
+    }
+  }
+  __syncthreads();
   const float bias0 = __ldg(bias);
-  const int tiles_x = W / kCoW, tiles_y = H / kCoRows;
-  const int n_tiles = n_img * tiles_y * tiles_x;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
-    __syncthreads();  // previous tile fully consumed (also covers s_w on the first pass)
-    if (threadIdx.x < kCoC) {
-      const int c = threadIdx.x, g = c >> 4;
-      const float mean = __ldg(mean_rstd + ((size_t)n * 8 + g) * 2), rstd = __ldg(mean_rstd + ((size_t)n * 8 + g) * 2 + 1);
-      const float a = rstd * __ldg(gamma + c);
-      s_a[c] = a;
-      s_b[c] = __ldg(beta + c) - mean * a;
-    }
-    __syncthreads();
-    const int h0 = ty * kCoRows - 1, w0 = tx * kCoW - 1;
-    // stage the halo tile: 5 independent 16-byte global loads in flight per thread before any is consumed
-    constexpr int kBatch = 5;
-    for (int base = 0; base < kCoTilePx * 16; base += kBatch * 256) {
-      uint4 raw[kBatch];
-      int pxs[kBatch], uns[kBatch];
-      bool inb[kBatch];
+  for (int o = threadIdx.x; o < R * W; o += blockDim.x) {
+    const int r = o / W, x = o - r * W;
+    const float* d = s_d + r * PW + x;
+    float s[3];
 #pragma unroll
-      for (int j = 0; j < kBatch; ++j) {
-        const int u = base + j * 256 + threadIdx.x;
-        const int px = u >> 4, un = u & 15;
-        const int pr = px / (kCoW + 2), pc = px - pr * (kCoW + 2);
-        const int ih = h0 + pr, iw = w0 + pc;
-        pxs[j] = px;
-        uns[j] = un;
-        inb[j] = u < kCoTilePx * 16 && ih >= 0 && ih < H && iw >= 0 && iw < W;
-        raw[j] = make_uint4(0u, 0u, 0u, 0u);
-        if (inb[j]) raw[j] = __ldg(reinterpret_cast<const uint4*>(src + (((size_t)n * H + ih) * W + iw) * kCoC + un * 8));
-      }
-#pragma unroll
-      for (int j = 0; j < kBatch; ++j) {
-        if (base + j * 256 + (int)threadIdx.x >= kCoTilePx * 16) continue;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);  // zero padding is applied AFTER GroupNorm+ReLU, as nn.Conv2d does
-        if (inb[j]) {
-          float f[8];
-          unpack8(raw[j], f);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], s_a[uns[j] * 8 + k], s_b[uns[j] * 8 + k]), 0.f);
-          v = pack8(f);
-        }
-        st_shared_v4(tile_u32 + pxs[j] * 256 + ((uns[j] ^ (pxs[j] & 7)) << 4), v.x, v.y, v.z, v.w);
-      }
-    }
-    __syncthreads();
-    const int r = threadIdx.x >> 6, c = threadIdx.x & 63;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;  // four chains: the FMAs are not latency bound
-#pragma unroll 1
-    for (int un = 0; un < 16; ++un) {
-      float wr[9][8];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const float4 w0v = *reinterpret_cast<const float4*>(s_w + t * kCoC + un * 8);
-        const float4 w1v = *reinterpret_cast<const float4*>(s_w + t * kCoC + un * 8 + 4);
-        wr[t][0] = w0v.x; wr[t][1] = w0v.y; wr[t][2] = w0v.z; wr[t][3] = w0v.w;
-        wr[t][4] = w1v.x; wr[t][5] = w1v.y; wr[t][6] = w1v.z; wr[t][7] = w1v.w;
-      }
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int px = (r + kh) * (kCoW + 2) + c + kw;
-          const uint4 v = ld_shared_v4(tile_u32 + px * 256 + ((un ^ (px & 7)) << 4));
-          const int t = kh * 3 + kw;
-          acc0 = fmaf(__uint_as_float(v.x << 16), wr[t][0], acc0);
-          acc1 = fmaf(__uint_as_float(v.x & 0xffff0000u), wr[t][1], acc1);
-          acc2 = fmaf(__uint_as_float(v.y << 16), wr[t][2], acc2);
-          acc3 = fmaf(__uint_as_float(v.y & 0xffff0000u), wr[t][3], acc3);
-          acc0 = fmaf(__uint_as_float(v.z << 16), wr[t][4], acc0);
-          acc1 = fmaf(__uint_as_float(v.z & 0xffff0000u), wr[t][5], acc1);
-          acc2 = fmaf(__uint_as_float(v.w << 16), wr[t][6], acc2);
-          acc3 = fmaf(__uint_as_float(v.w & 0xffff0000u), wr[t][7], acc3);
-        }
-    }
-    out[((size_t)n * H + ty * kCoRows + r) * W + tx * kCoW + c] = ((acc0 + acc1) + (acc2 + acc3)) + bias0;
+    for (int kh = 0; kh < 3; ++kh)
+      s[kh] = (d[(kh * 3) * PS + kh * PW] + d[(kh * 3 + 1) * PS + kh * PW + 1]) + d[(kh * 3 + 2) * PS + kh * PW + 2];
+    out[((size_t)n * H + ty * R + r) * W + x] = ((s[0] + s[1]) + s[2]) + bias0;
   }
 }
 
@@ -493,21 +525,28 @@ extern "C" int cdm_conv_in(const cdm_conv_in_args* a, void* stream) {
   return CDM_OK;
 }
 
-extern "C" int cdm_conv_out(const cdm_conv_out_args* a, void* stream) {
-  CDM_CHECK_ARG(a && a->src && a->mean_rstd && a->gamma && a->beta && a->weight && a->bias && a->out);
-  CDM_CHECK_ARG(a->n_img > 0 && a->H > 0 && a->W > 0 && a->W % kCoW == 0 && a->H % kCoRows == 0 && a->C == kCoC);
-  int rc = check_device();
-  if (rc) return rc;
+template <int R>
+static int launch_conv_out(const cdm_conv_out_args* a, cudaStream_t stream) {
   static bool attr_set = false;
+  const int smem = (9 * co_plane_stride(R, a->W) + 2 * kCoC) * (int)sizeof(float);
   if (!attr_set) {
-    CDM_CHECK_CUDA(cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCoSmem));
+    CDM_CHECK_CUDA(cudaFuncSetAttribute(conv_out_mma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set = true;
   }
-  const int tiles = a->n_img * (a->H / kCoRows) * (a->W / kCoW);
-  conv_out_kernel<<<tiles < 148 * 2 ? tiles : 148 * 2, 256, kCoSmem, (cudaStream_t)stream>>>(
+  conv_out_mma_kernel<R><<<a->n_img * (a->H / R), 256, smem, stream>>>(
       (const bf16*)a->src, a->n_img, a->H, a->W, a->mean_rstd, a->gamma, a->beta, a->weight, a->bias, a->out);
   CDM_CHECK_LAUNCH();
   return CDM_OK;
+}
+
+extern "C" int cdm_conv_out(const cdm_conv_out_args* a, void* stream) {
+  CDM_CHECK_ARG(a && a->src && a->mean_rstd && a->gamma && a->beta && a->weight && a->bias && a->out);
+  CDM_CHECK_ARG(a->n_img > 0 && a->H > 0 && a->W > 0 && a->W % 16 == 0 && a->W <= 64 && a->H % 8 == 0 && a->C == kCoC);
+  int rc = check_device();
+  if (rc) return rc;
+  // 32-row tiles (6 % halo re-read) once they fill the machine twice over, 8-row tiles for small batches
+  if (a->H % 32 == 0 && a->n_img * (a->H / 32) >= 2 * 148) return launch_conv_out<32>(a, (cudaStream_t)stream);
+  return launch_conv_out<8>(a, (cudaStream_t)stream);
 }
 
 extern "C" int cdm_embed_fc(const float* in, int rows, int din, const float* w1, const float* b1, const float* w2,
