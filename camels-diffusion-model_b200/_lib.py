@@ -106,7 +106,7 @@ EXPORTS = [
     "cdm_gemm_tn", "cdm_chan_reduce", "cdm_bn_finalize", "cdm_bn_apply", "cdm_bn_bwd_apply", "cdm_maxpool2_fwd",
     "cdm_maxpool2_bwd", "cdm_add_bf16", "cdm_space_to_depth", "cdm_film_bwd", "cdm_gn_bwd", "cdm_rows_sum",
     "cdm_avgpool_gelu_train", "cdm_avgpool_gelu_bwd", "cdm_outer_wgrad", "cdm_embed_bwd", "cdm_mse_grad",
-    "cdm_adam_step",
+    "cdm_adam_step", "cdm_power_spectrum", "cdm_pixel_histogram",
 ]
 
 
@@ -406,3 +406,21 @@ def mse_grad(pred, target, inv_count, dpred, partial, loss_sum):
 def adam_step(table, n_tensors, max_numel, lr, beta1, beta2, eps, step, lr_dev=None, step_dev=None):
     check(lib().cdm_adam_step(VP(rawptr(table)), n_tensors, LL(max_numel), F(lr), F(beta1), F(beta2), F(eps), step,
                               VP(rawptr(lr_dev)), VP(rawptr(step_dev)), stream_ptr()), "cdm_adam_step")
+
+
+# --------------------------------------------------------------------------- map statistics
+def power_spectrum(maps, bin_start, bin_items, scale, pk):
+    """maps fp32 [n,N,N]; bin_start int32 [n_bins+1]; bin_items int32 [N*N]; pk fp64 [n,n_bins]."""
+    n, N, _ = maps.shape
+    check(lib().cdm_power_spectrum(C.c_void_p(ptr(maps)), n, N, C.c_void_p(ptr(bin_start)), C.c_void_p(ptr(bin_items)),
+                                   pk.shape[1], C.c_double(scale), C.c_void_p(ptr(pk)), stream_ptr()),
+          "cdm_power_spectrum")
+    return pk
+
+
+def pixel_histogram(maps, edges, counts):
+    """maps fp32 [n,P]; edges fp64 [n_bins+1]; counts int32 [n,n_bins]."""
+    n, P = maps.shape
+    check(lib().cdm_pixel_histogram(C.c_void_p(ptr(maps)), n, P, C.c_void_p(ptr(edges)), counts.shape[1],
+                                    C.c_void_p(ptr(counts)), stream_ptr()), "cdm_pixel_histogram")
+    return counts

@@ -48,66 +48,131 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 
 // ------------------------------------------------------------------ conv_in
-// Conv2d(1, C, 3, 1, 1) + folded BatchNorm + ReLU.  K = 9: CUDA cores, bound by the
-// bf16 NHWC write (256 B / pixel).  A thread owns 8 output channels (its 72 weights
-// live in registers) and walks pixels; 16 threads cover one pixel's 128 channels,
-// so every store instruction of a warp writes 512 contiguous bytes.
-__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, int n_img, int H, int W, int C,
-                                                      const float* __restrict__ wgt, const float* __restrict__ scale,
-                                                      const float* __restrict__ shift, int relu,
-                                                      bf16* __restrict__ out) {
-  const int groups = C >> 3;              // threads per pixel
-  const int ppb = blockDim.x / groups;    // pixels per block iteration
-  const int cg = threadIdx.x % groups, psub = threadIdx.x / groups;
-  float wr[9][8], sc[8], sh[8];
+// Conv2d(1, C, 3, 1, 1) + per-channel scale/shift (folded BatchNorm) + ReLU, fp32 [n][H][W] -> bf16 NHWC.
+// 1152 FMAs per pixel on the CUDA cores made this the slowest memory-bound kernel of the step; it is a
+// [pixels x 9] x [9 x C] GEMM, so it runs on mma.sync with the fp32 operands split into bf16 hi + lo parts:
+// w' = scale*w = wh + wl, x = xh + xl, K = 29 of 32: xh*wh (9) + xl*wh (9) + xh*wl (9) + 1*shift_hi + 1*shift_lo,
+// fp32 accumulate.  The dropped xl*wl term is 2^-16 of a product, i.e. the result keeps fp32-level accuracy
+// before the one bf16 rounding of the output, and the whole epilogue is "round, max(.,0), store".
+// A CTA stages a zero-bordered (4+2)-row halo of the image in shared memory (row pitch = 10 mod 32: the
+// three tap rows land in disjoint banks); one warp = 16 consecutive pixels x 128 channels = 32 MMAs.  The N
+// (channel) order of the MMA is permuted so that a thread owns 8 CONSECUTIVE channels per 16-byte store and
+// a warp-level store covers 8 pixels x 64 contiguous bytes.  Bound by the 256 B/pixel write.
+__device__ __forceinline__ void mma_bf16_m16n8k16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                  uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float bf16_hi(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+constexpr int kCiRows = 4;     // output rows per CTA tile
+constexpr int kCiMaxW = 64;
+constexpr int kCiPitch = kCiMaxW + 10;
+
+template <bool RELU>
+__global__ void __launch_bounds__(256, 2) conv_in_mma_kernel(const float* __restrict__ x, int n_img, int H, int W, int C,
+                                                             const float* __restrict__ wgt,
+                                                             const float* __restrict__ scale,
+                                                             const float* __restrict__ shift,
+                                                             bf16* __restrict__ out) {
+  __shared__ float s_x[2][(kCiRows + 2) * kCiPitch];  // column 0 <-> image column -1
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int slice = blockIdx.y;  // 128-channel slice of the output
+  for (int i = threadIdx.x; i < 2 * (kCiRows + 2) * kCiPitch; i += blockDim.x) (&s_x[0][0])[i] = 0.f;
+  // this thread's 8 A-fragment slots: slot i <-> k = 16*(i>>2) + 8*((i>>1)&1) + 2t + (i&1);
+  // k in [0,9): xh, [9,18): xl, [18,27): xh (times wl), 27/28: the constant 1 (times shift hi / lo), 29..31: 0
+  int aoff[8], akind[8];  // shared-memory offset of the tap relative to the pixel; 0 = hi, 1 = lo, 2 = one, 3 = zero
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) wr[t][j] = __ldg(wgt + t * C + cg * 8 + j);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = __ldg(scale + cg * 8 + j);
-    sh[j] = __ldg(shift + cg * 8 + j);
+  for (int i = 0; i < 8; ++i) {
+    const int k = 16 * (i >> 2) + 8 * ((i >> 1) & 1) + 2 * t + (i & 1);
+    const int tap = k % 9;
+    aoff[i] = k < 27 ? (tap / 3) * kCiPitch + tap % 3 : 0;  // halo row 0 <-> image row y-1, column 0 <-> x-1
+    akind[i] = k < 27 ? (k / 9 == 1 ? 1 : 0) : (k < 29 ? 2 : 3);
   }
-  const int n_rows = n_img * H;
-  for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
-    const int h = row % H;
-    const float* xr = x + (size_t)row * W;
-    bf16* orow = out + (size_t)row * W * C;
-    for (int w = psub; w < W; w += 2 * ppb) {
-      // two pixels per iteration: all 18 input loads are issued before the first FMA
-      float xin[2][9];
+  // B fragments: n-tile jj (0..15) column g <-> channel 128*slice + 32*(jj>>2) + 8*(g>>1) + 2*(jj&3) + (g&1)
+  uint32_t bw[2][16][2];
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int wq = w + q * ppb;
+  for (int jj = 0; jj < 16; ++jj) {
+    const int ch = 128 * slice + 32 * (jj >> 2) + 8 * (g >> 1) + 2 * (jj & 3) + (g & 1);
+    const float sc = __ldg(scale + ch), sh = __ldg(shift + ch);
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          const int ih = h + kh - 1;
-          const bool okh = ih >= 0 && ih < H && wq < W;
+    for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const int iw = wq + kw - 1;
-            xin[q][kh * 3 + kw] = (okh && iw >= 0 && iw < W) ? __ldg(xr + (kh - 1) * W + iw) : 0.f;
+      for (int r = 0; r < 2; ++r) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int k = 16 * ks + 8 * r + 2 * t + e;
+          v[e] = 0.f;
+          if (k < 27) {
+            const float w = __ldg(wgt + (k % 9) * C + ch) * sc;
+            v[e] = k < 18 ? bf16_hi(w) : w - bf16_hi(w);
+          } else if (k == 27) {
+            v[e] = bf16_hi(sh);
+          } else if (k == 28) {
+            v[e] = sh - bf16_hi(sh);
           }
         }
+        bw[ks][jj][r] = pack_bf16x2(v[0], v[1]);
       }
+  }
+  const int mtx = W >> 4, tiles_y = H / kCiRows, n_tiles = n_img * tiles_y;
+  int buf = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    const int n = tile / tiles_y, y0 = (tile - n * tiles_y) * kCiRows;
+    float* sx = s_x[buf];
+    for (int i = threadIdx.x; i < (kCiRows + 2) * W; i += blockDim.x) {
+      const int rr = i / W, cc = i - rr * W, yy = y0 - 1 + rr;
+      sx[rr * kCiPitch + cc + 1] = (yy >= 0 && yy < H) ? __ldg(x + ((size_t)n * H + yy) * W + cc) : 0.f;
+    }
+    __syncthreads();  // one barrier per tile: the other buffer is rewritten only after the NEXT barrier
+    for (int tk = warp; tk < kCiRows * mtx; tk += 8) {
+      const int r_loc = tk / mtx, x0 = (tk - r_loc * mtx) * 16 + g;
+      const float* px = sx + r_loc * kCiPitch + x0;
+      float av[2][8];  // [pixel row g / g+8][slot]
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int wq = w + q * ppb;
-        if (wq >= W) break;
-        float acc[8];
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-        for (int t = 0; t < 9; ++t)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(xin[q][t], wr[t][j], acc[j]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float y = fmaf(acc[j], sc[j], sh[j]);
-          acc[j] = relu ? fmaxf(y, 0.f) : y;
+        for (int r = 0; r < 2; ++r) {
+          const float v = px[aoff[i] + 8 * r];
+          av[r][i] = akind[i] == 0 ? v : (akind[i] == 1 ? v - bf16_hi(v) : (akind[i] == 2 ? 1.f : 0.f));
         }
-        *reinterpret_cast<uint4*>(orow + (size_t)wq * C + cg * 8) = pack8(acc);
+      uint32_t a[2][4];  // a0: (g, 2t..), a1: (g+8, 2t..), a2: (g, 2t+8..), a3: (g+8, 2t+8..)
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        a[ks][0] = pack_bf16x2(av[0][4 * ks + 0], av[0][4 * ks + 1]);
+        a[ks][1] = pack_bf16x2(av[1][4 * ks + 0], av[1][4 * ks + 1]);
+        a[ks][2] = pack_bf16x2(av[0][4 * ks + 2], av[0][4 * ks + 3]);
+        a[ks][3] = pack_bf16x2(av[1][4 * ks + 2], av[1][4 * ks + 3]);
+      }
+      bf16* o0 = out + (((size_t)n * H + y0 + r_loc) * W + x0) * C + 128 * slice + 8 * t;
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        float acc[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+          mma_bf16_m16n8k16(acc[q], a[0][0], a[0][1], a[0][2], a[0][3], bw[0][4 * s4 + q][0], bw[0][4 * s4 + q][1]);
+          mma_bf16_m16n8k16(acc[q], a[1][0], a[1][1], a[1][2], a[1][3], bw[1][4 * s4 + q][0], bw[1][4 * s4 + q][1]);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          uint4 v;
+          v.x = pack_bf16x2(acc[0][2 * r], acc[0][2 * r + 1]);
+          v.y = pack_bf16x2(acc[1][2 * r], acc[1][2 * r + 1]);
+          v.z = pack_bf16x2(acc[2][2 * r], acc[2][2 * r + 1]);
+          v.w = pack_bf16x2(acc[3][2 * r], acc[3][2 * r + 1]);
+          if (RELU) {
+            v.x = bf16x2_max(v.x, 0u);
+            v.y = bf16x2_max(v.y, 0u);
+            v.z = bf16x2_max(v.z, 0u);
+            v.w = bf16x2_max(v.w, 0u);
+          }
+          *reinterpret_cast<uint4*>(o0 + (size_t)(8 * r) * C + 32 * s4) = v;
+        }
       }
     }
   }
@@ -126,14 +191,6 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
 // 8 pixels x 64 contiguous bytes.  HBM-bound: 1 MiB in + 16 KiB out per image.
 constexpr int kCoC = 128;
 
-__device__ __forceinline__ void mma_bf16_m16n8k16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                                  uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-      "{%0, %1, %2, %3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
 // relu(a * x + b) on 8 bf16 channels, re-packed to bf16x2 (the one rounding of this layer's input).
 __device__ __forceinline__ uint4 gn_relu8(const uint4& v, const float4& a0, const float4& a1, const float4& b0,
                                           const float4& b1) {
@@ -514,13 +571,18 @@ using namespace cdm;
 
 extern "C" int cdm_conv_in(const cdm_conv_in_args* a, void* stream) {
   CDM_CHECK_ARG(a && a->x && a->weight && a->scale && a->shift && a->out);
-  CDM_CHECK_ARG(a->n_img > 0 && a->H > 0 && a->W > 0 && a->cout > 0 && a->cout % 8 == 0 && a->cout <= 512);
+  CDM_CHECK_ARG(a->n_img > 0 && a->H > 0 && a->H % kCiRows == 0 && a->W > 0 && a->W % 16 == 0 && a->W <= kCiMaxW);
+  CDM_CHECK_ARG(a->cout > 0 && a->cout % 128 == 0 && a->cout <= 512);
   int rc = check_device();
   if (rc) return rc;
-  CDM_CHECK_ARG(256 % (a->cout / 8) == 0);
-  const int rows = a->n_img * a->H;
-  conv_in_kernel<<<rows < 148 * 8 ? rows : 148 * 8, 256, 0, (cudaStream_t)stream>>>(
-      a->x, a->n_img, a->H, a->W, a->cout, a->weight, a->scale, a->shift, a->relu, (bf16*)a->out);
+  const int tiles = a->n_img * (a->H / kCiRows);
+  const dim3 grid(tiles < 148 * 2 ? tiles : 148 * 2, a->cout / 128);
+  if (a->relu)
+    conv_in_mma_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(a->x, a->n_img, a->H, a->W, a->cout, a->weight,
+                                                                     a->scale, a->shift, (bf16*)a->out);
+  else
+    conv_in_mma_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(a->x, a->n_img, a->H, a->W, a->cout, a->weight,
+                                                                      a->scale, a->shift, (bf16*)a->out);
   CDM_CHECK_LAUNCH();
   return CDM_OK;
 }

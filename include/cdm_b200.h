@@ -347,6 +347,21 @@ typedef struct {
 } cdm_gemm_tn_args;
 int cdm_gemm_tn(const cdm_gemm_tn_args* a, void* stream);
 
+/* Radial power spectrum of n_maps square N x N fp32 maps (N a power of two <= 64), one CTA per map.
+ * Replaces power_spectrum (code/diffusion_utilities.py:302-368), which compare_power_spectra (:370-431)
+ * calls per image: np.fft.fftn(box, norm="ortho"), |F|^2, mean over the modes of each radial bin, * dl^ndims.
+ * Bin membership is the reference's own rule int(round(|k|/dk)) evaluated once on the host and passed as a
+ * CSR list: bin_start int32 [n_bins+1], bin_items int32 [N*N] (flat mode indices l*N+k grouped by bin, ascending
+ * within a bin).  pk fp64 [n_maps][n_bins] = scale * mean (0 for an empty bin); scale = dl^2. */
+int cdm_power_spectrum(const float* maps, int n_maps, int N, const int* bin_start, const int* bin_items, int n_bins,
+                       double scale, double* pk, void* stream);
+
+/* Per-map pixel histogram with explicit fp64 bin edges (ascending, n_bins+1 of them): np.histogram(map.ravel(),
+ * edges) of compare_distributions (code/train_diffusion_paper.py:861-876) — half-open bins, last bin closed,
+ * values outside [edges[0], edges[n_bins]] dropped.  counts int32 [n_maps][n_bins]; n_bins <= 12288. */
+int cdm_pixel_histogram(const float* maps, int n_maps, int P, const double* edges, int n_bins, int* counts,
+                        void* stream);
+
 /* Measurement probe: every CTA streams `tile_bytes` TMA tiles from an
  * L2-resident buffer into a shared-memory ring; returns nothing, caller times it. */
 int cdm_probe_tma_l2(const void* buf, int n_rows, int iters, void* stream);

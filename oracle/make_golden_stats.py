@@ -40,6 +40,26 @@ def reference_histograms(a, b, delta=0.01):
     return bins, pa, pb
 
 
+def histogram_part(maps, other):
+    """An untrained network cannot denoise: x grows by ~1/sqrt(ab_T) ~ 2e3 over the trajectory, so the maps are
+    min-max normalised with the REFERENCE run's own extrema (stored) before the reference's 0.01-wide bins are
+    applied — the same [0,1] range the reference's normalised training maps live in (train_diffusion_paper.py:260).
+    `other` (the step-20 snapshot of the same run) is the second image set of the two-sided call."""
+    lo, hi = np.float32(maps.min()), np.float32(maps.max())
+    a, b = (maps - lo) / (hi - lo), (other - lo) / (hi - lo)
+    bins, pa, pb = reference_histograms(a, b)
+    return {"hist_lo": lo, "hist_hi": hi, "hist_other": other, "hist_bins": bins, "hist_a": pa, "hist_b": pb}
+
+
+def rehist():
+    """Recompute only the histogram part of an existing fixture (no 20-minute trajectory)."""
+    path = os.path.join(MG.GOLD, "sampler_stats.npz")
+    g = dict(np.load(path))
+    g.update(histogram_part(g["x"][:, 0], g["hist_other"]))
+    np.savez_compressed(path, **g)
+    print("rehist:", g["hist_bins"].shape, g["hist_lo"], g["hist_hi"])
+
+
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     T = int(sys.argv[2]) if len(sys.argv) > 2 else 1500
@@ -74,10 +94,7 @@ def main():
         k_bins, p = DU.power_spectrum(maps[i], dl=1.0)
         pk.append(p)
     out["pk_k"], out["pk"] = k_bins, np.stack(pk)
-    # a second set of maps for the two-sided histogram call: the step-20 snapshot of the same run
-    other = inter[snap_steps.index(20)][:, 0] if T >= 20 else maps
-    bins, pa, pb = reference_histograms(maps, other)
-    out["hist_other"], out["hist_bins"], out["hist_a"], out["hist_b"] = other, bins, pa, pb
+    out.update(histogram_part(maps, inter[snap_steps.index(20)][:, 0] if T >= 20 else maps))
     name = "sampler_stats.npz" if T == 1500 else f"sampler_stats_T{T}.npz"
     np.savez_compressed(os.path.join(MG.GOLD, name), **out)
     print(name, {k: np.asarray(v).shape for k, v in out.items()})
@@ -85,4 +102,7 @@ def main():
 
 if __name__ == "__main__":
     assert RH.available(), "reference checkout not found"
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "rehist":
+        rehist()
+    else:
+        main()

@@ -169,16 +169,20 @@ def test_gemm_resident_weights_path(L, n, H, c0, c1):
     assert rel_l2(o2.float(), a2.float() @ b2.float().t() + sh) < BF16_TOL
 
 
-def test_conv_in(L):
+@pytest.mark.parametrize("n,H,relu", [(5, 64, True), (1, 16, False), (300, 32, True)])
+def test_conv_in(L, n, H, relu):
     g = torch.Generator(device="cuda").manual_seed(2)
-    x = torch.randn(5, 64, 64, device="cuda", generator=g)
+    x = torch.randn(n, H, H, device="cuda", generator=g)
     w = torch.randn(128, 1, 3, 3, device="cuda", generator=g) / 3
     scale = torch.rand(128, device="cuda", generator=g) + 0.5
     shift = torch.randn(128, device="cuda", generator=g) * 0.1
-    out = torch.empty(5, 64, 64, 128, device="cuda", dtype=torch.bfloat16)
-    L.conv_in(x, w.reshape(128, 9).t().contiguous(), scale, shift, out)
-    ref = F.relu(F.conv2d(x.unsqueeze(1), w, padding=1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
-    assert rel_l2(out.float(), ref.permute(0, 2, 3, 1)) < BF16_TOL
+    out = torch.full((n, H, H, 128), float("nan"), device="cuda").to(torch.bfloat16)
+    L.conv_in(x, w.reshape(128, 9).t().contiguous(), scale, shift, out, relu=relu)
+    ref = F.conv2d(x.unsqueeze(1), w, padding=1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    ref = (F.relu(ref) if relu else ref).permute(0, 2, 3, 1)
+    assert rel_l2(out.float(), ref) < BF16_TOL
+    # hi/lo-split operands keep fp32-level accuracy: the only rounding left is the bf16 output
+    assert rel_l2(out.float(), ref.to(torch.bfloat16).float()) < 2e-4
 
 
 @pytest.mark.parametrize("n", [3, 160])  # 160 images: the 32-row-tile instantiation; 3: the 8-row one

@@ -109,3 +109,26 @@ def test_train_step():
     p0 = sd[name]
     p1, _, _ = O.adam_step(p0, grads[name], torch.zeros_like(p0), torch.zeros_like(p0), 1, float(g["lr"]))
     assert np.allclose(p1.reshape(-1)[:64].numpy(), g["pslice/" + name], rtol=0, atol=1e-7)
+
+
+def test_metrics_oracle_matches_reference_statistics():
+    """oracle/metrics_oracle.py vs the values the reference's own power_spectrum / compare_distributions
+    produced on the reference's generated maps (oracle/make_golden_stats.py)."""
+    from oracle import metrics_oracle as MO
+    g = load("sampler_stats.npz")
+    maps = g["x"][:, 0]
+    for i in range(len(maps)):
+        k, pk = MO.power_spectrum(maps[i])
+        np.testing.assert_allclose(k, g["pk_k"], rtol=1e-14)
+        np.testing.assert_allclose(pk, g["pk"][i], rtol=1e-12)
+    lo, hi = g["hist_lo"], g["hist_hi"]
+    bins, pa, pb = MO.histograms((maps - lo) / (hi - lo), (g["hist_other"] - lo) / (hi - lo))
+    assert np.array_equal(bins, g["hist_bins"]) and np.array_equal(pa, g["hist_a"]) and np.array_equal(pb, g["hist_b"])
+
+
+def test_sampler_draw_replay_matches_reference_run():
+    """The draw sequence the GPU trajectory test regenerates from the seed is the one the reference consumed."""
+    from tests._util import check_replay, replay_sampler_draws
+    g = load("sampler_stats.npz")
+    x_T, z, tab = replay_sampler_draws(int(g["seed"]), int(g["B"]), int(g["T"]))
+    check_replay(g, x_T, z, tab)
