@@ -414,7 +414,12 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 // --------------------------------------------------------------------------
 constexpr int kSwPitch = 10, kSwRows = 34, kSwABytes = kSwRows * kSwPitch * 128, kSwAStride = 44032, kSwNA = 3;
 constexpr int kSwEpiWarps = 8, kSwThreads = 128 + 32 * kSwEpiWarps;
-constexpr int conv_sw_smem_bytes() { return kSwNA * kSwAStride + kNB * kBBytes + 2 * 256 * 4 + 256 + 1024; }
+// Weight ring: 4 stages.  The issuer is blocked on it ~30 % of its cycles (tools/gpu_probe.py waits), but that is
+// back-pressure from the tensor pipe, not TMA latency: 6 stages changed neither the wait share nor the run time.
+// The shape itself is at the shared-memory limit: operand reads 12 KB / 128 clk = 96 B/clk plus TMA fills
+// (16 KB weights / 512 clk + 43.5 KB halo / 4608 clk = 41 B/clk) against 128 B/clk per SM.
+constexpr int kSwNB = 4;
+constexpr int conv_sw_smem_bytes() { return kSwNA * kSwAStride + kSwNB * kBBytes + 2 * 256 * 4 + 256 + 1024; }
 
 __global__ void __launch_bounds__(kSwThreads, 1)
 conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -423,14 +428,14 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smemA = smem;  // pixel halo tiles
   uint8_t* smemB = smemA + kSwNA * kSwAStride;  // weight tiles
-  float* s_scale = reinterpret_cast<float*>(smemB + kNB * kBBytes);
+  float* s_scale = reinterpret_cast<float*>(smemB + kSwNB * kBBytes);
   float* s_shift = s_scale + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kSwNA;
   uint64_t* b_full = a_empty + kSwNA;
-  uint64_t* b_empty = b_full + kNB;
-  uint64_t* t_full = b_empty + kNB;
+  uint64_t* b_empty = b_full + kSwNB;
+  uint64_t* t_full = b_empty + kSwNB;
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -443,7 +448,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
     }
-    for (int i = 0; i < kNB; ++i) {
+    for (int i = 0; i < kSwNB; ++i) {
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
@@ -497,7 +502,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           mbar_wait(&b_empty[sb], pb ^ 1);
           mbar_arrive_expect_tx(&b_full[sb], kBBytes);
           tma_load_2d(smemB + sb * kBBytes, &mapB, &b_full[sb], tap * cin + ch * 64, n_tile * 128);
-          if (++sb == kNB) {
+          if (++sb == kSwNB) {
             sb = 0;
             pb ^= 1;
           }
@@ -507,18 +512,28 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
     int sa = 0, sb = 0, it = 0;
     uint32_t pa = 0, pb = 0;
+    // probe (flag bit 28): cycles the issuer spends blocked on each barrier class -> gn_partial[cta][0..3]
+    const bool prof = p.flags & (1 << 28);
+    long long w_t = 0, w_a = 0, w_b = 0, c0 = 0;
+    const long long c_start = prof ? clock64() : 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
       const int buf = it & 1;
+      if (prof) c0 = clock64();
       mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);
+      if (prof) w_t += clock64() - c0;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
       bool first = true;
       for (int ch = 0; ch < p.chunks; ++ch) {
+        if (prof) c0 = clock64();
         mbar_wait(&a_full[sa], pa);
+        if (prof) w_a += clock64() - c0;
         tc_fence_after();
         const uint32_t px_base = smem_u32(smemA + sa * kSwAStride);
         for (int tap = 0; tap < 9; ++tap) {
+          if (prof) c0 = clock64();
           mbar_wait(&b_full[sb], pb);
+          if (prof) w_b += clock64() - c0;
           tc_fence_after();
           const uint32_t w_base = smem_u32(smemB + sb * kBBytes);
           const uint32_t px_addr = px_base + (uint32_t)((tap / 3) * kSwPitch + tap % 3) * 128u;
@@ -528,7 +543,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                       idesc, (first && k == 0) ? 0u : 1u);
           first = false;
           umma_commit(&b_empty[sb]);
-          if (++sb == kNB) {
+          if (++sb == kSwNB) {
             sb = 0;
             pb ^= 1;
           }
@@ -540,6 +555,13 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         }
       }
       umma_commit(&t_full[buf]);
+    }
+    if (prof) {
+      float* d = p.gn_partial + (size_t)blockIdx.x * 8;
+      d[0] = (float)w_t;
+      d[1] = (float)w_a;
+      d[2] = (float)w_b;
+      d[3] = (float)(clock64() - c_start);
     }
   } else if (warp >= 4) {
     // 8 epilogue warps: TMEM lane quadrant q = warp % 4 (hardware rule), column half = (warp - 4) / 4
@@ -557,7 +579,10 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       const int sx = s % px_tiles, sy = s / px_tiles;
       const int oh0 = sy * 32, ow0 = sx * 8;
       const int co = n_tile * 128 + co_l;
+      const bool prof = p.flags & (1 << 28);
+      const long long e0 = prof ? clock64() : 0;
       mbar_wait(&t_full[buf], (it >> 1) & 1);
+      const long long e1 = prof ? clock64() : 0;
       tc_fence_after();
       const float sc = s_scale[co], sh = s_shift[co];
       float fsv = 1.f, fbv = 0.f;
@@ -668,6 +693,11 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[buf]);
+      if (prof && et == 0) {  // warp 4: cycles idle (waiting for the accumulator) / busy (epilogue proper)
+        float* d = p.gn_partial + (size_t)blockIdx.x * 8;
+        d[4] = (it == 0 ? 0.f : d[4]) + (float)(e1 - e0);
+        d[5] = (it == 0 ? 0.f : d[5]) + (float)(clock64() - e1);
+      }
     }
   }
   tc_fence_before();

@@ -176,6 +176,29 @@ def case_perf(name, mode, n=256, H=64, cin=128, cout=128, flags=1):
     return True
 
 
+def case_waits(name, n=2048, H=64, cin=128, cout=128, flags=1):
+    """Where the MMA issuer of conv3x3_sw_kernel waits (probe flag bit 28): cycles blocked on the TMEM buffer
+    (epilogue too slow), on the pixel-halo ring and on the weight ring, per CTA, against the CTA's total."""
+    import torch
+    L = _load()
+    dev = "cuda"
+    x = torch.randn(n, H, H, cin, device=dev).to(torch.bfloat16)
+    w = (torch.randn(cout, 3, 3, cin, device=dev) / (3 * cin ** 0.5)).to(torch.bfloat16)
+    scale, shift = torch.ones(cout, device=dev), torch.zeros(cout, device=dev)
+    out = torch.empty(n, H, H, cout, device=dev, dtype=torch.bfloat16)
+    dbg = torch.zeros(148, 8, device=dev)
+    for _ in range(3):
+        L.conv3x3(x, w, scale, shift, out, mode=3, flags=flags | (1 << 28), gn_partial=dbg)
+    torch.cuda.synchronize()
+    d = dbg.cpu()
+    tot = d[:, 3]
+    print(f"CASE {name}: issuer cycles/CTA {tot.mean():.0f} (min {tot.min():.0f} max {tot.max():.0f}); blocked on "
+          f"tmem {100 * (d[:, 0] / tot).mean():.1f}%  halo ring {100 * (d[:, 1] / tot).mean():.1f}%  weight ring "
+          f"{100 * (d[:, 2] / tot).mean():.1f}%; epilogue warp: idle {100 * (d[:, 4] / tot).mean():.1f}%  busy "
+          f"{100 * (d[:, 5] / tot).mean():.1f}%  (n={n} H={H} cin={cin} cout={cout} flags={flags})", flush=True)
+    return True
+
+
 def case_probe_l2(name):
     import torch
     L = _load()
@@ -227,6 +250,11 @@ CASES = {
     "perf_m3_out0": lambda: case_perf("perf_m3_out0", 3, n=1024, H=64, cin=256, cout=128),
     "perf_m2_out0": lambda: case_perf("perf_m2_out0", 2, n=1024, H=64, cin=256, cout=128),
     "probe_l2": lambda: case_probe_l2("probe_l2"),
+    "waits": lambda: case_waits("waits"),
+    "waits_nostore": lambda: case_waits("waits_nostore", flags=1 | (1 << 30)),
+    "waits_c256": lambda: case_waits("waits_c256", H=32, cin=256, cout=256),
+    "waits_out0": lambda: case_waits("waits_out0", cin=256, cout=128),
+    "waits_pool": lambda: case_waits("waits_pool", flags=1 | 4),
 }
 
 
