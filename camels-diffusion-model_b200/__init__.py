@@ -11,3 +11,5 @@ from .diffusion import (DDPM, calculate_elbo_and_bpd, calculate_elbo_and_bpd_bat
                         calculate_likelihood, denoise_add_noise, make_schedule, perturb_input, sample_ddpm)
 from .metrics import (compare_distributions, compare_power_spectra, pixel_histograms, power_spectra,  # noqa: F401
                       power_spectrum)
+from .data import normalize_params, preprocess_maps  # noqa: F401
+from .checkpoint import load_checkpoint, load_model, save_checkpoint, save_model  # noqa: F401

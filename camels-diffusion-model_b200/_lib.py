@@ -107,6 +107,7 @@ EXPORTS = [
     "cdm_maxpool2_bwd", "cdm_add_bf16", "cdm_space_to_depth", "cdm_film_bwd", "cdm_gn_bwd", "cdm_rows_sum",
     "cdm_avgpool_gelu_train", "cdm_avgpool_gelu_bwd", "cdm_outer_wgrad", "cdm_embed_bwd", "cdm_mse_grad",
     "cdm_adam_step", "cdm_power_spectrum", "cdm_pixel_histogram",
+    "cdm_minmax", "cdm_preprocess_maps", "cdm_normalize_params",
 ]
 
 
@@ -424,3 +425,28 @@ def pixel_histogram(maps, edges, counts):
     check(lib().cdm_pixel_histogram(C.c_void_p(ptr(maps)), n, P, C.c_void_p(ptr(edges)), counts.shape[1],
                                     C.c_void_p(ptr(counts)), stream_ptr()), "cdm_pixel_histogram")
     return counts
+
+
+# --------------------------------------------------------------------------- data preparation
+def minmax(x, workspace, out):
+    """x fp32 (any shape, contiguous); workspace fp32 zero-filled once; out fp32 [2] = (min, max)."""
+    check(lib().cdm_minmax(C.c_void_p(ptr(x)), C.c_longlong(x.numel()), C.c_void_p(ptr(workspace)), workspace.numel(),
+                           C.c_void_p(ptr(out)), stream_ptr()), "cdm_minmax")
+    return out
+
+
+def preprocess_maps(maps, raw_minmax, out):
+    """maps fp32 [n,Hi,Wi]; raw_minmax fp32 [2] (device); out fp32 [n,Ho,Wo]."""
+    n, Hi, Wi = maps.shape
+    check(lib().cdm_preprocess_maps(C.c_void_p(ptr(maps)), n, Hi, Wi, C.c_void_p(ptr(raw_minmax)), out.shape[1],
+                                    out.shape[2], C.c_void_p(ptr(out)), stream_ptr()), "cdm_preprocess_maps")
+    return out
+
+
+def normalize_params(x, repeat, out, col_min, col_max):
+    """x fp32 [rows,cols]; out fp32 [rows*repeat,out_cols]; col_min/col_max fp32 [cols]."""
+    rows, cols = x.shape
+    check(lib().cdm_normalize_params(C.c_void_p(ptr(x)), rows, cols, repeat, out.shape[1], C.c_void_p(ptr(out)),
+                                     C.c_void_p(ptr(col_min)), C.c_void_p(ptr(col_max)), stream_ptr()),
+          "cdm_normalize_params")
+    return out

@@ -401,6 +401,8 @@ class FusedAdam(torch.optim.Optimizer):
                 st = self.state[p]
                 if not st:
                     st["exp_avg"], st["exp_avg_sq"] = torch.zeros_like(p), torch.zeros_like(p)
+                # same per-parameter keys as torch.optim.Adam, so optimizer state_dicts are interchangeable
+                st["step"] = torch.tensor(float(self._step))
             grads = [p.grad.contiguous() for p in ps]
             key = tuple((p.data_ptr(), g.data_ptr()) for p, g in zip(ps, grads))
             if self._tab is None or self._key != (gi, key):
@@ -411,6 +413,14 @@ class FusedAdam(torch.optim.Optimizer):
             self._grads_keepalive = grads
             b1, b2 = group["betas"]
             L.adam_step(self._tab, len(ps), max(p.numel() for p in ps), group["lr"], b1, b2, group["eps"], self._step)
+
+
+    def load_state_dict(self, state_dict):
+        """Accepts a FusedAdam or a torch.optim.Adam state_dict (code/train_diffusion_paper.py:318 optimiser)."""
+        super().load_state_dict(state_dict)
+        steps = [int(st["step"]) for st in self.state.values() if "step" in st]
+        self._step = max(steps) if steps else 0
+        self._tab = self._key = None  # exp_avg tensors were replaced: rebuild the pointer table
 
 
 def training_step(model, optim, x, param, timesteps, ab_t, *, noise=None, t=None, shortcut=None):
@@ -521,6 +531,27 @@ class GraphedTrainStep:
         for t in self.m + self.v:
             t.zero_()
         self.count.zero_()
+
+    def state_dict(self):
+        """Optimizer state in torch.optim.Adam's state_dict layout (state[i] = {step, exp_avg, exp_avg_sq} in
+        model.parameters() order), so a checkpoint moves between this step, FusedAdam and the reference's Adam."""
+        step = float(self.count.item())
+        state = {i: {"step": torch.tensor(step), "exp_avg": m.detach().clone(), "exp_avg_sq": v.detach().clone()}
+                 for i, (m, v) in enumerate(zip(self.m, self.v))} if step > 0 else {}
+        group = dict(lr=float(self.lr.item()), betas=self.betas, eps=self.eps, weight_decay=0, amsgrad=False,
+                     params=list(range(len(self.params))))
+        return {"state": state, "param_groups": [group], "seed": self.seed}
+
+    def load_state_dict(self, sd):
+        self.reset_optimizer()
+        steps = [int(st["step"]) for st in sd["state"].values()]
+        with torch.no_grad():
+            for i, st in sd["state"].items():
+                self.m[int(i)].copy_(st["exp_avg"])
+                self.v[int(i)].copy_(st["exp_avg_sq"])
+        self.count.fill_(max(steps) if steps else 0)
+        self.lr.fill_(float(sd["param_groups"][0]["lr"]))
+        self.seed = int(sd.get("seed", self.seed))
 
     def __call__(self, x, param, t=None, shortcut=None):
         """One optimisation step; returns the mean-squared-error loss as a 0-d device tensor (no host sync)."""

@@ -362,6 +362,22 @@ int cdm_power_spectrum(const float* maps, int n_maps, int N, const int* bin_star
 int cdm_pixel_histogram(const float* maps, int n_maps, int P, const double* edges, int n_bins, int* counts,
                         void* stream);
 
+/* ---- data preparation (code/train_diffusion_paper.py:232-262) ------------------------------------------------ */
+/* out[0] = min, out[1] = max of n fp32 values (x 16-byte aligned).  workspace: fp32 scratch the caller zero-fills
+ * ONCE (>= 17 floats; 2 per block + a ticket counter in the last slot, re-armed by the kernel). */
+int cdm_minmax(const float* x, long long n, float* workspace, int workspace_floats, float* out, void* stream);
+/* The map pipeline of :254-261 fused with the resize: with (min, max) of the RAW maps in raw_minmax (device),
+ *   v -> (min <= 0 ? v - min + 1e-8 : v) / max' -> log10 -> (. - lmin) / (lmax - lmin)
+ * evaluated only at the taps of F.interpolate(size=(Ho,Wo), mode='bilinear') (align_corners=False), fp32,
+ * every operation rounded separately in the reference's order.  in fp32 [n][Hi][Wi] -> out fp32 [n][Ho][Wo]. */
+int cdm_preprocess_maps(const float* in, int n, int Hi, int Wi, const float* raw_minmax, int Ho, int Wo, float* out,
+                        void* stream);
+/* Parameter table of :232-252: col_min / col_max over the rows of x [rows][cols]; out [rows*repeat][out_cols] =
+ * (x - min) / (max - min + 1e-8) with every row repeated `repeat` times (np.repeat(param_data, 15, axis=0)),
+ * columns cut (cols > out_cols) or zero-padded (cols < out_cols) to the number of conditioning parameters. */
+int cdm_normalize_params(const float* x, int rows, int cols, int repeat, int out_cols, float* out, float* col_min,
+                         float* col_max, void* stream);
+
 /* Measurement probe: every CTA streams `tile_bytes` TMA tiles from an
  * L2-resident buffer into a shared-memory ring; returns nothing, caller times it. */
 int cdm_probe_tma_l2(const void* buf, int n_rows, int iters, void* stream);

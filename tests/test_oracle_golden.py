@@ -132,3 +132,17 @@ def test_sampler_draw_replay_matches_reference_run():
     g = load("sampler_stats.npz")
     x_T, z, tab = replay_sampler_draws(int(g["seed"]), int(g["B"]), int(g["T"]))
     check_replay(g, x_T, z, tab)
+
+
+def test_data_oracle_matches_reference_statements():
+    """oracle/data_oracle.py vs the reference's own data-preparation statements run on the same synthetic arrays."""
+    from oracle import data_oracle as DO
+    g = load("data_prep.npz")
+    for tag, neg in (("pos", False), ("neg", True)):
+        maps = DO.synthetic_maps(11, n=30, size=256, negative=neg)
+        params = DO.synthetic_params(12, n_sets=2)
+        assert np.array_equal(DO.preprocess_maps(maps)[:4].numpy(), g[f"{tag}/maps"])
+        for k in (6, 2, 8) if tag == "pos" else (6,):
+            tab, pmin, pmax = DO.normalize_params(params, k)
+            assert np.array_equal(tab.numpy(), g[f"{tag}/params{k}"])
+        assert np.array_equal(pmin, g[f"{tag}/pmin"]) and np.array_equal(pmax, g[f"{tag}/pmax"])
