@@ -34,9 +34,15 @@ def test_pth_roundtrip_reference_layout(tmp_path):
 
 
 @pytest.mark.parametrize("kind", ["fused_adam", "graphed"])
-def test_resume_is_bit_exact(tmp_path, kind):
-    """2 steps, checkpoint, 2 more steps == load the checkpoint into fresh objects, 2 steps: weights, BatchNorm
-    buffers and optimizer moments bit-identical (CPU generator state restored, so t / shortcut draws match)."""
+def test_resume_continues_the_run(tmp_path, kind):
+    """2 steps, checkpoint, 1 more step == load the checkpoint into fresh objects, 1 step.
+    * what is restored (weights, BatchNorm buffers, Adam moments, step count) is bit-exact;
+    * the next step's LOSS is identical: the forward pass is deterministic, so this pins weights, BatchNorm
+      buffers, the restored CPU generator (t and shortcut draws) and the Philox noise counter together;
+    * the Adam moments after that step agree to the run-to-run noise of the backward pass (the split-K weight
+      gradient accumulates with fp32 atomics, as cuDNN's does; a lost moment would be off by ~90 %).
+    Parameters after further steps are not compared: at random init Adam's first updates are sign-like, which
+    amplifies last-bit gradient noise to a visible fraction of lr in two identical uninterrupted runs as well."""
     import camels_diffusion_model_b200 as cdm
     from camels_diffusion_model_b200 import diffusion as D, train as TR
     T = 1500
@@ -49,35 +55,44 @@ def test_resume_is_bit_exact(tmp_path, kind):
         return m, TR.FusedAdam(m.parameters(), lr=1e-4)
 
     def run(m, opt, k0, k1):
+        loss = None
         for k in range(k0, k1):
             x, p = _batch(100 + k)
             if kind == "graphed":
-                opt(x, p)
+                loss = opt(x, p)
             else:
                 g = torch.Generator(device="cuda").manual_seed(k)
                 noise = torch.randn(x.shape, device="cuda", generator=g)
-                TR.training_step(m, opt, x, p, T, ab_t, noise=noise)
+                loss = TR.training_step(m, opt, x, p, T, ab_t, noise=noise)
         torch.cuda.synchronize()
+        return float(loss)
 
     torch.manual_seed(7)
     m1, o1 = fresh()
     run(m1, o1, 0, 2)
     path = str(tmp_path / "resume.pt")
     cdm.save_checkpoint(path, m1, o1, epoch=3, step=2, extra={"lrate": 1e-4})
-    run(m1, o1, 2, 4)
+    loss1 = run(m1, o1, 2, 3)
 
     torch.manual_seed(999)  # a different generator state: load_checkpoint must restore the saved one
     m2, o2 = fresh()
     epoch, step, extra = cdm.load_checkpoint(path, m2, o2)
     assert (epoch, step, extra["lrate"]) == (3, 2, 1e-4)
-    run(m2, o2, 2, 4)
-    for (k, a), b in zip(m1.state_dict().items(), m2.state_dict().values()):
-        assert torch.equal(a, b), k
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v.cpu(), ck["model"][k]), k
+    for i, st in o2.state_dict()["state"].items():
+        assert torch.equal(st["exp_avg"].cpu(), ck["optim"]["state"][i]["exp_avg"]) and int(st["step"]) == 2
+        assert torch.equal(st["exp_avg_sq"].cpu(), ck["optim"]["state"][i]["exp_avg_sq"])
+    loss2 = run(m2, o2, 2, 3)
+    assert abs(loss1 - loss2) <= 1e-6 * abs(loss1), (loss1, loss2)
     s1, s2 = o1.state_dict()["state"], o2.state_dict()["state"]
     assert s1.keys() == s2.keys() and len(s1) == 102
     for i in s1:
-        assert torch.equal(s1[i]["exp_avg"], s2[i]["exp_avg"]) and torch.equal(s1[i]["exp_avg_sq"], s2[i]["exp_avg_sq"])
-        assert int(s1[i]["step"]) == int(s2[i]["step"]) == 4
+        assert int(s1[i]["step"]) == int(s2[i]["step"]) == 3
+        for key in ("exp_avg", "exp_avg_sq"):
+            d = (s1[i][key].double() - s2[i][key].double()).norm()
+            assert d <= 2e-2 * s1[i][key].double().norm() + 1e-12, (i, key)
 
 
 def test_optimizer_state_interchanges_with_torch_adam(tmp_path):
