@@ -60,3 +60,33 @@ def test_shard_range_covers_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(ws - 1))
             assert max(e - s for s, e in spans) - min(e - s for s, e in spans) <= 1
+
+
+def _ckpt_worker(rank, ws, port, tmpdir, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    import camels_diffusion_model_b200 as cdm
+    torch.manual_seed(rank)  # ranks start from DIFFERENT weights
+    m = cdm.ContextUnet(1, 128, 2, 64)
+    path = os.path.join(tmpdir, "model_epoch_0.pth")
+    cdm.save_model(m, path)  # rank 0 only writes
+    dist.barrier()
+    ret[f"exists{rank}"] = os.path.exists(path)
+    if rank == 0:
+        cdm.load_model(m, path)
+    from camels_diffusion_model_b200.checkpoint import broadcast_model
+    broadcast_model(m)  # rank 0's weights and BatchNorm buffers -> everyone
+    ret[rank] = {k: v.clone() for k, v in m.state_dict().items()}
+    dist.destroy_process_group()
+
+
+def test_rank0_save_and_broadcast_load_gloo(tmp_path):
+    ws = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_ckpt_worker, args=(ws, _free_port(), str(tmp_path), ret), nprocs=ws, join=True)
+    assert ret["exists0"] and ret["exists1"]
+    saved = torch.load(os.path.join(str(tmp_path), "model_epoch_0.pth"))
+    assert len(saved) == 156  # the reference's state_dict layout (n_cfeat only changes two shapes)
+    for k, v in ret[0].items():
+        assert torch.equal(v, ret[1][k]) and torch.equal(v, saved[k]), k
