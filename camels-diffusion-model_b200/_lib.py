@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcdm_b200.so")
 
-EPI_RELU, EPI_SHORTCUT, EPI_POOL, EPI_FILM, EPI_GNSTATS = 1, 2, 4, 8, 16
+EPI_RELU, EPI_SHORTCUT, EPI_POOL, EPI_FILM, EPI_GNSTATS, EPI_BNSTATS = 1, 2, 4, 8, 16, 32
 CONV_MODE_COPIES, CONV_MODE_SHIFT24, CONV_MODE_SHIFT18, CONV_MODE_SWAPPED = 0, 1, 2, 3
 
 
@@ -28,7 +28,18 @@ class Conv3x3Args(C.Structure):
         ("sc_x", C.c_void_p), ("sc_reps", C.c_int), ("sc_tab", C.c_void_p),
         ("film_scale", C.c_void_p), ("film_shift", C.c_void_p), ("film_shift_rows", C.c_int),
         ("step_ptr", C.c_void_p), ("gn_partial", C.c_void_p), ("mode", C.c_int),
+        ("bn_partial", C.c_void_p), ("bn_sums", C.c_void_p), ("xr", C.c_void_p),
     ]
+
+
+class XrankArgs(C.Structure):
+    """cdm_xrank: peer group of the fused reduce + cross-rank exchange (built by parallel.PeerExchange)."""
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("peer_slots", C.c_void_p), ("peer_flags", C.c_void_p),
+                ("seq", C.c_void_p), ("ticket", C.c_void_p)]
+
+
+def _xr_ptr(xr):
+    return None if xr is None else C.cast(C.pointer(xr), C.c_void_p)
 
 
 class GemmArgs(C.Structure):
@@ -107,7 +118,7 @@ EXPORTS = [
     "cdm_maxpool2_bwd", "cdm_add_bf16", "cdm_space_to_depth", "cdm_film_bwd", "cdm_gn_bwd", "cdm_rows_sum",
     "cdm_avgpool_gelu_train", "cdm_avgpool_gelu_bwd", "cdm_outer_wgrad", "cdm_embed_bwd", "cdm_mse_grad",
     "cdm_adam_step", "cdm_power_spectrum", "cdm_pixel_histogram",
-    "cdm_minmax", "cdm_preprocess_maps", "cdm_normalize_params",
+    "cdm_minmax", "cdm_preprocess_maps", "cdm_normalize_params", "cdm_xrank_sum",
 ]
 
 
@@ -130,7 +141,7 @@ def stream_ptr():
 
 def conv3x3(src0, weight, scale, shift, out, *, src1=None, flags=EPI_RELU, sc_x=None, sc_tab=None, sc_reps=1,
             film_scale=None, film_shift=None, film_shift_rows=1, step_ptr=None, gn_partial=None,
-            mode=CONV_MODE_SWAPPED):
+            mode=CONV_MODE_SWAPPED, bn_partial=None, bn_sums=None, xr=None):
     """src*: bf16 [n,H,W,c]; weight bf16 [cout,3,3,cin]; out bf16 NHWC. See cdm_conv3x3 in cdm_b200.h."""
     n, H, W, c0 = src0.shape
     a = Conv3x3Args()
@@ -143,6 +154,7 @@ def conv3x3(src0, weight, scale, shift, out, *, src1=None, flags=EPI_RELU, sc_x=
     a.sc_x, a.sc_reps, a.sc_tab = ptr(sc_x), sc_reps, ptr(sc_tab)
     a.film_scale, a.film_shift, a.film_shift_rows = ptr(film_scale), ptr(film_shift), film_shift_rows
     a.step_ptr, a.gn_partial, a.mode = ptr(step_ptr), ptr(gn_partial), mode
+    a.bn_partial, a.bn_sums, a.xr = ptr(bn_partial), ptr(bn_sums), _xr_ptr(xr)
     check(lib().cdm_conv3x3(C.byref(a), stream_ptr()), "cdm_conv3x3")
     return out
 
@@ -271,7 +283,7 @@ class GemmTnArgs(C.Structure):
 class ChanReduceArgs(C.Structure):
     _fields_ = [("a", VP), ("lda", I), ("z", VP), ("ldz", I), ("scale", VP), ("shift", VP), ("mean", VP),
                 ("rstd", VP), ("relu", I), ("mode", I), ("P", LL), ("C", I), ("workspace", VP),
-                ("workspace_blocks", I), ("out", VP)]
+                ("workspace_blocks", I), ("out", VP), ("xr", VP)]
 
 
 class BnApplyArgs(C.Structure):
@@ -313,9 +325,9 @@ def gemm_tn(a, b, c, *, n_img, H, W, a_c, b_c, M, N, ldc, m_off=0, n_off=0, taps
 
 
 def chan_reduce(a, lda, P, Cn, out, ws, *, mode=0, z=None, ldz=0, scale=None, shift=None, mean=None, rstd=None,
-                relu=1):
+                relu=1, xr=None):
     g = ChanReduceArgs(rawptr(a), lda, rawptr(z), ldz, rawptr(scale), rawptr(shift), rawptr(mean), rawptr(rstd),
-                       relu, mode, P, Cn, rawptr(ws), ws.numel() // (2 * Cn), rawptr(out))
+                       relu, mode, P, Cn, rawptr(ws), ws.numel() // (2 * Cn), rawptr(out), _xr_ptr(xr))
     check(lib().cdm_chan_reduce(C.byref(g), stream_ptr()), "cdm_chan_reduce")
 
 
@@ -449,4 +461,12 @@ def normalize_params(x, repeat, out, col_min, col_max):
     check(lib().cdm_normalize_params(C.c_void_p(ptr(x)), rows, cols, repeat, out.shape[1], C.c_void_p(ptr(out)),
                                      C.c_void_p(ptr(col_min)), C.c_void_p(ptr(col_max)), stream_ptr()),
           "cdm_normalize_params")
+    return out
+
+
+def xrank_sum(partial, out, xr=None):
+    """partial fp32 [n_blocks, n]; out fp32 [n] = sum over blocks (fixed order) and over the ranks of `xr`."""
+    n_blocks, n = partial.shape
+    check(lib().cdm_xrank_sum(C.c_void_p(ptr(partial)), n_blocks, n, C.c_void_p(ptr(out)), _xr_ptr(xr), stream_ptr()),
+          "cdm_xrank_sum")
     return out

@@ -124,6 +124,9 @@ extern "C" int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream) {
     CDM_CHECK_ARG(a->sc_x && a->sc_tab && a->sc_reps >= 1);
   if (a->flags & CDM_EPI_FILM) CDM_CHECK_ARG(a->film_scale && a->film_shift && a->film_shift_rows >= 1);
   if (a->flags & CDM_EPI_GNSTATS) CDM_CHECK_ARG(a->gn_partial && a->cout == 128 && !(a->flags & CDM_EPI_POOL));
+  if (a->flags & CDM_EPI_BNSTATS)
+    CDM_CHECK_ARG(a->bn_partial && a->bn_sums && a->mode == 3 && a->H % 32 == 0 && a->W % 8 == 0 &&
+                  !(a->flags & (CDM_EPI_POOL | CDM_EPI_SHORTCUT)));
   int rc = check_device();
   if (rc) return rc;
 
@@ -181,6 +184,7 @@ extern "C" int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream) {
   p.film_shift_rows = a->film_shift_rows;
   p.step_ptr = a->step_ptr;
   p.gn_partial = a->gn_partial;
+  p.bn_partial = a->bn_partial;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (mode == 3) {
     p.n_units = a->n_img * (a->W / 8) * (a->H / 32) * p.n_tiles;
@@ -193,6 +197,10 @@ extern "C" int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream) {
     const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
     conv3x3_sw_kernel<<<grid, kSwThreads, smem, st>>>(mA0, mA1, mB, p);
     CDM_CHECK_LAUNCH();
+    if (a->flags & CDM_EPI_BNSTATS) {  // fold the per-CTA rows (and the other ranks' sums) into bn_sums
+      launch_xrank_sum(a->bn_partial, grid, 2 * a->cout, a->bn_sums, a->xr, st);
+      CDM_CHECK_LAUNCH();
+    }
     return CDM_OK;
   }
   switch (mode) {

@@ -36,4 +36,7 @@ int check_device();  // CDM_OK or CDM_ERR_ARCH / CDM_ERR_CUDA
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
 
+// Final pass of a two-stage reduction (+ cross-rank exchange over peer memory when xr->world > 1); train.cu.
+int launch_xrank_sum(const float* partial, int n_blocks, int n, float* out, const cdm_xrank* xr, cudaStream_t st);
+
 }  // namespace cdm

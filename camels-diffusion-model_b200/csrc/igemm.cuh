@@ -48,6 +48,7 @@ struct ConvKParams {
   int film_shift_rows;
   const int* step_ptr;
   float* gn_partial;
+  float* bn_partial;  // CDM_EPI_BNSTATS: [gridDim.x][2][cout]
 };
 
 template <int MODE>
@@ -570,6 +571,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const int co_l = q * 32 + lane;    // this thread's channel inside the 128-wide tile
     const int step = p.step_ptr ? *p.step_ptr : 0;
     const bool pool = p.flags & CDM_EPI_POOL;
+    float bn_s0 = 0.f, bn_q0 = 0.f, bn_s1 = 0.f, bn_q1 = 0.f;  // CDM_EPI_BNSTATS, per n_tile (cout <= 256)
     int it = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -629,6 +631,22 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             for (int i = 0; i < 32; ++i) {
               gs += f[i];
               gq = fmaf(f[i], f[i], gq);
+            }
+          }
+          if (p.flags & CDM_EPI_BNSTATS) {  // statistics of what is stored (bf16), so BatchNorm normalises z exactly
+            float ts = 0.f, tq = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float r = __bfloat162float(__float2bfloat16_rn(f[i]));
+              ts += r;
+              tq = fmaf(r, r, tq);
+            }
+            if (n_tile == 0) {
+              bn_s0 += ts;
+              bn_q0 += tq;
+            } else {
+              bn_s1 += ts;
+              bn_q1 += tq;
             }
           }
           // NHWC store without shared memory: lanes 2k / 2k+1 own channels co, co+1.  One shuffle per pixel
@@ -697,6 +715,28 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         float* d = p.gn_partial + (size_t)blockIdx.x * 8;
         d[4] = (it == 0 ? 0.f : d[4]) + (float)(e1 - e0);
         d[5] = (it == 0 ? 0.f : d[5]) + (float)(clock64() - e1);
+      }
+    }
+    if (p.flags & CDM_EPI_BNSTATS) {
+      // the two column halves of a channel live in warps q and q+4: fold them through shared memory (the
+      // scale/shift staging area is free once the unit loop is over), then one partial row per CTA
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float* fold = s_scale;  // [2 n_tiles][128][2] floats = 2 KB
+      if (half == 1) {
+        fold[(0 * 128 + co_l) * 2] = bn_s0;
+        fold[(0 * 128 + co_l) * 2 + 1] = bn_q0;
+        fold[(1 * 128 + co_l) * 2] = bn_s1;
+        fold[(1 * 128 + co_l) * 2 + 1] = bn_q1;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0) {
+        float* dst = p.bn_partial + (size_t)blockIdx.x * 2 * p.cout;
+        dst[co_l] = bn_s0 + fold[(0 * 128 + co_l) * 2];
+        dst[p.cout + co_l] = bn_q0 + fold[(0 * 128 + co_l) * 2 + 1];
+        if (p.n_tiles == 2) {
+          dst[128 + co_l] = bn_s1 + fold[(1 * 128 + co_l) * 2];
+          dst[p.cout + 128 + co_l] = bn_q1 + fold[(1 * 128 + co_l) * 2 + 1];
+        }
       }
     }
   }

@@ -156,6 +156,102 @@ __global__ void chan_reduce_final_kernel(const float* __restrict__ partial, int 
   if (lane == 0) out[i] = t;
 }
 
+// --------------------------------------------------------------------------
+// xrank_sum: the fixed-order final pass of a two-stage reduction FUSED with its cross-rank exchange over
+// NVLink peer memory (data-parallel BatchNorm statistics; replaces chan_reduce_final + an NCCL all-reduce
+// of [2C] floats, 36 times per training step).  One warp per output sums the per-CTA partials in order and
+// stores the result into slot[rank] of EVERY rank's symmetric buffer (plain P2P stores).  The last block to
+// finish (ticket) publishes a sequence number to every peer's flag word (st.release.sys), waits for the
+// peers' (ld.acquire.sys, bounded spin -> trap instead of a hang), and adds the slots in rank order — so
+// every rank obtains the bit-identical global sum, with no host involvement: the launch is graph-capturable
+// and the sequence counter lives on the device.  Slots are double-buffered on the parity of the sequence
+// number: a rank can be at most one exchange ahead of a peer.  world == 1 degenerates to the final pass.
+// --------------------------------------------------------------------------
+constexpr int kXrMaxN = 512;
+struct XrankP {
+  const float* partial;
+  int n_blocks, n;
+  float* out;
+  int rank, world;
+  const unsigned long long* peer_slots;  // [world] device pointers: fp32 [2][world][kXrMaxN] on each rank
+  const unsigned long long* peer_flags;  // [world] device pointers: int32 [world] on each rank
+  int* seq;
+  unsigned int* ticket;
+};
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(256) xrank_sum_kernel(const XrankP p) {
+  __shared__ bool last;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int s = p.world > 1 ? *p.seq + 1 : 0;  // read before the ticket: only the last block advances it
+  const int par = s & 1;
+  if (i < p.n) {
+    float t = 0.f;
+    for (int b = lane; b < p.n_blocks; b += 32) t += p.partial[(size_t)b * p.n + i];
+    t = t_warp_sum(t);
+    if (p.world == 1) {
+      if (lane == 0) p.out[i] = t;
+    } else if (lane < p.world) {  // lane q delivers to rank q (its own slot included)
+      float* dst = reinterpret_cast<float*>(p.peer_slots[lane]);
+      dst[((size_t)par * p.world + p.rank) * kXrMaxN + i] = t;
+    }
+  }
+  if (p.world == 1) return;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();
+  if (threadIdx.x < p.world && threadIdx.x != p.rank) {
+    st_release_sys(reinterpret_cast<int*>(p.peer_flags[threadIdx.x]) + p.rank, s);
+    const int* mine = reinterpret_cast<const int*>(p.peer_flags[p.rank]) + threadIdx.x;
+    unsigned int spins = 0;
+    while (ld_acquire_sys(mine) - s < 0) {
+      if (++spins > (1u << 26)) {
+        printf("cdm: cross-rank exchange timed out (rank %d waiting for rank %d, seq %d)\n", p.rank, (int)threadIdx.x, s);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  const float* slots = reinterpret_cast<const float*>(p.peer_slots[p.rank]) + (size_t)par * p.world * kXrMaxN;
+  for (int k = threadIdx.x; k < p.n; k += blockDim.x) {
+    float acc = 0.f;
+    for (int q = 0; q < p.world; ++q) acc += ld_relaxed_sys(slots + (size_t)q * kXrMaxN + k);
+    p.out[k] = acc;
+  }
+  if (threadIdx.x == 0) {
+    *p.seq = s;
+    *p.ticket = 0;
+  }
+}
+int launch_xrank_sum(const float* partial, int n_blocks, int n, float* out, const cdm_xrank* xr, cudaStream_t st) {
+  XrankP p{partial, n_blocks, n, out, 0, 1, nullptr, nullptr, nullptr, nullptr};
+  if (xr && xr->world > 1) {
+    p.rank = xr->rank;
+    p.world = xr->world;
+    p.peer_slots = xr->peer_slots;
+    p.peer_flags = xr->peer_flags;
+    p.seq = xr->seq;
+    p.ticket = xr->ticket;
+  }
+  xrank_sum_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(p);
+  return 0;
+}
+
 // BatchNorm2d train-mode finalisation from (possibly all-reduced) sums over `count` elements.
 __global__ void bn_finalize_kernel(const float* __restrict__ sums, int C, float count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum,
@@ -744,6 +840,7 @@ extern "C" int cdm_chan_reduce(const cdm_chan_reduce_args* a, void* stream) {
   CDM_CHECK_ARG(a && a->a && a->out && a->workspace && a->P > 0 && a->C > 0 && a->C % 8 == 0 && 256 % (a->C / 8) == 0);
   CDM_CHECK_ARG(a->mode >= 0 && a->mode <= 2 && a->lda >= a->C);
   if (a->mode == 1) CDM_CHECK_ARG(a->z && a->scale && a->shift && a->mean && a->rstd && a->ldz >= a->C);
+  CDM_CHECK_ARG(2 * a->C <= kXrMaxN);
   int rc = check_device();
   if (rc) return rc;
   const int rows = 256 / (a->C / 8);
@@ -755,7 +852,20 @@ extern "C" int cdm_chan_reduce(const cdm_chan_reduce_args* a, void* stream) {
                 a->relu, a->mode, a->P, a->C, a->workspace};
   chan_reduce_kernel<<<blocks, 256, 0, ST(stream)>>>(p);
   CDM_CHECK_LAUNCH();
-  chan_reduce_final_kernel<<<(2 * a->C * 32 + 255) / 256, 256, 0, ST(stream)>>>(a->workspace, blocks, 2 * a->C, a->out);
+  // fixed-order final pass, fused with the cross-rank exchange when a->xr describes a peer group
+  launch_xrank_sum(a->workspace, blocks, 2 * a->C, a->out, a->xr, ST(stream));
+  CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
+extern "C" int cdm_xrank_sum(const float* partial, int n_blocks, int n, float* out, const cdm_xrank* xr, void* stream) {
+  CDM_CHECK_ARG(partial && out && n_blocks > 0 && n > 0 && n <= kXrMaxN);
+  if (xr && xr->world > 1)
+    CDM_CHECK_ARG(xr->world <= 32 && xr->rank >= 0 && xr->rank < xr->world && xr->peer_slots && xr->peer_flags &&
+                  xr->seq && xr->ticket);
+  int rc = check_device();
+  if (rc) return rc;
+  launch_xrank_sum(partial, n_blocks, n, out, xr, ST(stream));
   CDM_CHECK_LAUNCH();
   return CDM_OK;
 }

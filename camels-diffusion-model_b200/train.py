@@ -35,6 +35,24 @@ def _allreduce(t):
     return t
 
 
+PEER = None  # parallel.PeerExchange of this process (enable_peer_exchange), or None: NCCL all-reduce of the statistics
+
+
+def enable_peer_exchange(device=None, group=None):
+    """Route the cross-rank BatchNorm statistics (forward and backward, 36 exchanges of [2C] floats per step)
+    through the fused reduce + exchange kernel over NVLink peer memory instead of NCCL.  Call once per process
+    after init_process_group; a no-op for a single rank."""
+    global PEER
+    if _world() > 1 and PEER is None:
+        from .parallel import PeerExchange
+        PEER = PeerExchange(torch.device("cuda", torch.cuda.current_device()) if device is None else device, group)
+    return PEER
+
+
+def _xr():
+    return PEER.args if (PEER is not None and _world() > 1) else None
+
+
 class _Ctx:
     """Saved tensors of one training forward."""
     pass
@@ -92,14 +110,21 @@ def _conv_bn_relu(S, P, name, seq, src, n, H, *, first=False, **apply_kw):
     cout = conv.out_channels
     z = _bf(n, H, H, cout, dev=dev)
     bias = conv.bias.detach().float().contiguous()
-    if first:
-        L.conv_in(src, P[name + ".f"], S.ones[:cout], bias, z, relu=False)
-    else:
-        L.conv3x3(src, P[name + ".f"], S.ones[:cout], bias, z, flags=0, mode=S.mode)
     Pn = n * H * H
     sums = _f32(2, cout, dev=dev)
-    L.chan_reduce(z, cout, Pn, cout, sums, S.ws, mode=0)
-    _allreduce(sums)
+    xr = _xr()
+    if not first and S.mode == L.CONV_MODE_SWAPPED and H % 32 == 0:
+        # the batch statistics come out of the convolution's epilogue (+ the cross-rank exchange): one C call
+        L.conv3x3(src, P[name + ".f"], S.ones[:cout], bias, z, flags=L.EPI_BNSTATS, mode=S.mode, bn_partial=S.bnp,
+                  bn_sums=sums, xr=xr)
+    else:
+        if first:
+            L.conv_in(src, P[name + ".f"], S.ones[:cout], bias, z, relu=False)
+        else:
+            L.conv3x3(src, P[name + ".f"], S.ones[:cout], bias, z, flags=0, mode=S.mode)
+        L.chan_reduce(z, cout, Pn, cout, sums, S.ws, mode=0, xr=xr)
+    if xr is None:
+        _allreduce(sums)
     count = float(Pn * _world())
     ly = _Layer()
     ly.name, ly.conv, ly.bn, ly.x_in, ly.z, ly.count, ly.H = name, conv, bn, src, z, count, H
@@ -132,6 +157,7 @@ class _UnetFn(torch.autograd.Function):
         S.ones = torch.ones(256, device=dev)
         S.zeros = torch.zeros(65536, device=dev)
         S.ws = _f32(148 * 8, 9 * 256, dev=dev)  # reduction workspace (partials)
+        S.bnp = _f32(148, 2 * 256, dev=dev)  # per-CTA BatchNorm partial sums of the conv epilogue
         P = _pack_train(m)
         S.P = P
         x3 = x.detach().to(dev, torch.float32).reshape(n, h, h).contiguous()
@@ -231,9 +257,11 @@ class _UnetFn(torch.autograd.Function):
             ly = S.layers[name]
             Pn, C = n * ly.H * ly.H, ly.cout
             sums = _f32(2, C, dev=dev)
+            xr = _xr()
             L.chan_reduce(dy, lddy, Pn, C, sums, S.ws, mode=1, z=ly.z, ldz=C, scale=ly.scale, shift=ly.shift,
-                          mean=ly.mean, rstd=ly.rstd, relu=1)
-            _allreduce(sums)
+                          mean=ly.mean, rstd=ly.rstd, relu=1, xr=xr)
+            if xr is None:
+                _allreduce(sums)
             G[prefix + ".1.weight"], G[prefix + ".1.bias"] = sums[1].clone(), sums[0].clone()
             bn_affine.update((prefix + ".1.weight", prefix + ".1.bias"))
             dz = _bf(n, ly.H, ly.H, C, dev=dev)

@@ -43,6 +43,9 @@ int cdm_device_ok(void);
 #define CDM_EPI_POOL 4      /* 2x2 max-pool, output [n][H/2][W/2][cout]        */
 #define CDM_EPI_FILM 8      /* y = film_scale[n][co]*y + film_shift[..][co]    */
 #define CDM_EPI_GNSTATS 16  /* emit per-(n,slot,group) sum / sum-of-squares    */
+#define CDM_EPI_BNSTATS 32  /* per-channel sum / sum-of-squares of the (bf16-rounded) output over the whole
+                             * launch -> bn_sums, all ranks of `xr` included: the batch statistics of a
+                             * train-mode nn.BatchNorm2d come out of the convolution itself (MODE 3 only) */
 
 /* A-operand feeding strategy of cdm_conv3x3. */
 #define CDM_CONV_MODE_COPIES 0  /* three kw-shifted TMA copies, aligned views  */
@@ -57,6 +60,7 @@ int cdm_device_ok(void);
  * (ContextUnet.py:36,59) and the fresh 1x1 shortcut (diffusion_utilities.py:54).
  *   y[n,h,w,co] = scale[co] * sum_{kh,kw,ci} in[n,h+kh-1,w+kw-1,ci] * weight[co,kh,kw,ci] + shift[co]
  * `in` is the channel concatenation of src0 (c0 channels) and src1 (c1). */
+struct cdm_xrank_s; /* peer group of the cross-rank exchange, defined with cdm_chan_reduce below */
 typedef struct {
   const void* src0;   /* bf16 [n_img][H][W][c0] */
   const void* src1;   /* bf16 [n_img][H][W][c1] or NULL */
@@ -82,6 +86,11 @@ typedef struct {
   /* CDM_EPI_GNSTATS: fp32 [n_img][(H/16)*(W/16)*8][8][2] */
   float* gn_partial;
   int mode; /* CDM_CONV_MODE_* */
+  /* CDM_EPI_BNSTATS: workspace fp32 [148][2][cout]; bn_sums fp32 [2][cout] = (sum, sum of squares) per channel
+   * over every rank of `xr` (NULL: this rank only) */
+  float* bn_partial;
+  float* bn_sums;
+  const struct cdm_xrank_s* xr;
 } cdm_conv3x3_args;
 int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream);
 
@@ -230,6 +239,19 @@ int cdm_mse_accum(const cdm_mse_accum_args* a, void* stream);
  *   mode 1: sum g, sum g*xhat, g = dy*[relu mask] (BatchNorm2d + ReLU backward)
  *   mode 2: sum a, 0                             (bias gradients)
  * workspace: fp32 [workspace_blocks][2][C]. */
+/* Peer group of the fused reduce + cross-rank exchange (data-parallel BatchNorm statistics; what the reference
+ * would get from nn.SyncBatchNorm + NCCL).  Every rank owns one symmetric buffer: fp32 slots [2][world][512]
+ * followed by int32 flags [world], zero-filled once; peer_slots / peer_flags are DEVICE arrays of `world` device
+ * pointers to those regions on every rank (NVLink peer mappings; rank's own entry included).  seq / ticket: device
+ * int32 scalars owned by the caller, zero-initialised.  NULL or world == 1: rank-local reduction. */
+typedef struct cdm_xrank_s {
+  int rank, world;
+  const unsigned long long* peer_slots;
+  const unsigned long long* peer_flags;
+  int* seq;
+  unsigned int* ticket;
+} cdm_xrank;
+
 typedef struct {
   const void* a; int lda;
   const void* z; int ldz;
@@ -238,8 +260,12 @@ typedef struct {
   long long P; int C;
   float* workspace; int workspace_blocks;
   float* out;
+  const cdm_xrank* xr; /* NULL: rank-local sums; else `out` = sum over all ranks, bit-identical on every rank */
 } cdm_chan_reduce_args;
 int cdm_chan_reduce(const cdm_chan_reduce_args* a, void* stream);
+/* out[i] = sum over ranks of sum_b partial[b][i] (b in fixed order), i < n <= 512: the final pass of a two-stage
+ * reduction fused with its exchange over peer memory (one kernel, graph-capturable, deterministic). */
+int cdm_xrank_sum(const float* partial, int n_blocks, int n, float* out, const cdm_xrank* xr, void* stream);
 
 /* sums[2][C] (after the optional cross-rank all-reduce) -> scale = gamma*rstd, shift = beta - mean*scale,
  * mean, rstd; running_mean/var updated with `momentum` and the UNBIASED variance (torch semantics). */

@@ -373,3 +373,34 @@ def test_graphed_training_step_equals_eager():
         assert rel_l2(sd_g[k], sd_e[k]) < 1e-4, k
     for k in ("out.0.weight", "init_conv.conv1.0.weight"):   # parameters did move
         assert not torch.equal(sd_g[k].cpu(), O.init_state_dict(0, n_cfeat=NCF)[k])
+
+
+def test_conv_epilogue_batchnorm_statistics(L):
+    """CDM_EPI_BNSTATS: per-channel sum / sum of squares of the stored (bf16) conv output come out of the
+    convolution launch itself (per-CTA partial rows folded in a fixed order)."""
+    for n, H, cin, cout in ((5, 64, 128, 128), (3, 32, 128, 256), (40, 32, 256, 256)):
+        g = torch.Generator(device="cuda").manual_seed(n)
+        x = torch.randn(n, H, H, cin, device="cuda", generator=g).to(torch.bfloat16)
+        w = (torch.randn(cout, 3, 3, cin, device="cuda", generator=g) / (3 * cin ** 0.5)).to(torch.bfloat16)
+        bias = torch.randn(cout, device="cuda", generator=g)
+        ones = torch.ones(cout, device="cuda")
+        z = torch.empty(n, H, H, cout, device="cuda", dtype=torch.bfloat16)
+        part = torch.full((148, 2 * cout), float("nan"), device="cuda")
+        sums = torch.empty(2, cout, device="cuda")
+        L.conv3x3(x, w, ones, bias, z, flags=L.EPI_BNSTATS, bn_partial=part, bn_sums=sums)
+        z_plain = torch.empty_like(z)
+        L.conv3x3(x, w, ones, bias, z_plain, flags=0)
+        assert torch.equal(z, z_plain)
+        zf = z.float().reshape(-1, cout).double()
+        assert rel_l2(sums[0], zf.sum(0)) < 1e-5 and rel_l2(sums[1], (zf * zf).sum(0)) < 1e-5
+        sums2 = torch.empty_like(sums)
+        L.conv3x3(x, w, ones, bias, z, flags=L.EPI_BNSTATS, bn_partial=part, bn_sums=sums2)
+        assert torch.equal(sums, sums2), "fixed-order reduction must be deterministic"
+
+
+def test_xrank_sum_single_rank(L):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    part = torch.randn(592, 512, device="cuda", generator=g)
+    out = torch.empty(512, device="cuda")
+    L.xrank_sum(part, out)
+    assert rel_l2(out, part.double().sum(0)) < 1e-6

@@ -16,6 +16,29 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 NCF, T = 6, 1500
+from camels_diffusion_model_b200 import _lib as L
+from camels_diffusion_model_b200.parallel import PeerExchange
+# ---- the fused reduce + cross-rank exchange kernel on its own: rank-dependent partials, 50 back-to-back exchanges
+px = PeerExchange(dev)
+gx = torch.Generator().manual_seed(123)
+parts = [torch.randn(37, 300, generator=gx) for _ in range(world)]   # every rank knows every rank's partials
+out = torch.empty(300, device=dev)
+ok = True
+for it in range(50):
+    mine = (parts[rank] * (it + 1)).to(dev)
+    L.xrank_sum(mine, out, xr=px.args)
+    expect = torch.zeros(300, device=dev)
+    for r in range(world):  # rank order, each rank's row-sum computed by the same kernel path (world = 1)
+        loc = torch.empty(300, device=dev)
+        L.xrank_sum((parts[r] * (it + 1)).to(dev), loc)
+        expect += loc
+    ok = ok and torch.equal(out, expect)
+gath = [torch.empty_like(out) for _ in range(world)]
+dist.all_gather(gath, out)
+same = all(torch.equal(gath[0], g_) for g_ in gath)
+if rank == 0:
+    print(f"XRANK-SUM world={world}: 50 exchanges exact vs rank-ordered sum: {ok}; bit-identical on all ranks: {same}")
+del px
 torch.manual_seed(0)
 ref_model = cdm.ContextUnet(1, 128, NCF, 64)
 g = torch.Generator().manual_seed(1)
@@ -42,25 +65,30 @@ def step(xs, ps, ns, ts, dp):
     return m, float(loss)
 
 s, e = rank * 4, rank * 4 + 4
-m_dp, loss_dp = step(x[s:e], prm[s:e], noise[s:e], t[s:e], True)
 m_1, loss_1 = step(x, prm, noise, t, False)
-worst, key = 0.0, {}
-for (n1, p1), (n2, p2) in zip(m_1.named_parameters(), m_dp.named_parameters()):
-    if float(p1.grad.norm()) < 1e-7: continue
-    err = float((p1.grad - p2.grad).norm() / p1.grad.norm())
-    worst = max(worst, err)
-    if n1 in ("out.3.weight", "out.0.weight", "out.1.weight", "up2.model.2.conv2.1.weight", "up2.model.2.conv2.0.weight"):
-        key[n1] = f"{err:.2e}"
-bn_err = max(float((b1 - b2).abs().max()) for (k, b1), (_, b2) in zip(m_1.named_buffers(), m_dp.named_buffers())
-             if "running" in k)
-lt = torch.tensor([loss_dp], device=dev)
-dist.all_reduce(lt)
-if rank == 0:
-    # random-init train-mode BatchNorm stacks amplify ANY perturbation ~1.3x per layer (gradient explosion at
-    # init), so only the layers nearest the loss are a sharp check of the all-reduce logic; `worst` is informational
-    print("DP-CHECK well-conditioned gradients (sharded vs single-process rel-L2):", key)
-    print(f"DP-CHECK world={world}: worst grad rel-L2 (sharded vs single-process) {worst:.3e}; "
-          f"max |running-stat diff| {bn_err:.3e}; mean rank loss {float(lt) / world:.6f} vs global {loss_1:.6f}")
+for mode in ("nccl", "peer"):
+    if mode == "peer":
+        TR.DATA_PARALLEL = True
+        TR.enable_peer_exchange(dev)
+    m_dp, loss_dp = step(x[s:e], prm[s:e], noise[s:e], t[s:e], True)
+    worst, key = 0.0, {}
+    for (n1, p1), (n2, p2) in zip(m_1.named_parameters(), m_dp.named_parameters()):
+        if float(p1.grad.norm()) < 1e-7: continue
+        err = float((p1.grad - p2.grad).norm() / p1.grad.norm())
+        worst = max(worst, err)
+        if n1 in ("out.3.weight", "out.0.weight", "out.1.weight", "up2.model.2.conv2.1.weight", "up2.model.2.conv2.0.weight"):
+            key[n1] = f"{err:.2e}"
+    bn_err = max(float((b1 - b2).abs().max()) for (k, b1), (_, b2) in zip(m_1.named_buffers(), m_dp.named_buffers())
+                 if "running" in k)
+    lt = torch.tensor([loss_dp], device=dev)
+    dist.all_reduce(lt)
+    if rank == 0:
+        # random-init train-mode BatchNorm stacks amplify ANY perturbation ~1.3x per layer (gradient explosion at
+        # init), so only the layers nearest the loss are a sharp check of the exchange logic; `worst` is informational
+        print(f"DP-CHECK[{mode}] well-conditioned gradients (sharded vs single-process rel-L2):", key)
+        print(f"DP-CHECK[{mode}] world={world}: worst grad rel-L2 (sharded vs single-process) {worst:.3e}; "
+              f"max |running-stat diff| {bn_err:.3e}; mean rank loss {float(lt) / world:.6f} vs global {loss_1:.6f}")
+TR.PEER = None
 
 # ---- throughput of a training step, BASELINE config 3: global batch 256
 TR.DATA_PARALLEL = True
@@ -86,30 +114,36 @@ if rank == 0:
     tf = 3 * 19.1785e9 * GB / (float(ms) * 1e-3) / 1e12
     print(f"TRAIN-BENCH world={world} global_batch={GB}: {float(ms):.2f} ms/step, {GB / float(ms) * 1e3:.0f} img/s, "
           f"{tf:.0f} TFLOP/s aggregate (3x forward FLOPs), loss {float(loss):.4f}")
-# ---- the same step captured as a CUDA graph (NCCL all-reduces inside the capture), 32 and 128 images per GPU
-for per in (32, GB // world):
-    try:
-        torch.manual_seed(0)
-        model = cdm.ContextUnet(1, 128, NCF, 64)
-        model.load_state_dict(sd)
-        model = model.to(dev).train()
-        gs = TR.GraphedTrainStep(model, per, T, ab_t, lr=1e-5)
-        xb, pb = torch.rand(per, 1, 64, 64, generator=g).to(dev), torch.rand(per, NCF, generator=g).to(dev)
-        tb = torch.randint(1, T + 1, (per,), generator=g).to(dev)
-        for _ in range(3): gs(xb, pb, t=tb, shortcut=sc)
-        torch.cuda.synchronize(); dist.barrier()
-        e0.record()
-        for _ in range(K): loss = gs(xb, pb, t=tb, shortcut=sc)
-        e1.record(); torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1) / K], device=dev)
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            print(f"TRAIN-BENCH-GRAPH world={world} per_gpu={per}: {float(ms):.2f} ms/step, "
-                  f"{per * world / float(ms) * 1e3:.0f} img/s, loss {float(loss):.4f}")
-        del gs, model
-        torch.cuda.empty_cache()
-    except Exception as ex:  # noqa: BLE001
-        if rank == 0:
-            print("TRAIN-BENCH-GRAPH failed:", type(ex).__name__, str(ex)[:300])
-        break
+# ---- the same step captured as a CUDA graph, 32 and 128 images per GPU; BatchNorm statistics exchanged by NCCL
+# all-reduces inside the capture ("nccl") or by the fused reduce + exchange kernel over NVLink peer memory ("peer")
+for mode in ("nccl", "peer"):
+    TR.PEER = None
+    if mode == "peer":
+        TR.enable_peer_exchange(dev)
+    for per in (32, GB // world):
+        try:
+            torch.manual_seed(0)
+            model = cdm.ContextUnet(1, 128, NCF, 64)
+            model.load_state_dict(sd)
+            model = model.to(dev).train()
+            gs = TR.GraphedTrainStep(model, per, T, ab_t, lr=1e-5)
+            g2 = torch.Generator().manual_seed(77 + rank)
+            xb, pb = torch.rand(per, 1, 64, 64, generator=g2).to(dev), torch.rand(per, NCF, generator=g2).to(dev)
+            tb = torch.randint(1, T + 1, (per,), generator=g2).to(dev)
+            for _ in range(3): gs(xb, pb, t=tb, shortcut=sc)
+            torch.cuda.synchronize(); dist.barrier()
+            e0.record()
+            for _ in range(K): loss = gs(xb, pb, t=tb, shortcut=sc)
+            e1.record(); torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1) / K], device=dev)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print(f"TRAIN-BENCH-GRAPH[{mode}] world={world} per_gpu={per}: {float(ms):.2f} ms/step, "
+                      f"{per * world / float(ms) * 1e3:.0f} img/s, loss {float(loss):.4f}")
+            del gs, model
+            torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001
+            if rank == 0:
+                print(f"TRAIN-BENCH-GRAPH[{mode}] failed:", type(ex).__name__, str(ex)[:300])
+            break
 dist.destroy_process_group()
