@@ -277,7 +277,7 @@ VP, I, F, LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 class GemmTnArgs(C.Structure):
     _fields_ = [("a", VP), ("a_c", I), ("b", VP), ("b_c", I), ("n_img", I), ("H", I), ("W", I), ("taps", I),
                 ("m_off", I), ("M", I), ("n_off", I), ("N", I), ("c", VP), ("ldc", I), ("tap_stride", I),
-                ("k_split", I)]
+                ("k_split", I), ("workspace", VP), ("workspace_floats", LL), ("probe", VP)]
 
 
 class ChanReduceArgs(C.Structure):
@@ -318,9 +318,10 @@ def rawptr(t):
     return None if t is None else t.data_ptr()
 
 
-def gemm_tn(a, b, c, *, n_img, H, W, a_c, b_c, M, N, ldc, m_off=0, n_off=0, taps=1, tap_stride=0, k_split=0):
+def gemm_tn(a, b, c, *, n_img, H, W, a_c, b_c, M, N, ldc, m_off=0, n_off=0, taps=1, tap_stride=0, k_split=0,
+            workspace=None, probe=None):
     g = GemmTnArgs(rawptr(a), a_c, rawptr(b), b_c, n_img, H, W, taps, m_off, M, n_off, N, rawptr(c), ldc, tap_stride,
-                   k_split)
+                   k_split, rawptr(workspace), 0 if workspace is None else workspace.numel(), rawptr(probe))
     check(lib().cdm_gemm_tn(C.byref(g), stream_ptr()), "cdm_gemm_tn")
 
 

@@ -316,6 +316,67 @@ extern "C" int cdm_gemm_tn(const cdm_gemm_tn_args* a, void* stream) {
   CDM_CHECK_ARG(a->ldc > 0);
   int rc = check_device();
   if (rc) return rc;
+  if (a->taps == 9 && a->W % 8 == 0 && a->H % 16 == 0) {
+    // 3x3 weight gradient: 8 px x 16 row patches, one kernel row (three taps) per instruction (gemm_tn9_kernel)
+    CUtensorMap mA, mB;
+    {
+      uint64_t dims[4] = {(uint64_t)a->a_c, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
+      uint64_t str[3] = {(uint64_t)a->a_c * 2, (uint64_t)a->W * a->a_c * 2, (uint64_t)a->H * a->W * a->a_c * 2};
+      uint32_t box[4] = {64, 8, 16, 1};
+      rc = make_tmap_bf16(&mA, a->a, 4, dims, str, box);
+      if (rc) return rc;
+    }
+    {
+      uint64_t dims[4] = {(uint64_t)a->b_c, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
+      uint64_t str[3] = {(uint64_t)a->b_c * 2, (uint64_t)a->W * a->b_c * 2, (uint64_t)a->H * a->W * a->b_c * 2};
+      uint32_t box[4] = {64, 10, 16, 1};
+      rc = make_tmap_bf16(&mB, a->b, 4, dims, str, box);
+      if (rc) return rc;
+    }
+    GemmTnKParams p;
+    memset(&p, 0, sizeof(p));
+    p.m_tiles = a->M / 128;
+    p.n_tiles = a->N / 128;
+    p.taps = 9;
+    p.bw = 8;
+    p.bh = 16;
+    p.tiles_x = a->W / 8;
+    p.tiles_y = a->H / 16;
+    p.k_blocks = p.tiles_x * p.tiles_y * a->n_img;
+    const int base_units = 3 * p.m_tiles * p.n_tiles;
+    // one unit per CTA and no second wave: 150 units on 148 SMs would double the makespan
+    int ks = a->k_split > 0 ? a->k_split : num_sms() / base_units;
+    if (ks > p.k_blocks) ks = p.k_blocks;
+    if (ks < 1) ks = 1;
+    p.k_split = ks;
+    p.n_units = base_units * ks;
+    p.a_off = a->m_off;
+    p.b_off = a->n_off;
+    p.C = a->c;
+    p.ldc = a->ldc;
+    p.tap_stride = a->tap_stride;
+    p.probe = a->probe;
+    if (a->workspace) {
+      CDM_CHECK_ARG(a->workspace_floats >= (long long)p.n_units * 128 * 384);
+      p.partial = a->workspace;
+    }
+    constexpr int smem9 = gemm_tn9_smem_bytes();
+    static bool attr9_set = false;
+    if (!attr9_set) {
+      CDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem9));
+      attr9_set = true;
+    }
+    const int grid9 = p.n_units < num_sms() ? p.n_units : num_sms();
+    gemm_tn9_kernel<<<grid9, kConvThreads, smem9, reinterpret_cast<cudaStream_t>(stream)>>>(mA, mB, p);
+    CDM_CHECK_LAUNCH();
+    if (p.partial) {
+      const long long per_slice = (long long)base_units * 128 * 384;
+      gemm_tn9_reduce_kernel<<<(int)((per_slice + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+          p.partial, p.k_split, p.m_tiles, p.n_tiles, p.C, p.ldc, p.tap_stride);
+      CDM_CHECK_LAUNCH();
+    }
+    return CDM_OK;
+  }
   // a K block is 128 rows: [rows] mode (H == 1, n_img == 1) takes 128 consecutive rows (ragged tail zero-filled
   // by TMA); image mode takes a bw x bh pixel rectangle so that a tap shift is a coordinate offset
   int bw = 128, bh = 1;

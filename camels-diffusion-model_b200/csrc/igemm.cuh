@@ -1080,6 +1080,8 @@ struct GemmTnKParams {
   int a_off, b_off;             // first channel of the A / B windows
   float* C;
   int ldc, tap_stride;
+  float* probe;
+  float* partial;  // gemm_tn9: [unit][128][384] split-K tiles (NULL: atomics into C)
 };
 constexpr int kTnStages = 3;
 constexpr int kTnStageBytes = 4 * 16384;
@@ -1200,6 +1202,185 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
+// --------------------------------------------------------------------------
+// gemm_tn9: the 3x3-convolution weight gradient, three taps per instruction.
+//   dW[co][kh][kw][ci] += sum_px dz[px][co] * x[px + (kh-1, kw-1)][ci]
+// gemm_tn_kernel spends one M128 N128 K16 instruction stream per tap and re-loads both operands for every
+// tap: 8 KB of operand reads per 64 tensor-core cycles plus 64 KB of TMA fill per 512 cycles = 256 B/clk against
+// the 128 B/clk of shared memory, i.e. half rate (measured 805 TFLOP/s).  Here a K block is a patch of 8 px x 16
+// rows; for one kernel row kh the x operand is loaded ONCE with its left/right halo (box {64 ch, 10, 16}) and the
+// three kw taps are three 64-channel "MN blocks" of ONE descriptor whose leading-dimension byte offset is 128 B =
+// one pixel: block j of the B operand is the same shared-memory tile shifted by j pixels.  One M128 N192 K16
+// instruction per channel half therefore produces dW[:, kh, 0..2, half]: operand reads 10 KB / 96 clk, fill 72 KB
+// per 1536 clk = 151 B/clk.  Units = (K slice, kh, m_tile, n_tile); accumulators 2 x 192 TMEM columns; split-K
+// partial sums are added to C with fp32 atomics (the caller zero-fills C).
+// --------------------------------------------------------------------------
+constexpr int kTn9Stages = 3;
+constexpr int kTn9ABytes = 2 * 16384;            // dz: two channel halves of {64 ch, 8, 16}
+constexpr int kTn9BHalf = 10 * 16 * 128;         // x : {64 ch, 10, 16} = 20480 B per channel half
+constexpr int kTn9StageBytes = kTn9ABytes + 2 * kTn9BHalf;
+constexpr int gemm_tn9_smem_bytes() { return kTn9Stages * kTn9StageBytes + 256 + 1024; }
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+gemm_tn9_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                const GemmTnKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTn9Stages * kTn9StageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = full + kTn9Stages;
+  uint64_t* t_full = empty + kTn9Stages;
+  uint64_t* t_empty = t_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTn9Stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(t_full, 1);
+    mbar_init(t_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int kb_per_slice = (p.k_blocks + p.k_split - 1) / p.k_split;
+  // unit -> (slice, kh, m_tile, n_tile), slice slowest: concurrently running CTAs share K blocks in L2
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    int st = 0;
+    uint32_t ph = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int n_tile = u % p.n_tiles, m_tile = (u / p.n_tiles) % p.m_tiles;
+      const int kh = (u / (p.n_tiles * p.m_tiles)) % 3, slice = u / (p.n_tiles * p.m_tiles * 3);
+      const int kb0 = slice * kb_per_slice, kb1 = min(p.k_blocks, kb0 + kb_per_slice);
+      const int ca = p.a_off + m_tile * 128, cb = p.b_off + n_tile * 128;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int tx = kb % p.tiles_x, ty = (kb / p.tiles_x) % p.tiles_y, img = kb / (p.tiles_x * p.tiles_y);
+        mbar_wait(&empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&full[st], kTn9StageBytes);
+        uint8_t* sp = smem + st * kTn9StageBytes;
+        tma_load_4d(sp, &mapA, &full[st], ca, tx * 8, ty * 16, img);
+        tma_load_4d(sp + 16384, &mapA, &full[st], ca + 64, tx * 8, ty * 16, img);
+        tma_load_4d(sp + kTn9ABytes, &mapB, &full[st], cb, tx * 8 - 1, ty * 16 + kh - 1, img);
+        tma_load_4d(sp + kTn9ABytes + kTn9BHalf, &mapB, &full[st], cb + 64, tx * 8 - 1, ty * 16 + kh - 1, img);
+        if (++st == kTn9Stages) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = umma_idesc_bf16_mn(128, 192);
+    int st = 0, it = 0;
+    uint32_t ph = 0;
+    long long w_full = 0, w_acc = 0, c0 = 0;
+    const long long c_start = p.probe ? clock64() : 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
+      const int slice = u / (p.n_tiles * p.m_tiles * 3);
+      const int kb0 = slice * kb_per_slice, kb1 = min(p.k_blocks, kb0 + kb_per_slice);
+      if (p.probe) c0 = clock64();
+      mbar_wait(t_empty, (it & 1) ^ 1);
+      if (p.probe) w_acc += clock64() - c0;
+      tc_fence_after();
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if (p.probe) c0 = clock64();
+        mbar_wait(&full[st], ph);
+        if (p.probe) w_full += clock64() - c0;
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + st * kTn9StageBytes), b_base = a_base + kTn9ABytes;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {  // 16 K rows = two image rows of the patch per instruction
+          const uint64_t adesc = umma_desc_sw128_mn(a_base + ks * 2048, 16384, 1024);
+          const uint32_t acc = (kb == kb0 && ks == 0) ? 0u : 1u;
+          // B: 8-pixel atoms 1280 B apart (halo pitch 10), the three kw taps 128 B apart
+          umma_bf16(tmem_base, adesc, umma_desc_sw128_mn(b_base + ks * 2560, 128, 1280), idesc, acc);
+          umma_bf16(tmem_base + 192, adesc, umma_desc_sw128_mn(b_base + kTn9BHalf + ks * 2560, 128, 1280), idesc, acc);
+        }
+        umma_commit(&empty[st]);
+        if (++st == kTn9Stages) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+      umma_commit(t_full);
+    }
+    if (p.probe) {
+      p.probe[blockIdx.x * 4 + 0] = (float)w_full;
+      p.probe[blockIdx.x * 4 + 1] = (float)w_acc;
+      p.probe[blockIdx.x * 4 + 2] = (float)(clock64() - c_start);
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    int it = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
+      const int n_tile = u % p.n_tiles, m_tile = (u / p.n_tiles) % p.m_tiles;
+      const int kh = (u / (p.n_tiles * p.m_tiles)) % 3, slice = u / (p.n_tiles * p.m_tiles * 3);
+      const int kb0 = slice * kb_per_slice, kb1 = min(p.k_blocks, kb0 + kb_per_slice);
+      mbar_wait(t_full, it & 1);
+      const long long e0 = p.probe ? clock64() : 0;
+      tc_fence_after();
+      if (kb1 <= kb0 && p.partial) {  // an empty K slice still owns a tile of the fixed-order reduction
+        float4* zrow = reinterpret_cast<float4*>(p.partial + ((size_t)u * 128 + q * 32 + lane) * 384);
+        for (int i = 0; i < 96; ++i) zrow[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (kb1 > kb0) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        float* crow = p.C + (size_t)(m_tile * 128 + q * 32 + lane) * p.ldc + n_tile * 128;
+        float4* prow = p.partial ? reinterpret_cast<float4*>(p.partial + ((size_t)u * 128 + q * 32 + lane) * 384) : nullptr;
+#pragma unroll 1
+        for (int cc = 0; cc < 12; ++cc) {  // column = half*192 + kw*64 + c
+          uint32_t v[32];
+          tmem_ld_x32(taddr + cc * 32, v);
+          tmem_wait_ld();
+          if (prow) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              prow[cc * 8 + i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                             __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            continue;
+          }
+          const int col = cc * 32, half = col / 192, kw = (col % 192) / 64, c0 = col % 64;
+          float* dst = crow + (kh * 3 + kw) * p.tap_stride + half * 64 + c0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty);
+      if (p.probe && threadIdx.x == 128) p.probe[blockIdx.x * 4 + 3] = (it == 0 ? 0.f : p.probe[blockIdx.x * 4 + 3]) + (float)(clock64() - e0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// Fixed-order sum of the split-K tiles of gemm_tn9_kernel: C[...] += sum_slice partial[slice][kh][m_tile][n_tile][row][col].
+__global__ void __launch_bounds__(256) gemm_tn9_reduce_kernel(const float* __restrict__ partial, int k_split, int m_tiles,
+                                                              int n_tiles, float* __restrict__ C, int ldc, int tap_stride) {
+  const size_t tile = (size_t)128 * 384;
+  const size_t per_slice = (size_t)3 * m_tiles * n_tiles * tile;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per_slice) return;
+  const int col = (int)(idx % 384), row = (int)((idx / 384) % 128);
+  const int un = (int)(idx / tile);  // (kh * m_tiles + m_tile) * n_tiles + n_tile
+  const int n_tile = un % n_tiles, m_tile = (un / n_tiles) % m_tiles, kh = un / (n_tiles * m_tiles);
+  float acc = 0.f;
+  for (int sl = 0; sl < k_split; ++sl) acc += partial[(size_t)sl * per_slice + idx];
+  const int half = col / 192, kw = (col % 192) / 64, c = col % 64;
+  float* dst = C + (size_t)(m_tile * 128 + row) * ldc + (kh * 3 + kw) * tap_stride + n_tile * 128 + half * 64 + c;
+  *dst += acc;
 }
 
 // --------------------------------------------------------------------------

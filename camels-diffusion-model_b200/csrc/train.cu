@@ -191,7 +191,7 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
   asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
   return v;
 }
-__global__ void __launch_bounds__(256) xrank_sum_kernel(const XrankP p) {
+__global__ void __launch_bounds__(1024) xrank_sum_kernel(const XrankP p) {
   __shared__ bool last;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int s = p.world > 1 ? *p.seq + 1 : 0;  // read before the ticket: only the last block advances it
@@ -208,13 +208,17 @@ __global__ void __launch_bounds__(256) xrank_sum_kernel(const XrankP p) {
     }
   }
   if (p.world == 1) return;
-  __threadfence_system();
+  // one system-scope fence per block: bar.sync orders the block's peer stores before thread 0's fence, the fence
+  // is cumulative, and the ticket (then the flag) is written after it
   __syncthreads();
-  if (threadIdx.x == 0) last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+  }
   __syncthreads();
   if (!last) return;
-  __threadfence_system();
   if (threadIdx.x < p.world && threadIdx.x != p.rank) {
+    __threadfence_system();
     st_release_sys(reinterpret_cast<int*>(p.peer_flags[threadIdx.x]) + p.rank, s);
     const int* mine = reinterpret_cast<const int*>(p.peer_flags[p.rank]) + threadIdx.x;
     unsigned int spins = 0;
@@ -226,7 +230,6 @@ __global__ void __launch_bounds__(256) xrank_sum_kernel(const XrankP p) {
     }
   }
   __syncthreads();
-  __threadfence_system();
   const float* slots = reinterpret_cast<const float*>(p.peer_slots[p.rank]) + (size_t)par * p.world * kXrMaxN;
   for (int k = threadIdx.x; k < p.n; k += blockDim.x) {
     float acc = 0.f;
@@ -248,7 +251,7 @@ int launch_xrank_sum(const float* partial, int n_blocks, int n, float* out, cons
     p.seq = xr->seq;
     p.ticket = xr->ticket;
   }
-  xrank_sum_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(p);
+  xrank_sum_kernel<<<(n * 32 + 1023) / 1024, 1024, 0, st>>>(p);
   return 0;
 }
 

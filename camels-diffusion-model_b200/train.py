@@ -158,6 +158,7 @@ class _UnetFn(torch.autograd.Function):
         S.zeros = torch.zeros(65536, device=dev)
         S.ws = _f32(148 * 8, 9 * 256, dev=dev)  # reduction workspace (partials)
         S.bnp = _f32(148, 2 * 256, dev=dev)  # per-CTA BatchNorm partial sums of the conv epilogue
+        S.wgws = _f32(160 * 128 * 384, dev=dev)  # split-K tiles of the 3x3 weight gradients (fixed-order reduction)
         P = _pack_train(m)
         S.P = P
         x3 = x.detach().to(dev, torch.float32).reshape(n, h, h).contiguous()
@@ -249,7 +250,7 @@ class _UnetFn(torch.autograd.Function):
             Hh = dz.shape[1]
             for s in srcs:
                 L.gemm_tn(dz, s, dw.view(-1)[off:], n_img=n, H=Hh, W=Hh, a_c=cout, b_c=s.shape[3], M=cout,
-                          N=s.shape[3], ldc=9 * cin, taps=9, tap_stride=cin)
+                          N=s.shape[3], ldc=9 * cin, taps=9, tap_stride=cin, workspace=S.wgws)
                 off += s.shape[3]
             return dw.view(cout, 3, 3, cin).permute(0, 3, 1, 2).contiguous()
 

@@ -65,6 +65,16 @@ def test_gemm_tn_is_conv3x3_wgrad(L, n, H, cin, cout):
     y = F.conv2d(x.float().permute(0, 3, 1, 2), w, padding=1)
     y.backward(dz.float().permute(0, 3, 1, 2))
     assert rel_l2(dw.view(cout, 3, 3, cin).permute(0, 3, 1, 2), w.grad) < 1e-4
+    # split-K tiles through a workspace + fixed-order reduction: same result, bit-reproducible
+    ws = torch.empty(160 * 128 * 384, device="cuda")
+    outs = []
+    for _ in range(2):
+        d2 = torch.zeros(cout, 9 * cin, device="cuda")
+        L.gemm_tn(dz, x, d2, n_img=n, H=H, W=H, a_c=cout, b_c=cin, M=cout, N=cin, ldc=9 * cin, taps=9, tap_stride=cin,
+                  workspace=ws)
+        outs.append(d2)
+    assert rel_l2(outs[0].view(cout, 3, 3, cin).permute(0, 3, 1, 2), w.grad) < 1e-4
+    assert torch.equal(outs[0], outs[1])
 
 
 def test_conv_dgrad_is_conv_with_flipped_weights(L):

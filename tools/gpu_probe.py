@@ -199,6 +199,52 @@ def case_waits(name, n=2048, H=64, cin=128, cout=128, flags=1):
     return True
 
 
+def case_wgrad(name, n=256, H=64, cin=128, cout=128, use_ws=True):
+    """3x3 weight-gradient GEMM (cdm_gemm_tn taps=9): correctness vs autograd on a small case + throughput."""
+    import torch
+    import torch.nn.functional as F
+    L = _load()
+    dev = "cuda"
+    xs = torch.randn(2, H, H, cin, device=dev).to(torch.bfloat16)
+    dzs = torch.randn(2, H, H, cout, device=dev).to(torch.bfloat16)
+    dw = torch.zeros(cout, 9 * cin, device=dev)
+    L.gemm_tn(dzs, xs, dw, n_img=2, H=H, W=H, a_c=cout, b_c=cin, M=cout, N=cin, ldc=9 * cin, taps=9, tap_stride=cin)
+    w = torch.zeros(cout, cin, 3, 3, device=dev, requires_grad=True)
+    F.conv2d(xs.float().permute(0, 3, 1, 2), w, padding=1).backward(dzs.float().permute(0, 3, 1, 2))
+    err = rel_l2(dw.view(cout, 3, 3, cin).permute(0, 3, 1, 2), w.grad)
+    ws = torch.empty(160 * 128 * 384, device=dev) if use_ws else None
+    dw2 = torch.zeros(cout, 9 * cin, device=dev)
+    L.gemm_tn(dzs, xs, dw2, n_img=2, H=H, W=H, a_c=cout, b_c=cin, M=cout, N=cin, ldc=9 * cin, taps=9, tap_stride=cin,
+              workspace=ws)
+    err = max(err, rel_l2(dw2.view(cout, 3, 3, cin).permute(0, 3, 1, 2), w.grad))
+    x = torch.randn(n, H, H, cin, device=dev).to(torch.bfloat16)
+    dz = torch.randn(n, H, H, cout, device=dev).to(torch.bfloat16)
+    dw = torch.zeros(cout, 9 * cin, device=dev)
+    for _ in range(3):
+        L.gemm_tn(dz, x, dw, n_img=n, H=H, W=H, a_c=cout, b_c=cin, M=cout, N=cin, ldc=9 * cin, taps=9, tap_stride=cin,
+                  workspace=ws)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        L.gemm_tn(dz, x, dw, n_img=n, H=H, W=H, a_c=cout, b_c=cin, M=cout, N=cin, ldc=9 * cin, taps=9, tap_stride=cin,
+                  workspace=ws)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    flop = 2.0 * n * H * H * cout * 9 * cin
+    pr = torch.zeros(148, 4, device=dev)
+    L.gemm_tn(dz, x, dw, n_img=n, H=H, W=H, a_c=cout, b_c=cin, M=cout, N=cin, ldc=9 * cin, taps=9, tap_stride=cin, probe=pr)
+    torch.cuda.synchronize()
+    pr = pr.cpu()
+    tot = pr[:, 2].clamp_min(1)
+    print(f"   issuer: total {tot.mean():.0f} clk/CTA, blocked on TMA ring {100 * (pr[:, 0] / tot).mean():.1f}%, on accumulator "
+          f"{100 * (pr[:, 1] / tot).mean():.1f}%; epilogue {100 * (pr[:, 3] / tot).mean():.1f}% of the issuer's span")
+    print(f"CASE {name}: {'PASS' if err < 1e-4 else 'FAIL'} rel_l2={err:.2e}  PERF {ms:.3f} ms  {flop / ms / 1e9:.1f} TFLOP/s  "
+          f"(n={n} H={H} cin={cin} cout={cout})", flush=True)
+    return err < 1e-4
+
+
 def case_probe_l2(name):
     import torch
     L = _load()
@@ -250,6 +296,10 @@ CASES = {
     "perf_m3_out0": lambda: case_perf("perf_m3_out0", 3, n=1024, H=64, cin=256, cout=128),
     "perf_m2_out0": lambda: case_perf("perf_m2_out0", 2, n=1024, H=64, cin=256, cout=128),
     "probe_l2": lambda: case_probe_l2("probe_l2"),
+    "wgrad": lambda: case_wgrad("wgrad"),
+    "wgrad_atomics": lambda: case_wgrad("wgrad_atomics", use_ws=False),
+    "wgrad_c256": lambda: case_wgrad("wgrad_c256", H=32, cin=256, cout=256),
+    "wgrad_b32": lambda: case_wgrad("wgrad_b32", n=32),
     "waits": lambda: case_waits("waits"),
     "waits_nostore": lambda: case_waits("waits_nostore", flags=1 | (1 << 30)),
     "waits_c256": lambda: case_waits("waits_c256", H=32, cin=256, cout=256),
