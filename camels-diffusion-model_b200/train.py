@@ -49,6 +49,16 @@ def enable_peer_exchange(device=None, group=None):
     return PEER
 
 
+_SIDE = {}
+
+
+def _side_stream(dev):
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
 def _xr():
     return PEER.args if (PEER is not None and _world() > 1) else None
 
@@ -243,16 +253,28 @@ class _UnetFn(torch.autograd.Function):
         bn_affine = set()
         deps = deps.detach().to(dev, torch.float32).contiguous().view(n, h, h)
 
+        # The 3x3 weight gradients are leaves of the backward graph (nothing downstream reads them before the
+        # optimizer), so they run on a second stream next to the dz -> dx chain: at 32 images per GPU every kernel of
+        # the step is too small to fill 148 SMs and the two chains overlap (fork / join are CUDA-graph capturable).
+        main, side = torch.cuda.current_stream(), _side_stream(dev)
+        keep = []  # operands stay referenced until the join: the allocator must not recycle them under the side stream
+
         def conv_wgrad(dz, srcs, cout):
             cin = sum(s.shape[3] for s in srcs)
-            dw = _f32(cout, 9 * cin, dev=dev, zero=True)
-            off = 0
-            Hh = dz.shape[1]
-            for s in srcs:
-                L.gemm_tn(dz, s, dw.view(-1)[off:], n_img=n, H=Hh, W=Hh, a_c=cout, b_c=s.shape[3], M=cout,
-                          N=s.shape[3], ldc=9 * cin, taps=9, tap_stride=cin, workspace=S.wgws)
-                off += s.shape[3]
-            return dw.view(cout, 3, 3, cin).permute(0, 3, 1, 2).contiguous()
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                dw = _f32(cout, 9 * cin, dev=dev, zero=True)
+                off = 0
+                Hh = dz.shape[1]
+                for s in srcs:
+                    L.gemm_tn(dz, s, dw.view(-1)[off:], n_img=n, H=Hh, W=Hh, a_c=cout, b_c=s.shape[3], M=cout,
+                              N=s.shape[3], ldc=9 * cin, taps=9, tap_stride=cin, workspace=S.wgws)
+                    off += s.shape[3]
+                out = dw.view(cout, 3, 3, cin).permute(0, 3, 1, 2).contiguous()
+            keep.append((dz, srcs, dw, out))
+            return out
 
         def cbr_bwd(name, prefix, dy, lddy, need_dx=True):
             ly = S.layers[name]
@@ -393,6 +415,8 @@ class _UnetFn(torch.autograd.Function):
         embed_bwd(m.contextembed2, "contextembed2", S.c, dcemb2)
         embed_bwd(m.timeembed1, "timeembed1", S.t, dtemb1 if trows == n else dtemb1.sum(0, keepdim=True))
         embed_bwd(m.timeembed2, "timeembed2", S.t, dtemb2 if trows == n else dtemb2.sum(0, keepdim=True))
+        main.wait_stream(side)  # join: every weight gradient is complete before it is reduced / handed out
+        keep.clear()
         # ---- data parallel: one flat all-reduce, then the 1/world of the global-batch mean
         W = _world()
         if W > 1:

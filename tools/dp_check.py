@@ -19,14 +19,14 @@ NCF, T = 6, 1500
 from camels_diffusion_model_b200 import _lib as L
 from camels_diffusion_model_b200.parallel import PeerExchange
 # ---- the fused reduce + cross-rank exchange kernel on its own: rank-dependent partials, 50 back-to-back exchanges
-px = PeerExchange(dev)
+px = PeerExchange(dev) if world > 1 else None
 gx = torch.Generator().manual_seed(123)
 parts = [torch.randn(37, 300, generator=gx) for _ in range(world)]   # every rank knows every rank's partials
 out = torch.empty(300, device=dev)
 ok = True
 for it in range(50):
     mine = (parts[rank] * (it + 1)).to(dev)
-    L.xrank_sum(mine, out, xr=px.args)
+    L.xrank_sum(mine, out, xr=px.args if px else None)
     expect = torch.zeros(300, device=dev)
     for r in range(world):  # rank order, each rank's row-sum computed by the same kernel path (world = 1)
         loc = torch.empty(300, device=dev)
