@@ -181,8 +181,8 @@ __global__ void __launch_bounds__(256, 2) conv_in_mma_kernel(const float* __rest
 // ----------------------------------------------------------------- conv_out
 // out.1-out.3: GroupNorm(8,128) + ReLU on load, then Conv2d(128, 1, 3, 1, 1).  N = 1 would waste a
 // tcgen05 tile, but the nine taps are a perfectly good N: per INPUT pixel p the kernel computes the nine
-// dot products d[p][tap] = sum_c relu(gn(x[p][c])) * w[tap][c] as one [pixels x 128] x [128 x 16] bf16
-// mma.sync GEMM (9 of 16 columns used), parks them in shared memory as nine fp32 planes, and the output is
+// dot products d[p][tap] = sum_c relu(gn(x[p][c])) * w[tap][c] as one [pixels x 128] x [128 x 24] bf16
+// mma.sync GEMM (weights as bf16 hi + lo: 18 of 24 columns used), parks them in shared memory as nine fp32 planes, and the output is
 // the 9-point stencil out(y,x) = bias + sum_{kh,kw} d[(y+kh-1, x+kw-1)][kh*3+kw] (zero outside the image =
 // nn.Conv2d's padding, applied after GroupNorm+ReLU).  The activations go global -> registers -> tensor core:
 // every element is used once, so there is no shared-memory staging of the 1 MiB/image input.  The K
@@ -240,19 +240,28 @@ __global__ void __launch_bounds__(256, 2) conv_out_mma_kernel(const bf16* __rest
     const int plane = i / ((R + 2) * 2), rem = i - plane * (R + 2) * 2;
     s_d[plane * PS + (rem >> 1) * PW + ((rem & 1) ? W + 1 : 0)] = 0.f;
   }
-  // B fragments (weights), bf16, in the permuted channel order: k-step 2q+h, fragment columns {2t,2t+1} and
-  // {2t+8,2t+9} <-> channels 32q + 8t + 4h + {0,1} and + {2,3}.  n-tile 0 = taps 0..7, n-tile 1 = tap 8 (g == 0).
-  uint32_t bw0[8][2], bw1[8][2];
+  // B fragments (weights) in the permuted channel order: k-step 2q+h, fragment columns {2t,2t+1} and {2t+8,2t+9}
+  // <-> channels 32q + 8t + 4h + {0,1} and + {2,3}.  The fp32 weights are split into bf16 hi + lo parts so that the
+  // only rounding of this layer is the activation's: n-tile 0 = hi of taps 0..7, n-tile 1 = lo of taps 0..7 (both
+  // accumulate into the same registers), n-tile 2 = {hi, lo} of tap 8 in columns 0 and 1.  Kept in shared memory
+  // ([k-step][n-tile][lane], 8-byte entries: conflict-free) to leave the registers to the activation loads.
+  uint2* s_bw = reinterpret_cast<uint2*>(s_b + kCoC);
+  if (warp == 0) {
 #pragma unroll
-  for (int ks = 0; ks < 8; ++ks) {
-    const int ch = 32 * (ks >> 1) + 8 * t + 4 * (ks & 1);
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wgt + g * kCoC + ch));
-    bw0[ks][0] = pack_bf16x2(w0.x, w0.y);
-    bw0[ks][1] = pack_bf16x2(w0.z, w0.w);
-    float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g == 0) w1 = __ldg(reinterpret_cast<const float4*>(wgt + 8 * kCoC + ch));
-    bw1[ks][0] = pack_bf16x2(w1.x, w1.y);
-    bw1[ks][1] = pack_bf16x2(w1.z, w1.w);
+    for (int ks = 0; ks < 8; ++ks) {
+      const int ch = 32 * (ks >> 1) + 8 * t + 4 * (ks & 1);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wgt + g * kCoC + ch));
+      const float h0 = bf16_hi(w0.x), h1 = bf16_hi(w0.y), h2 = bf16_hi(w0.z), h3 = bf16_hi(w0.w);
+      s_bw[(ks * 3 + 0) * 32 + lane] = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+      s_bw[(ks * 3 + 1) * 32 + lane] = make_uint2(pack_bf16x2(w0.x - h0, w0.y - h1), pack_bf16x2(w0.z - h2, w0.w - h3));
+      float4 w8 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g < 2) {
+        w8 = __ldg(reinterpret_cast<const float4*>(wgt + 8 * kCoC + ch));
+        const float k0 = bf16_hi(w8.x), k1 = bf16_hi(w8.y), k2 = bf16_hi(w8.z), k3 = bf16_hi(w8.w);
+        w8 = g == 0 ? make_float4(k0, k1, k2, k3) : make_float4(w8.x - k0, w8.y - k1, w8.z - k2, w8.w - k3);
+      }
+      s_bw[(ks * 3 + 2) * 32 + lane] = make_uint2(pack_bf16x2(w8.x, w8.y), pack_bf16x2(w8.z, w8.w));
+    }
   }
   __syncthreads();
   const int mtx = W >> 4, n_mt = (R + 2) * mtx;
@@ -275,10 +284,15 @@ __global__ void __launch_bounds__(256, 2) conv_out_mma_kernel(const bf16* __rest
         const float4 a0 = sa4[8 * q + 2 * t], a1 = sa4[8 * q + 2 * t + 1];
         const float4 b0 = sb4[8 * q + 2 * t], b1 = sb4[8 * q + 2 * t + 1];
         const uint4 r0 = gn_relu8(v0[q], a0, a1, b0, b1), r1 = gn_relu8(v1[q], a0, a1, b0, b1);
-        mma_bf16_m16n8k16(acc0, r0.x, r1.x, r0.y, r1.y, bw0[2 * q][0], bw0[2 * q][1]);
-        mma_bf16_m16n8k16(acc1, r0.x, r1.x, r0.y, r1.y, bw1[2 * q][0], bw1[2 * q][1]);
-        mma_bf16_m16n8k16(acc0, r0.z, r1.z, r0.w, r1.w, bw0[2 * q + 1][0], bw0[2 * q + 1][1]);
-        mma_bf16_m16n8k16(acc1, r0.z, r1.z, r0.w, r1.w, bw1[2 * q + 1][0], bw1[2 * q + 1][1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t x0 = h ? r0.z : r0.x, x1 = h ? r1.z : r1.x, x2 = h ? r0.w : r0.y, x3 = h ? r1.w : r1.y;
+          const uint2 bh = s_bw[((2 * q + h) * 3 + 0) * 32 + lane], bl = s_bw[((2 * q + h) * 3 + 1) * 32 + lane];
+          const uint2 b8 = s_bw[((2 * q + h) * 3 + 2) * 32 + lane];
+          mma_bf16_m16n8k16(acc0, x0, x1, x2, x3, bh.x, bh.y);
+          mma_bf16_m16n8k16(acc0, x0, x1, x2, x3, bl.x, bl.y);
+          mma_bf16_m16n8k16(acc1, x0, x1, x2, x3, b8.x, b8.y);
+        }
       }
     }
     float* d0 = s_d + pr * PW + mx * 16 + g + 1;
@@ -286,9 +300,9 @@ __global__ void __launch_bounds__(256, 2) conv_out_mma_kernel(const bf16* __rest
     d0[(2 * t + 1) * PS] = acc0[1];
     d0[(2 * t) * PS + 8] = acc0[2];
     d0[(2 * t + 1) * PS + 8] = acc0[3];
-    if (t == 0) {
-      d0[8 * PS] = acc1[0];
-      d0[8 * PS + 8] = acc1[2];
+    if (t == 0) {  // columns 0 and 1 of n-tile 2: hi and lo part of tap 8
+      d0[8 * PS] = acc1[0] + acc1[1];
+      d0[8 * PS + 8] = acc1[2] + acc1[3];
     }
   }
   __syncthreads();
@@ -590,7 +604,7 @@ extern "C" int cdm_conv_in(const cdm_conv_in_args* a, void* stream) {
 template <int R>
 static int launch_conv_out(const cdm_conv_out_args* a, cudaStream_t stream) {
   static bool attr_set = false;
-  const int smem = (9 * co_plane_stride(R, a->W) + 2 * kCoC) * (int)sizeof(float);
+  const int smem = (9 * co_plane_stride(R, a->W) + 2 * kCoC) * (int)sizeof(float) + 8 * 3 * 32 * 8;
   if (!attr_set) {
     CDM_CHECK_CUDA(cudaFuncSetAttribute(conv_out_mma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set = true;
