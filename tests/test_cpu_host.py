@@ -110,3 +110,46 @@ def test_weight_packing_layouts():
     got = torch.nn.functional.conv2d(x, c2.weight) * 1  # noqa
     got = torch.nn.functional.conv2d(x, c2.weight, None, padding=1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
     assert torch.allclose(got, ref, atol=1e-5)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints ONE JSON line with the keys the
+    bench contract names; a second rank of a torchrun launch prints nothing and exits 0."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "cfg_ddpm_samples_per_sec_64x64_1500steps"
+    assert d["unit"] == "samples/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                        capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=60)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_radial_bins_follow_the_reference_rule():
+    """metrics._radial_bins is the reference's binning (diffusion_utilities.py:325-356) as a CSR list."""
+    from camels_diffusion_model_b200 import metrics as M
+    from oracle import metrics_oracle as MO
+    for n, dl in ((64, 1.0), (16, 0.5)):
+        k_bins, start, items = M._radial_bins(n, dl)
+        rng = np.random.RandomState(n)
+        power = rng.rand(n * n)
+        pk = np.array([power[items[start[b]:start[b + 1]]].mean() if start[b + 1] > start[b] else 0.0
+                       for b in range(len(k_bins))]) * dl ** 2
+        # feed the same "power" through the oracle's binning by inverting the FFT magnitude: compare bin membership
+        kx = 2 * np.pi * np.fft.fftfreq(n, dl)
+        kg = np.sqrt(kx[:, None] ** 2 + kx[None, :] ** 2).flatten()
+        dk = 2 * np.pi / (n * dl)
+        idx = np.array([int(round(v / dk)) for v in kg])
+        ref = np.array([power[idx == b].mean() if (idx == b).any() else 0.0 for b in range(len(k_bins))]) * dl ** 2
+        np.testing.assert_allclose(pk, ref, rtol=1e-12)
+        assert sorted(items.tolist()) == list(range(n * n)) and start[-1] == n * n
+        assert len(k_bins) == len(MO.power_spectrum(np.zeros((n, n), np.float32), dl)[0])
