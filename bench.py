@@ -69,7 +69,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -82,6 +82,13 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *exc):
+        if self.proc is not None and not self.rows:
+            try:  # a timed region shorter than one sampling period: one immediate reading while the GPU is still warm
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10)
+                self.rows.extend([c.strip() for c in l.split(",")] for l in o.stdout.splitlines() if l.strip())
+            except (OSError, subprocess.SubprocessError):
+                pass
         if self.proc is not None:
             self.proc.terminate()
             try:

@@ -118,7 +118,7 @@ EXPORTS = [
     "cdm_maxpool2_bwd", "cdm_add_bf16", "cdm_space_to_depth", "cdm_film_bwd", "cdm_gn_bwd", "cdm_rows_sum",
     "cdm_avgpool_gelu_train", "cdm_avgpool_gelu_bwd", "cdm_outer_wgrad", "cdm_embed_bwd", "cdm_mse_grad",
     "cdm_adam_step", "cdm_power_spectrum", "cdm_pixel_histogram",
-    "cdm_minmax", "cdm_preprocess_maps", "cdm_normalize_params", "cdm_xrank_sum",
+    "cdm_minmax", "cdm_preprocess_maps", "cdm_normalize_params", "cdm_xrank_sum", "cdm_pack_bf16",
 ]
 
 
@@ -471,3 +471,8 @@ def xrank_sum(partial, out, xr=None):
     check(lib().cdm_xrank_sum(C.c_void_p(ptr(partial)), n_blocks, n, C.c_void_p(ptr(out)), _xr_ptr(xr), stream_ptr()),
           "cdm_xrank_sum")
     return out
+
+
+def pack_bf16(table, n_rows, total_vec):
+    """table int64 [n_rows, 12] on the device (see cdm_pack_bf16)."""
+    check(lib().cdm_pack_bf16(C.c_void_p(ptr(table)), n_rows, C.c_longlong(total_vec), stream_ptr()), "cdm_pack_bf16")

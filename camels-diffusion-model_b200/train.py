@@ -35,13 +35,15 @@ def _allreduce(t):
     return t
 
 
-PEER = None  # parallel.PeerExchange of this process (enable_peer_exchange), or None: NCCL all-reduce of the statistics
+PEER = None            # parallel.PeerExchange of this process, created on the first data-parallel forward
+PEER_EXCHANGE = True   # False: all-reduce the BatchNorm statistics with NCCL instead (the baseline path)
 
 
 def enable_peer_exchange(device=None, group=None):
     """Route the cross-rank BatchNorm statistics (forward and backward, 36 exchanges of [2C] floats per step)
-    through the fused reduce + exchange kernel over NVLink peer memory instead of NCCL.  Call once per process
-    after init_process_group; a no-op for a single rank."""
+    through the fused reduce + exchange kernel over NVLink peer memory instead of NCCL (7.31 -> 6.70 ms per step at
+    8 x 32 images).  Collective: every rank calls it at the same point (the first data-parallel forward does, unless
+    PEER_EXCHANGE is False); a no-op for a single rank."""
     global PEER
     if _world() > 1 and PEER is None:
         from .parallel import PeerExchange
@@ -60,7 +62,11 @@ def _side_stream(dev):
 
 
 def _xr():
-    return PEER.args if (PEER is not None and _world() > 1) else None
+    if _world() <= 1 or not PEER_EXCHANGE:
+        return None
+    if PEER is None:
+        enable_peer_exchange()
+    return PEER.args
 
 
 class _Ctx:
@@ -82,29 +88,70 @@ def _rcb_list(m):
             ("up1.2", m.up1.model[2]), ("up2.1", m.up2.model[1]), ("up2.2", m.up2.model[2])]
 
 
+class _PackPlan:
+    """Persistent bf16 operand buffers + the device table of cdm_pack_bf16 for one model: every tensor-core layout of
+    the step (forward [co][kh][kw][ci] and data-gradient [ci][2-kh][2-kw][co] forms of the 3x3 convolutions, the
+    (kh,kw,co) x ci and ci x (kh,kw,co) forms of the transposed convolutions) is refreshed by ONE launch per step."""
+
+    def __init__(self, m):
+        self.P, rows, vec = {}, [], 0
+        self.key = self.key_of(m)
+
+        def add(key, w, perm, flips=()):
+            nonlocal vec
+            shape = [w.shape[d] for d in perm]
+            stride = [w.stride(d) for d in perm]
+            off = 0
+            for d in flips:  # a flipped source dim is walked backwards from its last element
+                k = perm.index(d)
+                off += (w.shape[d] - 1) * w.stride(d)
+                stride[k] = -stride[k]
+            assert w.is_contiguous() and w.dtype == torch.float32 and shape[3] % 8 == 0
+            dst = torch.empty(shape, device=w.device, dtype=torch.bfloat16)
+            rows.append([w.data_ptr(), dst.data_ptr(), shape[1], shape[2], shape[3], *stride, off, vec, 0])
+            vec += dst.numel() // 8
+            self.P[key] = dst
+
+        for name, blk in _rcb_list(m):
+            for cn, seq in (("c1", blk.conv1), ("c2", blk.conv2)):
+                w = seq[0].weight.detach()
+                if w.shape[1] != 1:
+                    add(f"{name}.{cn}.f", w, (0, 2, 3, 1))               # [co][kh][kw][ci]
+                    add(f"{name}.{cn}.d", w, (1, 2, 3, 0), flips=(2, 3))  # [ci][2-kh][2-kw][co]
+        w = m.out[0].weight.detach()
+        add("out0.f", w, (0, 2, 3, 1))
+        add("out0.d", w, (1, 2, 3, 0), flips=(2, 3))
+        for nm, mod in (("up0", m.up0[0]), ("up1", m.up1.model[0]), ("up2", m.up2.model[0])):
+            w = mod.weight.detach()  # IOHW
+            ci, co, kh, kw = w.shape
+            add(nm + ".f", w, (2, 3, 1, 0))
+            add(nm + ".d", w, (0, 2, 3, 1))
+            self.P[nm + ".f"] = self.P[nm + ".f"].view(kh * kw * co, ci)
+            self.P[nm + ".d"] = self.P[nm + ".d"].view(ci, kh * kw * co)
+        self.n_rows, self.total_vec = len(rows), vec
+        self.table = torch.tensor(rows, dtype=torch.int64).to(m.out[0].weight.device)
+
+    @staticmethod
+    def key_of(m):
+        return tuple(p.data_ptr() for p in m.parameters())
+
+    def refresh(self):
+        L.pack_bf16(self.table, self.n_rows, self.total_vec)
+
+
 def _pack_train(m):
     """bf16 operand packs for this step (weights change every optimizer step): forward and data-gradient forms."""
-    P = {}
-    for name, blk in _rcb_list(m):
-        for cn, seq in (("c1", blk.conv1), ("c2", blk.conv2)):
-            w = seq[0].weight.detach()
-            key = f"{name}.{cn}"
-            if w.shape[1] == 1:
-                P[key + ".f"] = w.float().reshape(w.shape[0], 9).t().contiguous()  # [9][cout] fp32
-            else:
-                P[key + ".f"] = w.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)  # [co][kh][kw][ci]
-                P[key + ".d"] = w.flip(2, 3).permute(1, 2, 3, 0).contiguous().to(torch.bfloat16)  # [ci][kh][kw][co]
-    w = m.out[0].weight.detach()
-    P["out0.f"] = w.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
-    P["out0.d"] = w.flip(2, 3).permute(1, 2, 3, 0).contiguous().to(torch.bfloat16)  # [256][3][3][128]
+    plan = getattr(m, "_train_pack_plan", None)
+    if plan is None or plan.key != _PackPlan.key_of(m):
+        plan = _PackPlan(m)
+        object.__setattr__(m, "_train_pack_plan", plan)
+    plan.refresh()
+    P = dict(plan.P)
+    blk = m.init_conv.conv1[0].weight.detach()
+    P["init_conv.c1.f"] = blk.float().reshape(blk.shape[0], 9).t().contiguous()  # [9][cout] fp32 (K = 9: no tensor core)
     w3 = m.out[3].weight.detach().float()[0].permute(1, 2, 0).reshape(9, -1)  # [tap][c]
     P["out3.f"] = w3.contiguous()
     P["out3.d"] = w3.flip(0).contiguous()  # flipped taps: dgrad of a 1-output-channel conv
-    for nm, mod in (("up0", m.up0[0]), ("up1", m.up1.model[0]), ("up2", m.up2.model[0])):
-        w = mod.weight.detach()  # IOHW
-        ci, co, kh, kw = w.shape
-        P[nm + ".f"] = w.permute(2, 3, 1, 0).reshape(kh * kw * co, ci).contiguous().to(torch.bfloat16)
-        P[nm + ".d"] = w.permute(0, 2, 3, 1).reshape(ci, kh * kw * co).contiguous().to(torch.bfloat16)
     return P
 
 
@@ -285,11 +332,11 @@ class _UnetFn(torch.autograd.Function):
                           mean=ly.mean, rstd=ly.rstd, relu=1, xr=xr)
             if xr is None:
                 _allreduce(sums)
-            G[prefix + ".1.weight"], G[prefix + ".1.bias"] = sums[1].clone(), sums[0].clone()
+            G[prefix + ".1.weight"], G[prefix + ".1.bias"] = sums[1], sums[0]  # `sums` is this layer's own buffer
             bn_affine.update((prefix + ".1.weight", prefix + ".1.bias"))
             dz = _bf(n, ly.H, ly.H, C, dev=dev)
             L.bn_bwd_apply(dy, lddy, ly.z, Pn, C, ly.scale, ly.shift, ly.mean, ly.rstd, sums, ly.count, dz, relu=1)
-            G[prefix + ".0.bias"] = torch.zeros(C, device=dev)  # a bias in front of train-mode BN has zero gradient
+            G[prefix + ".0.bias"] = S.zeros[:C]  # a bias in front of train-mode BN has zero gradient
             if ly.cin == 1:
                 w9 = _f32(9, C, dev=dev)
                 L.outer_wgrad(ly.x_in, dz, n, ly.H, ly.H, C, w9, S.ws, flip=0)
@@ -314,7 +361,7 @@ class _UnetFn(torch.autograd.Function):
             L.space_to_depth(dv, s2d)
             sums = _f32(2, nf, dev=dev)
             L.chan_reduce(dv, nf, Mrows * 4, nf, sums, S.ws, mode=2)
-            G[prefix + ".bias"] = sums[0].clone()
+            G[prefix + ".bias"] = sums[0]
             cin = sum(s.shape[-1] for s in srcs)
             da = _bf(Mrows, cin, dev=dev)
             L.gemm(s2d, P[nm + ".d"], S.zeros[:cin], da, shift_mod=cin)
@@ -355,7 +402,7 @@ class _UnetFn(torch.autograd.Function):
         # ---- out.0 (Conv 256->128 on cat(u2, x0))
         sums = _f32(2, nf, dev=dev)
         L.chan_reduce(do, nf, n * h * h, nf, sums, S.ws, mode=2)
-        G["out.0.bias"] = sums[0].clone()
+        G["out.0.bias"] = sums[0]
         G["out.0.weight"] = conv_wgrad(do, [S.u2, S.x0], nf)
         d_cat = _bf(n, h, h, 2 * nf, dev=dev)
         L.conv3x3(do, P["out0.d"], S.ones[:2 * nf], S.zeros[:2 * nf], d_cat, flags=0, mode=S.mode)
@@ -384,7 +431,7 @@ class _UnetFn(torch.autograd.Function):
         L.rows_sum(db_nc, n, 2 * nf, G["up0.1.bias"])
         sums = _f32(2, 2 * nf, dev=dev)
         L.chan_reduce(d_u0raw, 2 * nf, n * h4 * h4, 2 * nf, sums, S.ws, mode=2)
-        G["up0.0.bias"] = sums[0].clone()
+        G["up0.0.bias"] = sums[0]
         K0 = h4 * h4 * 2 * nf
         d_hid = _bf(n, 2 * nf, dev=dev)
         L.gemm(d_u0raw.view(n, K0), P["up0.d"], S.zeros[:2 * nf], d_hid, shift_mod=2 * nf)
@@ -417,8 +464,19 @@ class _UnetFn(torch.autograd.Function):
         embed_bwd(m.timeembed2, "timeembed2", S.t, dtemb2 if trows == n else dtemb2.sum(0, keepdim=True))
         main.wait_stream(side)  # join: every weight gradient is complete before it is reduced / handed out
         keep.clear()
-        # ---- data parallel: one flat all-reduce, then the 1/world of the global-batch mean
         W = _world()
+        flat_out = getattr(ctx, "flat_out", None)
+        if flat_out is not None:
+            # captured step: gradients land in ONE flat buffer that the parameters' .grad views alias ([all-reduced
+            # tensors | BatchNorm affine tensors, already global]): cat + all-reduce + scale = 3 launches, not ~300
+            assert set(flat_out["order"][flat_out["n_reduce"]:]) == bn_affine
+            torch.cat([G[k].reshape(-1) for k in flat_out["order"]], out=flat_out["flat"])
+            if W > 1:
+                dist.all_reduce(flat_out["flat"][:flat_out["numel_reduce"]])
+                flat_out["flat"].mul_(1.0 / W)
+            ctx.S = None
+            return None
+        # ---- data parallel: one flat all-reduce, then the 1/world of the global-batch mean
         if W > 1:
             names = [k for k in ctx.names if k not in bn_affine]
             flat = torch.cat([G[k].reshape(-1) for k in names])
@@ -530,8 +588,20 @@ class GraphedTrainStep:
         self.count = torch.zeros(1, device=dev, dtype=torch.int32)  # Adam step == Philox stream offset
         self.betas, self.eps, self.seed = betas, eps, seed
         self.params = [p for p in model.parameters()]
-        for p in self.params:
-            p.grad = torch.zeros_like(p)
+        # one flat gradient buffer, [tensors that are all-reduced | BatchNorm affine tensors (their gradients come from
+        # already-global sums)]; every parameter's .grad is a view into it
+        named = list(model.named_parameters())
+        is_bn = lambda nme: ".conv1.1." in nme or ".conv2.1." in nme  # noqa: E731  (the BatchNorm2d of a Conv-BN-ReLU)
+        order = [k for k, _ in named if not is_bn(k)] + [k for k, _ in named if is_bn(k)]
+        by_name = dict(named)
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev)
+        o = 0
+        for k in order:
+            p = by_name[k]
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        self.flat_out = {"flat": self.flat, "order": order, "n_reduce": sum(1 for k in order if not is_bn(k)),
+                         "numel_reduce": sum(by_name[k].numel() for k in order if not is_bn(k))}
         self.m = [torch.zeros_like(p) for p in self.params]
         self.v = [torch.zeros_like(p) for p in self.params]
         rows = [[p.data_ptr(), p.grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()]
@@ -570,9 +640,8 @@ class GraphedTrainStep:
         ctx = _Ctx()
         pred = _UnetFn.forward(ctx, m, self.x_pert, self.t / self.T, self.param, self.sc, *self.params)
         L.mse_grad(pred, self.noise, 1.0 / pred.numel(), self.dpred, self.partial, self.loss_sum)
-        grads = _UnetFn.backward(ctx, self.dpred)[5:]
-        for p, g in zip(self.params, grads):
-            p.grad.copy_(g)
+        ctx.flat_out = self.flat_out
+        _UnetFn.backward(ctx, self.dpred)  # gradients land in self.flat (= every p.grad)
         b1, b2 = self.betas
         L.adam_step(self.table, len(self.params), self.max_numel, 0.0, b1, b2, self.eps, 0, lr_dev=self.lr,
                     step_dev=self.count)

@@ -411,6 +411,13 @@ int cdm_preprocess_maps(const float* in, int n, int Hi, int Wi, const float* raw
 int cdm_normalize_params(const float* x, int rows, int cols, int repeat, int out_cols, float* out, float* col_min,
                          float* col_max, void* stream);
 
+/* All bf16 operand layouts of a training step in one launch (the weights change every optimizer step): `table` is
+ * a device array of n_rows rows of 12 x int64 {src fp32*, dst bf16*, d1, d2, d3, s0, s1, s2, s3, off, vec_start, 0}:
+ *   dst[i0][i1][i2][i3] = (bf16) src[off + i0 s0 + i1 s1 + i2 s2 + i3 s3],  d3 % 8 == 0,
+ * vec_start = running count of 8-element output vectors, total_vec their total.  Replaces the per-tensor
+ * w.permute(..).contiguous().to(bf16) / w.flip(2,3).permute(..) chains of the torch path. */
+int cdm_pack_bf16(const void* table, int n_rows, long long total_vec, void* stream);
+
 /* Measurement probe: every CTA streams `tile_bytes` TMA tiles from an
  * L2-resident buffer into a shared-memory ring; returns nothing, caller times it. */
 int cdm_probe_tma_l2(const void* buf, int n_rows, int iters, void* stream);

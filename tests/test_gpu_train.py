@@ -414,3 +414,63 @@ def test_xrank_sum_single_rank(L):
     out = torch.empty(512, device="cuda")
     L.xrank_sum(part, out)
     assert rel_l2(out, part.double().sum(0)) < 1e-6
+
+
+def test_pack_bf16_all_layouts_in_one_launch(L):
+    """cdm_pack_bf16 (one launch) == the per-tensor torch permute / flip / cast chains it replaces."""
+    import camels_diffusion_model_b200 as cdm
+    from camels_diffusion_model_b200 import train as TR
+    torch.manual_seed(3)
+    m = cdm.ContextUnet(1, 128, 6, 64).cuda()
+    P = TR._pack_train(m)
+    torch.cuda.synchronize()
+    n = 0
+    for name, blk in TR._rcb_list(m):
+        for cn, seq in (("c1", blk.conv1), ("c2", blk.conv2)):
+            w = seq[0].weight.detach()
+            if w.shape[1] != 1:
+                assert torch.equal(P[f"{name}.{cn}.f"], w.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+                assert torch.equal(P[f"{name}.{cn}.d"], w.flip(2, 3).permute(1, 2, 3, 0).contiguous().to(torch.bfloat16))
+                n += 2
+    w = m.out[0].weight.detach()
+    assert torch.equal(P["out0.f"], w.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+    assert torch.equal(P["out0.d"], w.flip(2, 3).permute(1, 2, 3, 0).contiguous().to(torch.bfloat16))
+    for nm, mod in (("up0", m.up0[0]), ("up1", m.up1.model[0]), ("up2", m.up2.model[0])):
+        w = mod.weight.detach()
+        ci, co, kh, kw = w.shape
+        assert torch.equal(P[nm + ".f"], w.permute(2, 3, 1, 0).reshape(kh * kw * co, ci).to(torch.bfloat16))
+        assert torch.equal(P[nm + ".d"], w.permute(0, 2, 3, 1).reshape(ci, kh * kw * co).to(torch.bfloat16))
+    assert n == 34
+    # the packs follow the weights: an in-place update is picked up by the next refresh
+    with torch.no_grad():
+        m.out[0].weight.mul_(2.0)
+    P2 = TR._pack_train(m)
+    assert torch.equal(P2["out0.f"], m.out[0].weight.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+
+
+def test_graphed_step_matches_eager_step(L):
+    """GraphedTrainStep (flat gradient buffer, captured launches) == training_step + FusedAdam on the same inputs."""
+    from camels_diffusion_model_b200 import diffusion as D, train as TR
+    from tests._util import cal_sd, make_model
+    Tn = 1500
+    ab_t = D.make_schedule(Tn)[2]
+    g = torch.Generator().manual_seed(5)
+    x, p = torch.rand(4, 1, 64, 64, generator=g).cuda(), torch.rand(4, 6, generator=g).cuda()
+    t = torch.tensor([3, 500, 999, 1500])
+    sc = torch.rand(256, generator=g) * 2 - 1
+    m1 = make_model(cal_sd()).train()
+    gs = TR.GraphedTrainStep(m1, 4, Tn, ab_t, lr=1e-4, seed=11)
+    loss_g = float(gs(x, p, t=t.cuda(), shortcut=sc))
+    noise = gs.noise.clone()  # the Philox noise the captured step drew
+    m2 = make_model(cal_sd()).train()
+    opt = TR.FusedAdam(m2.parameters(), lr=1e-4)
+    loss_e = float(TR.training_step(m2, opt, x, p, Tn, ab_t, noise=noise, t=t, shortcut=sc))
+    assert abs(loss_g - loss_e) <= 1e-6 * abs(loss_e)
+    for (k, a), b in zip(m1.state_dict().items(), m2.state_dict().values()):
+        if "num_batches" in k:
+            assert int(a) == int(b)
+            continue
+        # first Adam step moves every weight by ~lr * sign(g): agreement to a small fraction of lr (atomics noise
+        # of the remaining split-K gemm_tn calls can flip the sign of a near-zero gradient)
+        assert (a - b).abs().max() <= 2.1e-4, k
+        assert ((a - b).abs() > 2e-5).float().mean() < 1e-3, k

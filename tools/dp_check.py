@@ -67,9 +67,7 @@ def step(xs, ps, ns, ts, dp):
 s, e = rank * 4, rank * 4 + 4
 m_1, loss_1 = step(x, prm, noise, t, False)
 for mode in ("nccl", "peer"):
-    if mode == "peer":
-        TR.DATA_PARALLEL = True
-        TR.enable_peer_exchange(dev)
+    TR.PEER_EXCHANGE = mode == "peer"
     m_dp, loss_dp = step(x[s:e], prm[s:e], noise[s:e], t[s:e], True)
     worst, key = 0.0, {}
     for (n1, p1), (n2, p2) in zip(m_1.named_parameters(), m_dp.named_parameters()):
@@ -88,7 +86,7 @@ for mode in ("nccl", "peer"):
         print(f"DP-CHECK[{mode}] well-conditioned gradients (sharded vs single-process rel-L2):", key)
         print(f"DP-CHECK[{mode}] world={world}: worst grad rel-L2 (sharded vs single-process) {worst:.3e}; "
               f"max |running-stat diff| {bn_err:.3e}; mean rank loss {float(lt) / world:.6f} vs global {loss_1:.6f}")
-TR.PEER = None
+TR.PEER_EXCHANGE = False
 
 # ---- throughput of a training step, BASELINE config 3: global batch 256
 TR.DATA_PARALLEL = True
@@ -117,9 +115,7 @@ if rank == 0:
 # ---- the same step captured as a CUDA graph, 32 and 128 images per GPU; BatchNorm statistics exchanged by NCCL
 # all-reduces inside the capture ("nccl") or by the fused reduce + exchange kernel over NVLink peer memory ("peer")
 for mode in ("nccl", "peer"):
-    TR.PEER = None
-    if mode == "peer":
-        TR.enable_peer_exchange(dev)
+    TR.PEER_EXCHANGE = mode == "peer"
     for per in (32, GB // world):
         try:
             torch.manual_seed(0)
