@@ -47,6 +47,7 @@ class GemmArgs(C.Structure):
         ("a0", C.c_void_p), ("a1", C.c_void_p), ("k0", C.c_int), ("k1", C.c_int),
         ("M", C.c_int), ("N", C.c_int), ("bw", C.c_void_p), ("shift", C.c_void_p),
         ("shift_mod", C.c_int), ("out_mode", C.c_int), ("H", C.c_int), ("W", C.c_int), ("out", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_floats", C.c_longlong),
     ]
 
 
@@ -159,7 +160,7 @@ def conv3x3(src0, weight, scale, shift, out, *, src1=None, flags=EPI_RELU, sc_x=
     return out
 
 
-def gemm(a0, bw, shift, out, *, a1=None, shift_mod=None, out_mode=0, H=0, W=0):
+def gemm(a0, bw, shift, out, *, a1=None, shift_mod=None, out_mode=0, H=0, W=0, workspace=None):
     """a*: bf16 [M,k]; bw bf16 [N,K]; see cdm_gemm in cdm_b200.h."""
     g = GemmArgs()
     g.a0, g.k0 = ptr(a0), a0.shape[1]
@@ -169,6 +170,7 @@ def gemm(a0, bw, shift, out, *, a1=None, shift_mod=None, out_mode=0, H=0, W=0):
     g.bw, g.shift = ptr(bw), ptr(shift)
     g.shift_mod = shift_mod if shift_mod is not None else shift.numel()
     g.out_mode, g.H, g.W, g.out = out_mode, H, W, ptr(out)
+    g.workspace, g.workspace_floats = ptr(workspace), 0 if workspace is None else workspace.numel()
     check(lib().cdm_gemm(C.byref(g), stream_ptr()), "cdm_gemm")
     return out
 

@@ -295,6 +295,18 @@ extern "C" int cdm_gemm(const cdm_gemm_args* a, void* stream) {
   for (int v = a->H; v > 1; v >>= 1) ++p.h_shift;
   for (int v = a->W; v > 1; v >>= 1) ++p.w_shift;
   p.out = reinterpret_cast<bf16*>(a->out);
+  p.k_split = 1;
+  // few output tiles but a long K (the up0 data gradient: 2 tiles, K = 65536): split K over the idle SMs
+  if (a->workspace && a->out_mode == 0 && p.n_units * 4 <= num_sms() && p.chunks >= 64) {
+    int ks = num_sms() / p.n_units;
+    if (ks > p.chunks / 8) ks = p.chunks / 8;
+    const long long need = (long long)ks * p.m_tiles * 128 * a->N;
+    if (ks > 1 && a->workspace_floats >= need) {
+      p.k_split = ks;
+      p.partial = a->workspace;
+      p.n_units *= ks;
+    }
+  }
   constexpr int smem = gemm_smem_bytes();
   static bool attr_set = false;
   if (!attr_set) {
@@ -304,6 +316,12 @@ extern "C" int cdm_gemm(const cdm_gemm_args* a, void* stream) {
   const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
   gemm_kernel<<<grid, kConvThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(mA0, mA1, mB, p);
   CDM_CHECK_LAUNCH();
+  if (p.partial) {
+    const long long quads = ((long long)a->M * a->N + 3) / 4;
+    gemm_splitk_reduce_kernel<<<(int)((quads + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        p.partial, p.k_split, a->M, p.m_tiles * 128, a->N, a->shift, a->shift_mod, p.out);
+    CDM_CHECK_LAUNCH();
+  }
   return CDM_OK;
 }
 

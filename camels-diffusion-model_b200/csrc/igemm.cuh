@@ -756,6 +756,8 @@ struct GemmKParams {
   int shift_mod;
   int out_mode, H, W, h_shift, w_shift;
   bf16* out;
+  int k_split;     // > 1: unit = (K slice, m_tile, n_tile); each slice stores its fp32 tile to `partial`
+  float* partial;  // [k_split][m_tiles*128][N]; gemm_splitk_reduce_kernel adds the slices in order (+ shift -> bf16)
 };
 constexpr int kGemmStages = 5;
 constexpr int kGemmStageBytes = 2 * 16384;
@@ -796,6 +798,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const int cps = (p.chunks + p.k_split - 1) / p.k_split;  // K chunks per slice
 
   // unit -> (m_tile, n_tile): n fastest so concurrently running CTAs share the A rows in L2
   if (warp == 0 && lane == 0) {
@@ -805,8 +808,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
     int st = 0;
     uint32_t ph = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const int m_tile = u / p.n_tiles, n_tile = u % p.n_tiles;
-      for (int ch = 0; ch < p.chunks; ++ch) {
+      const int mn = u % (p.m_tiles * p.n_tiles), slice = u / (p.m_tiles * p.n_tiles);
+      const int m_tile = mn / p.n_tiles, n_tile = mn % p.n_tiles;
+      const int ch0 = slice * cps, ch1 = min(p.chunks, ch0 + cps);
+      for (int ch = ch0; ch < ch1; ++ch) {
         const CUtensorMap* m = ch < p.chunks0 ? &mapA0 : &mapA1;
         const int c_off = (ch < p.chunks0 ? ch : ch - p.chunks0) * 64;
         mbar_wait(&empty[st], ph ^ 1);
@@ -828,7 +833,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       const int buf = it & 1;
       mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
-      for (int ch = 0; ch < p.chunks; ++ch) {
+      const int slice = u / (p.m_tiles * p.n_tiles);
+      const int ch0 = slice * cps, ch1 = min(p.chunks, ch0 + cps);
+      for (int ch = ch0; ch < ch1; ++ch) {
         mbar_wait(&full[st], ph);
         tc_fence_after();
         const uint32_t a_base = smem_u32(smemAB + st * kGemmStageBytes);
@@ -836,7 +843,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tmem_base + buf * 128, umma_desc_sw128(a_base + k * 32, 1024),
-                    umma_desc_sw128(b_base + k * 32, 1024), idesc, (ch == 0 && k == 0) ? 0u : 1u);
+                    umma_desc_sw128(b_base + k * 32, 1024), idesc, (ch == ch0 && k == 0) ? 0u : 1u);
         umma_commit(&empty[st]);
         if (++st == kGemmStages) {
           st = 0;
@@ -851,10 +858,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
     int it = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
       const int buf = it & 1;
-      const int m_tile = u / p.n_tiles, n_tile = u % p.n_tiles;
+      const int mn = u % (p.m_tiles * p.n_tiles), slice = u / (p.m_tiles * p.n_tiles);
+      const int m_tile = mn / p.n_tiles, n_tile = mn % p.n_tiles;
       mbar_wait(&t_full[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128);
+      if (p.partial) {  // split-K: this slice's fp32 tile row, no shift, no rounding (an empty slice stores zeros)
+        float4* prow = reinterpret_cast<float4*>(
+            p.partial + ((size_t)slice * p.m_tiles * 128 + m_tile * 128 + q * 32 + lane) * p.N + n_tile * 128);
+        const bool live = slice * cps < p.chunks;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t v[32];
+          if (live) {
+            tmem_ld_x32(taddr + cc * 32, v);
+            tmem_wait_ld();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0u;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            prow[cc * 8 + i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                           __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[buf]);
+        continue;
+      }
       const float* shift = p.shift + (n_tile * 128) % p.shift_mod;  // shift_mod is a multiple of 128
       // this thread's output row: 128 contiguous bf16 (256 B) written straight from registers
       const int m = m_tile * 128 + q * 32 + lane;
@@ -896,6 +928,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
+// --------------------------------------------------------------------------
+
+// out[m][n] = bf16( sum_slice partial[slice][m][n] + shift[n % shift_mod] ), slices added in order (deterministic).
+__global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const float* __restrict__ partial, int k_split, int M,
+                                                                 int M_pad, int N, const float* __restrict__ shift,
+                                                                 int shift_mod, bf16* __restrict__ out) {
+  const size_t idx = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (idx >= (size_t)M * N) return;
+  const int n = (int)(idx % N);
+  const size_t m = idx / N;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int sl = 0; sl < k_split; ++sl) {
+    const float4 v = *reinterpret_cast<const float4*>(partial + ((size_t)sl * M_pad + m) * N + n);
+    acc.x += v.x;
+    acc.y += v.y;
+    acc.z += v.z;
+    acc.w += v.w;
+  }
+  const float* sh = shift + n % shift_mod;
+  uint2 o;
+  o.x = pack_bf16x2(acc.x + sh[0], acc.y + sh[1]);
+  o.y = pack_bf16x2(acc.z + sh[2], acc.w + sh[3]);
+  *reinterpret_cast<uint2*>(out + idx) = o;
 }
 
 // --------------------------------------------------------------------------

@@ -114,6 +114,10 @@ typedef struct {
   int out_mode;
   int H, W; /* out_mode 1 */
   void* out;
+  /* optional fp32 scratch: with few output tiles and a long K (M*N <= 37 tiles, K >= 4096) the K range is split over
+   * the idle SMs, each slice stores its tile here and a second kernel adds the slices in a fixed order */
+  float* workspace;
+  long long workspace_floats;
 } cdm_gemm_args;
 int cdm_gemm(const cdm_gemm_args* a, void* stream);
 

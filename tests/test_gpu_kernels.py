@@ -314,3 +314,23 @@ def test_bad_arguments_raise(L):
     out = torch.empty(1, 16, 16, 128, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(cdm.CdmError):
         L.conv3x3(x, w, scale, shift, out)
+
+
+def test_gemm_split_k_small_output_long_k(L):
+    """Two output tiles and K = 65536 (the up0 data gradient): the K range is split over the idle SMs through a
+    workspace; result == the unsplit kernel's up to fp32 summation order, and bit-reproducible."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    for M in (32, 200):
+        a = (torch.randn(M, 65536, device="cuda", generator=g) / 16).to(torch.bfloat16)
+        b = (torch.randn(256, 65536, device="cuda", generator=g) / 16).to(torch.bfloat16)
+        sh = torch.randn(256, device="cuda", generator=g)
+        ws = torch.empty(160 * 128 * 384, device="cuda")
+        o_split = torch.full((M, 256), float("nan"), device="cuda").to(torch.bfloat16)
+        L.gemm(a, b, sh, o_split, workspace=ws)
+        o_plain = torch.full((M, 256), float("nan"), device="cuda").to(torch.bfloat16)
+        L.gemm(a, b, sh, o_plain)
+        ref = a.float() @ b.float().t() + sh
+        assert rel_l2(o_split.float(), ref) < BF16_TOL and rel_l2(o_plain.float(), ref) < BF16_TOL
+        o2 = torch.empty_like(o_split)
+        L.gemm(a, b, sh, o2, workspace=ws)
+        assert torch.equal(o_split, o2)
