@@ -594,8 +594,49 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
       const int reps = (p.flags & CDM_EPI_SHORTCUT) ? p.sc_reps : 1;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
+      // Classifier-free guidance fan-out (init_conv.conv2: one image -> the conditional and the unconditional copy,
+      // which differ only in the shortcut row): read the accumulator and the shortcut input ONCE and emit both
+      // outputs; as two passes of the generic loop below this epilogue was the bottleneck of its layer.
+      const bool fan2 = (p.flags & ~(CDM_EPI_RELU | (1 << 28))) == CDM_EPI_SHORTCUT && reps == 2;
+      if (fan2) {
+        const float* row0 = p.sc_tab + ((size_t)(step * 2) * 2) * p.cout;
+        const float* row1 = row0 + 2 * p.cout;
+        const float w0 = __ldg(row0 + co), b0 = __ldg(row0 + p.cout + co);
+        const float w1 = __ldg(row1 + co), b1 = __ldg(row1 + p.cout + co);
+        const int odd = lane & 1;
 #pragma unroll 1
-      for (int rep = 0; rep < reps; ++rep) {
+        for (int c8 = half * 4; c8 < half * 4 + 4; ++c8) {
+          uint32_t v[32];
+          tmem_ld_x32(taddr + c8 * 32, v);
+          const float* xr = p.sc_x + ((size_t)img * p.H + oh0 + 4 * c8) * p.W + ow0;
+          float xs[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) xs[i] = __ldg(xr + (i >> 3) * p.W + (i & 7));
+          tmem_wait_ld();
+          float base[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float y = fmaf(__uint_as_float(v[i]), sc, sh);
+            base[i] = (p.flags & CDM_EPI_RELU) ? fmaxf(y, 0.f) : y;
+          }
+#pragma unroll
+          for (int rep = 0; rep < 2; ++rep) {
+            const float wc = rep ? w1 : w0, bc = rep ? b1 : b0;
+            bf16* gbase = p.out + (((size_t)(rep * p.n_img + img) * p.H + oh0 + 4 * c8) * p.W + ow0) * p.cout +
+                          n_tile * 128 + (co_l & ~1);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float f0 = base[i] + fmaf(wc, xs[i], bc), f1 = base[i + 1] + fmaf(wc, xs[i + 1], bc);
+              const float recv = __shfl_xor_sync(0xffffffffu, odd ? f0 : f1, 1);
+              const uint32_t w = odd ? pack_bf16x2(recv, f1) : pack_bf16x2(f0, recv);
+              const int px = i + odd;
+              *reinterpret_cast<uint32_t*>(gbase + ((size_t)(px >> 3) * p.W + (px & 7)) * p.cout) = w;
+            }
+          }
+        }
+      }
+#pragma unroll 1
+      for (int rep = 0; rep < (fan2 ? 0 : reps); ++rep) {
         float wcv = 0.f, bcv = 0.f;
         if (p.flags & CDM_EPI_SHORTCUT) {
           const float* row = p.sc_tab + ((size_t)(step * p.sc_reps + rep) * 2) * p.cout;
