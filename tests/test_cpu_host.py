@@ -153,3 +153,22 @@ def test_radial_bins_follow_the_reference_rule():
         np.testing.assert_allclose(pk, ref, rtol=1e-12)
         assert sorted(items.tolist()) == list(range(n * n)) and start[-1] == n * n
         assert len(k_bins) == len(MO.power_spectrum(np.zeros((n, n), np.float32), dl)[0])
+
+
+def test_header_is_plain_c_and_links(lib, tmp_path):
+    """include/cdm_b200.h compiles as C99 and a C program links the library directly (the boundary a non-Python
+    host — the reference ported to C++, a Go/Rust FFI — would bind)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(lib.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "abi", "abi_smoke.c"), "-o", exe, "-L", libdir, "-l:libcdm_b200.so",
+           f"-Wl,-rpath,{libdir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "version 1" in r.stdout and "conv3x3(NULL) -> -1" in r.stdout
