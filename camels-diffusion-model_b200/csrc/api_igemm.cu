@@ -274,7 +274,7 @@ extern "C" int cdm_gemm(const cdm_gemm_args* a, void* stream) {
       attr_b = true;
     }
     const int grid_b = (num_sms() / q.n_groups) * q.n_groups;
-    gemm_bres_kernel<<<grid_b, kConvThreads, smem_b, reinterpret_cast<cudaStream_t>(stream)>>>(mA0, mA1, mB, q);
+    gemm_bres_kernel<<<grid_b, kBresThreads, smem_b, reinterpret_cast<cudaStream_t>(stream)>>>(mA0, mA1, mB, q);
     CDM_CHECK_LAUNCH();
     return CDM_OK;
   }

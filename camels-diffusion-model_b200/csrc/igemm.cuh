@@ -1016,7 +1016,8 @@ struct GemmBresKParams {
 constexpr int kBresStages = 4;
 constexpr int gemm_bres_smem_bytes() { return 131072 + kBresStages * 16384 + 256 + 1024 + 1024; }
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+constexpr int kBresThreads = 128 + 8 * 32;  // 4 role warps + 8 epilogue warps (one set of 4 per resident n-tile)
+__global__ void __launch_bounds__(kBresThreads, 1)
 gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapB, const GemmBresKParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -1041,7 +1042,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&t_full[i], 1);
-      mbar_init(&t_empty[i], 4);
+      mbar_init(&t_empty[i], 8);
     }
     mbar_init(w_ready, 1);
     fence_barrier_init();
@@ -1062,9 +1063,9 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapB);
     mbar_arrive_expect_tx(w_ready, (uint32_t)(p.n_res * p.chunks * 16384));
-    for (int nt = 0; nt < p.n_res; ++nt)
+    for (int nt = 0; nt < p.n_res; ++nt)  // [chunk][n-tile]: the n-tiles of one K chunk are one contiguous N operand
       for (int ch = 0; ch < p.chunks; ++ch)
-        tma_load_2d(smemW + (nt * p.chunks + ch) * 16384, &mapB, w_ready, ch * 64, (n_tile0 + nt) * 128);
+        tma_load_2d(smemW + (ch * p.n_res + nt) * 16384, &mapB, w_ready, ch * 64, (n_tile0 + nt) * 128);
     int st = 0;
     uint32_t ph = 0;
     for (int mt = first; mt < p.m_tiles; mt += stride)
@@ -1080,7 +1081,9 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         }
       }
   } else if (warp == 1 && lane == 0) {
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+    // two resident n-tiles = ONE M128 N256 instruction per K step (12 KB of operand reads per 128 clk instead of
+    // 2 x 8 KB per 2 x 64: the N128 shape is shared-memory bound at half the tensor rate)
+    const uint32_t idesc = p.n_res == 2 ? umma_idesc_bf16(128, 256) : umma_idesc_bf16(128, 128);
     mbar_wait(w_ready, 0);
     tc_fence_after();
     const uint32_t w_base = smem_u32(smemW);
@@ -1094,13 +1097,11 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         mbar_wait(&full[st], ph);
         tc_fence_after();
         const uint32_t a_base = smem_u32(smemA + st * 16384);
-        for (int nt = 0; nt < p.n_res; ++nt) {
-          const uint32_t b_base = w_base + (uint32_t)((nt * p.chunks + ch) * 16384);
+        const uint32_t b_base = w_base + (uint32_t)(ch * p.n_res * 16384);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + (uint32_t)((buf * p.n_res + nt) * 128), umma_desc_sw128(a_base + k * 32, 1024),
-                      umma_desc_sw128(b_base + k * 32, 1024), idesc, (ch == 0 && k == 0) ? 0u : 1u);
-        }
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + (uint32_t)(buf * p.n_res * 128), umma_desc_sw128(a_base + k * 32, 1024),
+                    umma_desc_sw128(b_base + k * 32, 1024), idesc, (ch == 0 && k == 0) ? 0u : 1u);
         umma_commit(&empty[st]);
         if (++st == kBresStages) {
           st = 0;
@@ -1110,14 +1111,16 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       umma_commit(&t_full[buf]);
     }
   } else if (warp >= 4) {
-    const int q = warp - 4;
+    // TMEM lane quadrant q = warp % 4 (hardware rule); warps 4-7 drain n-tile 0, warps 8-11 n-tile 1 (with one
+    // resident n-tile the second set only keeps the barrier protocol): the epilogue, not the MMA, paced this kernel
+    const int q = warp & 3, set = (warp - 4) >> 2;
     int it = 0;
     for (int mt = first; mt < p.m_tiles; mt += stride, ++it) {
       const int buf = it & 1;
       mbar_wait(&t_full[buf], (it >> 1) & 1);
       tc_fence_after();
       const int m = mt * 128 + q * 32 + lane;
-      for (int nt = 0; nt < p.n_res; ++nt) {
+      for (int nt = set; nt < p.n_res; nt += 2) {
         const int n_tile = n_tile0 + nt;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.n_res + nt) * 128);
         const float* shift = s_shift + nt * 128;  // shared memory: broadcast reads, no global-load latency
