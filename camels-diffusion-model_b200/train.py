@@ -620,40 +620,54 @@ class GraphedTrainStep:
                 for p, m, v in zip(self.params, self.m, self.v)]
         self.table = torch.tensor(rows, dtype=torch.int64).to(dev)
         self.max_numel = max(p.numel() for p in self.params)
-        self.graph = None
-        if not use_graph:
-            return
-        # warm-up (kernel attributes, allocator) with lr = 0 so parameters do not move; BatchNorm buffers and the
-        # optimizer state it touches are restored afterwards, so the first real step starts from a clean state
-        saved = [b.detach().clone() for b in model.buffers()]
+        self.graphs, self.use_graph, self.warmup = {}, use_graph, warmup
+        if use_graph:
+            self._capture(batch)
+
+    @property
+    def graph(self):
+        return self.graphs.get(self.B)
+
+    def _capture(self, b):
+        """Capture the step for batch size b <= B (the ragged last batch of an epoch gets its own graph, lazily).
+        Warm-up and capture run with lr = 0, and everything a step mutates besides the parameters — BatchNorm
+        buffers, Adam moments, the step counter — is saved and restored, so capturing mid-training is invisible."""
+        model = self.model
+        saved_buf = [t.detach().clone() for t in model.buffers()]
+        saved_m, saved_v = [t.clone() for t in self.m], [t.clone() for t in self.v]
+        saved_count, saved_lr = self.count.clone(), self.lr.clone()
         self.lr.zero_()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(warmup):
-                self._step()
+            for _ in range(self.warmup):
+                self._step(b)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._step()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step(b)
         torch.cuda.synchronize()
         with torch.no_grad():
-            for b, sv in zip(model.buffers(), saved):
-                b.copy_(sv)
-        self.reset_optimizer()
-        self.lr.fill_(float(lr))
+            for t, sv in zip(model.buffers(), saved_buf):
+                t.copy_(sv)
+            for t, sv in zip(self.m + self.v, saved_m + saved_v):
+                t.copy_(sv)
+            self.count.copy_(saved_count)
+            self.lr.copy_(saved_lr)
+        self.graphs[b] = g
 
-    def _step(self):
+    def _step(self, b=None):
         m = self.model
+        b = self.B if b is None else b
+        x, x_pert, noise, dpred, t = self.x[:b], self.x_pert[:b], self.noise[:b], self.dpred[:b], self.t[:b]
         L.step_advance(self.count, 1)
-        L.perturb(self.x, self.x_pert, self.ca, self.cb, t_idx=self.t, step_ptr=self.count, seed=self.seed,
-                  noise_out=self.noise)
+        L.perturb(x, x_pert, self.ca, self.cb, t_idx=t, step_ptr=self.count, seed=self.seed, noise_out=noise)
         ctx = _Ctx()
-        pred = _UnetFn.forward(ctx, m, self.x_pert, self.t / self.T, self.param, self.sc, *self.params)
-        L.mse_grad(pred, self.noise, 1.0 / pred.numel(), self.dpred, self.partial, self.loss_sum)
+        pred = _UnetFn.forward(ctx, m, x_pert, t / self.T, self.param[:b], self.sc, *self.params)
+        L.mse_grad(pred, noise, 1.0 / pred.numel(), dpred, self.partial, self.loss_sum)
         ctx.flat_out = self.flat_out
-        _UnetFn.backward(ctx, self.dpred)  # gradients land in self.flat (= every p.grad)
+        _UnetFn.backward(ctx, dpred)  # gradients land in self.flat (= every p.grad)
         b1, b2 = self.betas
         L.adam_step(self.table, len(self.params), self.max_numel, 0.0, b1, b2, self.eps, 0, lr_dev=self.lr,
                     step_dev=self.count)
@@ -688,14 +702,20 @@ class GraphedTrainStep:
         self.seed = int(sd.get("seed", self.seed))
 
     def __call__(self, x, param, t=None, shortcut=None):
-        """One optimisation step; returns the mean-squared-error loss as a 0-d device tensor (no host sync)."""
+        """One optimisation step on a batch of b <= B samples; returns the mean-squared-error loss as a 0-d device
+        tensor (no host sync).  t / shortcut default to fresh draws from torch's CPU generator, like the reference."""
         m = self.model
-        self.x.copy_(x.reshape(self.x.shape), non_blocking=True)
-        self.param.copy_(param, non_blocking=True)
-        self.t.copy_(torch.randint(1, self.T + 1, (self.B,)) if t is None else t, non_blocking=True)
+        b = x.shape[0]
+        if b > self.B:
+            raise L.CdmError(f"batch of {b} samples exceeds the captured capacity {self.B}")
+        self.x[:b].copy_(x.reshape(b, *self.x.shape[1:]), non_blocking=True)
+        self.param[:b].copy_(param, non_blocking=True)
+        self.t[:b].copy_(torch.randint(1, self.T + 1, (b,)) if t is None else t, non_blocking=True)
         self.sc.copy_(m.draw_shortcut() if shortcut is None else shortcut, non_blocking=True)
-        if self.graph is not None:
-            self.graph.replay()
+        if self.use_graph:
+            if b not in self.graphs:
+                self._capture(b)
+            self.graphs[b].replay()
         else:
-            self._step()
-        return self.loss_sum[0] / self.x.numel()
+            self._step(b)
+        return self.loss_sum[0] / (b * self.x[0].numel())

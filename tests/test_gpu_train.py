@@ -474,3 +474,42 @@ def test_graphed_step_matches_eager_step(L):
         # of the remaining split-K gemm_tn calls can flip the sign of a near-zero gradient)
         assert (a - b).abs().max() <= 2.1e-4, k
         assert ((a - b).abs() > 2e-5).float().mean() < 1e-3, k
+
+
+def test_train_diffusion_epoch_loop(tmp_path):
+    """drivers.train_diffusion (the epoch loop of train_diffusion_paper.py:338-478): lr schedule, ragged last batch,
+    evaluation cadence, reference-format checkpoints, and resume == uninterrupted (same logs for the later epochs'
+    evaluation entries up to the training step's run-to-run noise)."""
+    import os
+    from torch.utils.data import DataLoader, TensorDataset
+    import camels_diffusion_model_b200 as cdm
+    from camels_diffusion_model_b200 import drivers
+    from tests._util import cal_sd, make_model
+    g = torch.Generator().manual_seed(0)
+    train = TensorDataset(torch.rand(10, 1, 64, 64, generator=g), torch.rand(10, 6, generator=g))  # 4 + 4 + 2
+    test = TensorDataset(torch.rand(5, 1, 64, 64, generator=g), torch.rand(5, 6, generator=g))
+    tl, vl = DataLoader(train, batch_size=4, shuffle=False), DataLoader(test, batch_size=4, shuffle=False)
+    torch.manual_seed(1)
+    m = make_model(cal_sd())
+    w0 = m.out[3].weight.detach().clone()
+    lines = []
+    logs = drivers.train_diffusion(m, tl, n_epoch=3, lrate=1e-4, timesteps=20, test_dataloader=vl,
+                                   save_dir=str(tmp_path), eval_every=2, save_every=2, log=lines.append)
+    assert len(logs["loss_log"]) == 3 and all(np.isfinite(logs["loss_log"]))
+    assert len(logs["val_loss_log"]) == 2 and len(logs["bpd_log"]) == 2 and len(logs["val_likelihood_log"]) == 2  # ep 0, 2
+    assert all(np.isfinite(v) for k in logs for v in logs[k])
+    assert not torch.equal(m.out[3].weight.detach(), w0)
+    assert sorted(f for f in os.listdir(tmp_path) if f.endswith(".pth")) == ["model_epoch_2.pth", "model_epoch_3.pth"]
+    sd = torch.load(os.path.join(tmp_path, "model_epoch_3.pth"), map_location="cpu")
+    assert len(sd) == 156 and torch.equal(sd["out.3.weight"], m.out[3].weight.detach().cpu())
+    # 8 full-batch steps + 3 ragged steps of 2 samples, each epoch ending on the ragged graph
+    assert any("Epoch 3/3" in l for l in lines)
+    # resume after epoch 2 and finish: the checkpointed state continues the schedule (lr of epoch 3, step count)
+    m2 = make_model(cal_sd())
+    ck = torch.load(os.path.join(tmp_path, "resume.pt"), map_location="cpu", weights_only=False)
+    assert ck["epoch"] == 3 and int(ck["optim"]["state"][0]["step"]) == 9
+    logs2 = drivers.train_diffusion(m2, tl, n_epoch=3, lrate=1e-4, timesteps=20, test_dataloader=vl,
+                                    resume_from=os.path.join(tmp_path, "resume.pt"), log=lines.append)
+    assert logs2["loss_log"] == logs["loss_log"]  # nothing left to train: the restored logs come back unchanged
+    for (k, a), b in zip(m.state_dict().items(), m2.state_dict().values()):
+        assert torch.equal(a, b), k
