@@ -65,7 +65,15 @@ def _xr():
     if _world() <= 1 or not PEER_EXCHANGE:
         return None
     if PEER is None:
-        enable_peer_exchange()
+        try:
+            enable_peer_exchange()
+        except Exception as ex:  # noqa: BLE001  (no NVLink peer access / symmetric memory on this system)
+            import warnings
+            global PEER_EXCHANGE
+            PEER_EXCHANGE = False
+            warnings.warn(f"peer-memory exchange unavailable ({type(ex).__name__}: {ex}); BatchNorm statistics fall "
+                          "back to NCCL all-reduce (still on the GPUs, every rank takes the same path)")
+            return None
     return PEER.args
 
 
