@@ -62,6 +62,7 @@ def _side_stream(dev):
 
 
 def _xr():
+    global PEER_EXCHANGE
     if _world() <= 1 or not PEER_EXCHANGE:
         return None
     if PEER is None:
@@ -69,7 +70,6 @@ def _xr():
             enable_peer_exchange()
         except Exception as ex:  # noqa: BLE001  (no NVLink peer access / symmetric memory on this system)
             import warnings
-            global PEER_EXCHANGE
             PEER_EXCHANGE = False
             warnings.warn(f"peer-memory exchange unavailable ({type(ex).__name__}: {ex}); BatchNorm statistics fall "
                           "back to NCCL all-reduce (still on the GPUs, every rank takes the same path)")
