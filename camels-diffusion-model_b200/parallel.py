@@ -72,6 +72,29 @@ def reduce_mean_scalar(total, count, device=None):
     return float(t[0] / t[1])
 
 
+def evaluate_sharded(eval_fn, maps, params, batch_size=32, device=None):
+    """Dataset-level NLL / ELBO over all ranks (BASELINE config 5: 4096 maps on 8 GPUs): rank r evaluates its
+    contiguous shard of `maps` / `params` in batches of `batch_size` — `eval_fn(loader)` is e.g.
+    `lambda dl: calculate_likelihood(model, dl, T, dev, ab_t, b_t, a_t)` or the ELBO/BPD variant and returns the
+    shard MEAN (a float, or a tuple of floats) — and the per-rank (sum, count) pairs meet in one scalar all-reduce.
+    No other communication: the maps are independent."""
+    rank, ws = world()
+    s, e = shard_range(maps.shape[0], rank, ws)
+    loader = [(maps[i:min(i + batch_size, e)], None if params is None else params[i:min(i + batch_size, e)])
+              for i in range(s, e, batch_size)]
+    n_local = e - s
+    res = eval_fn(loader) if n_local > 0 else ()  # a rank without maps contributes (0, 0) to every output
+    vals = [float(v) for v in res] if isinstance(res, tuple) else [float(res)]
+    arity = len(vals)
+    if ws > 1:  # ranks with an empty shard do not know how many outputs eval_fn has
+        a = torch.tensor([arity], device=device if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        arity = int(a.item())
+    vals += [0.0] * (arity - len(vals))
+    out = tuple(reduce_mean_scalar(v * n_local, n_local, device) for v in vals)
+    return out if (isinstance(res, tuple) and arity > 1) or arity > 1 else out[0]
+
+
 class PeerExchange:
     """Peer group for the fused reduce + cross-rank exchange kernels (cdm_xrank in include/cdm_b200.h).
 

@@ -90,3 +90,33 @@ def test_rank0_save_and_broadcast_load_gloo(tmp_path):
     assert len(saved) == 156  # the reference's state_dict layout (n_cfeat only changes two shapes)
     for k, v in ret[0].items():
         assert torch.equal(v, ret[1][k]) and torch.equal(v, saved[k]), k
+
+
+def _eval_worker(rank, ws, port, n_total, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    from camels_diffusion_model_b200 import parallel as P
+    g = torch.Generator().manual_seed(0)
+    maps = torch.rand(n_total, 1, 8, 8, generator=g)
+    prm = torch.rand(n_total, 6, generator=g)
+
+    def stub(loader):  # per-sample "nll" = sum of the map + first parameter; returns the shard mean like the real ones
+        vals = torch.cat([x.sum(dim=(1, 2, 3)) + p[:, 0] for x, p in loader])
+        assert all(x.shape[0] <= 3 for x, _ in loader)
+        return float(vals.mean()), float(vals.mean()) / 2
+
+    nll, bpd = P.evaluate_sharded(stub, maps, prm, batch_size=3)
+    ret[rank] = (nll, bpd, float((maps.sum(dim=(1, 2, 3)) + prm[:, 0]).double().mean()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [10, 7, 1])
+def test_sharded_evaluation_gloo(n_total):
+    ws = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_eval_worker, args=(ws, _free_port(), n_total, ret), nprocs=ws, join=True)
+    for r in range(ws):
+        nll, bpd, ref = ret[r]
+        assert abs(nll - ref) < 1e-5 and abs(bpd - ref / 2) < 1e-5
+    assert ret[0][:2] == ret[1][:2]
