@@ -432,7 +432,7 @@ extern "C" int cdm_gemm_tn(const cdm_gemm_tn_args* a, void* stream) {
   p.tiles_y = (a->H + bh - 1) / bh;
   p.k_blocks = p.tiles_x * p.tiles_y * a->n_img;
   const int base_units = p.taps * p.m_tiles * p.n_tiles;
-  int ks = a->k_split > 0 ? a->k_split : (2 * num_sms() + base_units - 1) / base_units;
+  int ks = a->k_split > 0 ? a->k_split : (2 * num_sms()) / base_units;  // at most two full waves of units
   if (ks > p.k_blocks) ks = p.k_blocks;
   if (ks < 1) ks = 1;
   p.k_split = ks;
@@ -442,6 +442,7 @@ extern "C" int cdm_gemm_tn(const cdm_gemm_tn_args* a, void* stream) {
   p.C = a->c;
   p.ldc = a->ldc;
   p.tap_stride = a->tap_stride;
+  if (a->workspace && ks > 1 && a->workspace_floats >= (long long)p.n_units * 128 * 128) p.partial = a->workspace;
   constexpr int smem = gemm_tn_smem_bytes();
   static bool attr_set = false;
   if (!attr_set) {
@@ -451,6 +452,12 @@ extern "C" int cdm_gemm_tn(const cdm_gemm_tn_args* a, void* stream) {
   const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
   gemm_tn_kernel<<<grid, kConvThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(mA, mB, p);
   CDM_CHECK_LAUNCH();
+  if (p.partial) {
+    const long long per_slice = (long long)base_units * 128 * 128;
+    gemm_tn_reduce_kernel<<<(int)((per_slice + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        p.partial, p.k_split, p.taps, p.m_tiles, p.n_tiles, p.C, p.ldc, p.tap_stride);
+    CDM_CHECK_LAUNCH();
+  }
   return CDM_OK;
 }
 

@@ -1283,7 +1283,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int buf = it & 1;
       mbar_wait(&t_full[buf], (it >> 1) & 1);
       tc_fence_after();
-      if (kb1 > kb0) {
+      if (p.partial) {  // split-K tile of this slice -> workspace (zeros for an empty slice); gemm_tn_reduce adds them
+        float4* prow = reinterpret_cast<float4*>(p.partial + ((size_t)u * 128 + q * 32 + lane) * 128);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128);
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t v[32];
+          if (kb1 > kb0) {
+            tmem_ld_x32(taddr + cc * 32, v);
+            tmem_wait_ld();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0u;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            prow[cc * 8 + i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                           __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        }
+      } else if (kb1 > kb0) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128);
         float* crow = p.C + (size_t)(m_tile * 128 + q * 32 + lane) * p.ldc + tap * p.tap_stride + n_tile * 128;
 #pragma unroll 1
@@ -1303,6 +1321,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
+// Fixed-order sum of the split-K tiles of gemm_tn_kernel: C[...] += sum_slice partial[slice][tap][m_tile][n_tile][row][col].
+__global__ void __launch_bounds__(256) gemm_tn_reduce_kernel(const float* __restrict__ partial, int k_split, int taps,
+                                                             int m_tiles, int n_tiles, float* __restrict__ C, int ldc,
+                                                             int tap_stride) {
+  const size_t tile = (size_t)128 * 128;
+  const size_t per_slice = (size_t)taps * m_tiles * n_tiles * tile;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per_slice) return;
+  const int col = (int)(idx % 128), row = (int)((idx / 128) % 128);
+  const int un = (int)(idx / tile);  // (tap * m_tiles + m_tile) * n_tiles + n_tile
+  const int n_tile = un % n_tiles, m_tile = (un / n_tiles) % m_tiles, tap = un / (n_tiles * m_tiles);
+  float acc = 0.f;
+  for (int sl = 0; sl < k_split; ++sl) acc += partial[(size_t)sl * per_slice + idx];
+  C[(size_t)(m_tile * 128 + row) * ldc + tap * tap_stride + n_tile * 128 + col] += acc;
 }
 
 // --------------------------------------------------------------------------

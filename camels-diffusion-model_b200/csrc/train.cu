@@ -617,13 +617,24 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdP p) {
       S2 = fmaf(dh, h, S2);
     }
   }
+  // per-channel sums over the threads that own the channel (thread t owns vector t % vpp), added in thread order:
+  // deterministic (shared-memory float atomics are not)
+  __shared__ float fold[256][8];
+#pragma unroll 1
+  for (int qn = 0; qn < 4; ++qn) {
+    const float* src = qn == 0 ? dg : (qn == 1 ? dbt : (qn == 2 ? dfs : dfb));
+    __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&chan[0][v * 8 + j], dg[j]);
-    atomicAdd(&chan[1][v * 8 + j], dbt[j]);
-    atomicAdd(&chan[2][v * 8 + j], dfs[j]);
-    atomicAdd(&chan[3][v * 8 + j], dfb[j]);
+    for (int j = 0; j < 8; ++j) fold[threadIdx.x][j] = src[j];
+    __syncthreads();
+    if (threadIdx.x < cpg) {
+      const int vv = threadIdx.x >> 3, jj = threadIdx.x & 7;
+      float acc = 0.f;
+      for (int t = vv; t < (int)blockDim.x; t += vpp) acc += fold[t][jj];
+      chan[qn][threadIdx.x] = acc;
+    }
   }
+  __syncthreads();
   const float M = (float)(p.P * cpg);
   const float s1 = t_block_sum(S1, red) / M;
   const float s2 = t_block_sum(S2, red) / M;

@@ -225,7 +225,8 @@ class _UnetFn(torch.autograd.Function):
         S.zeros = torch.zeros(65536, device=dev)
         S.ws = _f32(148 * 8, 9 * 256, dev=dev)  # reduction workspace (partials)
         S.bnp = _f32(148, 2 * 256, dev=dev)  # per-CTA BatchNorm partial sums of the conv epilogue
-        S.wgws = _f32(160 * 128 * 384, dev=dev)  # split-K tiles of the 3x3 weight gradients (fixed-order reduction)
+        S.wgws = _f32(160 * 128 * 384, dev=dev)  # split-K tiles of the 3x3 weight gradients (used on the SIDE stream only)
+        S.skws = _f32(160 * 128 * 384, dev=dev)  # split-K tiles of the main-stream GEMMs (transposed convs, up0)
         P = _pack_train(m)
         S.P = P
         x3 = x.detach().to(dev, torch.float32).reshape(n, h, h).contiguous()
@@ -379,7 +380,8 @@ class _UnetFn(torch.autograd.Function):
             off = 0
             for s in srcs:
                 cs = s.shape[-1]
-                L.gemm_tn(s, s2d, dw[off:], n_img=1, H=1, W=Mrows, a_c=cs, b_c=4 * nf, M=cs, N=4 * nf, ldc=4 * nf)
+                L.gemm_tn(s, s2d, dw[off:], n_img=1, H=1, W=Mrows, a_c=cs, b_c=4 * nf, M=cs, N=4 * nf, ldc=4 * nf,
+                          workspace=S.skws)
                 off += cs
             G[prefix + ".weight"] = dw.view(cin, 2, 2, nf).permute(0, 3, 1, 2).contiguous()
             return da
@@ -444,9 +446,10 @@ class _UnetFn(torch.autograd.Function):
         G["up0.0.bias"] = sums[0]
         K0 = h4 * h4 * 2 * nf
         d_hid = _bf(n, 2 * nf, dev=dev)
-        L.gemm(d_u0raw.view(n, K0), P["up0.d"], S.zeros[:2 * nf], d_hid, shift_mod=2 * nf, workspace=S.wgws)
+        L.gemm(d_u0raw.view(n, K0), P["up0.d"], S.zeros[:2 * nf], d_hid, shift_mod=2 * nf, workspace=S.skws)
         dw0 = _f32(2 * nf, K0, dev=dev, zero=True)
-        L.gemm_tn(S.hidden, d_u0raw, dw0, n_img=1, H=1, W=n, a_c=2 * nf, b_c=K0, M=2 * nf, N=K0, ldc=K0)
+        L.gemm_tn(S.hidden, d_u0raw, dw0, n_img=1, H=1, W=n, a_c=2 * nf, b_c=K0, M=2 * nf, N=K0, ldc=K0,
+                  workspace=S.skws)  # K = batch rows: a single K slice unless the batch exceeds 128
         dw0_iohw = dw0.view(2 * nf, h4, h4, 2 * nf).permute(0, 3, 1, 2)  # IOHW view of the [ci][(h,w,co)] GEMM output
         direct = getattr(ctx, "flat_out", None)
         if direct is not None:  # 78 % of all gradient bytes: permuted straight into its slot of the flat buffer

@@ -374,10 +374,11 @@ typedef struct {
   float* c;
   int ldc, tap_stride;
   int k_split; /* 0 = choose so that ~2 CTAs per SM have work */
-  float* workspace;            /* taps == 9: split-K partial tiles, >= units * 128 * 384 floats with units =
-                                * 3 * (M/128) * (N/128) * k_split.  Given: every K slice writes its tile with plain
-                                * stores and a second kernel adds the slices in a fixed order (deterministic, and
-                                * ~7 M fewer fp32 atomics per layer).  NULL: fp32 atomics straight into c. */
+  float* workspace;            /* split-K partial tiles: taps == 9 needs >= 3 * (M/128) * (N/128) * k_split * 128 * 384
+                                * floats, taps == 1 >= (M/128) * (N/128) * k_split * 128 * 128.  Given (and large enough):
+                                * every K slice writes its tile with plain stores and a second kernel adds the slices in
+                                * a fixed order (deterministic, and ~7 M fewer fp32 atomics per 3x3 layer).  NULL: fp32
+                                * atomics straight into c (run-to-run differences in the last bits). */
   long long workspace_floats;
   float* probe; /* measurement only (NULL in production): fp32 [148][4] = per-CTA issuer cycles blocked on the TMA
                  * ring, blocked on the accumulator, total, epilogue cycles (taps == 9 path) */

@@ -85,14 +85,21 @@ def test_resume_continues_the_run(tmp_path, kind):
         assert torch.equal(st["exp_avg"].cpu(), ck["optim"]["state"][i]["exp_avg"]) and int(st["step"]) == 2
         assert torch.equal(st["exp_avg_sq"].cpu(), ck["optim"]["state"][i]["exp_avg_sq"])
     loss2 = run(m2, o2, 2, 3)
-    assert abs(loss1 - loss2) <= 1e-6 * abs(loss1), (loss1, loss2)
+    assert loss1 == loss2, (loss1, loss2)
+    # every reduction of the step is fixed-order (BatchNorm statistics, split-K weight gradients through workspaces,
+    # GroupNorm sums): the continued run is BIT-identical to the uninterrupted one, parameters included
+    rng = torch.get_rng_state()  # both continuations draw their t / shortcut values from the same generator state
+    run(m1, o1, 3, 5)
+    torch.set_rng_state(rng)
+    run(m2, o2, 3, 5)
+    for (k, a), b in zip(m1.state_dict().items(), m2.state_dict().values()):
+        assert torch.equal(a, b), k
     s1, s2 = o1.state_dict()["state"], o2.state_dict()["state"]
     assert s1.keys() == s2.keys() and len(s1) == 102
     for i in s1:
-        assert int(s1[i]["step"]) == int(s2[i]["step"]) == 3
+        assert int(s1[i]["step"]) == int(s2[i]["step"]) == 5
         for key in ("exp_avg", "exp_avg_sq"):
-            d = (s1[i][key].double() - s2[i][key].double()).norm()
-            assert d <= 2e-2 * s1[i][key].double().norm() + 1e-12, (i, key)
+            assert torch.equal(s1[i][key], s2[i][key]), (i, key)
 
 
 def test_optimizer_state_interchanges_with_torch_adam(tmp_path):

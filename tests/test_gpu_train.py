@@ -513,3 +513,38 @@ def test_train_diffusion_epoch_loop(tmp_path):
     assert logs2["loss_log"] == logs["loss_log"]  # nothing left to train: the restored logs come back unchanged
     for (k, a), b in zip(m.state_dict().items(), m2.state_dict().values()):
         assert torch.equal(a, b), k
+
+
+def test_training_step_is_bit_reproducible():
+    """Every reduction of the step has a fixed order (BatchNorm statistics from per-CTA rows, split-K weight gradients
+    through workspaces, GroupNorm sums without float atomics): two identical steps give bit-identical predictions,
+    BatchNorm buffers and all 102 gradients — also after the allocator has been disturbed in between."""
+    import torch.nn.functional as Fn
+    import camels_diffusion_model_b200 as cdm
+    from camels_diffusion_model_b200 import diffusion as D
+    from tests._util import cal_sd
+    Tn = 1500
+    ab_t = D.make_schedule(Tn)[2]
+    g = torch.Generator().manual_seed(1)
+    x, p = torch.rand(6, 1, 64, 64, generator=g).cuda(), torch.rand(6, 6, generator=g).cuda()
+    noise = torch.randn(6, 1, 64, 64, generator=g).cuda()
+    t = torch.randint(1, Tn + 1, (6,), generator=g)
+    sc = torch.rand(256, generator=g) * 2 - 1
+    runs = []
+    for it in range(3):
+        m = cdm.ContextUnet(1, 128, 6, 64)
+        m.load_state_dict(cal_sd())
+        m = m.cuda().train()
+        pred = m(D.perturb_input(x, t, noise, ab_t), (t / Tn).cuda(), p, shortcut=sc)
+        Fn.mse_loss(pred, noise).backward()
+        torch.cuda.synchronize()
+        runs.append((pred.detach().clone(), {k: q.grad.detach().clone() for k, q in m.named_parameters()},
+                     {k: b.detach().clone() for k, b in m.named_buffers()}))
+        junk = [torch.randn(1 << 22, device="cuda") for _ in range(it + 1)]  # shift the allocator's free lists
+        del junk
+    for it in (1, 2):
+        assert torch.equal(runs[0][0], runs[it][0])
+        for k in runs[0][1]:
+            assert torch.equal(runs[0][1][k], runs[it][1][k]), k
+        for k in runs[0][2]:
+            assert torch.equal(runs[0][2][k], runs[it][2][k]), k
