@@ -331,7 +331,6 @@ struct BnApplyP {
 };
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyP p) {
   const int groups = p.C >> 3;  // 16 or 32: divides blockDim.x, so a thread keeps the same 8 channels
-  const long long total = p.P * groups;
   const int cg = (int)(threadIdx.x % groups);
   float sc[8], sh[8], sw[8], sb[8];
 #pragma unroll
@@ -341,8 +340,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyP p) {
     sw[j] = p.sc_x ? p.sc_w[cg * 8 + j] : 0.f;
     sb[j] = p.sc_x ? p.sc_b[cg * 8 + j] : 0.f;
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / groups;
+  // groups divides blockDim.x, so a thread's row advances by a constant: no 64-bit division in the loop
+  const long long r_step = (long long)gridDim.x * (blockDim.x / groups);
+  for (long long r = (long long)blockIdx.x * (blockDim.x / groups) + threadIdx.x / groups; r < p.P; r += r_step) {
     float f[8];
     t_unpack8(ld8(p.z + r * p.C + cg * 8), f);
 #pragma unroll
@@ -387,7 +387,6 @@ struct BnBwdP {
 };
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdP p) {
   const int groups = p.C >> 3;  // divides blockDim.x: a thread keeps the same 8 channels
-  const long long total = p.P * groups;
   const float inv = 1.f / p.count;
   const int cg = (int)(threadIdx.x % groups);
   float sc[8], sh[8], mu[8], rs[8], m0[8], m1[8];
@@ -401,18 +400,32 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdP p) {
     m0[j] = p.sums[c] * inv;
     m1[j] = p.sums[p.C + c] * inv;
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / groups;
-    float d[8], z[8];
-    t_unpack8(ld8(p.dy + r * p.lddy + cg * 8), d);
-    t_unpack8(ld8(p.z + r * p.C + cg * 8), z);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float g = (!p.relu || fmaf(z[j], sc[j], sh[j]) > 0.f) ? d[j] : 0.f;
-      const float xh = (z[j] - mu[j]) * rs[j];
-      d[j] = sc[j] * (g - m0[j] - xh * m1[j]);
+  // a thread's row advances by a constant (groups divides blockDim.x): no 64-bit division; two rows per iteration
+  // with all four loads issued first
+  const long long r_step = (long long)gridDim.x * (blockDim.x / groups);
+  for (long long r = (long long)blockIdx.x * (blockDim.x / groups) + threadIdx.x / groups; r < p.P; r += 2 * r_step) {
+    const long long r2 = r + r_step;
+    const bool two = r2 < p.P;
+    const uint4 rd0 = ld8(p.dy + r * p.lddy + cg * 8), rz0 = ld8(p.z + r * p.C + cg * 8);
+    uint4 rd1 = make_uint4(0u, 0u, 0u, 0u), rz1 = rd1;
+    if (two) {
+      rd1 = ld8(p.dy + r2 * p.lddy + cg * 8);
+      rz1 = ld8(p.z + r2 * p.C + cg * 8);
     }
-    *reinterpret_cast<uint4*>(p.dz + r * p.C + cg * 8) = t_pack8(d);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      float d[8], z[8];
+      t_unpack8(u ? rd1 : rd0, d);
+      t_unpack8(u ? rz1 : rz0, z);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g = (!p.relu || fmaf(z[j], sc[j], sh[j]) > 0.f) ? d[j] : 0.f;
+        const float xh = (z[j] - mu[j]) * rs[j];
+        d[j] = sc[j] * (g - m0[j] - xh * m1[j]);
+      }
+      *reinterpret_cast<uint4*>(p.dz + (u ? r2 : r) * p.C + cg * 8) = t_pack8(d);
+    }
   }
 }
 
