@@ -982,6 +982,7 @@ __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const float* __
   const int n = (int)(idx % N);
   const size_t m = idx / N;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
   for (int sl = 0; sl < k_split; ++sl) {
     const float4 v = *reinterpret_cast<const float4*>(partial + ((size_t)sl * M_pad + m) * N + n);
     acc.x += v.x;
@@ -1335,7 +1336,8 @@ __global__ void __launch_bounds__(256) gemm_tn_reduce_kernel(const float* __rest
   const int un = (int)(idx / tile);  // (tap * m_tiles + m_tile) * n_tiles + n_tile
   const int n_tile = un % n_tiles, m_tile = (un / n_tiles) % m_tiles, tap = un / (n_tiles * m_tiles);
   float acc = 0.f;
-  for (int sl = 0; sl < k_split; ++sl) acc += partial[(size_t)sl * per_slice + idx];
+#pragma unroll 8
+  for (int sl = 0; sl < k_split; ++sl) acc += partial[(size_t)sl * per_slice + idx];  // loads in flight, fixed order
   C[(size_t)(m_tile * 128 + row) * ldc + tap * tap_stride + n_tile * 128 + col] += acc;
 }
 
@@ -1512,7 +1514,8 @@ __global__ void __launch_bounds__(256) gemm_tn9_reduce_kernel(const float* __res
   const int un = (int)(idx / tile);  // (kh * m_tiles + m_tile) * n_tiles + n_tile
   const int n_tile = un % n_tiles, m_tile = (un / n_tiles) % m_tiles, kh = un / (n_tiles * m_tiles);
   float acc = 0.f;
-  for (int sl = 0; sl < k_split; ++sl) acc += partial[(size_t)sl * per_slice + idx];
+#pragma unroll 8
+  for (int sl = 0; sl < k_split; ++sl) acc += partial[(size_t)sl * per_slice + idx];  // loads in flight, fixed order
   const int half = col / 192, kw = (col % 192) / 64, c = col % 64;
   float* dst = C + (size_t)(m_tile * 128 + row) * ldc + (kh * 3 + kw) * tap_stride + n_tile * 128 + half * 64 + c;
   *dst += acc;

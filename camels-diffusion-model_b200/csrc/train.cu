@@ -233,9 +233,18 @@ __global__ void __launch_bounds__(1024) xrank_sum_kernel(const XrankP p) {
   const int s = p.world > 1 ? *p.seq + 1 : 0;  // read before the ticket: only the last block advances it
   const int par = s & 1;
   if (i < p.n) {
-    float t = 0.f;
-    for (int b = lane; b < p.n_blocks; b += 32) t += p.partial[(size_t)b * p.n + i];
-    t = t_warp_sum(t);
+    // four independent chains so that the (up to 19) strided loads of a lane are all in flight at once; the order of
+    // the additions is still fixed
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    int b = lane;
+    for (; b + 96 < p.n_blocks; b += 128) {
+      t0 += p.partial[(size_t)b * p.n + i];
+      t1 += p.partial[(size_t)(b + 32) * p.n + i];
+      t2 += p.partial[(size_t)(b + 64) * p.n + i];
+      t3 += p.partial[(size_t)(b + 96) * p.n + i];
+    }
+    for (; b < p.n_blocks; b += 32) t0 += p.partial[(size_t)b * p.n + i];
+    float t = t_warp_sum((t0 + t1) + (t2 + t3));
     if (p.world == 1) {
       if (lane == 0) p.out[i] = t;
     } else if (lane < p.world) {  // lane q delivers to rank q (its own slot included)
