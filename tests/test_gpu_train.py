@@ -184,10 +184,10 @@ def test_space_to_depth_add_film_bwd(L):
     assert rel_l2(dfs, (d * y.float()).sum(1)) < 1e-5 and rel_l2(dfb, d.sum(1)) < 1e-5
 
 
-@pytest.mark.parametrize("P,C,film", [(256, 256, True), (4096, 128, False)])
-def test_groupnorm_relu_film_backward(L, P, C, film):
+@pytest.mark.parametrize("P,C,film,n", [(256, 256, True, 3), (4096, 128, False, 3), (256, 256, True, 130),
+                                        (1024, 128, False, 128)])  # n >= 128: the image-major kernel
+def test_groupnorm_relu_film_backward(L, P, C, film, n):
     g = _g(8)
-    n = 3
     x = (torch.randn(n, P, C, device="cuda", generator=g) * 2 + 0.5).to(torch.bfloat16)
     dyf = torch.randn(n, P, C, device="cuda", generator=g).to(torch.bfloat16)
     gamma = (torch.rand(C, device="cuda", generator=g) + 0.5).requires_grad_(True)
