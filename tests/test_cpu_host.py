@@ -172,3 +172,42 @@ def test_header_is_plain_c_and_links(lib, tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "version 1" in r.stdout and "conv3x3(NULL) -> -1" in r.stdout
+
+
+def test_pack_plan_table_addresses_the_torch_layouts(monkeypatch):
+    """The cdm_pack_bf16 table (train._PackPlan) on CPU: emulate the kernel's addressing
+    out[i0][i1][i2][i3] = src[off + sum i_k s_k] and compare with the permute / flip expressions it replaces."""
+    import camels_diffusion_model_b200 as cdm
+    from camels_diffusion_model_b200 import train as TR
+    monkeypatch.setattr(TR.L, "pack_bf16", lambda *a: None)
+    torch.manual_seed(0)
+    m = cdm.ContextUnet(1, 128, 2, 64)
+    plan = TR._PackPlan(m)
+    tab = plan.table.numpy()
+    by_ptr = {p.data_ptr(): p.detach().reshape(-1).numpy() for p in m.parameters()}
+    refs = {}
+    for name, blk in TR._rcb_list(m):
+        for cn, seq in (("c1", blk.conv1), ("c2", blk.conv2)):
+            w = seq[0].weight.detach()
+            if w.shape[1] != 1:
+                refs[f"{name}.{cn}.f"] = w.permute(0, 2, 3, 1).contiguous()
+                refs[f"{name}.{cn}.d"] = w.flip(2, 3).permute(1, 2, 3, 0).contiguous()
+    w = m.out[0].weight.detach()
+    refs["out0.f"], refs["out0.d"] = w.permute(0, 2, 3, 1).contiguous(), w.flip(2, 3).permute(1, 2, 3, 0).contiguous()
+    for nm, mod in (("up0", m.up0[0]), ("up1", m.up1.model[0]), ("up2", m.up2.model[0])):
+        w = mod.weight.detach()
+        refs[nm + ".f"], refs[nm + ".d"] = w.permute(2, 3, 1, 0).contiguous(), w.permute(0, 2, 3, 1).contiguous()
+    assert list(plan.P) == list(refs) and len(tab) == 42 and tab.shape[1] == 12
+    rng = np.random.RandomState(0)
+    vec = 0
+    for key, row in zip(plan.P, tab):
+        src, _, d1, d2, d3, s0, s1, s2, s3, off, v0, _ = (int(v) for v in row)
+        ref = refs[key].reshape(-1).numpy()
+        assert v0 == vec and d3 % 8 == 0 and plan.P[key].numel() == ref.size
+        vec += ref.size // 8
+        for e in rng.randint(0, ref.size, 64):
+            i3, t2 = e % d3, e // d3
+            i2, t1 = t2 % d2, t2 // d2
+            i1, i0 = t1 % d1, t1 // d1
+            assert by_ptr[src][off + i0 * s0 + i1 * s1 + i2 * s2 + i3 * s3] == ref[e], key
+    assert vec == plan.total_vec
