@@ -1,6 +1,6 @@
 """Diagnostic: per-parameter gradient error of one training step vs the CPU oracle's autograd."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ -> repo root
 sys.path.insert(0, ROOT)
 import torch
 import torch.nn.functional as F
