@@ -501,8 +501,12 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       for (int ch = 0; ch < p.chunks; ++ch)
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(&b_empty[sb], pb ^ 1);
-          mbar_arrive_expect_tx(&b_full[sb], kBBytes);
-          tma_load_2d(smemB + sb * kBBytes, &mapB, &b_full[sb], tap * cin + ch * 64, n_tile * 128);
+          if ((p.flags & (1 << 27)) && (tap & 1)) {  // probe: half the weight traffic (stale tiles, wrong numbers)
+            mbar_arrive(&b_full[sb]);
+          } else {
+            mbar_arrive_expect_tx(&b_full[sb], kBBytes);
+            tma_load_2d(smemB + sb * kBBytes, &mapB, &b_full[sb], tap * cin + ch * 64, n_tile * 128);
+          }
           if (++sb == kSwNB) {
             sb = 0;
             pb ^= 1;
@@ -704,12 +708,17 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           if (!pool) {
             bf16* gbase = p.out + (((size_t)oimg * p.H + oh0 + 4 * c8) * p.W + ow0) * p.cout + n_tile * 128 +
                           (co_l & ~1);
+            int wrow = p.W;
+            if (p.flags & (1 << 26)) {  // probe: same stores, but into a per-CTA 64 KB window that stays in L2
+              gbase = p.out + (size_t)blockIdx.x * 32768 + (size_t)(4 * c8) * 8 * p.cout + (co_l & ~1);
+              wrow = 8;
+            }
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
               const float recv = __shfl_xor_sync(0xffffffffu, odd ? f[i] : f[i + 1], 1);
               const uint32_t w = odd ? pack_bf16x2(recv, f[i + 1]) : pack_bf16x2(f[i], recv);
               const int px = i + odd;  // rows 4*c8 + (px >> 3), column px & 7
-              *reinterpret_cast<uint32_t*>(gbase + ((size_t)(px >> 3) * p.W + (px & 7)) * p.cout) = w;
+              *reinterpret_cast<uint32_t*>(gbase + ((size_t)(px >> 3) * wrow + (px & 7)) * p.cout) = w;
             }
           } else {
             float m[8];

@@ -290,6 +290,9 @@ CASES = {
     "perf_m3": lambda: case_perf("perf_m3", 3, n=1024),
     "perf_m3_nostore": lambda: case_perf("perf_m3_nostore", 3, n=1024, flags=1 | (1 << 30)),
     "perf_m3_noepi": lambda: case_perf("perf_m3_noepi", 3, n=1024, flags=1 | (1 << 29)),
+    "perf_m3_l2store": lambda: case_perf("perf_m3_l2store", 3, n=1024, flags=1 | (1 << 26)),
+    "perf_m3_halfw": lambda: case_perf("perf_m3_halfw", 3, n=1024, flags=1 | (1 << 27)),
+    "perf_m3_halfw_nostore": lambda: case_perf("perf_m3_halfw_nostore", 3, n=1024, flags=1 | (1 << 27) | (1 << 30)),
     "perf_m2_big": lambda: case_perf("perf_m2_big", 2, n=1024),
     "perf_m3_c256": lambda: case_perf("perf_m3_c256", 3, n=1024, H=32, cin=256, cout=256),
     "perf_m2_c256": lambda: case_perf("perf_m2_c256", 2, n=1024, H=32, cin=256, cout=256),
