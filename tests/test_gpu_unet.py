@@ -86,6 +86,33 @@ def test_forward_batch_split_invariance_and_determinism(models):
     assert torch.equal(full, parts)
 
 
+def test_full_bench_size_is_batch_position_invariant(models):
+    """BASELINE-size property test (1024 samples per forward, the bench's per-GPU batch): six distinct samples tiled
+    170x, plus the sampler's CFG step on the full batch — every copy must be BIT-identical to the 6-sample result,
+    whatever its position in the batch, the CTA that processed it or the tile-height heuristics picked at that size."""
+    from camels_diffusion_model_b200 import diffusion as D
+    m = models["cal"]
+    g = torch.Generator().manual_seed(3)
+    x6 = torch.randn(6, 1, 64, 64, generator=g)
+    c6 = torch.rand(6, NCF, generator=g)
+    sc = torch.rand(256, generator=g) * 2 - 1
+    t = torch.tensor([0.7]).cuda()
+    small = m(x6.cuda(), t, c6.cuda(), shortcut=sc)
+    reps = 170
+    big = m(x6.repeat(reps, 1, 1, 1).cuda(), t, c6.repeat(reps, 1).cuda(), shortcut=sc)  # 1020 samples
+    assert big.shape[0] == 1020
+    assert torch.equal(big.view(reps, 6, 1, 64, 64), small.unsqueeze(0).expand(reps, -1, -1, -1, -1))
+    # three CFG sampler steps (2 x 1020 images per forward) against the same steps on the six samples
+    Tn = 3
+    sched = D.make_schedule(Tn)
+    tab = torch.rand(Tn + 1, 2, 2, 128, generator=g) * 2 - 1
+    z6 = torch.randn(Tn, 6, 1, 64, 64, generator=g)
+    xs, _, _ = D._sample(m, x6.cuda(), c6.cuda(), 2.0, Tn, sched, z_all=z6, shortcut_tab=tab)
+    xb, _, _ = D._sample(m, x6.repeat(reps, 1, 1, 1).cuda(), c6.repeat(reps, 1).cuda(), 2.0, Tn, sched,
+                         z_all=z6.repeat(1, reps, 1, 1, 1), shortcut_tab=tab)
+    assert torch.equal(xb.view(reps, 6, 1, 64, 64), xs.unsqueeze(0).expand(reps, -1, -1, -1, -1))
+
+
 def test_context_and_time_matter(models):
     """Guards against a path that ignores c / t (invisible with raw random init)."""
     m = models["cal"]
