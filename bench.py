@@ -249,26 +249,20 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         z_host = torch.randn(args.steps, B, 1, 64, 64, generator=g).pin_memory()
+        ddpm = D.DDPM(model, TIMESTEPS)
         barrier()
         t0 = time.perf_counter()
-        run2 = D._SamplerRun(model, x_T.to(dev, non_blocking=True), params.to(dev, non_blocking=True), args.guide_w,
-                             TIMESTEPS, sched, shortcut_tab=sc_tab, seed=1, snapshots=True)
-        run2.z = torch.empty(B * 4096, device=dev)
-        run2.z_stride = 0
-        run2.capture()
+        # the public step-wise sampler: pinned host x_T / params in, graph captured inside
+        sess = ddpm.open_sampler(x_T, params, args.guide_w, shortcut_tab=sc_tab, seed=1)
         barrier()
         t_setup = time.perf_counter() - t0
         d2h = 0
         t1 = time.perf_counter()
         for k in range(args.steps):
-            run2.z.copy_(z_host[k].view(-1), non_blocking=True)  # this step's noise: pinned host -> device
-            run2.graph.replay()
-            int(run2.step.item())  # device -> host read of the step's result (step counter) every step
+            sess.step(z_host[k])  # this step's noise: pinned host -> device; returns the device step counter (D2H)
             d2h += 4
-        x_host = run2.x.cpu()  # final samples back on the host
-        n_snap = sum(1 for i in run2.snap_steps if i > TIMESTEPS - args.steps)  # snapshots taken in these steps
-        inter = run2.snap[:n_snap].cpu()
-        d2h += x_host.numel() * 4 + inter.numel() * 4
+        x_host, inter = sess.result()  # final samples + the snapshots taken in these steps, back on the host
+        d2h += x_host.numel() * 4 + inter.size * 4
         barrier()
         dt = time.perf_counter() - t1
         tt = torch.tensor([dt], device=dev)
@@ -279,8 +273,8 @@ def run_b200(args):
         e2e = {"value": args.batch / (ms_e2e / 1e3 * TIMESTEPS), "unit": "samples/s",
                "h2d_bytes_per_step": int(h2d_step) * world, "d2h_bytes_per_step": int(d2h / args.steps) * world,
                "ms_per_step": ms_e2e, "setup_s": t_setup,
-               "note": "public sampler path with pinned host x_T/params/per-step z in and x + snapshots out; "
-                       "graph capture/setup reported separately in setup_s"}
+               "note": "public API DDPM.open_sampler(...).step(z).result(): pinned host x_T/params/per-step z in, "
+                       "step counter every step and x + snapshots out; graph capture/setup reported separately in setup_s"}
 
     # ---- roofline of the dominant kernel (3x3 128->128 conv at 64x64: 9 of 26 launches, ~57% of the FLOPs)
     pk = peaks()

@@ -246,6 +246,14 @@ class DDPM:
                                self.sched, save_rate=save_rate, **kw)
         return x, inter, time.time() - t0, [dt / self.timesteps] * self.timesteps
 
+    @torch.no_grad()
+    def open_sampler(self, noise_images, params=None, guide_w=0.0, save_rate=20, shortcut_tab=None, seed=None):
+        """Step-wise form of `sample_ddpm_from_noise` for callers that drive the loop themselves (progress bars,
+        early stopping, feeding their own noise): returns a `SamplerSession`; `session.step(z)` advances one
+        reverse-diffusion step (z: the step's noise as a pinned host or device tensor, or None for the in-kernel
+        Philox stream), `session.result()` returns (x, intermediate) on the host."""
+        return SamplerSession(self, noise_images, params, guide_w, save_rate, shortcut_tab, seed)
+
     def calculate_likelihood(self, dataloader, **kw):
         return calculate_likelihood(self.nn_model, dataloader, self.timesteps, self.device, self.ab_t, self.b_t,
                                     self.a_t, **kw)
@@ -253,6 +261,38 @@ class DDPM:
     def calculate_elbo_and_bpd(self, dataloader, **kw):
         return calculate_elbo_and_bpd(self.nn_model, dataloader, self.timesteps, self.device, self.ab_t, self.b_t,
                                       self.a_t, **kw)
+
+
+class SamplerSession:
+    """One sampling run driven step by step through the captured CUDA graph (see DDPM.open_sampler)."""
+
+    def __init__(self, ddpm, noise_images, params, guide_w, save_rate, shortcut_tab, seed):
+        dev = ddpm.device
+        x_T = noise_images.to(dev, non_blocking=True)
+        prm = None if params is None else params.to(dev, non_blocking=True)
+        self.run = _SamplerRun(ddpm.nn_model, x_T, prm, guide_w, ddpm.timesteps, ddpm.sched, shortcut_tab=shortcut_tab,
+                               save_rate=save_rate, seed=seed, snapshots=True)
+        self.run.z = torch.empty(self.run.B * ddpm.nn_model.h * ddpm.nn_model.h, device=dev)  # this step's noise
+        self.run.z_stride = 0
+        self.run.capture()
+        self.steps_done = 0
+
+    def step(self, z):
+        """One reverse-diffusion step with the caller's noise `z` [B,1,H,W] (host tensors are copied asynchronously;
+        pin them to overlap the copy).  Returns the remaining step count read back from the device (one 4-byte
+        device-to-host read: the caller's per-step synchronisation point)."""
+        self.run.z.copy_(z.reshape(-1), non_blocking=True)
+        if self.run.graph is not None:
+            self.run.graph.replay()
+        else:
+            self.run._one_step()
+        self.steps_done += 1
+        return int(self.run.step.item())
+
+    def result(self):
+        """(x [B,1,H,W], intermediate [n_snapshots_taken,B,1,H,W]) on the host, like the reference's return values."""
+        n_snap = sum(1 for i in self.run.snap_steps if i > self.run.T - self.steps_done)
+        return self.run.x.cpu(), self.run.snap[:n_snap].cpu().numpy()
 
 
 # --------------------------------------------------------------------------- likelihood / ELBO

@@ -113,6 +113,25 @@ def test_full_bench_size_is_batch_position_invariant(models):
     assert torch.equal(xb.view(reps, 6, 1, 64, 64), xs.unsqueeze(0).expand(reps, -1, -1, -1, -1))
 
 
+def test_stepwise_sampler_session_equals_batch_sampler(models):
+    """DDPM.open_sampler(...).step(z) (the caller-driven form the bench's end-to-end leg uses) == the all-steps sampler."""
+    import camels_diffusion_model_b200 as cdm
+    from camels_diffusion_model_b200 import diffusion as D
+    m = models["cal"]
+    Tn = 9
+    g = torch.Generator().manual_seed(11)
+    x_T, prm = torch.randn(3, 1, 64, 64, generator=g), torch.rand(3, NCF, generator=g)
+    z = torch.randn(Tn, 3, 1, 64, 64, generator=g)
+    tab = torch.rand(Tn + 1, 2, 2, 128, generator=g) * 2 - 1
+    ddpm = cdm.DDPM(m, Tn)
+    ref, inter_ref, _ = D._sample(m, x_T.cuda(), prm.cuda(), 2.0, Tn, ddpm.sched, z_all=z, shortcut_tab=tab, save_rate=4)
+    sess = ddpm.open_sampler(x_T.pin_memory(), prm.pin_memory(), guide_w=2.0, save_rate=4, shortcut_tab=tab)
+    left = [sess.step(z[k].pin_memory()) for k in range(Tn)]
+    assert left == list(range(Tn - 1, -1, -1))
+    x, inter = sess.result()
+    assert torch.equal(x, ref.cpu()) and np.array_equal(inter, inter_ref)
+
+
 def test_context_and_time_matter(models):
     """Guards against a path that ignores c / t (invisible with raw random init)."""
     m = models["cal"]
