@@ -187,15 +187,52 @@ extern "C" int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream) {
   p.bn_partial = a->bn_partial;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (mode == 3) {
-    p.n_units = a->n_img * (a->W / 8) * (a->H / 32) * p.n_tiles;
-    constexpr int smem = conv_sw_smem_bytes();
+    const int units32 = a->n_img * (a->W / 8) * (a->H / 32) * p.n_tiles;
+    const int grid_cap = num_sms();
+    // small launches (batch-1 sampling): when 8 x 32 patches would leave three quarters of the SMs idle, use 8 x 8
+    // patches — four times the units (still one wave), a quarter of the MMA chain each.  Not with the statistics epilogues, whose
+    // partial-sum layout (and summation order) is tied to the 32-row patch.
+    const bool small = units32 * 4 <= grid_cap && !(a->flags & (CDM_EPI_GNSTATS | CDM_EPI_BNSTATS));  // one wave
+    if (small) {
+      p.n_units = units32 * 4;
+      constexpr int smem = conv_sw_smem_bytes<8>();
+      static bool attr_set8 = false;
+      if (!attr_set8) {
+        CDM_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_sw_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set8 = true;
+      }
+      // the halo box of the 8-row patch is {64, 10, 10, 1}: its own tensor maps
+      CUtensorMap sA0, sA1;
+      {
+        uint64_t dims[4] = {(uint64_t)a->c0, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
+        uint64_t str[3] = {(uint64_t)a->c0 * 2, (uint64_t)a->W * a->c0 * 2, (uint64_t)a->H * a->W * a->c0 * 2};
+        uint32_t box[4] = {64, 10, 10, 1};
+        rc = make_tmap_bf16(&sA0, a->src0, 4, dims, str, box);
+        if (rc) return rc;
+      }
+      if (a->src1) {
+        uint64_t dims[4] = {(uint64_t)a->c1, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
+        uint64_t str[3] = {(uint64_t)a->c1 * 2, (uint64_t)a->W * a->c1 * 2, (uint64_t)a->H * a->W * a->c1 * 2};
+        uint32_t box[4] = {64, 10, 10, 1};
+        rc = make_tmap_bf16(&sA1, a->src1, 4, dims, str, box);
+        if (rc) return rc;
+      } else {
+        sA1 = sA0;
+      }
+      const int grid = p.n_units < grid_cap ? p.n_units : grid_cap;
+      conv3x3_sw_kernel<8><<<grid, kSwThreads, smem, st>>>(sA0, sA1, mB, p);
+      CDM_CHECK_LAUNCH();
+      return CDM_OK;
+    }
+    p.n_units = units32;
+    constexpr int smem = conv_sw_smem_bytes<32>();
     static bool attr_set = false;
     if (!attr_set) {
-      CDM_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CDM_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_sw_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       attr_set = true;
     }
     const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
-    conv3x3_sw_kernel<<<grid, kSwThreads, smem, st>>>(mA0, mA1, mB, p);
+    conv3x3_sw_kernel<32><<<grid, kSwThreads, smem, st>>>(mA0, mA1, mB, p);
     CDM_CHECK_LAUNCH();
     if (a->flags & CDM_EPI_BNSTATS) {  // fold the per-CTA rows (and the other ranks' sums) into bn_sums
       launch_xrank_sum(a->bn_partial, grid, 2 * a->cout, a->bn_sums, a->xr, st);

@@ -413,18 +413,28 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 // GroupNorm sums are register-local, and only the NHWC store needs a transpose through shared memory.
 // Halo tile: TMA box {64 ch, 10, 34, 1}, pitch 10 (SBO 1280 B), tap (kh,kw) = start row kh*10 + kw.
 // --------------------------------------------------------------------------
-constexpr int kSwPitch = 10, kSwRows = 34, kSwABytes = kSwRows * kSwPitch * 128, kSwAStride = 44032, kSwNA = 3;
+// ROWS = patch height: 32 (N = 256 pixels per instruction, the throughput shape) or 8 (N = 64: four times as many
+// units, each with a quarter of the MMA chain — the latency shape for launches that cannot fill the machine).
+constexpr int kSwPitch = 10, kSwNA = 3;
+template <int ROWS>
+struct SwCfg {
+  static constexpr int kHalo = ROWS + 2, kNPix = 8 * ROWS, kABytes = kHalo * kSwPitch * 128;
+  static constexpr int kAStride = (kABytes + 1023) / 1024 * 1024, kChunksPerHalf = ROWS / 8;
+};
 constexpr int kSwEpiWarps = 8, kSwThreads = 128 + 32 * kSwEpiWarps;
 // Weight ring: 4 stages.  The issuer is blocked on it ~30 % of its cycles (tools/gpu_probe.py waits), but that is
 // back-pressure from the tensor pipe, not TMA latency: 6 stages changed neither the wait share nor the run time.
 // The shape itself is at the shared-memory limit: operand reads 12 KB / 128 clk = 96 B/clk plus TMA fills
 // (16 KB weights / 512 clk + 43.5 KB halo / 4608 clk = 41 B/clk) against 128 B/clk per SM.
 constexpr int kSwNB = 4;
-constexpr int conv_sw_smem_bytes() { return kSwNA * kSwAStride + kSwNB * kBBytes + 2 * 256 * 4 + 256 + 1024; }
+template <int ROWS>
+constexpr int conv_sw_smem_bytes() { return kSwNA * SwCfg<ROWS>::kAStride + kSwNB * kBBytes + 2 * 256 * 4 + 256 + 1024; }
 
+template <int ROWS>
 __global__ void __launch_bounds__(kSwThreads, 1)
 conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapB, const ConvKParams p) {
+  constexpr int kSwABytes = SwCfg<ROWS>::kABytes, kSwAStride = SwCfg<ROWS>::kAStride, kNPix = SwCfg<ROWS>::kNPix;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smemA = smem;  // pixel halo tiles
@@ -468,7 +478,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int cin = p.chunks * 64;
-  const int px_tiles = p.W >> 3, py_tiles = p.H >> 5;  // patches of 8 px x 32 rows
+  const int px_tiles = p.W >> 3, py_tiles = p.H / ROWS;  // patches of 8 px x ROWS rows
   const int units_per_img = px_tiles * py_tiles * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
@@ -485,7 +495,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         const int c_off = (ch < p.chunks0 ? ch : ch - p.chunks0) * 64;
         mbar_wait(&a_empty[sa], pa ^ 1);
         mbar_arrive_expect_tx(&a_full[sa], kSwABytes);
-        tma_load_4d(smemA + sa * kSwAStride, m, &a_full[sa], c_off, sx * 8 - 1, sy * 32 - 1, img);
+        tma_load_4d(smemA + sa * kSwAStride, m, &a_full[sa], c_off, sx * 8 - 1, sy * ROWS - 1, img);
         if (++sa == kSwNA) {
           sa = 0;
           pa ^= 1;
@@ -514,7 +524,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         }
     }
   } else if (warp == 1 && lane == 0) {
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+    constexpr uint32_t idesc = umma_idesc_bf16(128, kNPix);
     int sa = 0, sb = 0, it = 0;
     uint32_t pa = 0, pb = 0;
     // probe (flag bit 28): cycles the issuer spends blocked on each barrier class -> gn_partial[cta][0..3]
@@ -527,7 +537,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);
       if (prof) w_t += clock64() - c0;
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kNPix);
       bool first = true;
       for (int ch = 0; ch < p.chunks; ++ch) {
         if (prof) c0 = clock64();
@@ -583,7 +593,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       const int n_tile = (u % units_per_img) % p.n_tiles;
       const int s = (u % units_per_img) / p.n_tiles;
       const int sx = s % px_tiles, sy = s / px_tiles;
-      const int oh0 = sy * 32, ow0 = sx * 8;
+      const int oh0 = sy * ROWS, ow0 = sx * 8;
       const int co = n_tile * 128 + co_l;
       const bool prof = p.flags & (1 << 28);
       const long long e0 = prof ? clock64() : 0;
@@ -597,7 +607,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         fbv = __ldg(p.film_shift + ((size_t)step * p.film_shift_rows + (p.film_shift_rows == 1 ? 0 : img)) * p.cout + co);
       }
       const int reps = (p.flags & CDM_EPI_SHORTCUT) ? p.sc_reps : 1;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kNPix);
       // Classifier-free guidance fan-out (init_conv.conv2: one image -> the conditional and the unconditional copy,
       // which differ only in the shortcut row): read the accumulator and the shortcut input ONCE and emit both
       // outputs; as two passes of the generic loop below this epilogue was the bottleneck of its layer.
@@ -609,7 +619,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         const float w1 = __ldg(row1 + co), b1 = __ldg(row1 + p.cout + co);
         const int odd = lane & 1;
 #pragma unroll 1
-        for (int c8 = half * 4; c8 < half * 4 + 4; ++c8) {
+        for (int c8 = half * SwCfg<ROWS>::kChunksPerHalf; c8 < (half + 1) * SwCfg<ROWS>::kChunksPerHalf; ++c8) {
           uint32_t v[32];
           tmem_ld_x32(taddr + c8 * 32, v);
           const float* xr = p.sc_x + ((size_t)img * p.H + oh0 + 4 * c8) * p.W + ow0;
@@ -650,7 +660,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         const int oimg = rep * p.n_img + img;
         float gs = 0.f, gq = 0.f;
 #pragma unroll 1
-        for (int c8 = half * 4; c8 < half * 4 + 4; ++c8) {  // 32 pixels: patch rows 4*c8 .. 4*c8+3, 8 px each
+        for (int c8 = half * SwCfg<ROWS>::kChunksPerHalf; c8 < (half + 1) * SwCfg<ROWS>::kChunksPerHalf; ++c8) {  // 32 pixels: patch rows 4*c8 .. 4*c8+3, 8 px each
           if (p.flags & (1 << 29)) continue;  // probe: no epilogue work at all
           uint32_t v[32];
           tmem_ld_x32(taddr + c8 * 32, v);
