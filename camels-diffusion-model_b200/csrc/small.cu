@@ -356,7 +356,12 @@ __global__ void __launch_bounds__(256) avgpool_gelu_kernel(const bf16* __restric
 // ----------------------------------------------- GroupNorm + ReLU + FiLM (up0)
 // One block per (image, group): statistics over P pixels x cpg channels, then
 // y = film_scale * relu(gn(x)) + film_shift.  src/out bf16 [n][P][C].
-__global__ void __launch_bounds__(256) gn_relu_film_kernel(const bf16* __restrict__ src, int P, int C, int groups,
+// VPT > 0: the group is exactly VPT 16-byte vectors per thread (up0: 256 px x 32 ch = 4 x 256 vectors) and is
+// read from global memory ONCE, all VPT loads in flight together, and kept in registers for the two statistics
+// passes and the apply pass.  VPT == 0: any size, three passes over global memory (the later ones hit L1/L2).
+// Both walk a thread's elements in the same order, so their results are bit-identical.
+template <int VPT>
+__global__ void __launch_bounds__(256, 3) gn_relu_film_kernel(const bf16* __restrict__ src, int P, int C, int groups,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float eps,
                                                            const float* __restrict__ film_scale,
@@ -369,23 +374,52 @@ __global__ void __launch_bounds__(256) gn_relu_film_kernel(const bf16* __restric
   const int vec_per_px = cpg / 8;  // uint4 per pixel
   const int n_vec = P * vec_per_px;
   const bf16* base = src + (size_t)n * P * C + g * cpg;
-  float s = 0.f;
-  for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
-    const int p = i / vec_per_px, v = i % vec_per_px;
-    float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(base + (size_t)p * C + v * 8), f);
+  constexpr int kHeld = VPT > 0 ? VPT : 1;
+  uint4 held[kHeld];
+  if (VPT > 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += f[j];
+    for (int k = 0; k < kHeld; ++k) {
+      const int i = threadIdx.x + k * 256;
+      held[k] = *reinterpret_cast<const uint4*>(base + (size_t)(i / vec_per_px) * C + (i % vec_per_px) * 8);
+    }
+  }
+  float s = 0.f;
+  if (VPT > 0) {
+#pragma unroll
+    for (int k = 0; k < kHeld; ++k) {
+      float f[8];
+      unpack8(held[k], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[j];
+    }
+  } else {
+    for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
+      const int p = i / vec_per_px, v = i % vec_per_px;
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(base + (size_t)p * C + v * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[j];
+    }
   }
   const float cnt = (float)(P * cpg);
   const float mean = block_sum(s, red) / cnt;
   float q = 0.f;
-  for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
-    const int p = i / vec_per_px, v = i % vec_per_px;
-    float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(base + (size_t)p * C + v * 8), f);
+  if (VPT > 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) q = fmaf(f[j] - mean, f[j] - mean, q);
+    for (int k = 0; k < kHeld; ++k) {
+      float f[8];
+      unpack8(held[k], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q = fmaf(f[j] - mean, f[j] - mean, q);
+    }
+  } else {
+    for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
+      const int p = i / vec_per_px, v = i % vec_per_px;
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(base + (size_t)p * C + v * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q = fmaf(f[j] - mean, f[j] - mean, q);
+    }
   }
   const float rstd = rsqrtf(block_sum(q, red) / cnt + eps);
   if (mean_rstd_out && threadIdx.x == 0) {
@@ -396,18 +430,50 @@ __global__ void __launch_bounds__(256) gn_relu_film_kernel(const bf16* __restric
   const float* fs = film_scale ? film_scale + (size_t)n * C + g * cpg : nullptr;
   const float* fb =
       film_shift ? film_shift + ((size_t)step * film_rows + (film_rows == 1 ? 0 : n)) * C + g * cpg : nullptr;
-  for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
-    const int p = i / vec_per_px, v = i % vec_per_px;
-    float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(base + (size_t)p * C + v * 8), f);
+  auto norm1 = [&](float x, int c_in_group) {  // one element: GroupNorm affine, ReLU, FiLM
+    const int c = g * cpg + c_in_group;
+    float y = fmaxf(fmaf((x - mean) * rstd, gamma[c], beta[c]), 0.f);
+    if (fs) y = fmaf(fs[c_in_group], y, fb[c_in_group]);
+    return y;
+  };
+  if (VPT > 0) {
+    // the launch guarantees 256 % vec_per_px == 0: all of a thread's vectors cover the same 8 channels, so the
+    // coefficients of a channel pair are fetched once and applied to the VPT held vectors (in place)
+    const int v = threadIdx.x % vec_per_px;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = g * cpg + v * 8 + j;
-      float y = fmaxf(fmaf((f[j] - mean) * rstd, gamma[c], beta[c]), 0.f);
-      if (fs) y = fmaf(fs[v * 8 + j], y, fb[v * 8 + j]);
-      f[j] = y;
+    for (int w = 0; w < 4; ++w) {
+      const int c0 = v * 8 + w * 2;
+      const int c = g * cpg + c0;
+      const float g0 = gamma[c], g1 = gamma[c + 1], b0 = beta[c], b1 = beta[c + 1];
+      const float s0 = fs ? fs[c0] : 0.f, s1 = fs ? fs[c0 + 1] : 0.f;
+      const float t0 = fs ? fb[c0] : 0.f, t1 = fs ? fb[c0 + 1] : 0.f;
+#pragma unroll
+      for (int k = 0; k < kHeld; ++k) {
+        uint32_t& word = w == 0 ? held[k].x : w == 1 ? held[k].y : w == 2 ? held[k].z : held[k].w;
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&word);
+        float y0 = fmaxf(fmaf((__low2float(h) - mean) * rstd, g0, b0), 0.f);
+        float y1 = fmaxf(fmaf((__high2float(h) - mean) * rstd, g1, b1), 0.f);
+        if (fs) {
+          y0 = fmaf(s0, y0, t0);
+          y1 = fmaf(s1, y1, t1);
+        }
+        word = pack_bf16x2(y0, y1);
+      }
     }
-    *reinterpret_cast<uint4*>(out + (size_t)n * P * C + (size_t)p * C + g * cpg + v * 8) = pack8(f);
+#pragma unroll
+    for (int k = 0; k < kHeld; ++k) {
+      const int i = threadIdx.x + k * 256;
+      *reinterpret_cast<uint4*>(out + (size_t)n * P * C + (size_t)(i / vec_per_px) * C + g * cpg + v * 8) = held[k];
+    }
+  } else {
+    for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
+      const int p = i / vec_per_px, v = i % vec_per_px;
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(base + (size_t)p * C + v * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = norm1(f[j], v * 8 + j);
+      *reinterpret_cast<uint4*>(out + (size_t)n * P * C + (size_t)p * C + g * cpg + v * 8) = pack8(f);
+    }
   }
 }
 
@@ -651,7 +717,9 @@ extern "C" int cdm_gn_relu_film(const cdm_gn_relu_film_args* a, void* stream) {
   CDM_CHECK_ARG(!a->film_scale || a->film_rows >= 1);
   int rc = check_device();
   if (rc) return rc;
-  gn_relu_film_kernel<<<a->n_img * a->groups, 256, 0, (cudaStream_t)stream>>>(
+  const int n_vec = a->P * (a->C / a->groups / 8);
+  auto kern = (n_vec == 4 * 256 && 256 % (a->C / a->groups / 8) == 0) ? gn_relu_film_kernel<4> : gn_relu_film_kernel<0>;  // up0: 256 px x 32 ch
+  kern<<<a->n_img * a->groups, 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)a->src, a->P, a->C, a->groups, a->gamma, a->beta, a->eps, a->film_scale, a->film_shift,
       a->film_rows, a->step_ptr, (bf16*)a->out, a->mean_rstd_out);
   CDM_CHECK_LAUNCH();

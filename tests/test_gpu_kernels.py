@@ -221,9 +221,11 @@ def test_embed_fc(L, din, emb, rows):
     assert rel_l2(out, F.linear(F.gelu(F.linear(inp, w1, b1)), w2, b2)) < 1e-5
 
 
-def test_avgpool_gelu_and_gn_relu_film(L):
+# (256, 256) is up0's shape: the register-resident instantiation; the others take the generic three-pass one
+@pytest.mark.parametrize("P,C", [(256, 256), (100, 256), (256, 128)])
+def test_avgpool_gelu_and_gn_relu_film(L, P, C):
     g = torch.Generator(device="cuda").manual_seed(5)
-    n, P, C = 5, 256, 256
+    n = 5
     src = torch.randn(n, P, C, device="cuda", generator=g).to(torch.bfloat16)
     hid = torch.empty(n, C, device="cuda", dtype=torch.bfloat16)
     L.avgpool_gelu(src, hid)
