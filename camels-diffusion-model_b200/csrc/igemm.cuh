@@ -1034,7 +1034,10 @@ struct GemmBresKParams {
   bf16* out;
 };
 constexpr int kBresStages = 4;
-constexpr int gemm_bres_smem_bytes() { return 131072 + kBresStages * 16384 + 256 + 1024 + 1024; }
+constexpr int kBresStageTile = 32 * 128;  // per epilogue warp: 32 rows x 128 B of bf16 output, 16-byte chunks XOR-swizzled
+constexpr int gemm_bres_smem_bytes() {
+  return 131072 + kBresStages * 16384 + 256 + 1024 + 8 * kBresStageTile + 1024;
+}
 
 constexpr int kBresThreads = 128 + 8 * 32;  // 4 role warps + 8 epilogue warps (one set of 4 per resident n-tile)
 __global__ void __launch_bounds__(kBresThreads, 1)
@@ -1052,6 +1055,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint64_t* w_ready = t_empty + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_ready + 1);
   float* s_shift = reinterpret_cast<float*>(tmem_ptr + 2);  // [n_res][128]
+  const uint32_t stage_base = smem_u32(reinterpret_cast<uint8_t*>(bars) + 256 + 1024);  // 8 x kBresStageTile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < p.n_res * 128; i += blockDim.x)
     s_shift[i] = p.shift[(((blockIdx.x % p.n_groups) * p.n_res) * 128 + i) % p.shift_mod];
@@ -1139,39 +1143,60 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const int buf = it & 1;
       mbar_wait(&t_full[buf], (it >> 1) & 1);
       tc_fence_after();
-      const int m = mt * 128 + q * 32 + lane;
+      // The accumulator gives a thread 32 columns of ONE row, so a register-direct store would touch 32 different
+      // 128-byte lines per warp instruction (16 B each).  Rows are transposed through a warp-private staging tile
+      // instead: lane = row writes its 64 columns (128 B) as eight 16-byte chunks, chunk c of row r at
+      // r*128 + ((c ^ (r & 7)) << 4) (conflict-free both ways); reading back, 8 lanes hold one row's 128
+      // contiguous bytes and every warp-level global store writes FOUR FULL LINES.
+      const uint32_t stage = stage_base + (uint32_t)((warp - 4) * kBresStageTile);
+      const int sub_row = lane >> 3, sub_chunk = lane & 7;
       for (int nt = set; nt < p.n_res; nt += 2) {
         const int n_tile = n_tile0 + nt;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.n_res + nt) * 128);
         const float* shift = s_shift + nt * 128;  // shared memory: broadcast reads, no global-load latency
-        bf16* g = nullptr;
-        if (m < p.M) {
-          if (p.out_mode == 0) {
-            g = p.out + (size_t)m * p.N + n_tile * 128;
+        size_t row_off[8];  // element offset of the eight rows this lane stores (row = sub_row + 4*it); ~0 = beyond M
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = mt * 128 + q * 32 + sub_row + 4 * it;
+          if (m >= p.M) {
+            row_off[it] = ~(size_t)0;
+          } else if (p.out_mode == 0) {
+            row_off[it] = (size_t)m * p.N + n_tile * 128;
           } else {
             const int w = m & (p.W - 1), h = (m >> p.w_shift) & (p.H - 1), img = m >> (p.w_shift + p.h_shift);
             const int kh = n_tile >> 1, kw = n_tile & 1;
-            g = p.out + (((size_t)img * 2 * p.H + 2 * h + kh) * (2 * p.W) + 2 * w + kw) * 128;
+            row_off[it] = (((size_t)img * 2 * p.H + 2 * h + kh) * (2 * p.W) + 2 * w + kw) * 128;
           }
         }
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          uint32_t v[32];
-          tmem_ld_x32(taddr + cc * 32, v);
-          tmem_wait_ld();
-          if (g) {
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const int col0 = (half * 2 + c2) * 32;
+            uint32_t v[32];
+            tmem_ld_x32(taddr + col0, v);
+            tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 s0 = *reinterpret_cast<const float4*>(shift + cc * 32 + j * 8);
-              const float4 s1 = *reinterpret_cast<const float4*>(shift + cc * 32 + j * 8 + 4);
-              uint4 o;
-              o.x = pack_bf16x2(__uint_as_float(v[j * 8 + 0]) + s0.x, __uint_as_float(v[j * 8 + 1]) + s0.y);
-              o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]) + s0.z, __uint_as_float(v[j * 8 + 3]) + s0.w);
-              o.z = pack_bf16x2(__uint_as_float(v[j * 8 + 4]) + s1.x, __uint_as_float(v[j * 8 + 5]) + s1.y);
-              o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]) + s1.z, __uint_as_float(v[j * 8 + 7]) + s1.w);
-              reinterpret_cast<uint4*>(g)[cc * 4 + j] = o;
+              const float4 s0 = *reinterpret_cast<const float4*>(shift + col0 + j * 8);
+              const float4 s1 = *reinterpret_cast<const float4*>(shift + col0 + j * 8 + 4);
+              const int chunk = c2 * 4 + j;
+              st_shared_v4(stage + (uint32_t)(lane * 128 + ((chunk ^ (lane & 7)) << 4)),
+                           pack_bf16x2(__uint_as_float(v[j * 8 + 0]) + s0.x, __uint_as_float(v[j * 8 + 1]) + s0.y),
+                           pack_bf16x2(__uint_as_float(v[j * 8 + 2]) + s0.z, __uint_as_float(v[j * 8 + 3]) + s0.w),
+                           pack_bf16x2(__uint_as_float(v[j * 8 + 4]) + s1.x, __uint_as_float(v[j * 8 + 5]) + s1.y),
+                           pack_bf16x2(__uint_as_float(v[j * 8 + 6]) + s1.z, __uint_as_float(v[j * 8 + 7]) + s1.w));
             }
           }
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = sub_row + 4 * it;
+            const uint4 o = ld_shared_v4(stage + (uint32_t)(row * 128 + ((sub_chunk ^ (row & 7)) << 4)));
+            if (row_off[it] != ~(size_t)0)
+              *reinterpret_cast<uint4*>(p.out + row_off[it] + half * 64 + sub_chunk * 8) = o;
+          }
+          __syncwarp();  // the tile is rewritten by the next half
         }
       }
       tc_fence_before();
