@@ -286,7 +286,12 @@ extern "C" int cdm_gemm(const cdm_gemm_args* a, void* stream) {
   // small N (transposed convolutions): keep the weight tiles resident, stream A once per weight group
   const int n_tiles_total = a->N / 128;
   const int n_res = K <= 256 ? 2 : (K <= 512 ? 1 : 0);
-  if (n_res > 0 && n_tiles_total <= 4 && n_tiles_total % n_res == 0 && a->M >= 128 * 64) {
+  // few_n: the 2x2 transposed convolutions (N = 512): one weight group per CTA.  many_n: up0 at sampling batch
+  // sizes (N = 65536): several groups per CTA, swapped in turn; needs the same shift rows for every group.
+  const bool few_n = n_res > 0 && n_tiles_total <= 4 && n_tiles_total % n_res == 0 && a->M >= 128 * 64;
+  const bool many_n = n_res == 2 && n_tiles_total % 2 == 0 && n_tiles_total / 2 > num_sms() && a->out_mode == 0 &&
+                      256 % a->shift_mod == 0 && a->M >= 1024;
+  if (few_n || many_n) {
     GemmBresKParams q;
     memset(&q, 0, sizeof(q));
     q.M = a->M;
@@ -310,7 +315,8 @@ extern "C" int cdm_gemm(const cdm_gemm_args* a, void* stream) {
       CDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
       attr_b = true;
     }
-    const int grid_b = (num_sms() / q.n_groups) * q.n_groups;
+    const int groups_per_cta = (q.n_groups + num_sms() - 1) / num_sms();
+    const int grid_b = many_n ? (q.n_groups + groups_per_cta - 1) / groups_per_cta : (num_sms() / q.n_groups) * q.n_groups;
     gemm_bres_kernel<<<grid_b, kBresThreads, smem_b, reinterpret_cast<cudaStream_t>(stream)>>>(mA0, mA1, mB, q);
     CDM_CHECK_LAUNCH();
     return CDM_OK;

@@ -1023,6 +1023,10 @@ __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const float* __
 // n_res accumulations per stage, so L2->smem traffic per output tile drops from 2*K*256 B to K*256/n_res B
 // and the kernel sits at the DRAM roofline of its output instead of the L2 refill rate.
 // CTA b serves weight group b % n_groups and the row tiles b / n_groups, + gridDim.x / n_groups, ...
+// With MORE groups than CTAs (up0: N = 65536 = 256 groups of two n-tiles, 16 row tiles) CTA b serves the groups
+// b, b + gridDim.x, ... with all row tiles each: the resident weights are swapped between groups once the last
+// MMA that reads them has completed (w_free), the A rows (1 MB, L2-resident) are streamed again per group, and
+// L2->smem traffic per 128x256 output tile falls from 192 KB (gemm_kernel: A and B per tile) to 64 KB + 8 KB.
 // --------------------------------------------------------------------------
 struct GemmBresKParams {
   int M, N;
@@ -1053,8 +1057,9 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint64_t* t_full = empty + kBresStages;
   uint64_t* t_empty = t_full + 2;
   uint64_t* w_ready = t_empty + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_ready + 1);
-  float* s_shift = reinterpret_cast<float*>(tmem_ptr + 2);  // [n_res][128]
+  uint64_t* w_free = w_ready + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_free + 1);
+  float* s_shift = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);  // [n_res][128], 16-byte aligned
   const uint32_t stage_base = smem_u32(reinterpret_cast<uint8_t*>(bars) + 256 + 1024);  // 8 x kBresStageTile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < p.n_res * 128; i += blockDim.x)
@@ -1069,6 +1074,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       mbar_init(&t_empty[i], 8);
     }
     mbar_init(w_ready, 1);
+    mbar_init(w_free, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -1079,67 +1085,79 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const int group = blockIdx.x % p.n_groups, first = blockIdx.x / p.n_groups, stride = gridDim.x / p.n_groups;
-  const int n_tile0 = group * p.n_res;
+  // groups <= CTAs: one group per CTA, its row tiles shared by gridDim.x / n_groups CTAs; else: several groups per
+  // CTA with all row tiles each (the host guarantees the shift rows are the same for every group in that case)
+  const bool many = p.n_groups > (int)gridDim.x;
+  const int g_first = many ? (int)blockIdx.x : (int)blockIdx.x % p.n_groups, g_stride = many ? (int)gridDim.x : p.n_groups;
+  const int first = many ? 0 : (int)blockIdx.x / p.n_groups, stride = many ? 1 : (int)gridDim.x / p.n_groups;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
     tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapB);
-    mbar_arrive_expect_tx(w_ready, (uint32_t)(p.n_res * p.chunks * 16384));
-    for (int nt = 0; nt < p.n_res; ++nt)  // [chunk][n-tile]: the n-tiles of one K chunk are one contiguous N operand
-      for (int ch = 0; ch < p.chunks; ++ch)
-        tma_load_2d(smemW + (ch * p.n_res + nt) * 16384, &mapB, w_ready, ch * 64, (n_tile0 + nt) * 128);
-    int st = 0;
+    int st = 0, gi = 0;
     uint32_t ph = 0;
-    for (int mt = first; mt < p.m_tiles; mt += stride)
-      for (int ch = 0; ch < p.chunks; ++ch) {
-        const CUtensorMap* m = ch < p.chunks0 ? &mapA0 : &mapA1;
-        const int c_off = (ch < p.chunks0 ? ch : ch - p.chunks0) * 64;
-        mbar_wait(&empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&full[st], 16384);
-        tma_load_2d(smemA + st * 16384, m, &full[st], c_off, mt * 128);
-        if (++st == kBresStages) {
-          st = 0;
-          ph ^= 1;
+    for (int group = g_first; group < p.n_groups; group += g_stride, ++gi) {
+      const int n_tile0 = group * p.n_res;
+      if (gi > 0) mbar_wait(w_free, (uint32_t)((gi - 1) & 1));  // every MMA of the previous group has read its weights
+      mbar_arrive_expect_tx(w_ready, (uint32_t)(p.n_res * p.chunks * 16384));
+      for (int nt = 0; nt < p.n_res; ++nt)  // [chunk][n-tile]: the n-tiles of one K chunk are one contiguous N operand
+        for (int ch = 0; ch < p.chunks; ++ch)
+          tma_load_2d(smemW + (ch * p.n_res + nt) * 16384, &mapB, w_ready, ch * 64, (n_tile0 + nt) * 128);
+      for (int mt = first; mt < p.m_tiles; mt += stride)
+        for (int ch = 0; ch < p.chunks; ++ch) {
+          const CUtensorMap* m = ch < p.chunks0 ? &mapA0 : &mapA1;
+          const int c_off = (ch < p.chunks0 ? ch : ch - p.chunks0) * 64;
+          mbar_wait(&empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&full[st], 16384);
+          tma_load_2d(smemA + st * 16384, m, &full[st], c_off, mt * 128);
+          if (++st == kBresStages) {
+            st = 0;
+            ph ^= 1;
+          }
         }
-      }
+    }
   } else if (warp == 1 && lane == 0) {
     // two resident n-tiles = ONE M128 N256 instruction per K step (12 KB of operand reads per 128 clk instead of
     // 2 x 8 KB per 2 x 64: the N128 shape is shared-memory bound at half the tensor rate)
     const uint32_t idesc = p.n_res == 2 ? umma_idesc_bf16(128, 256) : umma_idesc_bf16(128, 128);
-    mbar_wait(w_ready, 0);
-    tc_fence_after();
     const uint32_t w_base = smem_u32(smemW);
-    int st = 0, it = 0;
+    int st = 0, it = 0, gi = 0;
     uint32_t ph = 0;
-    for (int mt = first; mt < p.m_tiles; mt += stride, ++it) {
-      const int buf = it & 1;
-      mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);
+    for (int group = g_first; group < p.n_groups; group += g_stride, ++gi) {
+      mbar_wait(w_ready, (uint32_t)(gi & 1));
       tc_fence_after();
-      for (int ch = 0; ch < p.chunks; ++ch) {
-        mbar_wait(&full[st], ph);
+      for (int mt = first; mt < p.m_tiles; mt += stride, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smemA + st * 16384);
-        const uint32_t b_base = w_base + (uint32_t)(ch * p.n_res * 16384);
+        for (int ch = 0; ch < p.chunks; ++ch) {
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smemA + st * 16384);
+          const uint32_t b_base = w_base + (uint32_t)(ch * p.n_res * 16384);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + (uint32_t)(buf * p.n_res * 128), umma_desc_sw128(a_base + k * 32, 1024),
-                    umma_desc_sw128(b_base + k * 32, 1024), idesc, (ch == 0 && k == 0) ? 0u : 1u);
-        umma_commit(&empty[st]);
-        if (++st == kBresStages) {
-          st = 0;
-          ph ^= 1;
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + (uint32_t)(buf * p.n_res * 128), umma_desc_sw128(a_base + k * 32, 1024),
+                      umma_desc_sw128(b_base + k * 32, 1024), idesc, (ch == 0 && k == 0) ? 0u : 1u);
+          umma_commit(&empty[st]);
+          if (++st == kBresStages) {
+            st = 0;
+            ph ^= 1;
+          }
         }
+        umma_commit(&t_full[buf]);
       }
-      umma_commit(&t_full[buf]);
+      umma_commit(w_free);  // arrives when every MMA issued so far (all that read this group's weights) is done
     }
   } else if (warp >= 4) {
     // TMEM lane quadrant q = warp % 4 (hardware rule); warps 4-7 drain n-tile 0, warps 8-11 n-tile 1 (with one
     // resident n-tile the second set only keeps the barrier protocol): the epilogue, not the MMA, paced this kernel
     const int q = warp & 3, set = (warp - 4) >> 2;
     int it = 0;
+    for (int group = g_first; group < p.n_groups; group += g_stride)
     for (int mt = first; mt < p.m_tiles; mt += stride, ++it) {
+      const int n_tile0 = group * p.n_res;
       const int buf = it & 1;
       mbar_wait(&t_full[buf], (it >> 1) & 1);
       tc_fence_after();

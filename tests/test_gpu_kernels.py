@@ -131,6 +131,28 @@ def test_gemm_plain(L, M, k0, k1, N):
     assert rel_l2(out.float(), a.float() @ bw.float().t() + shift) < BF16_TOL
 
 
+@pytest.mark.parametrize("M,k0,k1,N,shift_mod", [(2048, 256, 0, 65536, 256), (1100, 128, 128, 76800, 128),
+                                                 (1024, 64, 0, 38912, 256)])
+def test_gemm_resident_weights_many_groups(L, M, k0, k1, N, shift_mod):
+    """up0 at sampling batch sizes: more two-tile weight groups than CTAs (256 / 300 / 152 groups = 2 / 3 / 2 per
+    CTA), weights swapped between groups; ragged last row tile; bias indexed modulo shift_mod."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    K = k0 + k1
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    bw = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
+    shift = torch.randn(shift_mod, device="cuda", generator=g)
+    out = torch.full((M, N), float("nan"), device="cuda").to(torch.bfloat16)
+    L.gemm(a[:, :k0].contiguous(), bw, shift, out, a1=a[:, k0:].contiguous() if k1 else None, shift_mod=shift_mod)
+    ref = a.float() @ bw.float().t() + shift.repeat(N // shift_mod)
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out.float(), ref) < BF16_TOL
+    # the streaming kernel (taken below 1024 rows) accumulates in the same order: bit-identical rows
+    out_small = torch.empty(512, N, device="cuda", dtype=torch.bfloat16)
+    L.gemm(a[:512, :k0].contiguous(), bw, shift, out_small, a1=a[:512, k0:].contiguous() if k1 else None,
+           shift_mod=shift_mod)
+    assert torch.equal(out[:512], out_small)
+
+
 def test_gemm_pixel_shuffle_is_conv_transpose(L):
     """out_mode 1 == nn.ConvTranspose2d(cin, 128, 2, 2) on the channel concat of two NHWC sources."""
     g = torch.Generator(device="cuda").manual_seed(1)
