@@ -61,7 +61,7 @@ def peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,power.limit")
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
@@ -102,8 +102,16 @@ class ClockSampler:
         mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k].lower() == "active" for r in self.rows)]
+        def num(r, k):
+            try:
+                return float(r[k])
+            except (IndexError, ValueError):
+                return None
+        pw = sorted(v for v in (num(r, 6) for r in self.rows) if v is not None)
+        lim = [v for v in (num(r, 7) for r in self.rows) if v is not None]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "power_w": pw[len(pw) // 2] if pw else None,
+                "power_limit_w": max(lim) if lim else None}
 
 
 # --------------------------------------------------------------------------- CPU reference arm
@@ -259,7 +267,9 @@ def run_b200(args):
         d2h = 0
         t1 = time.perf_counter()
         for k in range(args.steps):
-            sess.step(z_host[k])  # this step's noise: pinned host -> device; returns the device step counter (D2H)
+            # this step's noise (pinned host -> device; the next step's upload is handed over now and overlaps this
+            # step's kernels); returns the device step counter (D2H)
+            sess.step(z_host[k], z_next=z_host[k + 1] if k + 1 < args.steps else None)
             d2h += 4
         x_host, inter = sess.result()  # final samples + the snapshots taken in these steps, back on the host
         d2h += x_host.numel() * 4 + inter.size * 4
@@ -273,7 +283,8 @@ def run_b200(args):
         e2e = {"value": args.batch / (ms_e2e / 1e3 * TIMESTEPS), "unit": "samples/s",
                "h2d_bytes_per_step": int(h2d_step) * world, "d2h_bytes_per_step": int(d2h / args.steps) * world,
                "ms_per_step": ms_e2e, "setup_s": t_setup,
-               "note": "public API DDPM.open_sampler(...).step(z).result(): pinned host x_T/params/per-step z in, "
+               "note": "public API DDPM.open_sampler(...).step(z, z_next).result(): pinned host x_T/params/per-step z in "
+                       "(double-buffered upload), "
                        "step counter every step and x + snapshots out; graph capture/setup reported separately in setup_s"}
 
     # ---- roofline of the dominant kernel (3x3 128->128 conv at 64x64: 9 of 26 launches, ~57% of the FLOPs)

@@ -276,16 +276,43 @@ class SamplerSession:
         self.run.z_stride = 0
         self.run.capture()
         self.steps_done = 0
+        # double-buffered noise upload (step(z, z_next=...)): z_next travels host -> device on a side stream
+        # while the step's graph runs
+        self._stage = torch.empty_like(self.run.z)
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._staged = torch.cuda.Event()       # the staged noise has arrived
+        self._stage_free = torch.cuda.Event()   # the staged noise has been consumed (stage may be overwritten)
+        self._stage_free.record()
+        self._staged_key, self._staged_ref = None, None
 
-    def step(self, z):
+    @staticmethod
+    def _key(t):
+        return (t.data_ptr(), t.numel(), t.device)
+
+    def step(self, z, z_next=None):
         """One reverse-diffusion step with the caller's noise `z` [B,1,H,W] (host tensors are copied asynchronously;
-        pin them to overlap the copy).  Returns the remaining step count read back from the device (one 4-byte
-        device-to-host read: the caller's per-step synchronisation point)."""
-        self.run.z.copy_(z.reshape(-1), non_blocking=True)
+        pin them to overlap the copy).  `z_next`, if given, is the NEXT step's noise: its host-to-device copy runs
+        on a side stream underneath this step's kernels, and the next `step(z_next, ...)` finds it on the device
+        (keep the tensor alive and unchanged until then).  Returns the remaining step count read back from the
+        device (one 4-byte device-to-host read: the caller's per-step synchronisation point)."""
+        main = torch.cuda.current_stream()
+        if self._staged_key is not None and self._staged_key == self._key(z):
+            main.wait_event(self._staged)
+            self.run.z.copy_(self._stage, non_blocking=True)
+            self._stage_free.record(main)
+        else:
+            self.run.z.copy_(z.reshape(-1), non_blocking=True)
+        self._staged_key, self._staged_ref = None, None
         if self.run.graph is not None:
             self.run.graph.replay()
         else:
             self.run._one_step()
+        if z_next is not None:
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._stage_free)
+                self._stage.copy_(z_next.reshape(-1), non_blocking=True)
+                self._staged.record(self._copy_stream)
+            self._staged_key, self._staged_ref = self._key(z_next), z_next
         self.steps_done += 1
         return int(self.run.step.item())
 

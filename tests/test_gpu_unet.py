@@ -130,6 +130,13 @@ def test_stepwise_sampler_session_equals_batch_sampler(models):
     assert left == list(range(Tn - 1, -1, -1))
     x, inter = sess.result()
     assert torch.equal(x, ref.cpu()) and np.array_equal(inter, inter_ref)
+    # double-buffered upload: the next step's noise is handed over one step early (and once not at all)
+    zp = z.pin_memory()
+    sess = ddpm.open_sampler(x_T.pin_memory(), prm.pin_memory(), guide_w=2.0, save_rate=4, shortcut_tab=tab)
+    for k in range(Tn):
+        sess.step(zp[k], z_next=zp[k + 1] if k + 1 < Tn and k != 4 else None)
+    x2, inter2 = sess.result()
+    assert torch.equal(x2, ref.cpu()) and np.array_equal(inter2, inter_ref)
 
 
 def test_context_and_time_matter(models):
