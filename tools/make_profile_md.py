@@ -139,6 +139,21 @@ def main(tag):
                   f"{fnum(r, 'sm__cycles_elapsed.avg.per_second'):.2f} | {flop / t / 1e9:.0f} |")
     md.append("\n*under ncu (serialised, its own clocks). DRAM traffic equals the algorithmic bytes of each layer (NHWC bf16 in "
               "+ out): the halo tile and its nine tap views are served from shared memory, the weights from L2.\n")
+    bres = os.path.join(O, "ev_prof_gemm_bres.ncu-rep")
+    if os.path.exists(bres):
+        rws, un = raw_rows(bres)
+        md.append("`-k regex:gemm_bres -s 3 -c 3` on the same command (the resident-weight GEMMs of one step; up0 "
+                  "`[2048,256]x[256,65536]`, up1 and up2 = the 2x2 transposed convolutions with their pixel-shuffle store):\n")
+        md.append("| launch | time us | DRAM read GB | DRAM write GB | DRAM GB/s | tensor pipe active % | grid |")
+        md.append("|---|---|---|---|---|---|---|")
+        for r in rws:
+            t = ms(r, un)
+            rd, wr = gb(r, un, "dram__bytes_read.sum"), gb(r, un, "dram__bytes_write.sum")
+            kind = "up0" if wr < 0.4 else ("up1" if wr < 0.8 else "up2")
+            md.append(f"| {kind} | {t * 1e3:.1f} | {rd:.3f} | {wr:.3f} | {(rd + wr) / t * 1e3:.0f} | "
+                      f"{fnum(r, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed'):.1f} | "
+                      f"{fnum(r, 'launch__grid_size'):.0f} |")
+        md.append("")
     for name, rep in (("conv_out_mma_kernel<32> (2048 images)", "ev_prof_conv_out.ncu-rep"),
                       ("conv_in_mma_kernel (1024 images)", "ev_prof_conv_in.ncu-rep"),
                       ("ddpm_step_kernel (1024 samples)", "ev_prof_ddpm.ncu-rep"),
