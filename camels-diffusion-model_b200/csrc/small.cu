@@ -353,6 +353,49 @@ __global__ void __launch_bounds__(256) avgpool_gelu_kernel(const bf16* __restric
   }
 }
 
+// Vectorised form for C % 8 == 0 and 256 % (C / 8) == 0 (C = 128, 256): a thread owns 8 consecutive channels
+// (one 16-byte load per pixel) of every (256 / (C/8))-th pixel, four loads in flight; the row groups are then
+// added in a fixed order through shared memory (deterministic).
+__global__ void __launch_bounds__(256) avgpool_gelu_vec_kernel(const bf16* __restrict__ src, int P, int C,
+                                                               bf16* __restrict__ out) {
+  __shared__ float red[256][8];
+  const size_t n = blockIdx.x;
+  const int vecs = C >> 3, rows = 256 / vecs;
+  const int v = threadIdx.x % vecs, r = threadIdx.x / vecs;
+  const bf16* base = src + n * P * C + v * 8;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  for (int p0 = r; p0 < P; p0 += 4 * rows) {
+    uint4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * rows;
+      raw[u] = p < P ? __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * C)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(raw[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += f[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = s[j];
+  __syncthreads();
+  if (r == 0) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = 0.f;
+      for (int q = 0; q < rows; ++q) t += red[q * vecs + v][j];
+      f[j] = gelu_erf(t / (float)P);
+    }
+    *reinterpret_cast<uint4*>(out + n * C + v * 8) = pack8(f);
+  }
+}
+
 // ----------------------------------------------- GroupNorm + ReLU + FiLM (up0)
 // One block per (image, group): statistics over P pixels x cpg channels, then
 // y = film_scale * relu(gn(x)) + film_shift.  src/out bf16 [n][P][C].
@@ -705,7 +748,10 @@ extern "C" int cdm_avgpool_gelu(const void* src, int n_img, int P, int C, void* 
   CDM_CHECK_ARG(src && out && n_img > 0 && P > 0 && C > 0);
   int rc = check_device();
   if (rc) return rc;
-  avgpool_gelu_kernel<<<n_img, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, P, C, (bf16*)out);
+  if (C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0)
+    avgpool_gelu_vec_kernel<<<n_img, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, P, C, (bf16*)out);
+  else
+    avgpool_gelu_kernel<<<n_img, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, P, C, (bf16*)out);
   CDM_CHECK_LAUNCH();
   return CDM_OK;
 }

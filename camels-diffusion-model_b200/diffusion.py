@@ -250,8 +250,9 @@ class DDPM:
     def open_sampler(self, noise_images, params=None, guide_w=0.0, save_rate=20, shortcut_tab=None, seed=None):
         """Step-wise form of `sample_ddpm_from_noise` for callers that drive the loop themselves (progress bars,
         early stopping, feeding their own noise): returns a `SamplerSession`; `session.step(z)` advances one
-        reverse-diffusion step (z: the step's noise as a pinned host or device tensor, or None for the in-kernel
-        Philox stream), `session.result()` returns (x, intermediate) on the host."""
+        reverse-diffusion step (z: the step's noise [B,1,H,W] as a pinned host or device tensor; callers that do not
+        feed their own noise use `sample_ddpm` / `sample_ddpm_from_noise`, which draw it in-kernel),
+        `session.result()` returns (x, intermediate) on the host."""
         return SamplerSession(self, noise_images, params, guide_w, save_rate, shortcut_tab, seed)
 
     def calculate_likelihood(self, dataloader, **kw):
@@ -295,6 +296,9 @@ class SamplerSession:
         on a side stream underneath this step's kernels, and the next `step(z_next, ...)` finds it on the device
         (keep the tensor alive and unchanged until then).  Returns the remaining step count read back from the
         device (one 4-byte device-to-host read: the caller's per-step synchronisation point)."""
+        if z is None or z.numel() != self.run.z.numel():
+            raise L.CdmError(f"step(z): z must hold this step's noise, {self.run.z.numel()} values "
+                             f"([B,1,H,W] = [{self.run.B},1,{self.run.model.h},{self.run.model.h}])")
         main = torch.cuda.current_stream()
         if self._staged_key is not None and self._staged_key == self._key(z):
             main.wait_event(self._staged)

@@ -137,6 +137,9 @@ def test_stepwise_sampler_session_equals_batch_sampler(models):
         sess.step(zp[k], z_next=zp[k + 1] if k + 1 < Tn and k != 4 else None)
     x2, inter2 = sess.result()
     assert torch.equal(x2, ref.cpu()) and np.array_equal(inter2, inter_ref)
+    for bad in (None, zp[0][:2]):
+        with pytest.raises(cdm.CdmError):
+            sess.step(bad)
 
 
 def test_context_and_time_matter(models):
