@@ -211,3 +211,45 @@ def test_pack_plan_table_addresses_the_torch_layouts(monkeypatch):
             i1, i0 = t1 % d1, t1 // d1
             assert by_ptr[src][off + i0 * s0 + i1 * s1 + i2 * s2 + i3 * s3] == ref[e], key
     assert vec == plan.total_vec
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6])
+def test_driver_contexts_match_the_reference_statements(n):
+    """Parameter grid / guidance sweep / sensitivity (BASELINE config 4, num_params 1..6): what the drivers hand to
+    the sampler equals, bit for bit and call for call, what the reference's module-level statements hand to its
+    `sample_ddpm` (vectors recorded by oracle/make_golden_drivers.py exec'ing those lines).  The sampler is a
+    recorder here, so no GPU is involved."""
+    from camels_diffusion_model_b200 import drivers
+
+    g = load("driver_contexts.npz")
+    base = T(g[f"base/{n}"])[0]
+    calls = []
+
+    class Recorder:  # the slice of DDPM the drivers use
+        n_cfeat = n
+
+        class nn_model:
+            h = 64
+
+        def sample_ddpm(self, n_sample=1, size=64, device=None, params=None, guide_w=0.0):
+            calls.append((n_sample, params.clone(), float(guide_w)))
+            return torch.zeros(n_sample, 1, size, size), None, 0.0, None
+
+    d = Recorder()
+    assert torch.equal(drivers.parameter_grid_contexts(base, n), T(g[f"grid/{n}"]))
+    _, _, _, ctx = drivers.sample_parameter_grid(d, base)
+    assert torch.equal(ctx, T(g[f"grid/{n}"])) and calls[-1][0] == 25 and torch.equal(calls[-1][1], ctx)
+    assert calls[-1][2] == 0.0  # the reference's grid call leaves guide_w at its default
+    del calls[:]
+    out = drivers.guidance_sweep(d, base)
+    assert [c[2] for c in calls] == list(g[f"guidance_w/{n}"]) == list(out.keys())
+    assert all(c[0] == 5 for c in calls)
+    assert torch.equal(torch.stack([c[1] for c in calls]), T(g[f"guidance_params/{n}"]))
+    del calls[:]
+    assert torch.equal(drivers.sensitivity_contexts(base, n), T(g[f"sensitivity/{n}"]))
+    _, ctx, _ = drivers.parameter_sensitivity(d, base, batched=False)  # the reference's call pattern: batch-1 calls
+    assert [c[0] for c in calls] == [1] * (5 * n) and all(c[2] == 0.0 for c in calls)
+    assert torch.equal(torch.cat([c[1] for c in calls]), T(g[f"sensitivity/{n}"]))
+    del calls[:]
+    _, ctx_b, _ = drivers.parameter_sensitivity(d, base, batched=True)  # same contexts as one batch
+    assert len(calls) == 1 and calls[0][0] == 5 * n and torch.equal(calls[0][1], T(g[f"sensitivity/{n}"]))
