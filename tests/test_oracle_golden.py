@@ -28,6 +28,20 @@ def test_unet_forward(name, tn):
     assert rel_l2(eps, g[f"{name}/{tn}/eps"]) < TOL
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("tn", ["t1", "tB"])
+def test_unet_forward_other_context_widths(n, tn):
+    """BASELINE config 4 (n_cfeat 1..5): seeded init and forward against the reference module at that width."""
+    g = load("unet_widths.npz")
+    init = O.init_state_dict(5, n_cfeat=n)
+    assert abs(O.state_dict_checksum(init) - float(g[f"{n}/checksum_init"])) < 1e-6
+    sd = O.calibrate_state_dict(init)
+    with torch.no_grad():
+        eps = O.unet_forward(sd, T(g[f"{n}/x"]), T(g[f"{n}/{tn}/t"]), T(g[f"{n}/c"]),
+                             split_shortcut(g[f"{n}/{tn}/shortcut"]), n_cfeat=n)
+    assert rel_l2(eps, g[f"{n}/{tn}/eps"]) < TOL
+
+
 def test_schedule_and_elementwise():
     g = load("sampler.npz")
     b_t, a_t, ab_t = O.make_schedule(int(g["T"]))
