@@ -268,7 +268,37 @@ def case_probe_l2(name):
     return True
 
 
+def case_hbm_rates(name, gib=2):
+    """Write-only, read-only and copy HBM rates of this box (torch fill_ / sum / copy_ over `gib` GiB, best of 10,
+    CUDA events): conv_in writes 1 MiB per image and reads 16 KB, conv_out the opposite, so their rooflines are the
+    one-directional rates, not the read+write copy figure of MEASURED_PEAKS.json."""
+    import torch
+    n = gib * (1 << 30) // 4
+    a, b = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
+    flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
+
+    def best(fn, nbytes):
+        t = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t.append(e0.elapsed_time(e1))
+        return nbytes / (min(t) * 1e-3) / 1e9
+
+    w = best(lambda: a.fill_(1.0), 4 * n)
+    r = best(lambda: a.sum(), 4 * n)
+    c = best(lambda: b.copy_(a), 8 * n)
+    print(f"CASE {name}: PERF write-only {w:.0f} GB/s, read-only {r:.0f} GB/s, copy (read+write) {c:.0f} GB/s "
+          f"over {gib} GiB", flush=True)
+    return True
+
+
 CASES = {
+    "hbm_rates": lambda: case_hbm_rates("hbm_rates"),
     "gemm_basic": lambda: case_gemm("gemm_basic", 256, 64, 0, 128),
     "gemm_ragged": lambda: case_gemm("gemm_ragged", 300, 128, 64, 256),
     "gemm_shuffle": lambda: case_gemm("gemm_shuffle", 2 * 16 * 16, 256, 256, 512, out_mode=1, H=16, W=16),
