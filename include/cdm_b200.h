@@ -102,7 +102,10 @@ int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream);
  *   out_mode 0: C row-major [M][N]                               (up0)
  *   out_mode 1: 2x2 stride-2 pixel shuffle: row m = (img,h,w) of an
  *               [n_img][H][W] grid, n = (kh*2+kw)*128 + co  ->
- *               out[img][2h+kh][2w+kw][co], N must be 512        (UnetUp) */
+ *               out[img][2h+kh][2w+kw][co], N must be 512        (UnetUp)
+ * Kernel choice is internal and does not change results (same K order, bit-identical rows): weights resident in
+ * shared memory for N = 512 with M >= 8192 and for N >= 256 * (SM count + 1) with K <= 256, M >= 1024 and
+ * 256 % shift_mod == 0; a streaming kernel otherwise. */
 typedef struct {
   const void* a0; /* bf16 [M][k0] */
   const void* a1; /* bf16 [M][k1] or NULL */
