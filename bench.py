@@ -169,37 +169,25 @@ KERNELS_PER_STEP = 28  # 26 per (2B-batched) forward + ddpm_step + step_advance
 
 
 def kernel_breakdown(run):
-    """One eager step with a CUDA event pair around every C-ABI launch (same stream as the launches)."""
+    """One eager step with a CUDA event after every launch, recorded by the library on the launch stream
+    (cdm_plan_profile: the 26 launches of the reps*B-image forward) + ddpm_step / step_advance timed here."""
     import torch
     from camels_diffusion_model_b200 import _lib as L
-    names = ["conv3x3", "gemm", "conv_in", "conv_out", "embed_fc", "avgpool_gelu", "gn_relu_film", "gn_finalize",
-             "ddpm_step", "step_advance"]
-    recs, orig = [], {}
-    for nme in names:
-        fn = getattr(L, nme)
-        orig[nme] = fn
-
-        def wrap(*a, _fn=fn, _n=nme, **k):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            r = _fn(*a, **k)
-            e1.record()
-            desc = _n
-            if _n == "conv3x3":
-                src, w = a[0], a[1]
-                desc = f"conv3x3 {tuple(src.shape)} cin{w.shape[3]}->cout{w.shape[0]} flags{k.get('flags', 1)}"
-            elif _n == "gemm":
-                desc = f"gemm M{a[0].shape[0]} K{a[1].shape[1]} N{a[1].shape[0]}"
-            recs.append((desc, e0, e1))
-            return r
-        setattr(L, nme, wrap)
-    try:
-        run._one_step()
-        torch.cuda.synchronize()
-    finally:
-        for nme, fn in orig.items():
-            setattr(L, nme, fn)
-    return [(d, e0.elapsed_time(e1)) for d, e0, e1 in recs]
+    m = run.model
+    pl = m.plan(run.B, run.reps)[0]
+    recs = pl.profile(run.x.view(run.B, m.h, m.h), run.sc_tab, run.cemb1, run.temb1, run.cemb2, run.temb2, 1,
+                      step_ptr=run.step)
+    ws = m.workspace(run.B, run.reps)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    L.ddpm_step(run.x, ws.eps, run.coef, run.T, reps=run.reps, guide_w=run.guide_w, step_ptr=run.step, z=run.z,
+                z_iter_stride=run.z_stride, seed=run.seed, snap=run.snap, snap_slot=run.snap_slot,
+                sample_offset=run.sample_offset)
+    ev[1].record()
+    L.step_advance(run.step, -1)
+    ev[2].record()
+    torch.cuda.synchronize()
+    return recs + [("ddpm_step", ev[0].elapsed_time(ev[1])), ("step_advance", ev[1].elapsed_time(ev[2]))]
 
 
 def run_b200(args):
@@ -292,7 +280,8 @@ def run_b200(args):
     pk = peaks()
     bd = kernel_breakdown(run)
     step_ms = sum(v for _, v in bd)
-    conv64 = [v for d, v in bd if d.startswith("conv3x3") and "64, 64, 128) cin128->cout128" in d]
+    # the eight 128->128 convolutions at 64x64 that run on all 2B images (down1.*, up2.*)
+    conv64 = [v for d, v in bd if d.startswith("conv3x3 down1.") or d.startswith("conv3x3 up2.")]
     n_img = 2 * B
     conv_ms = sum(conv64) / max(len(conv64), 1)
     achieved = CONV64_FLOP_PER_IMAGE * n_img / (conv_ms * 1e-3) / 1e12
@@ -309,7 +298,7 @@ def run_b200(args):
     # the memory-bound kernels against the measured HBM copy bandwidth (conv_in runs on B images, conv_out on 2B)
     hbm = []
     for name, imgs in (("conv_out", n_img), ("conv_in", B)):
-        t = [v for d, v in bd if d == name]
+        t = [v for d, v in bd if d.split()[0] == name]
         if t:
             gbs = HBM_BYTES_PER_IMAGE[name] * imgs / (t[0] * 1e-3) / 1e9
             hbm.append({"kernel": name, "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],

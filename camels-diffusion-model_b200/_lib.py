@@ -9,10 +9,11 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcdm_b200.so")
+# CDM_LIB selects another build of the same ABI (tools/gpu_probe.py loads the -DCDM_PROBES library this way)
+LIB_PATH = os.environ.get("CDM_LIB") or os.path.join(_HERE, "libcdm_b200.so")
 
-EPI_RELU, EPI_SHORTCUT, EPI_POOL, EPI_FILM, EPI_GNSTATS, EPI_BNSTATS = 1, 2, 4, 8, 16, 32
-CONV_MODE_COPIES, CONV_MODE_SHIFT24, CONV_MODE_SHIFT18, CONV_MODE_SWAPPED = 0, 1, 2, 3
+EPI_RELU, EPI_SHORTCUT, EPI_POOL, EPI_FILM, EPI_GNSTATS, EPI_BNSTATS, EPI_GELU, EPI_RESSCALE = 1, 2, 4, 8, 16, 32, 64, 128
+CONV_MODE_COPIES, CONV_MODE_SHIFT24, CONV_MODE_SHIFT18, CONV_MODE_SWAPPED, CONV_MODE_SWAPPED_TMA = 0, 1, 2, 3, 4
 
 
 class CdmError(RuntimeError):
@@ -28,7 +29,7 @@ class Conv3x3Args(C.Structure):
         ("sc_x", C.c_void_p), ("sc_reps", C.c_int), ("sc_tab", C.c_void_p),
         ("film_scale", C.c_void_p), ("film_shift", C.c_void_p), ("film_shift_rows", C.c_int),
         ("step_ptr", C.c_void_p), ("gn_partial", C.c_void_p), ("mode", C.c_int),
-        ("bn_partial", C.c_void_p), ("bn_sums", C.c_void_p), ("xr", C.c_void_p),
+        ("bn_partial", C.c_void_p), ("bn_sums", C.c_void_p), ("xr", C.c_void_p), ("res_scale", C.c_float),
     ]
 
 
@@ -74,19 +75,41 @@ class DdpmStepArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("eps", C.c_void_p), ("n", C.c_int), ("hw", C.c_int), ("reps", C.c_int),
                 ("guide_w", C.c_float), ("coef", C.c_void_p), ("step_ptr", C.c_void_p), ("step", C.c_int),
                 ("timesteps", C.c_int), ("z", C.c_void_p), ("z_iter_stride", C.c_longlong),
-                ("seed", C.c_ulonglong), ("snap", C.c_void_p), ("snap_slot", C.c_void_p)]
+                ("seed", C.c_ulonglong), ("snap", C.c_void_p), ("snap_slot", C.c_void_p),
+                ("sample_offset", C.c_longlong)]
 
 
 class PerturbArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("noise", C.c_void_p), ("out", C.c_void_p), ("n", C.c_int), ("hw", C.c_int),
                 ("ca", C.c_void_p), ("cb", C.c_void_p), ("t_idx", C.c_void_p), ("t_shared", C.c_int),
-                ("step_ptr", C.c_void_p), ("seed", C.c_ulonglong), ("stream_id", C.c_uint), ("noise_out", C.c_void_p)]
+                ("step_ptr", C.c_void_p), ("seed", C.c_ulonglong), ("stream_id", C.c_uint), ("noise_out", C.c_void_p),
+                ("sample_offset", C.c_longlong)]
 
 
 class MseAccumArgs(C.Structure):
     _fields_ = [("pred", C.c_void_p), ("target", C.c_void_p), ("n", C.c_int), ("hw", C.c_int),
                 ("weight_tab", C.c_void_p), ("t_idx", C.c_void_p), ("t_shared", C.c_int),
-                ("step_ptr", C.c_void_p), ("mse_out", C.c_void_p), ("acc", C.c_void_p)]
+                ("step_ptr", C.c_void_p), ("mse_out", C.c_void_p), ("acc", C.c_void_p),
+                ("weight_tab2", C.c_void_p), ("acc2", C.c_void_p)]
+
+
+class PlanDesc(C.Structure):
+    _fields_ = [("n_cfeat", C.c_int), ("batch", C.c_int), ("reps", C.c_int), ("tensors", C.POINTER(C.c_void_p)),
+                ("arena", C.c_void_p), ("arena_bytes", C.c_longlong), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_longlong), ("conv_mode", C.c_int)]
+
+
+class ForwardArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("sc_tab", C.c_void_p), ("cemb1", C.c_void_p), ("temb1", C.c_void_p),
+                ("cemb2", C.c_void_p), ("temb2", C.c_void_p), ("temb_rows", C.c_int), ("step_ptr", C.c_void_p),
+                ("eps", C.c_void_p)]
+
+
+class SampleStepArgs(C.Structure):
+    _fields_ = [("fwd", ForwardArgs), ("x", C.c_void_p), ("step_ptr", C.c_void_p), ("guide_w", C.c_float),
+                ("coef", C.c_void_p), ("timesteps", C.c_int), ("z", C.c_void_p), ("z_iter_stride", C.c_longlong),
+                ("seed", C.c_ulonglong), ("sample_offset", C.c_longlong), ("snap", C.c_void_p),
+                ("snap_slot", C.c_void_p)]
 
 
 _lib = None
@@ -103,6 +126,12 @@ def lib():
             "(nvcc, sm_100a). There is no CPU/PyTorch fallback for the hot path.")
     l = C.CDLL(LIB_PATH)
     l.cdm_last_error.restype = C.c_char_p
+    l.cdm_plan_tensor_name.restype = C.c_char_p
+    l.cdm_plan_launch_name.restype = C.c_char_p
+    for fn in ("cdm_plan_tensor_numel", "cdm_plan_arena_bytes", "cdm_plan_workspace_bytes"):
+        getattr(l, fn).restype = C.c_longlong
+    l.cdm_plan_destroy.restype = None
+    l.cdm_plan_destroy.argtypes = [C.c_void_p]
     for name in EXPORTS:
         getattr(l, name)  # raises AttributeError if the header and the library disagree
     _lib = l
@@ -111,7 +140,7 @@ def lib():
 
 # every symbol include/cdm_b200.h declares
 EXPORTS = [
-    "cdm_version", "cdm_last_error", "cdm_device_ok",
+    "cdm_version", "cdm_last_error", "cdm_device_ok", "cdm_num_sms",
     "cdm_conv3x3", "cdm_gemm", "cdm_probe_tma_l2",
     "cdm_conv_in", "cdm_conv_out", "cdm_embed_fc", "cdm_avgpool_gelu", "cdm_gn_relu_film", "cdm_gn_finalize",
     "cdm_ddpm_step", "cdm_step_advance", "cdm_perturb", "cdm_mse_accum",
@@ -119,7 +148,11 @@ EXPORTS = [
     "cdm_maxpool2_bwd", "cdm_add_bf16", "cdm_space_to_depth", "cdm_film_bwd", "cdm_gn_bwd", "cdm_rows_sum",
     "cdm_avgpool_gelu_train", "cdm_avgpool_gelu_bwd", "cdm_outer_wgrad", "cdm_embed_bwd", "cdm_mse_grad",
     "cdm_adam_step", "cdm_power_spectrum", "cdm_pixel_histogram",
-    "cdm_minmax", "cdm_preprocess_maps", "cdm_normalize_params", "cdm_xrank_sum", "cdm_pack_bf16",
+    "cdm_minmax", "cdm_preprocess_maps", "cdm_normalize_params", "cdm_xrank_sum", "cdm_xrank_set_timeout", "cdm_pack_bf16",
+    "cdm_plan_n_tensors", "cdm_plan_tensor_name", "cdm_plan_tensor_numel", "cdm_plan_arena_bytes",
+    "cdm_plan_workspace_bytes", "cdm_plan_create", "cdm_plan_refresh", "cdm_plan_destroy", "cdm_plan_buffer",
+    "cdm_plan_embed", "cdm_forward_eval", "cdm_sample_step", "cdm_plan_n_launches", "cdm_plan_launch_name",
+    "cdm_plan_profile",
 ]
 
 
@@ -140,9 +173,23 @@ def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_SMS = {}
+
+
+def num_sms():
+    """Multiprocessor count of the current device (sizes the per-CTA partial-sum workspaces)."""
+    d = torch.cuda.current_device()
+    if d not in _SMS:
+        n = lib().cdm_num_sms()
+        if n <= 0:
+            raise CdmError("cdm_num_sms failed: " + lib().cdm_last_error().decode())
+        _SMS[d] = n
+    return _SMS[d]
+
+
 def conv3x3(src0, weight, scale, shift, out, *, src1=None, flags=EPI_RELU, sc_x=None, sc_tab=None, sc_reps=1,
             film_scale=None, film_shift=None, film_shift_rows=1, step_ptr=None, gn_partial=None,
-            mode=CONV_MODE_SWAPPED, bn_partial=None, bn_sums=None, xr=None):
+            mode=CONV_MODE_SWAPPED, bn_partial=None, bn_sums=None, xr=None, res_scale=1.0):
     """src*: bf16 [n,H,W,c]; weight bf16 [cout,3,3,cin]; out bf16 NHWC. See cdm_conv3x3 in cdm_b200.h."""
     n, H, W, c0 = src0.shape
     a = Conv3x3Args()
@@ -155,7 +202,7 @@ def conv3x3(src0, weight, scale, shift, out, *, src1=None, flags=EPI_RELU, sc_x=
     a.sc_x, a.sc_reps, a.sc_tab = ptr(sc_x), sc_reps, ptr(sc_tab)
     a.film_scale, a.film_shift, a.film_shift_rows = ptr(film_scale), ptr(film_shift), film_shift_rows
     a.step_ptr, a.gn_partial, a.mode = ptr(step_ptr), ptr(gn_partial), mode
-    a.bn_partial, a.bn_sums, a.xr = ptr(bn_partial), ptr(bn_sums), _xr_ptr(xr)
+    a.bn_partial, a.bn_sums, a.xr, a.res_scale = ptr(bn_partial), ptr(bn_sums), _xr_ptr(xr), res_scale
     check(lib().cdm_conv3x3(C.byref(a), stream_ptr()), "cdm_conv3x3")
     return out
 
@@ -237,13 +284,14 @@ def gn_finalize(partial, count, mean_rstd, eps=1e-5):
 
 
 def ddpm_step(x, eps, coef, timesteps, *, reps=1, guide_w=0.0, step=0, step_ptr=None, z=None, z_iter_stride=0,
-              seed=0, snap=None, snap_slot=None):
+              seed=0, snap=None, snap_slot=None, sample_offset=0):
     """x fp32 [n,...] in place; eps fp32 [reps*n,...]; coef fp32 [T+1,4]."""
     a = DdpmStepArgs()
     n = x.shape[0]
     a.x, a.eps, a.n, a.hw, a.reps, a.guide_w = ptr(x), ptr(eps), n, x.numel() // n, reps, guide_w
     a.coef, a.step_ptr, a.step, a.timesteps = ptr(coef), ptr(step_ptr), step, timesteps
     a.z, a.z_iter_stride, a.seed, a.snap, a.snap_slot = ptr(z), z_iter_stride, seed, ptr(snap), ptr(snap_slot)
+    a.sample_offset = sample_offset
     check(lib().cdm_ddpm_step(C.byref(a), stream_ptr()), "cdm_ddpm_step")
     return x
 
@@ -253,23 +301,103 @@ def step_advance(step_ptr, delta):
 
 
 def perturb(x, out, ca, cb, *, noise=None, t_idx=None, t_shared=0, step_ptr=None, seed=0, stream_id=0,
-            noise_out=None):
+            noise_out=None, sample_offset=0):
     a = PerturbArgs()
     n = x.shape[0]
     a.x, a.noise, a.out, a.n, a.hw = ptr(x), ptr(noise), ptr(out), n, x.numel() // n
     a.ca, a.cb, a.t_idx, a.t_shared, a.step_ptr = ptr(ca), ptr(cb), ptr(t_idx), t_shared, ptr(step_ptr)
-    a.seed, a.stream_id, a.noise_out = seed, stream_id, ptr(noise_out)
+    a.seed, a.stream_id, a.noise_out, a.sample_offset = seed, stream_id, ptr(noise_out), sample_offset
     check(lib().cdm_perturb(C.byref(a), stream_ptr()), "cdm_perturb")
     return out
 
 
-def mse_accum(pred, target, *, weight_tab=None, t_idx=None, t_shared=0, step_ptr=None, mse_out=None, acc=None):
+def mse_accum(pred, target, *, weight_tab=None, t_idx=None, t_shared=0, step_ptr=None, mse_out=None, acc=None,
+              weight_tab2=None, acc2=None):
     a = MseAccumArgs()
     n = pred.shape[0]
     a.pred, a.target, a.n, a.hw = ptr(pred), ptr(target), n, pred.numel() // n
     a.weight_tab, a.t_idx, a.t_shared, a.step_ptr = ptr(weight_tab), ptr(t_idx), t_shared, ptr(step_ptr)
-    a.mse_out, a.acc = ptr(mse_out), ptr(acc)
+    a.mse_out, a.acc, a.weight_tab2, a.acc2 = ptr(mse_out), ptr(acc), ptr(weight_tab2), ptr(acc2)
     check(lib().cdm_mse_accum(C.byref(a), stream_ptr()), "cdm_mse_accum")
+
+
+# ----------------------------------------------------------------------------- composite plan API
+def plan_tensor_names():
+    l = lib()
+    return [l.cdm_plan_tensor_name(i).decode() for i in range(l.cdm_plan_n_tensors())]
+
+
+class Plan:
+    """cdm_plan handle: packed weights + activation workspace + every layer's prepared launch for one
+    (batch, reps) shape.  The arena / workspace are torch byte tensors owned here (the library allocates nothing)."""
+
+    def __init__(self, tensors, n_cfeat, batch, reps, device, conv_mode=0):
+        l = lib()
+        self.names = plan_tensor_names()
+        assert len(tensors) == len(self.names)
+        for nme, t in zip(self.names, tensors):
+            if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+                raise CdmError(f"plan tensor {nme}: need a contiguous fp32 device tensor")
+        self.tensors = list(tensors)  # keep-alive: the plan reads the small fp32 vectors in place
+        self._ptrs = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        self.batch, self.reps, self.n = batch, reps, batch * reps
+        self.arena = torch.empty(int(l.cdm_plan_arena_bytes(n_cfeat)), device=device, dtype=torch.uint8)
+        self.ws = torch.empty(int(l.cdm_plan_workspace_bytes(batch, reps)), device=device, dtype=torch.uint8)
+        d = PlanDesc(n_cfeat, batch, reps, self._ptrs, self.arena.data_ptr(), self.arena.numel(), self.ws.data_ptr(),
+                     self.ws.numel(), conv_mode)
+        h = C.c_void_p()
+        check(l.cdm_plan_create(C.byref(d), stream_ptr(), C.byref(h)), "cdm_plan_create")
+        self.handle = h
+
+    def refresh(self):
+        check(lib().cdm_plan_refresh(self.handle, stream_ptr()), "cdm_plan_refresh")
+
+    def buffer(self, name, dtype, shape):
+        """Typed view of a named workspace buffer."""
+        p, nb = C.c_void_p(), C.c_longlong()
+        check(lib().cdm_plan_buffer(self.handle, name.encode(), C.byref(p), C.byref(nb)), "cdm_plan_buffer")
+        off = p.value - self.ws.data_ptr()
+        return self.ws[off:off + nb.value].view(dtype).view(shape)
+
+    def embed(self, which, inp, out):
+        check(lib().cdm_plan_embed(self.handle, which, C.c_void_p(ptr(inp)), inp.shape[0], C.c_void_p(ptr(out)),
+                                   stream_ptr()), "cdm_plan_embed")
+        return out
+
+    def _fwd_args(self, x, sc_tab, cemb1, temb1, cemb2, temb2, temb_rows, step_ptr, eps):
+        return ForwardArgs(ptr(x), ptr(sc_tab), ptr(cemb1), ptr(temb1), ptr(cemb2), ptr(temb2), temb_rows,
+                           ptr(step_ptr), ptr(eps))
+
+    def forward_eval(self, x, sc_tab, cemb1, temb1, cemb2, temb2, temb_rows, step_ptr=None, eps=None):
+        f = self._fwd_args(x, sc_tab, cemb1, temb1, cemb2, temb2, temb_rows, step_ptr, eps)
+        check(lib().cdm_forward_eval(self.handle, C.byref(f), stream_ptr()), "cdm_forward_eval")
+
+    def profile(self, x, sc_tab, cemb1, temb1, cemb2, temb2, temb_rows, step_ptr=None):
+        """[(launch name, ms)] of one forward, CUDA events on the launch stream (cdm_plan_profile)."""
+        l = lib()
+        n = l.cdm_plan_n_launches()
+        ms = (C.c_float * n)()
+        f = self._fwd_args(x, sc_tab, cemb1, temb1, cemb2, temb2, temb_rows, step_ptr, None)
+        check(l.cdm_plan_profile(self.handle, C.byref(f), ms, stream_ptr()), "cdm_plan_profile")
+        return [(l.cdm_plan_launch_name(i).decode(), float(ms[i])) for i in range(n)]
+
+    def sample_step(self, x, sc_tab, cemb1, temb1, cemb2, temb2, step_ptr, coef, timesteps, *, guide_w=0.0, z=None,
+                    z_iter_stride=0, seed=0, sample_offset=0, snap=None, snap_slot=None):
+        f = self._fwd_args(None, sc_tab, cemb1, temb1, cemb2, temb2, 1, None, None)
+        a = SampleStepArgs(f, ptr(x), ptr(step_ptr), guide_w, ptr(coef), timesteps, ptr(z), z_iter_stride, seed,
+                           sample_offset, ptr(snap), ptr(snap_slot))
+        check(lib().cdm_sample_step(self.handle, C.byref(a), stream_ptr()), "cdm_sample_step")
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and _lib is not None:
+            _lib.cdm_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
 
 
 # ----------------------------------------------------------------------------- training path
@@ -473,6 +601,10 @@ def xrank_sum(partial, out, xr=None):
     check(lib().cdm_xrank_sum(C.c_void_p(ptr(partial)), n_blocks, n, C.c_void_p(ptr(out)), _xr_ptr(xr), stream_ptr()),
           "cdm_xrank_sum")
     return out
+
+
+def xrank_set_timeout(seconds):
+    check(lib().cdm_xrank_set_timeout(C.c_double(seconds)), "cdm_xrank_set_timeout")
 
 
 def pack_bf16(table, n_rows, total_vec):

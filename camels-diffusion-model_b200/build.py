@@ -12,6 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcdm_b200.so")
+LIB_PROBES = os.path.join(HERE, "libcdm_b200_probes.so")  # same sources with -DCDM_PROBES (tools/gpu_probe.py only)
 STAMP = os.path.join(HERE, ".libcdm_b200.stamp")
 
 NVCC_FLAGS = [
@@ -44,13 +45,18 @@ def build(force=False, verbose=False):
             if fh.read().strip() == dig:
                 return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + _sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libcdm_b200.so")
-    if verbose:
-        sys.stderr.write(res.stderr)
+    jobs = [(LIB, []), (LIB_PROBES, ["-DCDM_PROBES"])]
+    procs = []
+    for lib, extra in jobs:  # the two libraries compile side by side
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-t", "4", "-o", lib] + _sources()
+        procs.append((lib, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for lib, pr in procs:
+        out, err = pr.communicate()
+        if pr.returncode != 0:
+            sys.stderr.write(out + err)
+            raise RuntimeError(f"nvcc failed building {os.path.basename(lib)}")
+        if verbose:
+            sys.stderr.write(err)
     with open(STAMP, "w") as fh:
         fh.write(dig)
     return LIB

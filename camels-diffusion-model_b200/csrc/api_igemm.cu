@@ -4,6 +4,7 @@
 
 #include "common.h"
 #include "igemm.cuh"
+#include "launch.h"
 
 namespace cdm {
 
@@ -80,88 +81,87 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return CDM_OK;
 }
 
-static int num_sms() {
-  static int n = 0;
-  if (n) return n;
+int num_sms() {
+  static int cache[64];
   int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  return n;
-}
-
-template <int MODE>
-static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvKParams& p,
-                       cudaStream_t st) {
-  constexpr int smem = conv_smem_bytes<MODE>();
-  static bool attr_set = false;
-  if (!attr_set) {
-    CDM_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
-  const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
-  conv3x3_kernel<MODE><<<grid, kConvThreads, smem, st>>>(a0, a1, b, p);
-  CDM_CHECK_LAUNCH();
-  return CDM_OK;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (!cache[dev]) cudaDeviceGetAttribute(&cache[dev], cudaDevAttrMultiProcessorCount, dev);
+  return cache[dev];
 }
 
 }  // namespace cdm
 
 using namespace cdm;
 
-extern "C" int cdm_version(void) { return 100; }
+extern "C" int cdm_version(void) { return 200; }
 extern "C" const char* cdm_last_error(void) { return g_err; }
 extern "C" int cdm_device_ok(void) { return check_device(); }
+extern "C" int cdm_num_sms(void) { return check_device() == CDM_OK ? num_sms() : 0; }
 
-extern "C" int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream) {
+// ---------------------------------------------------------------------------------------------------------------
+// cdm_conv3x3 / cdm_gemm are split into a PREPARE step (argument checks, tensor maps, kernel choice: everything that
+// depends only on shapes and pointers) and a LAUNCH step, so that a cdm_plan (plan.cu) encodes each layer's tensor
+// maps once and a forward is nothing but kernel launches.
+// ---------------------------------------------------------------------------------------------------------------
+namespace cdm {
+
+static int g_attr_done[64][16];  // [device][kernel variant]: cudaFuncSetAttribute is per device, not per process
+
+template <typename K>
+static int set_smem_attr(K kernel, int variant, int bytes) {
+  int dev = 0;
+  CDM_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 63;
+  if (dev == 63 || !g_attr_done[dev][variant]) {
+    CDM_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    g_attr_done[dev][variant] = 1;
+  }
+  return CDM_OK;
+}
+
+static int act_tmap(CUtensorMap* m, const void* base, int c, int W, int H, int n, uint32_t bw, uint32_t bh) {
+  uint64_t dims[4] = {(uint64_t)c, (uint64_t)W, (uint64_t)H, (uint64_t)n};
+  uint64_t str[3] = {(uint64_t)c * 2, (uint64_t)W * c * 2, (uint64_t)H * W * c * 2};
+  uint32_t box[4] = {64, bw, bh, 1};
+  return make_tmap_bf16(m, base, 4, dims, str, box);
+}
+
+int conv_prepare(const cdm_conv3x3_args* a, ConvLaunch* L) {
   CDM_CHECK_ARG(a != nullptr);
   CDM_CHECK_ARG(a->src0 && a->weight && a->scale && a->shift && a->out);
   CDM_CHECK_ARG(a->c0 > 0 && a->c0 % 64 == 0 && a->c1 >= 0 && a->c1 % 64 == 0);
   CDM_CHECK_ARG((a->c1 == 0) == (a->src1 == nullptr));
   CDM_CHECK_ARG(a->n_img > 0 && a->H >= 16 && a->W >= 16 && a->H % 16 == 0 && a->W % 16 == 0);
   CDM_CHECK_ARG(a->cout > 0 && a->cout % 128 == 0 && a->cout <= 256);
-  CDM_CHECK_ARG(a->mode >= 0 && a->mode <= 3);
+  CDM_CHECK_ARG(a->mode >= 0 && a->mode <= 4);
+#ifdef CDM_PROBES
+  CDM_CHECK_ARG((a->flags & ~(CDM_EPI_ALL | (31 << 26))) == 0);
+#else
+  CDM_CHECK_ARG((a->flags & ~CDM_EPI_ALL) == 0);  // unknown bits are an error, never silently forwarded to the kernel
+#endif
   if (a->flags & CDM_EPI_SHORTCUT)
     CDM_CHECK_ARG(a->sc_x && a->sc_tab && a->sc_reps >= 1);
   if (a->flags & CDM_EPI_FILM) CDM_CHECK_ARG(a->film_scale && a->film_shift && a->film_shift_rows >= 1);
   if (a->flags & CDM_EPI_GNSTATS) CDM_CHECK_ARG(a->gn_partial && a->cout == 128 && !(a->flags & CDM_EPI_POOL));
   if (a->flags & CDM_EPI_BNSTATS)
-    CDM_CHECK_ARG(a->bn_partial && a->bn_sums && a->mode == 3 && a->H % 32 == 0 && a->W % 8 == 0 &&
+    CDM_CHECK_ARG(a->bn_partial && a->bn_sums && a->mode >= 3 && a->H % 32 == 0 && a->W % 8 == 0 &&
                   !(a->flags & (CDM_EPI_POOL | CDM_EPI_SHORTCUT)));
   int rc = check_device();
   if (rc) return rc;
+  memset(L, 0, sizeof(*L));
 
-  // MODE 3 (swapped operands, 8 px x 32 row patches) needs H % 32 == 0; otherwise fall back to SHIFT18
-  const int mode = (a->mode == 3 && (a->H % 32 != 0 || a->W % 8 != 0)) ? 2 : a->mode;
-  static const int pitch_of_mode[4] = {16, 24, 18, 10};
-  const uint32_t pitch = pitch_of_mode[mode];
-  const uint32_t box_rows = mode == 3 ? 34 : 18;
-  CUtensorMap mA0, mA1, mB;
-  {
-    uint64_t dims[4] = {(uint64_t)a->c0, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
-    uint64_t str[3] = {(uint64_t)a->c0 * 2, (uint64_t)a->W * a->c0 * 2, (uint64_t)a->H * a->W * a->c0 * 2};
-    uint32_t box[4] = {64, pitch, box_rows, 1};
-    rc = make_tmap_bf16(&mA0, a->src0, 4, dims, str, box);
-    if (rc) return rc;
-  }
-  if (a->src1) {
-    uint64_t dims[4] = {(uint64_t)a->c1, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
-    uint64_t str[3] = {(uint64_t)a->c1 * 2, (uint64_t)a->W * a->c1 * 2, (uint64_t)a->H * a->W * a->c1 * 2};
-    uint32_t box[4] = {64, pitch, box_rows, 1};
-    rc = make_tmap_bf16(&mA1, a->src1, 4, dims, str, box);
-    if (rc) return rc;
-  } else {
-    mA1 = mA0;
-  }
+  // MODE 3 / 4 (swapped operands, 8 px x 32 row patches) need H % 32 == 0; otherwise fall back to SHIFT18
+  const bool swapped = a->mode >= 3 && a->H % 32 == 0 && a->W % 8 == 0;
+  const int mode = swapped ? a->mode : (a->mode >= 3 ? 2 : a->mode);
   const int cin = a->c0 + a->c1;
   {
     uint64_t dims[2] = {(uint64_t)9 * cin, (uint64_t)a->cout};
     uint64_t str[1] = {(uint64_t)9 * cin * 2};
     uint32_t box[2] = {64, 128};
-    rc = make_tmap_bf16(&mB, a->weight, 2, dims, str, box);
+    rc = make_tmap_bf16(&L->b, a->weight, 2, dims, str, box);
     if (rc) return rc;
   }
-  ConvKParams p;
-  memset(&p, 0, sizeof(p));
+  ConvKParams& p = L->p;
   p.H = a->H;
   p.W = a->W;
   p.n_img = a->n_img;
@@ -185,69 +185,106 @@ extern "C" int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream) {
   p.step_ptr = a->step_ptr;
   p.gn_partial = a->gn_partial;
   p.bn_partial = a->bn_partial;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (mode == 3) {
+  p.res_scale = (a->flags & CDM_EPI_RESSCALE) ? a->res_scale : 1.f;
+  const int sms = num_sms();
+  uint32_t pitch = 18, box_rows = 18;
+  if (swapped) {
     const int units32 = a->n_img * (a->W / 8) * (a->H / 32) * p.n_tiles;
-    const int grid_cap = num_sms();
     // small launches (batch-1 sampling): when 8 x 32 patches would leave three quarters of the SMs idle, use 8 x 8
-    // patches — four times the units (still one wave), a quarter of the MMA chain each.  Not with the statistics epilogues, whose
-    // partial-sum layout (and summation order) is tied to the 32-row patch.
-    const bool small = units32 * 4 <= grid_cap && !(a->flags & (CDM_EPI_GNSTATS | CDM_EPI_BNSTATS));  // one wave
-    if (small) {
-      p.n_units = units32 * 4;
-      constexpr int smem = conv_sw_smem_bytes<8>();
-      static bool attr_set8 = false;
-      if (!attr_set8) {
-        CDM_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_sw_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set8 = true;
-      }
-      // the halo box of the 8-row patch is {64, 10, 10, 1}: its own tensor maps
-      CUtensorMap sA0, sA1;
-      {
-        uint64_t dims[4] = {(uint64_t)a->c0, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
-        uint64_t str[3] = {(uint64_t)a->c0 * 2, (uint64_t)a->W * a->c0 * 2, (uint64_t)a->H * a->W * a->c0 * 2};
-        uint32_t box[4] = {64, 10, 10, 1};
-        rc = make_tmap_bf16(&sA0, a->src0, 4, dims, str, box);
-        if (rc) return rc;
-      }
-      if (a->src1) {
-        uint64_t dims[4] = {(uint64_t)a->c1, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
-        uint64_t str[3] = {(uint64_t)a->c1 * 2, (uint64_t)a->W * a->c1 * 2, (uint64_t)a->H * a->W * a->c1 * 2};
-        uint32_t box[4] = {64, 10, 10, 1};
-        rc = make_tmap_bf16(&sA1, a->src1, 4, dims, str, box);
-        if (rc) return rc;
-      } else {
-        sA1 = sA0;
-      }
-      const int grid = p.n_units < grid_cap ? p.n_units : grid_cap;
-      conv3x3_sw_kernel<8><<<grid, kSwThreads, smem, st>>>(sA0, sA1, mB, p);
-      CDM_CHECK_LAUNCH();
-      return CDM_OK;
+    // patches — four times the units (still one wave), a quarter of the MMA chain each.  Not with the statistics
+    // epilogues, whose partial-sum layout (and summation order) is tied to the 32-row patch.
+    const bool small = units32 * 4 <= sms && !(a->flags & (CDM_EPI_GNSTATS | CDM_EPI_BNSTATS));
+    const bool tma = mode == 4;
+    L->variant = (small ? kConvSw8 : kConvSw32) + (tma ? 2 : 0);
+    p.n_units = small ? units32 * 4 : units32;
+    pitch = 10;
+    box_rows = small ? 10 : 34;
+    if (a->flags & CDM_EPI_BNSTATS) {
+      L->bn_fold = 1;
+      L->bn_sums = a->bn_sums;
+      L->xr = a->xr;
     }
-    p.n_units = units32;
-    constexpr int smem = conv_sw_smem_bytes<32>();
-    static bool attr_set = false;
-    if (!attr_set) {
-      CDM_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_sw_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr_set = true;
-    }
-    const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
-    conv3x3_sw_kernel<32><<<grid, kSwThreads, smem, st>>>(mA0, mA1, mB, p);
-    CDM_CHECK_LAUNCH();
-    if (a->flags & CDM_EPI_BNSTATS) {  // fold the per-CTA rows (and the other ranks' sums) into bn_sums
-      launch_xrank_sum(a->bn_partial, grid, 2 * a->cout, a->bn_sums, a->xr, st);
-      CDM_CHECK_LAUNCH();
-    }
-    return CDM_OK;
+    // output map of the TMA-store epilogue: box {64 ch, 8 px, 4 rows}; all images the epilogue may fan out to
+    const int reps = (a->flags & CDM_EPI_SHORTCUT) ? p.sc_reps : 1;
+    const int sh = (a->flags & CDM_EPI_POOL) ? 1 : 0;
+    rc = act_tmap(&L->out, a->out, a->cout, a->W >> sh, a->H >> sh, a->n_img * reps, 8, 4);
+    if (rc) return rc;
+  } else {
+    static const int pitch_of_mode[3] = {16, 24, 18};
+    pitch = pitch_of_mode[mode];
+    L->variant = mode;
   }
-  switch (mode) {
-    case 0: return launch_conv<0>(mA0, mA1, mB, p, st);
-    case 1: return launch_conv<1>(mA0, mA1, mB, p, st);
-    default: return launch_conv<2>(mA0, mA1, mB, p, st);
+  rc = act_tmap(&L->a0, a->src0, a->c0, a->W, a->H, a->n_img, pitch, box_rows);
+  if (rc) return rc;
+  if (a->src1) {
+    rc = act_tmap(&L->a1, a->src1, a->c1, a->W, a->H, a->n_img, pitch, box_rows);
+    if (rc) return rc;
+  } else {
+    L->a1 = L->a0;
   }
+  if (!swapped) L->out = L->a0;
+  L->grid = p.n_units < sms ? p.n_units : sms;
+  return CDM_OK;
 }
 
-extern "C" int cdm_gemm(const cdm_gemm_args* a, void* stream) {
+int conv_launch(const ConvLaunch& L, cudaStream_t st) {
+  int rc = CDM_OK;
+  switch (L.variant) {
+    case 0: {
+      constexpr int smem = conv_smem_bytes<0>();
+      if ((rc = set_smem_attr(conv3x3_kernel<0>, 0, smem))) return rc;
+      conv3x3_kernel<0><<<L.grid, kConvThreads, smem, st>>>(L.a0, L.a1, L.b, L.p);
+      break;
+    }
+    case 1: {
+      constexpr int smem = conv_smem_bytes<1>();
+      if ((rc = set_smem_attr(conv3x3_kernel<1>, 1, smem))) return rc;
+      conv3x3_kernel<1><<<L.grid, kConvThreads, smem, st>>>(L.a0, L.a1, L.b, L.p);
+      break;
+    }
+    case 2: {
+      constexpr int smem = conv_smem_bytes<2>();
+      if ((rc = set_smem_attr(conv3x3_kernel<2>, 2, smem))) return rc;
+      conv3x3_kernel<2><<<L.grid, kConvThreads, smem, st>>>(L.a0, L.a1, L.b, L.p);
+      break;
+    }
+    case kConvSw32: {
+      constexpr int smem = conv_sw_smem_bytes<32, false>();
+      if ((rc = set_smem_attr(conv3x3_sw_kernel<32, false>, kConvSw32, smem))) return rc;
+      conv3x3_sw_kernel<32, false><<<L.grid, kSwThreads, smem, st>>>(L.a0, L.a1, L.b, L.out, L.p);
+      break;
+    }
+    case kConvSw8: {
+      constexpr int smem = conv_sw_smem_bytes<8, false>();
+      if ((rc = set_smem_attr(conv3x3_sw_kernel<8, false>, kConvSw8, smem))) return rc;
+      conv3x3_sw_kernel<8, false><<<L.grid, kSwThreads, smem, st>>>(L.a0, L.a1, L.b, L.out, L.p);
+      break;
+    }
+    case kConvSw32 + 2: {
+      constexpr int smem = conv_sw_smem_bytes<32, true>();
+      if ((rc = set_smem_attr(conv3x3_sw_kernel<32, true>, kConvSw32 + 2, smem))) return rc;
+      conv3x3_sw_kernel<32, true><<<L.grid, kSwThreads, smem, st>>>(L.a0, L.a1, L.b, L.out, L.p);
+      break;
+    }
+    case kConvSw8 + 2: {
+      constexpr int smem = conv_sw_smem_bytes<8, true>();
+      if ((rc = set_smem_attr(conv3x3_sw_kernel<8, true>, kConvSw8 + 2, smem))) return rc;
+      conv3x3_sw_kernel<8, true><<<L.grid, kSwThreads, smem, st>>>(L.a0, L.a1, L.b, L.out, L.p);
+      break;
+    }
+    default:
+      set_error("conv_launch: bad variant %d", L.variant);
+      return CDM_ERR_ARG;
+  }
+  CDM_CHECK_LAUNCH();
+  if (L.bn_fold) {  // fold the per-CTA rows (and the other ranks' sums) into bn_sums
+    launch_xrank_sum(L.p.bn_partial, L.grid, 2 * L.p.cout, L.bn_sums, L.xr, st);
+    CDM_CHECK_LAUNCH();
+  }
+  return CDM_OK;
+}
+
+int gemm_prepare(const cdm_gemm_args* a, GemmLaunch* G) {
   CDM_CHECK_ARG(a != nullptr);
   CDM_CHECK_ARG(a->a0 && a->bw && a->shift && a->out);
   CDM_CHECK_ARG(a->k0 > 0 && a->k0 % 64 == 0 && a->k1 >= 0 && a->k1 % 64 == 0);
@@ -258,42 +295,45 @@ extern "C" int cdm_gemm(const cdm_gemm_args* a, void* stream) {
                                      a->M % (a->H * a->W) == 0));
   int rc = check_device();
   if (rc) return rc;
-  CUtensorMap mA0, mA1, mB;
+  memset(G, 0, sizeof(*G));
   {
     uint64_t dims[2] = {(uint64_t)a->k0, (uint64_t)a->M};
     uint64_t str[1] = {(uint64_t)a->k0 * 2};
     uint32_t box[2] = {64, 128};
-    rc = make_tmap_bf16(&mA0, a->a0, 2, dims, str, box);
+    rc = make_tmap_bf16(&G->a0, a->a0, 2, dims, str, box);
     if (rc) return rc;
   }
   if (a->a1) {
     uint64_t dims[2] = {(uint64_t)a->k1, (uint64_t)a->M};
     uint64_t str[1] = {(uint64_t)a->k1 * 2};
     uint32_t box[2] = {64, 128};
-    rc = make_tmap_bf16(&mA1, a->a1, 2, dims, str, box);
+    rc = make_tmap_bf16(&G->a1, a->a1, 2, dims, str, box);
     if (rc) return rc;
   } else {
-    mA1 = mA0;
+    G->a1 = G->a0;
   }
   const int K = a->k0 + a->k1;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)a->N};
     uint64_t str[1] = {(uint64_t)K * 2};
     uint32_t box[2] = {64, 128};
-    rc = make_tmap_bf16(&mB, a->bw, 2, dims, str, box);
+    rc = make_tmap_bf16(&G->b, a->bw, 2, dims, str, box);
     if (rc) return rc;
   }
+  const int sms = num_sms();
   // small N (transposed convolutions): keep the weight tiles resident, stream A once per weight group
   const int n_tiles_total = a->N / 128;
   const int n_res = K <= 256 ? 2 : (K <= 512 ? 1 : 0);
   // few_n: the 2x2 transposed convolutions (N = 512): one weight group per CTA.  many_n: up0 at sampling batch
   // sizes (N = 65536): several groups per CTA, swapped in turn; needs the same shift rows for every group.
   const bool few_n = n_res > 0 && n_tiles_total <= 4 && n_tiles_total % n_res == 0 && a->M >= 128 * 64;
-  const bool many_n = n_res == 2 && n_tiles_total % 2 == 0 && n_tiles_total / 2 > num_sms() && a->out_mode == 0 &&
+  const bool many_n = n_res == 2 && n_tiles_total % 2 == 0 && n_tiles_total / 2 > sms && a->out_mode == 0 &&
                       256 % a->shift_mod == 0 && a->M >= 1024;
+  int h_shift = 0, w_shift = 0;
+  for (int v = a->H; v > 1; v >>= 1) ++h_shift;
+  for (int v = a->W; v > 1; v >>= 1) ++w_shift;
   if (few_n || many_n) {
-    GemmBresKParams q;
-    memset(&q, 0, sizeof(q));
+    GemmBresKParams& q = G->q;
     q.M = a->M;
     q.N = a->N;
     q.chunks0 = a->k0 / 64;
@@ -306,23 +346,15 @@ extern "C" int cdm_gemm(const cdm_gemm_args* a, void* stream) {
     q.out_mode = a->out_mode;
     q.H = a->H;
     q.W = a->W;
-    for (int v = a->H; v > 1; v >>= 1) ++q.h_shift;
-    for (int v = a->W; v > 1; v >>= 1) ++q.w_shift;
+    q.h_shift = h_shift;
+    q.w_shift = w_shift;
     q.out = reinterpret_cast<bf16*>(a->out);
-    constexpr int smem_b = gemm_bres_smem_bytes();
-    static bool attr_b = false;
-    if (!attr_b) {
-      CDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
-      attr_b = true;
-    }
-    const int groups_per_cta = (q.n_groups + num_sms() - 1) / num_sms();
-    const int grid_b = many_n ? (q.n_groups + groups_per_cta - 1) / groups_per_cta : (num_sms() / q.n_groups) * q.n_groups;
-    gemm_bres_kernel<<<grid_b, kBresThreads, smem_b, reinterpret_cast<cudaStream_t>(stream)>>>(mA0, mA1, mB, q);
-    CDM_CHECK_LAUNCH();
+    const int groups_per_cta = (q.n_groups + sms - 1) / sms;
+    G->grid = many_n ? (q.n_groups + groups_per_cta - 1) / groups_per_cta : (sms / q.n_groups) * q.n_groups;
+    G->variant = 1;
     return CDM_OK;
   }
-  GemmKParams p;
-  memset(&p, 0, sizeof(p));
+  GemmKParams& p = G->p;
   p.M = a->M;
   p.N = a->N;
   p.chunks0 = a->k0 / 64;
@@ -335,13 +367,13 @@ extern "C" int cdm_gemm(const cdm_gemm_args* a, void* stream) {
   p.out_mode = a->out_mode;
   p.H = a->H;
   p.W = a->W;
-  for (int v = a->H; v > 1; v >>= 1) ++p.h_shift;
-  for (int v = a->W; v > 1; v >>= 1) ++p.w_shift;
+  p.h_shift = h_shift;
+  p.w_shift = w_shift;
   p.out = reinterpret_cast<bf16*>(a->out);
   p.k_split = 1;
   // few output tiles but a long K (the up0 data gradient: 2 tiles, K = 65536): split K over the idle SMs
-  if (a->workspace && a->out_mode == 0 && p.n_units * 4 <= num_sms() && p.chunks >= 64) {
-    int ks = num_sms() / p.n_units;
+  if (a->workspace && a->out_mode == 0 && p.n_units * 4 <= sms && p.chunks >= 64) {
+    int ks = sms / p.n_units;
     if (ks > p.chunks / 8) ks = p.chunks / 8;
     const long long need = (long long)ks * p.m_tiles * 128 * a->N;
     if (ks > 1 && a->workspace_floats >= need) {
@@ -350,22 +382,49 @@ extern "C" int cdm_gemm(const cdm_gemm_args* a, void* stream) {
       p.n_units *= ks;
     }
   }
-  constexpr int smem = gemm_smem_bytes();
-  static bool attr_set = false;
-  if (!attr_set) {
-    CDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+  G->grid = p.n_units < sms ? p.n_units : sms;
+  G->variant = 0;
+  G->M = a->M;
+  return CDM_OK;
+}
+
+int gemm_launch(const GemmLaunch& G, cudaStream_t st) {
+  int rc = CDM_OK;
+  if (G.variant == 1) {
+    constexpr int smem_b = gemm_bres_smem_bytes();
+    if ((rc = set_smem_attr(gemm_bres_kernel, 8, smem_b))) return rc;
+    gemm_bres_kernel<<<G.grid, kBresThreads, smem_b, st>>>(G.a0, G.a1, G.b, G.q);
+    CDM_CHECK_LAUNCH();
+    return CDM_OK;
   }
-  const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
-  gemm_kernel<<<grid, kConvThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(mA0, mA1, mB, p);
+  constexpr int smem = gemm_smem_bytes();
+  if ((rc = set_smem_attr(gemm_kernel, 9, smem))) return rc;
+  gemm_kernel<<<G.grid, kConvThreads, smem, st>>>(G.a0, G.a1, G.b, G.p);
   CDM_CHECK_LAUNCH();
-  if (p.partial) {
-    const long long quads = ((long long)a->M * a->N + 3) / 4;
-    gemm_splitk_reduce_kernel<<<(int)((quads + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        p.partial, p.k_split, a->M, p.m_tiles * 128, a->N, a->shift, a->shift_mod, p.out);
+  if (G.p.partial) {
+    const long long quads = ((long long)G.M * G.p.N + 3) / 4;
+    gemm_splitk_reduce_kernel<<<(int)((quads + 255) / 256), 256, 0, st>>>(G.p.partial, G.p.k_split, G.M,
+                                                                          G.p.m_tiles * 128, G.p.N, G.p.shift,
+                                                                          G.p.shift_mod, G.p.out);
     CDM_CHECK_LAUNCH();
   }
   return CDM_OK;
+}
+
+}  // namespace cdm
+
+extern "C" int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream) {
+  ConvLaunch L;
+  int rc = conv_prepare(a, &L);
+  if (rc) return rc;
+  return conv_launch(L, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int cdm_gemm(const cdm_gemm_args* a, void* stream) {
+  GemmLaunch G;
+  int rc = gemm_prepare(a, &G);
+  if (rc) return rc;
+  return gemm_launch(G, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int cdm_gemm_tn(const cdm_gemm_tn_args* a, void* stream) {
@@ -422,11 +481,7 @@ extern "C" int cdm_gemm_tn(const cdm_gemm_tn_args* a, void* stream) {
       p.partial = a->workspace;
     }
     constexpr int smem9 = gemm_tn9_smem_bytes();
-    static bool attr9_set = false;
-    if (!attr9_set) {
-      CDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem9));
-      attr9_set = true;
-    }
+    if ((rc = set_smem_attr(gemm_tn9_kernel, 10, smem9))) return rc;
     const int grid9 = p.n_units < num_sms() ? p.n_units : num_sms();
     gemm_tn9_kernel<<<grid9, kConvThreads, smem9, reinterpret_cast<cudaStream_t>(stream)>>>(mA, mB, p);
     CDM_CHECK_LAUNCH();
@@ -487,11 +542,7 @@ extern "C" int cdm_gemm_tn(const cdm_gemm_tn_args* a, void* stream) {
   p.tap_stride = a->tap_stride;
   if (a->workspace && ks > 1 && a->workspace_floats >= (long long)p.n_units * 128 * 128) p.partial = a->workspace;
   constexpr int smem = gemm_tn_smem_bytes();
-  static bool attr_set = false;
-  if (!attr_set) {
-    CDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  if ((rc = set_smem_attr(gemm_tn_kernel, 11, smem))) return rc;
   const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
   gemm_tn_kernel<<<grid, kConvThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(mA, mB, p);
   CDM_CHECK_LAUNCH();
@@ -515,11 +566,7 @@ extern "C" int cdm_probe_tma_l2(const void* buf, int n_rows, int iters, void* st
   rc = make_tmap_bf16(&m, buf, 2, dims, str, box);
   if (rc) return rc;
   const int smem = 8 * 16384 + 256 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CDM_CHECK_CUDA(cudaFuncSetAttribute(probe_tma_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  if ((rc = set_smem_attr(probe_tma_l2_kernel, 12, smem))) return rc;
   probe_tma_l2_kernel<<<num_sms(), 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(m, n_rows, iters);
   CDM_CHECK_LAUNCH();
   return CDM_OK;

@@ -11,6 +11,7 @@ namespace cdm {
 
 void set_error(const char* fmt, ...);
 int check_device();  // CDM_OK or CDM_ERR_ARCH / CDM_ERR_CUDA
+int num_sms();       // multiprocessor count of the current device (cached per device)
 
 #define CDM_CHECK_ARG(cond)                                             \
   do {                                                                  \

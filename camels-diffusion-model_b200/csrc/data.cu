@@ -158,7 +158,7 @@ extern "C" int cdm_minmax(const float* x, long long n, float* workspace, int wor
   if (rc) return rc;
   long long want = (n / 4 + 255) / 256;
   int blocks = (workspace_floats - 1) / 2;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
   if (want < blocks) blocks = (int)(want < 1 ? 1 : want);
   // the last workspace float is the ticket counter: the caller zero-fills the workspace once
   minmax_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
@@ -174,7 +174,7 @@ extern "C" int cdm_preprocess_maps(const float* in, int n, int Hi, int Wi, const
   if (rc) return rc;
   const long long total = (long long)n * Ho * Wo;
   long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
   preprocess_maps_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, n, Hi, Wi, raw_minmax, Ho, Wo, out);
   CDM_CHECK_LAUNCH();
   return CDM_OK;

@@ -14,11 +14,19 @@
 //   warps 4..7     : epilogue (tcgen05.ld -> fp32 math -> bf16 -> smem transpose -> coalesced stores)
 #pragma once
 #include "../../include/cdm_b200.h"
+#include "kparams.h"
 #include "ptx.cuh"
 
 namespace cdm {
 
-typedef __nv_bfloat16 bf16;
+
+// Measurement probes (tools/gpu_probe.py) exist only in the -DCDM_PROBES build (libcdm_b200_probes.so); in the
+// production library the predicates are compile-time false and the public ABI rejects the probe flag bits.
+#ifdef CDM_PROBES
+#define CDM_PROBE_BIT(flags, bit) (((flags) >> (bit)) & 1)
+#else
+#define CDM_PROBE_BIT(flags, bit) false
+#endif
 
 // --------------------------------------------------------------------------
 // conv3x3: geometry
@@ -30,26 +38,8 @@ typedef __nv_bfloat16 bf16;
 //   CTA work unit = strip of 16x16 pixels = 2 patches (2 accumulators), one
 //   128-wide slice of Cout.
 // --------------------------------------------------------------------------
-struct ConvKParams {
-  int H, W, n_img;
-  int chunks0, chunks;  // 64-channel K chunks from src0 / in total
-  int n_tiles, cout;
-  int strips_x, strips_y;
-  int n_units;
-  int flags;
-  const float* scale;
-  const float* shift;
-  bf16* out;
-  const float* sc_x;
-  const float* sc_tab;
-  int sc_reps;
-  const float* film_scale;
-  const float* film_shift;
-  int film_shift_rows;
-  const int* step_ptr;
-  float* gn_partial;
-  float* bn_partial;  // CDM_EPI_BNSTATS: [gridDim.x][2][cout]
-};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
 template <int MODE>
 struct ConvCfg;
@@ -93,6 +83,7 @@ struct EpiCtx {
   // film
   const float* film_scale;
   const float* film_shift;
+  float res_scale;
 };
 
 __device__ __forceinline__ void epi_tile_to_staging(uint32_t taddr, uint32_t stg, int lane, const EpiCtx& e,
@@ -108,11 +99,16 @@ __device__ __forceinline__ void epi_tile_to_staging(uint32_t taddr, uint32_t stg
       const int c = cc * 32 + i;
       float y = fmaf(__uint_as_float(v[i]), e.s_scale[c], e.s_shift[c]);
       if (e.flags & CDM_EPI_RELU) y = fmaxf(y, 0.f);
+      if (e.flags & CDM_EPI_GELU) y = gelu_erf(y);
       f[i] = y;
     }
     if (e.flags & CDM_EPI_SHORTCUT) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] += fmaf(__ldg(e.sc_w + cc * 32 + i), e.xpix, __ldg(e.sc_b + cc * 32 + i));
+    }
+    if (e.flags & CDM_EPI_RESSCALE) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] *= e.res_scale;
     }
     if (e.flags & CDM_EPI_FILM) {
 #pragma unroll
@@ -309,6 +305,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       e.s_shift = s_shift + n_tile * 128;
       e.flags = p.flags;
       e.xpix = 0.f;
+      e.res_scale = p.res_scale;
       e.sc_w = e.sc_b = e.film_scale = e.film_shift = nullptr;
       if (p.flags & CDM_EPI_FILM) {
         e.film_scale = p.film_scale + (size_t)img * p.cout + n_tile * 128;
@@ -427,21 +424,30 @@ constexpr int kSwEpiWarps = 8, kSwThreads = 128 + 32 * kSwEpiWarps;
 // The shape itself is at the shared-memory limit: operand reads 12 KB / 128 clk = 96 B/clk plus TMA fills
 // (16 KB weights / 512 clk + 43.5 KB halo / 4608 clk = 41 B/clk) against 128 B/clk per SM.
 constexpr int kSwNB = 4;
-template <int ROWS>
-constexpr int conv_sw_smem_bytes() { return kSwNA * SwCfg<ROWS>::kAStride + kSwNB * kBBytes + 2 * 256 * 4 + 256 + 1024; }
+// TMAST (TMA-store epilogue): the NHWC output leaves through shared memory + cp.async.bulk.tensor stores.  A store box
+// is {64 ch, 8 px, 4 rows} = 32 rows of 128 B (one 32-pixel accumulator chunk of one channel half), written by the
+// two epilogue warps that own those 64 channels; 4 warp pairs x 2 buffers x 4 KB of staging replace the scale/shift
+// staging area (the per-thread coefficients come straight from global memory instead).
+constexpr int kSwStoreBox = 32 * 128, kSwStageBytes = 4 * 2 * kSwStoreBox;
+template <int ROWS, bool TMAST = false>
+constexpr int conv_sw_smem_bytes() {
+  return kSwNA * SwCfg<ROWS>::kAStride + kSwNB * kBBytes + (TMAST ? kSwStageBytes : 2 * 256 * 4) + 256 + 1024;
+}
 
-template <int ROWS>
+template <int ROWS, bool TMAST = false>
 __global__ void __launch_bounds__(kSwThreads, 1)
 conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                  const __grid_constant__ CUtensorMap mapB, const ConvKParams p) {
+                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
+                  const ConvKParams p) {
   constexpr int kSwABytes = SwCfg<ROWS>::kABytes, kSwAStride = SwCfg<ROWS>::kAStride, kNPix = SwCfg<ROWS>::kNPix;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smemA = smem;  // pixel halo tiles
   uint8_t* smemB = smemA + kSwNA * kSwAStride;  // weight tiles
-  float* s_scale = reinterpret_cast<float*>(smemB + kSwNB * kBBytes);
+  uint8_t* smemStage = smemB + kSwNB * kBBytes;  // TMAST: store staging (1024-byte aligned); else scale / shift
+  float* s_scale = reinterpret_cast<float*>(smemStage);
   float* s_shift = s_scale + 256;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemStage + (TMAST ? kSwStageBytes : 2 * 256 * 4));
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kSwNA;
   uint64_t* b_full = a_empty + kSwNA;
@@ -450,9 +456,11 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < p.cout; i += blockDim.x) {
-    s_scale[i] = p.scale[i];
-    s_shift[i] = p.shift[i];
+  if constexpr (!TMAST) {
+    for (int i = threadIdx.x; i < p.cout; i += blockDim.x) {
+      s_scale[i] = p.scale[i];
+      s_shift[i] = p.shift[i];
+    }
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < kSwNA; ++i) {
@@ -511,7 +519,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       for (int ch = 0; ch < p.chunks; ++ch)
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(&b_empty[sb], pb ^ 1);
-          if ((p.flags & (1 << 27)) && (tap & 1)) {  // probe: half the weight traffic (stale tiles, wrong numbers)
+          if (CDM_PROBE_BIT(p.flags, 27) && (tap & 1)) {  // probe: half the weight traffic (stale tiles, wrong numbers)
             mbar_arrive(&b_full[sb]);
           } else {
             mbar_arrive_expect_tx(&b_full[sb], kBBytes);
@@ -528,7 +536,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     int sa = 0, sb = 0, it = 0;
     uint32_t pa = 0, pb = 0;
     // probe (flag bit 28): cycles the issuer spends blocked on each barrier class -> gn_partial[cta][0..3]
-    const bool prof = p.flags & (1 << 28);
+    const bool prof = CDM_PROBE_BIT(p.flags, 28);
     long long w_t = 0, w_a = 0, w_b = 0, c0 = 0;
     const long long c_start = prof ? clock64() : 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
@@ -586,6 +594,37 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const int step = p.step_ptr ? *p.step_ptr : 0;
     const bool pool = p.flags & CDM_EPI_POOL;
     float bn_s0 = 0.f, bn_q0 = 0.f, bn_s1 = 0.f, bn_q1 = 0.f;  // CDM_EPI_BNSTATS, per n_tile (cout <= 256)
+    // TMAST: this warp pair (64 channels of one column half) owns two 4 KB staging boxes; lane 0 of its first warp
+    // issues the stores and tracks their bulk groups
+    const int ph = q >> 1, pair = half * 2 + ph;
+    const bool st_elect = TMAST && (q & 1) == 0 && lane == 0;
+    const uint32_t stg_pair = smem_u32(smemStage) + (uint32_t)(pair * 2 * kSwStoreBox);
+    int sidx = 0;  // stores issued so far by this pair (buffer = sidx & 1)
+    // One 32-pixel chunk (f[i]: pixel row i >> 3, column i & 7 of this thread's channel) -> staging box -> TMA store.
+    // Lanes 2k / 2k+1 own channels c, c+1: one shuffle hands the even lane both channels of pixel ia and the odd lane
+    // both channels of pixel ia + 4; the 128-byte-swizzle chunk index of a row is XORed with (row & 7), so rows that
+    // differ in bit 2 land in different bank halves and every st.shared is one conflict-free 128-byte wavefront.
+    auto stage_store = [&](const float (&f)[32], int c_crd, int w_crd, int h_crd, int n_crd) {
+      const int odd = lane & 1;
+      const uint32_t base = stg_pair + (uint32_t)((sidx & 1) * kSwStoreBox) + (uint32_t)(odd * 4 * 128 + (lane & 6) * 2);
+      const uint32_t jsw = (uint32_t)((q & 1) * 4 + (lane >> 3)) ^ (uint32_t)(odd * 4);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int ia = (k >> 2) * 8 + (k & 3), ib = ia + 4;
+        const float recv = __shfl_xor_sync(0xffffffffu, odd ? f[ia] : f[ib], 1);
+        const uint32_t w = odd ? pack_bf16x2(recv, f[ib]) : pack_bf16x2(f[ia], recv);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)(ia * 128) + ((jsw ^ (uint32_t)(k & 3)) << 4)), "r"(w)
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      if (st_elect) tma_store_wait_read<0>();  // the OTHER buffer's store (one chunk ago) has left shared memory
+      named_bar_sync(2 + pair, 64);
+      if (st_elect) {
+        tma_store_4d(&mapOut, stg_pair + (uint32_t)((sidx & 1) * kSwStoreBox), c_crd, w_crd, h_crd, n_crd);
+        tma_store_commit();
+      }
+      ++sidx;
+    };
     int it = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -595,12 +634,12 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       const int sx = s % px_tiles, sy = s / px_tiles;
       const int oh0 = sy * ROWS, ow0 = sx * 8;
       const int co = n_tile * 128 + co_l;
-      const bool prof = p.flags & (1 << 28);
+      const bool prof = CDM_PROBE_BIT(p.flags, 28);
       const long long e0 = prof ? clock64() : 0;
       mbar_wait(&t_full[buf], (it >> 1) & 1);
       const long long e1 = prof ? clock64() : 0;
       tc_fence_after();
-      const float sc = s_scale[co], sh = s_shift[co];
+      const float sc = TMAST ? __ldg(p.scale + co) : s_scale[co], sh = TMAST ? __ldg(p.shift + co) : s_shift[co];
       float fsv = 1.f, fbv = 0.f;
       if (p.flags & CDM_EPI_FILM) {
         fsv = __ldg(p.film_scale + (size_t)img * p.cout + co);
@@ -636,6 +675,13 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 #pragma unroll
           for (int rep = 0; rep < 2; ++rep) {
             const float wc = rep ? w1 : w0, bc = rep ? b1 : b0;
+            if constexpr (TMAST) {
+              float f2[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f2[i] = base[i] + fmaf(wc, xs[i], bc);
+              stage_store(f2, n_tile * 128 + ph * 64, ow0, oh0 + 4 * c8, rep * p.n_img + img);
+              continue;
+            }
             bf16* gbase = p.out + (((size_t)(rep * p.n_img + img) * p.H + oh0 + 4 * c8) * p.W + ow0) * p.cout +
                           n_tile * 128 + (co_l & ~1);
 #pragma unroll
@@ -661,7 +707,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         float gs = 0.f, gq = 0.f;
 #pragma unroll 1
         for (int c8 = half * SwCfg<ROWS>::kChunksPerHalf; c8 < (half + 1) * SwCfg<ROWS>::kChunksPerHalf; ++c8) {  // 32 pixels: patch rows 4*c8 .. 4*c8+3, 8 px each
-          if (p.flags & (1 << 29)) continue;  // probe: no epilogue work at all
+          if (CDM_PROBE_BIT(p.flags, 29)) continue;  // probe: no epilogue work at all
           uint32_t v[32];
           tmem_ld_x32(taddr + c8 * 32, v);
           tmem_wait_ld();
@@ -672,10 +718,18 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             if (p.flags & CDM_EPI_RELU) y = fmaxf(y, 0.f);
             f[i] = y;
           }
+          if (p.flags & CDM_EPI_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+          }
           if (p.flags & CDM_EPI_SHORTCUT) {
             const float* xr = p.sc_x + ((size_t)img * p.H + oh0 + 4 * c8) * p.W + ow0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] += fmaf(wcv, __ldg(xr + (i >> 3) * p.W + (i & 7)), bcv);
+          }
+          if (p.flags & CDM_EPI_RESSCALE) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] *= p.res_scale;
           }
           if (p.flags & CDM_EPI_FILM) {
 #pragma unroll
@@ -708,18 +762,20 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           // pair gives the even lane both channels of pixel i and the odd lane both channels of pixel i+1, so a
           // warp instruction writes 2 x 64 contiguous bytes (full sectors) as 32-bit bf16x2 words.
           const int odd = lane & 1;
-          if (p.flags & (1 << 30)) {  // probe: everything but the global stores
+          if (CDM_PROBE_BIT(p.flags, 30)) {  // probe: everything but the global stores
             float acc = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc += f[i];
             if (acc == 123.456f) p.out[0] = __float2bfloat16(acc);
             continue;
           }
-          if (!pool) {
+          if (TMAST && !pool) {
+            stage_store(f, n_tile * 128 + ph * 64, ow0, oh0 + 4 * c8, oimg);
+          } else if (!pool) {
             bf16* gbase = p.out + (((size_t)oimg * p.H + oh0 + 4 * c8) * p.W + ow0) * p.cout + n_tile * 128 +
                           (co_l & ~1);
             int wrow = p.W;
-            if (p.flags & (1 << 26)) {  // probe: same stores, but into a per-CTA 64 KB window that stays in L2
+            if (CDM_PROBE_BIT(p.flags, 26)) {  // probe: same stores, but into a per-CTA 64 KB window that stays in L2
               gbase = p.out + (size_t)blockIdx.x * 32768 + (size_t)(4 * c8) * 8 * p.cout + (co_l & ~1);
               wrow = 8;
             }
@@ -777,6 +833,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         d[5] = (it == 0 ? 0.f : d[5]) + (float)(clock64() - e1);
       }
     }
+    if (st_elect) tma_store_wait_read<0>();  // the staging boxes are read before the CTA (and its shared memory) goes
     if (p.flags & CDM_EPI_BNSTATS) {
       // the two column halves of a channel live in warps q and q+4: fold them through shared memory (the
       // scale/shift staging area is free once the unit loop is over), then one partial row per CTA
@@ -808,17 +865,6 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 // --------------------------------------------------------------------------
 // gemm: C[M][N] = A[M][K] * Bw[N][K]^T, work unit = one 128x128 output tile.
 // --------------------------------------------------------------------------
-struct GemmKParams {
-  int M, N;
-  int chunks0, chunks;
-  int m_tiles, n_tiles, n_units;
-  const float* shift;
-  int shift_mod;
-  int out_mode, H, W, h_shift, w_shift;
-  bf16* out;
-  int k_split;     // > 1: unit = (K slice, m_tile, n_tile); each slice stores its fp32 tile to `partial`
-  float* partial;  // [k_split][m_tiles*128][N]; gemm_splitk_reduce_kernel adds the slices in order (+ shift -> bf16)
-};
 constexpr int kGemmStages = 5;
 constexpr int kGemmStageBytes = 2 * 16384;
 constexpr int gemm_smem_bytes() { return kGemmStages * kGemmStageBytes + kStageBytes + 256 + 1024; }
@@ -1028,15 +1074,6 @@ __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const float* __
 // MMA that reads them has completed (w_free), the A rows (1 MB, L2-resident) are streamed again per group, and
 // L2->smem traffic per 128x256 output tile falls from 192 KB (gemm_kernel: A and B per tile) to 64 KB + 8 KB.
 // --------------------------------------------------------------------------
-struct GemmBresKParams {
-  int M, N;
-  int chunks0, chunks;
-  int m_tiles, n_res, n_groups;
-  const float* shift;
-  int shift_mod;
-  int out_mode, H, W, h_shift, w_shift;
-  bf16* out;
-};
 constexpr int kBresStages = 4;
 constexpr int kBresStageTile = 32 * 128;  // per epilogue warp: 32 rows x 128 B of bf16 output, 16-byte chunks XOR-swizzled
 constexpr int gemm_bres_smem_bytes() {

@@ -557,8 +557,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   }
   return c;
 }
-__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, uint32_t idx, uint32_t stream) {
-  const uint4 r = philox4x32_10(make_uint4(idx, stream, 0x1234567u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+// idx = GLOBAL index of the 4-element vector (sample_offset * hw / 4 + local index): the draw of a sample does not
+// depend on which rank holds it or where it sits in the rank's shard
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long idx, uint32_t stream) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, stream, 0x1234567u, (uint32_t)(idx >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   const float k = 5.9604644775390625e-8f;  // 2^-24
   const float u0 = ((r.x >> 8) + 0.5f) * k, u1 = ((r.y >> 8) + 0.5f) * k;
   const float u2 = ((r.z >> 8) + 0.5f) * k, u3 = ((r.w >> 8) + 0.5f) * k;
@@ -586,6 +589,7 @@ struct DdpmKParams {
   unsigned long long seed;
   float* snap;
   const int* snap_slot;
+  unsigned long long vec_offset;  // sample_offset * hw / 4
 };
 __global__ void __launch_bounds__(256) ddpm_step_kernel(const DdpmKParams p) {
   const int i = p.step_ptr ? *p.step_ptr : p.step;
@@ -605,7 +609,7 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(const DdpmKParams p) {
       e4.w = __fadd_rn(u4.w, __fmul_rn(p.guide_w, __fsub_rn(e4.w, u4.w)));
     }
     float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i > 1) z4 = zbase ? reinterpret_cast<const float4*>(zbase)[v] : philox_normal4(p.seed, (uint32_t)v, (uint32_t)i);
+    if (i > 1) z4 = zbase ? reinterpret_cast<const float4*>(zbase)[v] : philox_normal4(p.seed, p.vec_offset + v, (uint32_t)i);
     x4.x = __fadd_rn(__fdiv_rn(__fsub_rn(x4.x, __fmul_rn(e4.x, k2)), sa), __fmul_rn(sb, z4.x));
     x4.y = __fadd_rn(__fdiv_rn(__fsub_rn(x4.y, __fmul_rn(e4.y, k2)), sa), __fmul_rn(sb, z4.y));
     x4.z = __fadd_rn(__fdiv_rn(__fsub_rn(x4.z, __fmul_rn(e4.z, k2)), sa), __fmul_rn(sb, z4.z));
@@ -624,7 +628,8 @@ __global__ void __launch_bounds__(256) perturb_kernel(const float* __restrict__ 
                                                       const float* __restrict__ ca, const float* __restrict__ cb,
                                                       const long long* __restrict__ t_idx, int t_shared,
                                                       const int* __restrict__ step_ptr, unsigned long long seed,
-                                                      uint32_t stream, float* __restrict__ noise_out) {
+                                                      uint32_t stream, float* __restrict__ noise_out,
+                                                      unsigned long long vec_offset) {
   const int hw4 = hw / 4;
   if (step_ptr) {
     t_shared = *step_ptr;
@@ -640,7 +645,7 @@ __global__ void __launch_bounds__(256) perturb_kernel(const float* __restrict__ 
     if (noise) {
       n4 = reinterpret_cast<const float4*>(noise)[v];
     } else {
-      n4 = philox_normal4(seed, (uint32_t)v, stream);
+      n4 = philox_normal4(seed, vec_offset + v, stream);
       reinterpret_cast<float4*>(noise_out)[v] = n4;
     }
     float4 o;
@@ -659,7 +664,9 @@ __global__ void __launch_bounds__(256) mse_accum_kernel(const float* __restrict_
                                                         const float* __restrict__ weight_tab,
                                                         const long long* __restrict__ t_idx, int t_shared,
                                                         const int* __restrict__ step_ptr,
-                                                        float* __restrict__ mse_out, float* __restrict__ acc) {
+                                                        float* __restrict__ mse_out, float* __restrict__ acc,
+                                                        const float* __restrict__ weight_tab2,
+                                                        float* __restrict__ acc2) {
   __shared__ float red[32];
   if (step_ptr) t_shared = *step_ptr;
   const size_t s = blockIdx.x;
@@ -679,12 +686,16 @@ __global__ void __launch_bounds__(256) mse_accum_kernel(const float* __restrict_
       const int t = t_idx ? (int)t_idx[s] : t_shared;
       acc[s] += (weight_tab ? weight_tab[t] : 1.f) * mse;
     }
+    if (acc2) {  // second accumulator of the same sweep (NLL and ELBO weights over one set of forwards)
+      const int t = t_idx ? (int)t_idx[s] : t_shared;
+      acc2[s] += (weight_tab2 ? weight_tab2[t] : 1.f) * mse;
+    }
   }
 }
 
 static int grid_for(size_t work_items, int block) {
   size_t g = (work_items + block - 1) / block;
-  const size_t cap = 148 * 16;
+  const size_t cap = num_sms() * 16;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -699,7 +710,7 @@ extern "C" int cdm_conv_in(const cdm_conv_in_args* a, void* stream) {
   int rc = check_device();
   if (rc) return rc;
   const int tiles = a->n_img * (a->H / kCiRows);
-  const dim3 grid(tiles < 148 * 2 ? tiles : 148 * 2, a->cout / 128);
+  const dim3 grid(tiles < num_sms() * 2 ? tiles : num_sms() * 2, a->cout / 128);
   if (a->relu)
     conv_in_mma_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(a->x, a->n_img, a->H, a->W, a->cout, a->weight,
                                                                      a->scale, a->shift, (bf16*)a->out);
@@ -730,7 +741,7 @@ extern "C" int cdm_conv_out(const cdm_conv_out_args* a, void* stream) {
   int rc = check_device();
   if (rc) return rc;
   // 32-row tiles (6 % halo re-read) once they fill the machine twice over, 8-row tiles for small batches
-  if (a->H % 32 == 0 && a->n_img * (a->H / 32) >= 2 * 148) return launch_conv_out<32>(a, (cudaStream_t)stream);
+  if (a->H % 32 == 0 && a->n_img * (a->H / 32) >= 2 * num_sms()) return launch_conv_out<32>(a, (cudaStream_t)stream);
   return launch_conv_out<8>(a, (cudaStream_t)stream);
 }
 
@@ -807,6 +818,8 @@ extern "C" int cdm_ddpm_step(const cdm_ddpm_step_args* a, void* stream) {
   p.seed = a->seed;
   p.snap = a->snap;
   p.snap_slot = a->snap_slot;
+  CDM_CHECK_ARG(a->sample_offset >= 0);
+  p.vec_offset = (unsigned long long)a->sample_offset * (unsigned long long)(a->hw / 4);
   ddpm_step_kernel<<<grid_for((size_t)a->n * a->hw / 4, 256), 256, 0, (cudaStream_t)stream>>>(p);
   CDM_CHECK_LAUNCH();
   return CDM_OK;
@@ -824,11 +837,12 @@ extern "C" int cdm_step_advance(int* step_ptr, int delta, void* stream) {
 extern "C" int cdm_perturb(const cdm_perturb_args* a, void* stream) {
   CDM_CHECK_ARG(a && a->x && a->out && a->ca && a->cb && a->n > 0 && a->hw > 0 && a->hw % 4 == 0);
   CDM_CHECK_ARG(a->noise || a->noise_out);
+  CDM_CHECK_ARG(a->sample_offset >= 0);
   int rc = check_device();
   if (rc) return rc;
   perturb_kernel<<<grid_for((size_t)a->n * a->hw / 4, 256), 256, 0, (cudaStream_t)stream>>>(
       a->x, a->noise, a->out, a->n, a->hw, a->ca, a->cb, a->t_idx, a->t_shared, a->step_ptr, a->seed, a->stream_id,
-      a->noise_out);
+      a->noise_out, (unsigned long long)a->sample_offset * (unsigned long long)(a->hw / 4));
   CDM_CHECK_LAUNCH();
   return CDM_OK;
 }
@@ -838,7 +852,8 @@ extern "C" int cdm_mse_accum(const cdm_mse_accum_args* a, void* stream) {
   int rc = check_device();
   if (rc) return rc;
   mse_accum_kernel<<<a->n, 256, 0, (cudaStream_t)stream>>>(a->pred, a->target, a->hw, a->weight_tab, a->t_idx,
-                                                           a->t_shared, a->step_ptr, a->mse_out, a->acc);
+                                                           a->t_shared, a->step_ptr, a->mse_out, a->acc,
+                                                           a->weight_tab2, a->acc2);
   CDM_CHECK_LAUNCH();
   return CDM_OK;
 }

@@ -7,6 +7,8 @@
 // fixed order (deterministic); nothing here uses atomics on global memory.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -213,7 +215,13 @@ struct XrankP {
   const unsigned long long* peer_flags;  // [world] device pointers: int32 [world] on each rank
   int* seq;
   unsigned int* ticket;
+  unsigned long long timeout_ns;
 };
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -266,11 +274,21 @@ __global__ void __launch_bounds__(1024) xrank_sum_kernel(const XrankP p) {
     __threadfence_system();
     st_release_sys(reinterpret_cast<int*>(p.peer_flags[threadIdx.x]) + p.rank, s);
     const int* mine = reinterpret_cast<const int*>(p.peer_flags[p.rank]) + threadIdx.x;
+    // A peer may legitimately be late by a long time (rank 0 writing a checkpoint, a slow dataloader, lazy graph
+    // capture): the bound is wall-clock time (cdm_xrank_set_timeout, default 600 s), where an NCCL all-reduce would
+    // simply wait; it only exists so that a dead peer surfaces as a CUDA error instead of a silent hang.
     unsigned int spins = 0;
+    unsigned long long t_start = 0;
     while (ld_acquire_sys(mine) - s < 0) {
-      if (++spins > (1u << 26)) {
-        printf("cdm: cross-rank exchange timed out (rank %d waiting for rank %d, seq %d)\n", p.rank, (int)threadIdx.x, s);
-        __trap();
+      if ((++spins & 0xFFFu) == 0) {
+        const unsigned long long now = global_timer_ns();
+        if (t_start == 0) t_start = now;
+        if (now - t_start > p.timeout_ns) {
+          printf("cdm: cross-rank exchange timed out after %llu s (rank %d waiting for rank %d, seq %d)\n",
+                 p.timeout_ns / 1000000000ull, p.rank, (int)threadIdx.x, s);
+          __trap();
+        }
+        __nanosleep(200);  // back off: the spinning warp shares its SM with nothing useful, but spare the fabric
       }
     }
   }
@@ -286,8 +304,17 @@ __global__ void __launch_bounds__(1024) xrank_sum_kernel(const XrankP p) {
     *p.ticket = 0;
   }
 }
+static unsigned long long g_xrank_timeout_ns = 0;
+static unsigned long long xrank_timeout_ns() {
+  if (g_xrank_timeout_ns == 0) {
+    const char* e = getenv("CDM_XRANK_TIMEOUT_S");
+    const double s = e ? atof(e) : 600.0;
+    g_xrank_timeout_ns = (unsigned long long)((s > 0.001 ? s : 600.0) * 1e9);
+  }
+  return g_xrank_timeout_ns;
+}
 int launch_xrank_sum(const float* partial, int n_blocks, int n, float* out, const cdm_xrank* xr, cudaStream_t st) {
-  XrankP p{partial, n_blocks, n, out, 0, 1, nullptr, nullptr, nullptr, nullptr};
+  XrankP p{partial, n_blocks, n, out, 0, 1, nullptr, nullptr, nullptr, nullptr, xrank_timeout_ns()};
   if (xr && xr->world > 1) {
     p.rank = xr->rank;
     p.world = xr->world;
@@ -1038,7 +1065,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTensor* __restrict_
   }
 }
 
-static int grid1d(long long work, int block = 256, int cap = 148 * 8) {
+static int grid1d(long long work, int block = 256, int cap = num_sms() * 8) {
   long long g = (work + block - 1) / block;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
@@ -1057,7 +1084,7 @@ extern "C" int cdm_chan_reduce(const cdm_chan_reduce_args* a, void* stream) {
   if (rc) return rc;
   const int rows = 256 / (a->C / 8);
   int blocks = (int)((a->P + rows * 8 - 1) / (rows * 8));
-  if (blocks > 148 * 4) blocks = 148 * 4;  // the fixed-order final pass walks the partials serially: keep them few
+  if (blocks > num_sms() * 4) blocks = num_sms() * 4;  // the fixed-order final pass walks the partials serially: keep them few
   if (blocks > a->workspace_blocks) blocks = a->workspace_blocks;
   if (blocks < 1) blocks = 1;
   ChanReduceP p{(const bf16*)a->a, a->lda, (const bf16*)a->z, a->ldz, a->scale, a->shift, a->mean, a->rstd,
@@ -1075,9 +1102,15 @@ extern "C" int cdm_pack_bf16(const void* table, int n_rows, long long total_vec,
   int rc = check_device();
   if (rc) return rc;
   long long blocks = (total_vec + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks > num_sms() * 32) blocks = num_sms() * 32;
   pack_bf16_kernel<<<(int)blocks, 256, 0, ST(stream)>>>(reinterpret_cast<const PackRow*>(table), n_rows, total_vec);
   CDM_CHECK_LAUNCH();
+  return CDM_OK;
+}
+
+extern "C" int cdm_xrank_set_timeout(double seconds) {
+  CDM_CHECK_ARG(seconds > 0.001 && seconds < 1e7);
+  g_xrank_timeout_ns = (unsigned long long)(seconds * 1e9);
   return CDM_OK;
 }
 
@@ -1226,7 +1259,7 @@ extern "C" int cdm_outer_wgrad(const cdm_outer_wgrad_args* a, void* stream) {
   int rc = check_device();
   if (rc) return rc;
   int blocks = a->n_img * a->H;  // one image row per block iteration
-  if (blocks > 148 * 2) blocks = 148 * 2;
+  if (blocks > num_sms() * 2) blocks = num_sms() * 2;
   if (blocks > a->workspace_blocks) blocks = a->workspace_blocks;
   if (blocks < 1) blocks = 1;
   OuterWgradP p{a->s, (const bf16*)a->v, a->n_img, a->H, a->W, a->C, a->flip, a->mean_rstd, a->gamma, a->beta,

@@ -19,7 +19,7 @@ def preprocess_maps(camels_data, size=64, device=None):
     raw = torch.as_tensor(camels_data).to(dev, torch.float32).contiguous()
     if raw.dim() != 3:
         raise L.CdmError("preprocess_maps: expected [N,H,W] maps")
-    ws = torch.zeros(2 * 148 * 8 + 1, device=dev)
+    ws = torch.zeros(2 * L.num_sms() * 8 + 1, device=dev)
     mm = torch.empty(2, device=dev)
     L.minmax(raw, ws, mm)
     out = torch.empty(raw.shape[0], size, size, device=dev)

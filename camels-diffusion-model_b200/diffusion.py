@@ -106,7 +106,7 @@ class _SamplerRun:
     """Device state of one sampling run + the captured one-step CUDA graph."""
 
     def __init__(self, model, x_T, params, guide_w, timesteps, sched, *, z_all=None, shortcut_tab=None,
-                 save_rate=20, seed=None, use_graph=True, snapshots=True):
+                 save_rate=20, seed=None, use_graph=True, snapshots=True, sample_offset=0):
         dev = model._check_supported()
         if model.training:
             raise L.CdmError("sampling needs eval mode (BatchNorm running statistics): call model.eval()")
@@ -144,16 +144,20 @@ class _SamplerRun:
         else:
             self.z, self.z_stride = None, 0
         self.seed = int(seed) if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        # in-kernel noise is keyed by the GLOBAL sample index: a shard [offset, offset + B) of a larger batch draws
+        # exactly what the unsharded run draws for those samples, and two ranks never share noise
+        self.sample_offset = int(sample_offset)
         self.graph = None
         self.use_graph = use_graph
 
     def _one_step(self):
+        """One reverse-diffusion step = ONE C call (cdm_sample_step: the 26 launches of the reps*B-image forward,
+        the CFG mix + x_{t-1} update, the step counter)."""
         m = self.model
-        eps = m.forward_eval_into(self.x.view(self.B, m.h, m.h), self.sc_tab, self.cemb1, self.temb1, self.cemb2,
-                                  self.temb2, 1, reps=self.reps, step_ptr=self.step)
-        L.ddpm_step(self.x, eps, self.coef, self.T, reps=self.reps, guide_w=self.guide_w, step_ptr=self.step,
-                    z=self.z, z_iter_stride=self.z_stride, seed=self.seed, snap=self.snap, snap_slot=self.snap_slot)
-        L.step_advance(self.step, -1)
+        pl = m.plan(self.B, self.reps)[0]
+        pl.sample_step(self.x, self.sc_tab, self.cemb1, self.temb1, self.cemb2, self.temb2, self.step, self.coef,
+                       self.T, guide_w=self.guide_w, z=self.z, z_iter_stride=self.z_stride, seed=self.seed,
+                       sample_offset=self.sample_offset, snap=self.snap, snap_slot=self.snap_slot)
 
     def capture(self):
         """Warm up once on scratch state (sets kernel attributes, fills caches), then capture one step."""
@@ -330,7 +334,8 @@ class SamplerSession:
 class _EvalLoop:
     """perturb -> U-Net -> per-sample MSE accumulate for one (x, param) batch at a device-resident step t."""
 
-    def __init__(self, model, x, param, timesteps, sched, cb_kind, weight_tab, *, shortcut_tab=None, seed=0):
+    def __init__(self, model, x, param, timesteps, sched, cb_kind, weight_tab, *, shortcut_tab=None, seed=0,
+                 weight_tab2=None, sample_offset=0):
         dev = model._check_supported()
         if model.training:
             raise L.CdmError("likelihood / ELBO evaluation needs eval mode: call model.eval()")
@@ -355,7 +360,11 @@ class _EvalLoop:
         self.noise = torch.empty_like(self.x)
         self.acc = torch.zeros(self.B, device=dev)
         self.mse = torch.zeros(self.B, device=dev)
+        # optional second weighted sum over the SAME forwards (BASELINE config 5: NLL and ELBO weights in one sweep)
+        self.weight2 = None if weight_tab2 is None else weight_tab2.to(dev, torch.float32).contiguous()
+        self.acc2 = None if weight_tab2 is None else torch.zeros(self.B, device=dev)
         self.seed = seed
+        self.sample_offset = int(sample_offset)  # global index of x[0]: in-kernel noise is keyed by the global sample
         self.graph = None
 
     def one(self, noise=None):
@@ -364,10 +373,12 @@ class _EvalLoop:
             self.noise.copy_(noise.reshape(self.noise.shape))
             L.perturb(self.x, self.xt, self.ca, self.cb, noise=self.noise, step_ptr=self.step)
         else:
-            L.perturb(self.x, self.xt, self.ca, self.cb, step_ptr=self.step, seed=self.seed, noise_out=self.noise)
+            L.perturb(self.x, self.xt, self.ca, self.cb, step_ptr=self.step, seed=self.seed, noise_out=self.noise,
+                      sample_offset=self.sample_offset)
         eps = m.forward_eval_into(self.xt.view(self.B, m.h, m.h), self.sc_tab, self.cemb1, self.temb1, self.cemb2,
                                   self.temb2, 1, reps=1, step_ptr=self.step)
-        L.mse_accum(eps, self.noise, weight_tab=self.weight, step_ptr=self.step, mse_out=self.mse, acc=self.acc)
+        L.mse_accum(eps, self.noise, weight_tab=self.weight, step_ptr=self.step, mse_out=self.mse, acc=self.acc,
+                    weight_tab2=self.weight2, acc2=self.acc2)
 
     def sweep_all(self):
         """t = 1..T with in-kernel noise, one captured graph replayed T times."""
@@ -375,11 +386,15 @@ class _EvalLoop:
         self.one()
         torch.cuda.synchronize()
         self.acc.zero_()
+        if self.acc2 is not None:
+            self.acc2.zero_()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self.one()
             L.step_advance(self.step, 1)
         self.acc.zero_()
+        if self.acc2 is not None:
+            self.acc2.zero_()
         self.step.fill_(1)
         for _ in range(self.T):
             g.replay()

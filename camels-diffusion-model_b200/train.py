@@ -223,8 +223,8 @@ class _UnetFn(torch.autograd.Function):
         S.dev, S.mode, S.layers, S.n = dev, m.conv_mode, {}, n
         S.ones = torch.ones(256, device=dev)
         S.zeros = torch.zeros(65536, device=dev)
-        S.ws = _f32(148 * 8, 9 * 256, dev=dev)  # reduction workspace (partials)
-        S.bnp = _f32(148, 2 * 256, dev=dev)  # per-CTA BatchNorm partial sums of the conv epilogue
+        S.ws = _f32(L.num_sms() * 8, 9 * 256, dev=dev)  # reduction workspace (partials)
+        S.bnp = _f32(L.num_sms(), 2 * 256, dev=dev)  # per-CTA BatchNorm partial sums of the conv epilogue
         S.wgws = _f32(160 * 128 * 384, dev=dev)  # split-K tiles of the 3x3 weight gradients (used on the SIDE stream only)
         S.skws = _f32(160 * 128 * 384, dev=dev)  # split-K tiles of the main-stream GEMMs (transposed convs, up0)
         P = _pack_train(m)
@@ -313,7 +313,7 @@ class _UnetFn(torch.autograd.Function):
 
         # The 3x3 weight gradients are leaves of the backward graph (nothing downstream reads them before the
         # optimizer), so they run on a second stream next to the dz -> dx chain: at 32 images per GPU every kernel of
-        # the step is too small to fill 148 SMs and the two chains overlap (fork / join are CUDA-graph capturable).
+        # the step is too small to fill the SMs and the two chains overlap (fork / join are CUDA-graph capturable).
         main, side = torch.cuda.current_stream(), _side_stream(dev)
         keep = []  # operands stay referenced until the join: the allocator must not recycle them under the side stream
 
@@ -585,7 +585,7 @@ def training_step(model, optim, x, param, timesteps, ab_t, *, noise=None, t=None
     pred = model(x_pert, t / timesteps, param, shortcut=shortcut)
     # F.mse_loss + its gradient in one kernel; the backward pass starts from d pred directly
     dpred = torch.empty_like(pred)
-    partial = torch.empty(148 * 8, device=dev)
+    partial = torch.empty(L.num_sms() * 8, device=dev)
     loss_sum = torch.empty(1, device=dev)
     L.mse_grad(pred.detach(), noise, 1.0 / pred.numel(), dpred, partial, loss_sum)
     pred.backward(dpred)
@@ -612,7 +612,7 @@ class GraphedTrainStep:
         self.ca, self.cb = ab_t.to(dev).sqrt().contiguous(), (1 - ab_t.to(dev)).contiguous()
         self.noise, self.x_pert = torch.empty_like(self.x), torch.empty_like(self.x)
         self.dpred = torch.empty_like(self.x)
-        self.partial, self.loss_sum = torch.empty(148 * 8, device=dev), torch.zeros(1, device=dev)
+        self.partial, self.loss_sum = torch.empty(L.num_sms() * 8, device=dev), torch.zeros(1, device=dev)
         self.lr = torch.full((1,), float(lr), device=dev)
         self.count = torch.zeros(1, device=dev, dtype=torch.int32)  # Adam step == Philox stream offset
         self.betas, self.eps, self.seed = betas, eps, seed

@@ -163,32 +163,31 @@ def _pack_convT(convt):
 
 
 class _Workspace:
-    """Activation buffers (NHWC bf16) for `n` images in flight (n = reps * batch)."""
+    """Named views of a plan's activation workspace (NHWC bf16) for `n` = reps * batch images in flight."""
 
-    def __init__(self, batch, reps, nf, h, dev):
-        n = batch * reps
-        bf = dict(device=dev, dtype=torch.bfloat16)
-        f32 = dict(device=dev, dtype=torch.float32)
+    def __init__(self, plan, nf, h):
+        n, batch = plan.n, plan.batch
+        bf, f32 = torch.bfloat16, torch.float32
         h2, h4 = h // 2, h // 4
-        self.n, self.batch, self.reps = n, batch, reps
-        self.x0 = torch.empty(n, h, h, nf, **bf)
-        self.p64 = torch.empty(n, h, h, nf, **bf)
-        self.q64 = torch.empty(n, h, h, nf, **bf)
+        self.n, self.batch, self.reps, self.plan = n, batch, plan.reps, plan
+        self.x0 = plan.buffer("x0", bf, (n, h, h, nf))
+        self.p64 = plan.buffer("p64", bf, (n, h, h, nf))
+        self.q64 = plan.buffer("q64", bf, (n, h, h, nf))
         self.a1 = self.q64[:batch]  # init_conv.conv1 output, dead before q64 is first written
-        self.d1 = torch.empty(n, h2, h2, nf, **bf)
-        self.p32w = torch.empty(n, h2, h2, 2 * nf, **bf)
-        self.q32w = torch.empty(n, h2, h2, 2 * nf, **bf)
+        self.d1 = plan.buffer("d1", bf, (n, h2, h2, nf))
+        self.p32w = plan.buffer("p32w", bf, (n, h2, h2, 2 * nf))
+        self.q32w = plan.buffer("q32w", bf, (n, h2, h2, 2 * nf))
         # the nf-wide h/2 buffers of up1 alias the (dead by then) 2nf-wide ones of down2
         self.p32 = self.p32w.view(-1)[: n * h2 * h2 * nf].view(n, h2, h2, nf)
         self.q32 = self.q32w.view(-1)[: n * h2 * h2 * nf].view(n, h2, h2, nf)
-        self.u1f = torch.empty(n, h2, h2, nf, **bf)
-        self.d2 = torch.empty(n, h4, h4, 2 * nf, **bf)
-        self.hidden = torch.empty(n, 2 * nf, **bf)
-        self.u0raw = torch.empty(n, h4 * h4, 2 * nf, **bf)
-        self.u0f = torch.empty(n, h4 * h4, 2 * nf, **bf)
-        self.gn_partial = torch.empty(n, (h // 16) * (h // 16) * 8, 8, 2, **f32)
-        self.gn_mr = torch.empty(n, 8, 2, **f32)
-        self.eps = torch.empty(n, 1, h, h, **f32)
+        self.u1f = plan.buffer("u1f", bf, (n, h2, h2, nf))
+        self.d2 = plan.buffer("d2", bf, (n, h4, h4, 2 * nf))
+        self.hidden = plan.buffer("hidden", bf, (n, 2 * nf))
+        self.u0raw = plan.buffer("u0raw", bf, (n, h4 * h4, 2 * nf))
+        self.u0f = plan.buffer("u0f", bf, (n, h4 * h4, 2 * nf))
+        self.gn_partial = plan.buffer("gn_partial", f32, (n, (h // 16) * (h // 16) * 8, 8, 2))
+        self.gn_mr = plan.buffer("gn_mr", f32, (n, 8, 2))
+        self.eps = plan.buffer("eps", f32, (n, 1, h, h))
 
 
 class ContextUnet(nn.Module):
@@ -215,10 +214,9 @@ class ContextUnet(nn.Module):
         self.up2 = UnetUp(2 * n_feat, n_feat)
         self.out = nn.Sequential(nn.Conv2d(2 * n_feat, n_feat, 3, 1, 1), nn.GroupNorm(8, n_feat), nn.ReLU(),
                                  nn.Conv2d(n_feat, self.in_channels, 3, 1, 1))
-        self._packed = None
-        self._packed_key = None
-        self._ws = {}
-        self.conv_mode = int(os.environ.get("CDM_CONV_MODE", L.CONV_MODE_SWAPPED))
+        self._plans = {}   # (batch, reps) -> (_lib.Plan, _Workspace, pointer key, version key)
+        self._dirty = False
+        self.conv_mode = int(os.environ.get("CDM_CONV_MODE", L.CONV_MODE_SWAPPED_TMA))
 
     # ------------------------------------------------------------------ weights
     def _check_supported(self):
@@ -231,53 +229,49 @@ class ContextUnet(nn.Module):
                              "move the module to an sm_100 device with .to('cuda')")
         return dev
 
-    def _key(self):
-        return tuple((id(t), t._version) for t in list(self.parameters()) + list(self.buffers()))
+    def _plan_tensors(self):
+        sd = dict(self.named_parameters())
+        sd.update(dict(self.named_buffers()))
+        return [sd[k].detach() for k in L.plan_tensor_names()]
 
     def invalidate(self):
-        """Drop packed (bf16, BN-folded) weights; called automatically when parameters change."""
-        self._packed, self._packed_key = None, None
+        """Parameters / buffers were changed behind autograd's back (raw-pointer kernels, .data writes): re-pack the
+        bf16 weights and folded BatchNorm vectors on the next eval forward."""
+        self._dirty = True
 
-    def packed(self):
-        """BF16 K-major weights + folded eval-BatchNorm vectors, rebuilt when any parameter/buffer changed."""
-        key = self._key()
-        if self._packed is not None and key == self._packed_key:
-            return self._packed
-        P = {}
-        rcbs = {"init_conv": self.init_conv, "down1.0": self.down1.model[0], "down1.1": self.down1.model[1],
-                "down2.0": self.down2.model[0], "down2.1": self.down2.model[1],
-                "up1.1": self.up1.model[1], "up1.2": self.up1.model[2],
-                "up2.1": self.up2.model[1], "up2.2": self.up2.model[2]}
-        for name, blk in rcbs.items():
-            for cname, seq in (("c1", blk.conv1), ("c2", blk.conv2)):
-                scale, shift = _fold_bn(seq[0], seq[1])
-                if name == "init_conv" and cname == "c1":
-                    w = seq[0].weight.detach().float().reshape(self.n_feat, 9).t().contiguous()  # [9][cout]
-                else:
-                    w = _pack_conv3(seq[0])
-                P[f"{name}.{cname}"] = (w, scale, shift)
-        dev = self.out[3].weight.device
-        P["up0.w"] = _pack_convT(self.up0[0])
-        P["up0.b"] = self.up0[0].bias.detach().float().contiguous()
-        P["up0.gn"] = (self.up0[1].weight.detach().float().contiguous(), self.up0[1].bias.detach().float().contiguous())
-        for nm, mod in (("up1", self.up1), ("up2", self.up2)):
-            P[nm + ".w"] = _pack_convT(mod.model[0])
-            P[nm + ".b"] = mod.model[0].bias.detach().float().contiguous()
-        P["out0"] = (_pack_conv3(self.out[0]), torch.ones(self.n_feat, device=dev),
-                     self.out[0].bias.detach().float().contiguous())
-        P["out.gn"] = (self.out[1].weight.detach().float().contiguous(), self.out[1].bias.detach().float().contiguous())
-        P["out3.w"] = self.out[3].weight.detach().float()[0].permute(1, 2, 0).reshape(9, self.n_feat).contiguous()
-        P["out3.b"] = self.out[3].bias.detach().float().contiguous()
-        self._packed, self._packed_key = P, key
-        return P
+    def plan(self, batch, reps):
+        """The cdm_plan (packed weights, workspace, prepared launches) for `reps` passes over `batch` inputs: built on
+        first use, re-packed when a parameter / buffer changed (version counters, or invalidate()), rebuilt when the
+        tensors moved (other device, load_state_dict(assign=True))."""
+        ts = self._plan_tensors()
+        pkey = tuple((t.data_ptr(), str(t.device)) for t in ts)
+        vkey = tuple(t._version for t in ts)
+        if self._dirty:  # applies to every cached plan
+            for k, (pl, ws, pk, vk) in list(self._plans.items()):
+                self._plans[k] = (pl, ws, pk, None)
+            self._dirty = False
+        ent = self._plans.get((batch, reps))
+        if ent is not None and ent[2] == pkey:
+            if ent[3] != vkey:
+                ent[0].refresh()
+                self._plans[(batch, reps)] = (ent[0], ent[1], pkey, vkey)
+            return self._plans[(batch, reps)]
+        if ent is not None:
+            ent[0].close()
+        if len(self._plans) > 4:
+            for pl, *_ in self._plans.values():
+                pl.close()
+            self._plans.clear()
+        dev = self._check_supported()
+        with torch.cuda.device(dev):
+            pl = L.Plan([t if (t.is_contiguous() and t.dtype == torch.float32) else t.float().contiguous() for t in ts],
+                        self.n_cfeat, batch, reps, dev, conv_mode=self.conv_mode)
+        ws = _Workspace(pl, self.n_feat, self.h)
+        self._plans[(batch, reps)] = (pl, ws, pkey, vkey)
+        return self._plans[(batch, reps)]
 
     def workspace(self, batch, reps):
-        k = (batch, reps)
-        if k not in self._ws:
-            if len(self._ws) > 4:
-                self._ws.clear()
-            self._ws[k] = _Workspace(batch, reps, self.n_feat, self.h, self.out[3].weight.device)
-        return self._ws[k]
+        return self.plan(batch, reps)[1]
 
     # ------------------------------------------------------------------ embeddings
     def embed(self, t, c):
@@ -290,51 +284,10 @@ class ContextUnet(nn.Module):
         classifier-free-guidance passes).  x fp32 [B,64,64]; sc_tab fp32 [steps][reps][2][128];
         cemb* fp32 [reps*B,C]; temb* fp32 [steps][temb_rows][C] (row picked by *step_ptr).
         Returns the workspace's eps buffer, fp32 [reps*B,1,64,64] (overwritten by the next call)."""
-        P = self.packed()
         B = x.shape[0]
-        ws = self.workspace(B, reps)
-        n, h, nf, mode = ws.n, self.h, self.n_feat, self.conv_mode
-        R, POOL, FILM, SC, GN = L.EPI_RELU, L.EPI_POOL, L.EPI_FILM, L.EPI_SHORTCUT, L.EPI_GNSTATS
-
-        def conv(src, name, out, flags=R, **kw):
-            w, s, b = P[name]
-            return L.conv3x3(src, w, s, b, out, flags=flags, mode=mode, **kw)
-
-        w, s, b = P["init_conv.c1"]
-        L.conv_in(x, w, s, b, ws.a1)
-        conv(ws.a1, "init_conv.c2", ws.x0, R | SC, sc_x=x, sc_tab=sc_tab, sc_reps=reps, step_ptr=step_ptr)
-        conv(ws.x0, "down1.0.c1", ws.p64)
-        conv(ws.p64, "down1.0.c2", ws.q64)
-        conv(ws.q64, "down1.1.c1", ws.p64)
-        conv(ws.p64, "down1.1.c2", ws.d1, R | POOL)
-        conv(ws.d1, "down2.0.c1", ws.p32w)
-        conv(ws.p32w, "down2.0.c2", ws.q32w)
-        conv(ws.q32w, "down2.1.c1", ws.p32w)
-        conv(ws.p32w, "down2.1.c2", ws.d2, R | POOL)
-        h4 = h // 4
-        L.avgpool_gelu(ws.d2.view(n, h4 * h4, 2 * nf), ws.hidden)
-        L.gemm(ws.hidden, P["up0.w"], P["up0.b"], ws.u0raw, shift_mod=2 * nf)
-        g, bt = P["up0.gn"]
-        L.gn_relu_film(ws.u0raw, g, bt, ws.u0f, groups=8, eps=GN_EPS, film_scale=cemb1, film_shift=temb1,
-                       film_rows=temb_rows, step_ptr=step_ptr)
-        L.gemm(ws.u0f.view(n * h4 * h4, 2 * nf), P["up1.w"], P["up1.b"], ws.p32,
-               a1=ws.d2.view(n * h4 * h4, 2 * nf), out_mode=1, H=h4, W=h4, shift_mod=nf)
-        conv(ws.p32, "up1.1.c1", ws.q32)
-        conv(ws.q32, "up1.1.c2", ws.p32)
-        conv(ws.p32, "up1.2.c1", ws.q32)
-        conv(ws.q32, "up1.2.c2", ws.u1f, R | FILM, film_scale=cemb2, film_shift=temb2, film_shift_rows=temb_rows,
-             step_ptr=step_ptr)
-        h2 = h // 2
-        L.gemm(ws.u1f.view(n * h2 * h2, nf), P["up2.w"], P["up2.b"], ws.p64, a1=ws.d1.view(n * h2 * h2, nf),
-               out_mode=1, H=h2, W=h2, shift_mod=nf)
-        conv(ws.p64, "up2.1.c1", ws.q64)
-        conv(ws.q64, "up2.1.c2", ws.p64)
-        conv(ws.p64, "up2.2.c1", ws.q64)
-        conv(ws.q64, "up2.2.c2", ws.p64)
-        conv(ws.p64, "out0", ws.q64, GN, src1=ws.x0, gn_partial=ws.gn_partial)
-        L.gn_finalize(ws.gn_partial, float((nf // 8) * h * h), ws.gn_mr, GN_EPS)
-        g, bt = P["out.gn"]
-        L.conv_out(ws.q64, ws.gn_mr, g, bt, P["out3.w"], P["out3.b"], ws.eps.view(n, h, h))
+        pl, ws = self.plan(B, reps)[:2]
+        # ONE C call: 26 launches over the plan's prepared tensor maps (cdm_forward_eval, csrc/plan.cu)
+        pl.forward_eval(x, sc_tab, cemb1, temb1, cemb2, temb2, temb_rows, step_ptr=step_ptr)
         return ws.eps
 
     def draw_shortcut(self):
@@ -367,5 +320,5 @@ class ContextUnet(nn.Module):
         return eps.clone()
 
     def train(self, mode=True):
-        self.invalidate()
+        self.invalidate()  # a mode switch brackets raw-pointer updates (optimizer, BatchNorm running statistics)
         return super().train(mode)

@@ -36,6 +36,8 @@ int cdm_version(void);
 const char* cdm_last_error(void);
 /* 0 if the current device can run the kernels (compute capability 10.x). */
 int cdm_device_ok(void);
+/* Multiprocessor count of the current device (148 on B200): per-CTA partial-sum workspaces are sized from it. */
+int cdm_num_sms(void);
 
 /* ---- epilogue flags for the implicit-GEMM kernels ------------------------ */
 #define CDM_EPI_RELU 1      /* max(y,0) after scale/shift                      */
@@ -45,13 +47,19 @@ int cdm_device_ok(void);
 #define CDM_EPI_GNSTATS 16  /* emit per-(n,slot,group) sum / sum-of-squares    */
 #define CDM_EPI_BNSTATS 32  /* per-channel sum / sum-of-squares of the (bf16-rounded) output over the whole
                              * launch -> bn_sums, all ranks of `xr` included: the batch statistics of a
-                             * train-mode nn.BatchNorm2d come out of the convolution itself (MODE 3 only) */
+                             * train-mode nn.BatchNorm2d come out of the convolution itself (MODE 3 / 4 only) */
+#define CDM_EPI_GELU 64     /* exact-erf GELU after scale/shift instead of ReLU (the activation the reference's
+                             * comment names, code/diffusion_utilities.py:29,36; the code itself runs nn.ReLU) */
+#define CDM_EPI_RESSCALE 128 /* y *= res_scale after the shortcut add (the reference's disabled `/ 1.414`,
+                              * code/diffusion_utilities.py:59: res_scale = 1 / 1.414) */
+#define CDM_EPI_ALL 255     /* every defined bit; any other bit in `flags` is rejected with CDM_ERR_ARG */
 
 /* A-operand feeding strategy of cdm_conv3x3. */
 #define CDM_CONV_MODE_COPIES 0  /* three kw-shifted TMA copies, aligned views  */
 #define CDM_CONV_MODE_SHIFT24 1 /* one halo tile, pitch 24, row-shifted views  */
 #define CDM_CONV_MODE_SHIFT18 2 /* one halo tile, pitch 18, row-shifted views  */
 #define CDM_CONV_MODE_SWAPPED 3 /* weights = M operand, 256 pixels = N operand (M128 N256 K16); H % 32 == 0 */
+#define CDM_CONV_MODE_SWAPPED_TMA 4 /* as 3, output through shared-memory staging + TMA stores (bit-identical) */
 
 /* 3x3, stride 1, pad 1 convolution as tcgen05 implicit GEMM.
  * Replaces nn.Conv2d(+BatchNorm2d eval +ReLU) of ResidualConvBlock
@@ -86,11 +94,12 @@ typedef struct {
   /* CDM_EPI_GNSTATS: fp32 [n_img][(H/16)*(W/16)*8][8][2] */
   float* gn_partial;
   int mode; /* CDM_CONV_MODE_* */
-  /* CDM_EPI_BNSTATS: workspace fp32 [148][2][cout]; bn_sums fp32 [2][cout] = (sum, sum of squares) per channel
+  /* CDM_EPI_BNSTATS: workspace fp32 [cdm_num_sms()][2][cout]; bn_sums fp32 [2][cout] = (sum, sum of squares) per channel
    * over every rank of `xr` (NULL: this rank only) */
   float* bn_partial;
   float* bn_sums;
   const struct cdm_xrank_s* xr;
+  float res_scale; /* CDM_EPI_RESSCALE */
 } cdm_conv3x3_args;
 int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream);
 
@@ -199,6 +208,9 @@ typedef struct {
   unsigned long long seed;
   float* snap;          /* optional snapshot ring [n_snap][n][hw] ... */
   const int* snap_slot; /* ... slot per step i ([timesteps+1], -1 = none)  (paper.py:617-618) */
+  /* in-kernel noise: global index of x[0] in the whole (all-rank) sample batch.  The Philox counter is the GLOBAL
+   * element index, so the draw of a sample is the same whichever rank holds it and two ranks never share noise */
+  long long sample_offset;
 } cdm_ddpm_step_args;
 int cdm_ddpm_step(const cdm_ddpm_step_args* a, void* stream);
 int cdm_step_advance(int* step_ptr, int delta, void* stream);
@@ -218,6 +230,7 @@ typedef struct {
   unsigned long long seed;
   unsigned int stream_id;
   float* noise_out;
+  long long sample_offset; /* in-kernel noise: global index of x[0] (see cdm_ddpm_step_args) */
 } cdm_perturb_args;
 int cdm_perturb(const cdm_perturb_args* a, void* stream);
 
@@ -233,6 +246,10 @@ typedef struct {
   const int* step_ptr; /* device int32 overriding t_shared, or NULL */
   float* mse_out; /* fp32 [n] or NULL */
   float* acc;     /* fp32 [n] or NULL */
+  /* optional second weighted accumulator over the same MSE: BASELINE config 5 sums mse/(2 b_t) (NLL,
+   * code/train_diffusion_elbo.py:108-149) and 0.5 (1/(1-ab_t) - 1) mse (ELBO, :91-103) in one sweep */
+  const float* weight_tab2; /* fp32 [T+1] or NULL (weight 1) */
+  float* acc2;              /* fp32 [n] or NULL */
 } cdm_mse_accum_args;
 int cdm_mse_accum(const cdm_mse_accum_args* a, void* stream);
 
@@ -273,6 +290,9 @@ int cdm_chan_reduce(const cdm_chan_reduce_args* a, void* stream);
 /* out[i] = sum over ranks of sum_b partial[b][i] (b in fixed order), i < n <= 512: the final pass of a two-stage
  * reduction fused with its exchange over peer memory (one kernel, graph-capturable, deterministic). */
 int cdm_xrank_sum(const float* partial, int n_blocks, int n, float* out, const cdm_xrank* xr, void* stream);
+/* How long a rank waits for a late peer before the exchange kernel gives up with a CUDA error (wall-clock seconds,
+ * default 600 or the CDM_XRANK_TIMEOUT_S environment variable).  A late peer (checkpoint I/O, dataloader) is normal. */
+int cdm_xrank_set_timeout(double seconds);
 
 /* sums[2][C] (after the optional cross-rank all-reduce) -> scale = gamma*rstd, shift = beta - mean*scale,
  * mean, rstd; running_mean/var updated with `momentum` and the UNBIASED variance (torch semantics). */
@@ -425,6 +445,81 @@ int cdm_normalize_params(const float* x, int rows, int cols, int repeat, int out
  * vec_start = running count of 8-element output vectors, total_vec their total.  Replaces the per-tensor
  * w.permute(..).contiguous().to(bf16) / w.flip(2,3).permute(..) chains of the torch path. */
 int cdm_pack_bf16(const void* table, int n_rows, long long total_vec, void* stream);
+
+/* ======================= composite entry points: one eval forward / one sampling step per C call ===============
+ * ContextUnet.forward in eval mode (ContextUnet.py:42-60) and one iteration of sample_ddpm's loop
+ * (code/train_diffusion_paper.py:594-618).  A plan packs the fp32 PyTorch-layout parameters into the tensor-core
+ * layouts once (bf16 K-major weights, eval BatchNorm folded to scale / shift), carves the activation workspace and
+ * encodes every layer's tensor maps; cdm_forward_eval is then 26 kernel launches and nothing else (no descriptor
+ * encoding, no allocation, no host sync; CUDA-graph capturable).  The library allocates no device memory: arena
+ * and workspace are the caller's.  A plan is used from one host thread on one stream at a time. */
+typedef struct cdm_plan cdm_plan;
+
+/* Parameter / buffer tensors in ContextUnet.state_dict() order without the num_batches_tracked entries:
+ * 102 parameters + 36 BatchNorm running statistics = 138 fp32 tensors, PyTorch shapes (Conv2d OIHW,
+ * ConvTranspose2d IOHW, Linear [out][in]). */
+int cdm_plan_n_tensors(void);
+const char* cdm_plan_tensor_name(int i);              /* state_dict key, e.g. "down1.model.0.conv1.0.weight" */
+long long cdm_plan_tensor_numel(int i, int n_cfeat);  /* element count for a context width of n_cfeat */
+
+#define CDM_CONV_MODE_DEFAULT CDM_CONV_MODE_SWAPPED_TMA
+typedef struct {
+  int n_cfeat;      /* width of the context vector (1..6 in the reference's sweeps) */
+  int batch, reps;  /* batch inputs x, each evaluated `reps` times (2 = the conditional + unconditional passes of
+                     * classifier-free guidance, run as ONE 2*batch-image forward); images in flight = batch*reps */
+  const float* const* tensors; /* HOST array of cdm_plan_n_tensors() DEVICE pointers; the tensors must outlive the
+                                * plan (small fp32 vectors are used in place); after updating them in place call
+                                * cdm_plan_refresh */
+  void* arena;      /* packed weights, 256-byte aligned, >= cdm_plan_arena_bytes(n_cfeat) */
+  long long arena_bytes;
+  void* workspace;  /* activations, 256-byte aligned, >= cdm_plan_workspace_bytes(batch, reps) */
+  long long workspace_bytes;
+  int conv_mode;    /* CDM_CONV_MODE_*; 0 selects CDM_CONV_MODE_DEFAULT */
+} cdm_plan_desc;
+long long cdm_plan_arena_bytes(int n_cfeat);
+long long cdm_plan_workspace_bytes(int batch, int reps);
+int cdm_plan_create(const cdm_plan_desc* d, void* stream, cdm_plan** out); /* packing kernels run on `stream` */
+int cdm_plan_refresh(cdm_plan* p, void* stream);                            /* re-pack after an in-place update */
+void cdm_plan_destroy(cdm_plan* p);
+/* Named view into the workspace (tests / taps): "x0", "d1", "d2", "hidden", "u0f", "u1f", "p64", "q64", "eps", ... */
+int cdm_plan_buffer(const cdm_plan* p, const char* name, void** ptr, long long* bytes);
+/* EmbedFC with the plan's weights: which = 0 contextembed1, 1 timeembed1, 2 contextembed2, 3 timeembed2
+ * (ContextUnet.py:51-54).  in fp32 [rows][n_cfeat or 1] -> out fp32 [rows][256 or 128]. */
+int cdm_plan_embed(const cdm_plan* p, int which, const float* in, int rows, float* out, void* stream);
+
+typedef struct {
+  const float* x;      /* fp32 [batch][64][64] */
+  const float* sc_tab; /* fp32 [steps][reps][2][128]: the fresh 1x1 shortcut draws (w_c, b_c) per pass */
+  const float* cemb1;  /* fp32 [reps*batch][256]  contextembed1(c) */
+  const float* temb1;  /* fp32 [steps][temb_rows][256] timeembed1(t) */
+  const float* cemb2;  /* fp32 [reps*batch][128] */
+  const float* temb2;  /* fp32 [steps][temb_rows][128] */
+  int temb_rows;       /* 1 (t shared by the batch) or reps*batch */
+  const int* step_ptr; /* device int32 selecting the sc_tab / temb row, NULL = row 0 */
+  float* eps;          /* fp32 [reps*batch][64][64]; NULL = the plan's "eps" buffer */
+} cdm_forward_args;
+int cdm_forward_eval(cdm_plan* p, const cdm_forward_args* f, void* stream);
+/* Measurement: the forward's launches by name, and one forward with a CUDA event after every launch on `stream`
+ * (synchronises; ms_host[cdm_plan_n_launches()] = per-launch durations).  bench.py's roofline figures. */
+int cdm_plan_n_launches(void);
+const char* cdm_plan_launch_name(int i);
+int cdm_plan_profile(cdm_plan* p, const cdm_forward_args* f, float* ms_host, void* stream);
+
+typedef struct {
+  cdm_forward_args fwd; /* x, step_ptr and eps are taken from the fields below */
+  float* x;             /* fp32 [batch][64][64] = x_t, updated in place to x_{t-1} */
+  int* step_ptr;        /* device int32 holding i; decremented by the call */
+  float guide_w;
+  const float* coef;    /* fp32 [timesteps+1][4] (cdm_ddpm_step_args) */
+  int timesteps;
+  const float* z;       /* host-fed noise or NULL -> in-kernel Philox */
+  long long z_iter_stride;
+  unsigned long long seed;
+  long long sample_offset;
+  float* snap;
+  const int* snap_slot;
+} cdm_sample_step_args;
+int cdm_sample_step(cdm_plan* p, const cdm_sample_step_args* s, void* stream);
 
 /* Measurement probe: every CTA streams `tile_bytes` TMA tiles from an
  * L2-resident buffer into a shared-memory ring; returns nothing, caller times it. */

@@ -171,7 +171,7 @@ def test_header_is_plain_c_and_links(lib, tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "version 1" in r.stdout and "conv3x3(NULL) -> -1" in r.stdout
+    assert "version 200" in r.stdout and "conv3x3(NULL) -> -1" in r.stdout
 
 
 def test_pack_plan_table_addresses_the_torch_layouts(monkeypatch):

@@ -36,7 +36,7 @@ def _conv_inputs(n, H, cin, cout, seed=0):
     return x, w, scale, shift
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("n,H,c0,c1,cout", [(3, 32, 128, 0, 128), (2, 64, 64, 64, 256), (1, 16, 256, 0, 128)])
 def test_conv3x3_modes(L, mode, n, H, c0, c1, cout):
     x, w, scale, shift = _conv_inputs(n, H, c0 + c1, cout)
@@ -46,7 +46,7 @@ def test_conv3x3_modes(L, mode, n, H, c0, c1, cout):
     assert rel_l2(out.float(), _conv_ref(x, w, scale, shift).clamp_min(0)) < BF16_TOL
 
 
-@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("mode", [2, 3, 4])
 def test_conv3x3_many_units_persistent(L, mode):
     """More work units than SMs x 2: exercises the persistent loop, ring wrap-around and TMEM double buffering."""
     x, w, scale, shift = _conv_inputs(40, 64, 128, 128, seed=3)
@@ -58,7 +58,7 @@ def test_conv3x3_many_units_persistent(L, mode):
     assert torch.equal(out, out2), "conv3x3 must be deterministic"
 
 
-@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("mode", [2, 3, 4])
 def test_conv3x3_pool(L, mode):
     x, w, scale, shift = _conv_inputs(4, 32, 128, 256, seed=1)
     out = torch.empty(4, 16, 16, 256, device="cuda", dtype=torch.bfloat16)
@@ -67,7 +67,7 @@ def test_conv3x3_pool(L, mode):
     assert rel_l2(out.float(), ref) < BF16_TOL
 
 
-@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("mode", [2, 3, 4])
 @pytest.mark.parametrize("rows", [1, 4])
 def test_conv3x3_film(L, rows, mode):
     n, cout = 4, 128
@@ -83,7 +83,7 @@ def test_conv3x3_film(L, rows, mode):
     assert rel_l2(out.float(), ref) < BF16_TOL
 
 
-@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("mode", [2, 3, 4])
 @pytest.mark.parametrize("reps", [1, 2])
 def test_conv3x3_shortcut_fanout(L, reps, mode):
     n, H, cout = 3, 64, 128
@@ -100,7 +100,55 @@ def test_conv3x3_shortcut_fanout(L, reps, mode):
         assert rel_l2(out[r * n:(r + 1) * n].float(), ref) < BF16_TOL
 
 
-@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("flags_kind", ["plain", "c256", "out0", "shortcut2", "small_batch"])
+def test_conv3x3_tma_store_epilogue_is_bit_identical(L, flags_kind):
+    """MODE 4 (staging + cp.async.bulk.tensor stores) writes exactly what MODE 3 (register-direct stores) writes."""
+    n, H, c0, c1, cout, kw, reps = {"plain": (5, 64, 128, 0, 128, {}, 1), "c256": (5, 32, 256, 0, 256, {}, 1),
+                                    "out0": (3, 64, 128, 128, 128, {}, 1), "small_batch": (1, 64, 128, 0, 128, {}, 1),
+                                    "shortcut2": (3, 64, 128, 0, 128, None, 2)}[flags_kind]
+    x, w, scale, shift = _conv_inputs(n, H, c0 + c1, cout, seed=11)
+    flags = L.EPI_RELU
+    if kw is None:
+        flags |= L.EPI_SHORTCUT
+        kw = dict(sc_x=torch.randn(n, H, H, device="cuda"), sc_tab=torch.rand(2, 2, 2, cout, device="cuda") * 2 - 1,
+                  sc_reps=2, step_ptr=torch.tensor([1], device="cuda", dtype=torch.int32))
+    outs = []
+    for mode in (3, 4):
+        out = torch.full((reps * n, H, H, cout), float("nan"), device="cuda").to(torch.bfloat16)
+        L.conv3x3(x[..., :c0].contiguous(), w, scale, shift, out, src1=x[..., c0:].contiguous() if c1 else None,
+                  flags=flags, mode=mode, **kw)
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    assert bool(torch.isfinite(outs[1].float()).all())
+
+
+@pytest.mark.parametrize("mode", [2, 3, 4])
+def test_conv3x3_gelu_and_res_scale(L, mode):
+    """The activation / residual-scale parameters north_star lists (GELU, /1.414): off by default (the reference
+    runs ReLU and has the scale commented out, diffusion_utilities.py:29,36,59), parity-tested here."""
+    n, H, cout = 3, 64, 128
+    x, w, scale, shift = _conv_inputs(n, H, 128, cout, seed=6)
+    xs = torch.randn(n, H, H, device="cuda")
+    tab = torch.rand(1, 1, 2, cout, device="cuda") * 2 - 1
+    out = torch.empty(n, H, H, cout, device="cuda", dtype=torch.bfloat16)
+    L.conv3x3(x, w, scale, shift, out, flags=L.EPI_GELU | L.EPI_SHORTCUT | L.EPI_RESSCALE, sc_x=xs, sc_tab=tab,
+              sc_reps=1, res_scale=1 / 1.414, mode=mode)
+    ref = F.gelu(_conv_ref(x, w, scale, shift))
+    ref = (ref + xs.view(n, H, H, 1) * tab[0, 0, 0].view(1, 1, 1, cout) + tab[0, 0, 1].view(1, 1, 1, cout)) / 1.414
+    assert rel_l2(out.float(), ref) < BF16_TOL
+
+
+def test_conv3x3_rejects_unknown_flag_bits(L):
+    """Bits outside CDM_EPI_ALL (e.g. the measurement probes of the -DCDM_PROBES build) are an argument error in the
+    production library, never forwarded to the kernel."""
+    x, w, scale, shift = _conv_inputs(1, 32, 128, 128)
+    out = torch.empty(1, 32, 32, 128, device="cuda", dtype=torch.bfloat16)
+    for bit in (8, 26, 27, 28, 29, 30):
+        with pytest.raises(L.CdmError):
+            L.conv3x3(x, w, scale, shift, out, flags=L.EPI_RELU | (1 << bit))
+
+
+@pytest.mark.parametrize("mode", [2, 3, 4])
 def test_conv3x3_gnstats(L, mode):
     n, H = 3, 64
     x, w, scale, shift = _conv_inputs(n, H, 256, 128, seed=5)

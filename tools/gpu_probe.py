@@ -9,6 +9,8 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+# the measurement probes (flag bits 26-30, cdm_gemm_tn_args.probe) exist only in the -DCDM_PROBES build
+os.environ.setdefault("CDM_LIB", os.path.join(ROOT, "camels-diffusion-model_b200", "libcdm_b200_probes.so"))
 
 
 def _load():
@@ -176,7 +178,7 @@ def case_perf(name, mode, n=256, H=64, cin=128, cout=128, flags=1):
     return True
 
 
-def case_waits(name, n=2048, H=64, cin=128, cout=128, flags=1):
+def case_waits(name, n=2048, H=64, cin=128, cout=128, flags=1, mode=3):
     """Where the MMA issuer of conv3x3_sw_kernel waits (probe flag bit 28): cycles blocked on the TMEM buffer
     (epilogue too slow), on the pixel-halo ring and on the weight ring, per CTA, against the CTA's total."""
     import torch
@@ -188,7 +190,7 @@ def case_waits(name, n=2048, H=64, cin=128, cout=128, flags=1):
     out = torch.empty(n, H, H, cout, device=dev, dtype=torch.bfloat16)
     dbg = torch.zeros(148, 8, device=dev)
     for _ in range(3):
-        L.conv3x3(x, w, scale, shift, out, mode=3, flags=flags | (1 << 28), gn_partial=dbg)
+        L.conv3x3(x, w, scale, shift, out, mode=mode, flags=flags | (1 << 28), gn_partial=dbg)
     torch.cuda.synchronize()
     d = dbg.cpu()
     tot = d[:, 3]
@@ -318,6 +320,14 @@ CASES = {
     "perf_m2": lambda: case_perf("perf_m2", 2),
     "perf_m0_c256": lambda: case_perf("perf_m0_c256", 0, n=256, H=32, cin=256, cout=256),
     "perf_m3": lambda: case_perf("perf_m3", 3, n=1024),
+    "perf_m4": lambda: case_perf("perf_m4", 4, n=1024),
+    "perf_m4_c256": lambda: case_perf("perf_m4_c256", 4, n=1024, H=32, cin=256, cout=256),
+    "perf_m4_out0": lambda: case_perf("perf_m4_out0", 4, n=1024, H=64, cin=256, cout=128),
+    "perf_m3_pool": lambda: case_perf("perf_m3_pool", 3, n=1024, flags=1 | 4),
+    "perf_m4_pool": lambda: case_perf("perf_m4_pool", 4, n=1024, flags=1 | 4),
+    "perf_m3_b2048": lambda: case_perf("perf_m3_b2048", 3, n=2048),
+    "perf_m4_b2048": lambda: case_perf("perf_m4_b2048", 4, n=2048),
+    "waits_m4": lambda: case_waits("waits_m4", mode=4),
     "perf_m3_nostore": lambda: case_perf("perf_m3_nostore", 3, n=1024, flags=1 | (1 << 30)),
     "perf_m3_noepi": lambda: case_perf("perf_m3_noepi", 3, n=1024, flags=1 | (1 << 29)),
     "perf_m3_l2store": lambda: case_perf("perf_m3_l2store", 3, n=1024, flags=1 | (1 << 26)),
