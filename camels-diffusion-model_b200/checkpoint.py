@@ -52,7 +52,7 @@ def save_checkpoint(path, model, optim, epoch, step=0, extra=None):
 def load_checkpoint(path, model, optim=None, restore_rng=True):
     """-> (epoch, step, extra).  Restores weights + BatchNorm buffers, optimizer moments / step count and (by default)
     the CPU generator state."""
-    ck = torch.load(path, map_location="cpu", weights_only=False)
+    ck = torch.load(path, map_location="cpu", weights_only=True)  # tensors and plain containers only: no pickle code
     if not (isinstance(ck, dict) and ck.get("format", "").startswith("cdm_b200/")):
         raise ValueError(f"{path} is not a resume checkpoint (weights-only .pth files go through load_model)")
     model.load_state_dict(ck["model"])
@@ -71,6 +71,8 @@ def broadcast_model(model, src=0):
     with torch.no_grad():
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, src=src)
+    if hasattr(model, "invalidate"):
+        model.invalidate()  # .data writes do not bump version counters: re-pack the eval weights on next use
 
 
 def _to_cpu(o):

@@ -403,19 +403,25 @@ class _EvalLoop:
 
 @torch.no_grad()
 def calculate_likelihood(model, dataloader, timesteps, device, ab_t, b_t, a_t, *, noises=None, shortcuts=None,
-                         seed=0):
+                         seed=0, sample_offset=0, with_elbo=False):
     """Mean over the dataset of sum_{t=1..T} mse_t / (2 b_t)  (train_diffusion_paper.py:142-183).
     noises / shortcuts: optional per-batch lists of recorded draws (tests); default: in-kernel Philox noise
-    and shortcut draws from the global CPU generator."""
+    and shortcut draws from the global CPU generator.  sample_offset: global index of the loader's first map when
+    the dataset is sharded over ranks (the in-kernel noise is keyed by the global map index, so two ranks never
+    share noise).  with_elbo=True (BASELINE config 5, train_diffusion_elbo.py:91-103 over all timesteps): the same
+    forwards also accumulate 0.5 (1/(1-ab_t) - 1) mse and the call returns (nll, elbo, bpd)."""
     model.eval()
-    total_nll, num_samples = 0.0, 0
+    total_nll, total_elbo, num_samples = 0.0, 0.0, 0
     w = 1.0 / (2 * b_t.float())
+    w2 = 0.5 * (1.0 / (1.0 - ab_t.float()) - 1.0) if with_elbo else None
+    if w2 is not None:
+        w2[0] = 0.0  # ab_t[0] = 1: t = 0 is never evaluated
     for bi, (x, param) in enumerate(dataloader):
         sc = None
         if shortcuts is not None:
             sc = shortcut_table_from_list(shortcuts[bi], timesteps, 1, order="ascending")
         loop = _EvalLoop(model, x, param, timesteps, (b_t, a_t, ab_t), "one_minus", w, shortcut_tab=sc,
-                         seed=seed + 7919 * bi)
+                         seed=seed + 7919 * bi, weight_tab2=w2, sample_offset=sample_offset + num_samples)
         if noises is None:
             acc = loop.sweep_all()
         else:
@@ -424,13 +430,23 @@ def calculate_likelihood(model, dataloader, timesteps, device, ab_t, b_t, a_t, *
                 loop.one(noises[bi][t - 1].to(loop.dev))
             acc = loop.acc
         total_nll += acc.sum().item()
+        if with_elbo:
+            total_elbo += loop.acc2.sum().item()
         num_samples += x.shape[0]
+    if with_elbo:
+        elbo = total_elbo / num_samples
+        return total_nll / num_samples, elbo, elbo / (64 * 64 * np.log(2))
     return total_nll / num_samples
+
+
+def calculate_likelihood_and_elbo(model, dataloader, timesteps, device, ab_t, b_t, a_t, **kw):
+    """BASELINE config 5 in one sweep: (NLL, ELBO, BPD) over all `timesteps` per map, one forward per (map, t)."""
+    return calculate_likelihood(model, dataloader, timesteps, device, ab_t, b_t, a_t, with_elbo=True, **kw)
 
 
 @torch.no_grad()
 def calculate_elbo_and_bpd(model, dataloader, timesteps, device, ab_t, b_t, a_t, *, noises=None, shortcuts=None,
-                           seed=0):
+                           seed=0, sample_offset=0):
     """Dataloader ELBO/BPD of train_diffusion_paper.py:77-139: 10 timesteps linspace(1,T,10).long(),
     x_t = sqrt(ab) x + sqrt(1-ab) noise, weight 0.5 b_t/(1-ab_t), t<=1 skipped, /10."""
     model.eval()
@@ -445,7 +461,7 @@ def calculate_elbo_and_bpd(model, dataloader, timesteps, device, ab_t, b_t, a_t,
             for k, t in enumerate(ts):  # later duplicates of t (tiny T) overwrite: replay needs distinct t
                 sc[t, 0, 0], sc[t, 0, 1] = shortcuts[bi][k][0].view(-1), shortcuts[bi][k][1].view(-1)
         loop = _EvalLoop(model, x, param, timesteps, (b_t, a_t, ab_t), "sqrt", w, shortcut_tab=sc,
-                         seed=seed + 104729 * bi)
+                         seed=seed + 104729 * bi, sample_offset=sample_offset + num)
         for k, t in enumerate(ts):
             loop.step.fill_(t)
             loop.seed = seed + 104729 * bi + 31 * k

@@ -5,8 +5,18 @@ data-path collective (independent samples / maps); only the per-forward shortcut
 be identical on every rank, and results are gathered once at the end.  Training is data-parallel: gradient
 all-reduce + cross-rank BatchNorm statistics (see train.py).
 """
+import inspect
+
 import torch
 import torch.distributed as dist
+
+
+def _accepts(fn, name):
+    try:
+        ps = inspect.signature(fn).parameters
+    except (TypeError, ValueError):
+        return False
+    return name in ps or any(p.kind == inspect.Parameter.VAR_KEYWORD for p in ps.values())
 
 
 def world():
@@ -51,13 +61,17 @@ def gather_shards(local, n_total, dim=0):
 
 def sample_sharded(sample_fn, x_T_all, params_all, shortcut_tab, gather=True, device=None):
     """Batch-sharded sampling: rank r runs `sample_fn(x_T_shard, params_shard, shortcut_tab)` on its contiguous
-    shard.  `shortcut_tab` is taken from rank 0.  Returns the gathered [n_total, ...] samples (or the local shard)."""
+    shard.  `shortcut_tab` is taken from rank 0.  Returns the gathered [n_total, ...] samples (or the local shard).
+    A `sample_fn` that takes a `sample_offset` keyword receives the shard's first global sample index: forwarded to
+    the sampler (`_SamplerRun(..., sample_offset=)`), it keys the in-kernel noise by the GLOBAL sample, so ranks never
+    share noise and the sharded run draws what the single-process run draws."""
     rank, ws = world()
     n = x_T_all.shape[0]
     s, e = shard_range(n, rank, ws)
     tab = broadcast_from_rank0(shortcut_tab, device)
     prm = None if params_all is None else params_all[s:e]
-    local = sample_fn(x_T_all[s:e], prm, tab)
+    kw = {"sample_offset": s} if _accepts(sample_fn, "sample_offset") else {}
+    local = sample_fn(x_T_all[s:e], prm, tab, **kw)
     return gather_shards(local, n) if gather else local
 
 
@@ -77,13 +91,16 @@ def evaluate_sharded(eval_fn, maps, params, batch_size=32, device=None):
     contiguous shard of `maps` / `params` in batches of `batch_size` — `eval_fn(loader)` is e.g.
     `lambda dl: calculate_likelihood(model, dl, T, dev, ab_t, b_t, a_t)` or the ELBO/BPD variant and returns the
     shard MEAN (a float, or a tuple of floats) — and the per-rank (sum, count) pairs meet in one scalar all-reduce.
-    No other communication: the maps are independent."""
+    No other communication: the maps are independent.  An `eval_fn` that takes a `sample_offset` keyword receives the
+    shard's first global map index (pass it on: `calculate_likelihood(..., sample_offset=sample_offset)`), which keys
+    the in-kernel noise by the global map so that no two ranks evaluate with the same noise."""
     rank, ws = world()
     s, e = shard_range(maps.shape[0], rank, ws)
     loader = [(maps[i:min(i + batch_size, e)], None if params is None else params[i:min(i + batch_size, e)])
               for i in range(s, e, batch_size)]
     n_local = e - s
-    res = eval_fn(loader) if n_local > 0 else ()  # a rank without maps contributes (0, 0) to every output
+    kw = {"sample_offset": s} if _accepts(eval_fn, "sample_offset") else {}
+    res = eval_fn(loader, **kw) if n_local > 0 else ()  # a rank without maps contributes (0, 0) to every output
     vals = [float(v) for v in res] if isinstance(res, tuple) else [float(res)]
     arity = len(vals)
     if ws > 1:  # ranks with an empty shard do not know how many outputs eval_fn has
@@ -110,8 +127,17 @@ class PeerExchange:
         group = dist.group.WORLD if group is None else group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         n_slot = 2 * self.world * self.MAX_N
-        self.buf = symm.empty(n_slot + 64, dtype=torch.float32, device=device)
-        self.buf.zero_()
+        err = None
+        try:
+            self.buf = symm.empty(n_slot + 64, dtype=torch.float32, device=device)
+            self.buf.zero_()
+        except Exception as ex:  # noqa: BLE001
+            err = ex
+        # agree before the (collective) rendezvous: a rank that could not allocate must not leave the others waiting
+        ok = torch.tensor([0 if err is not None else 1], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            raise RuntimeError(f"symmetric memory unavailable on at least one rank ({err})")
         handle = symm.rendezvous(self.buf, group.group_name)
         ptrs = [int(p) for p in handle.buffer_ptrs]
         self.slot_ptrs = torch.tensor(ptrs, dtype=torch.int64).to(device)

@@ -29,6 +29,12 @@ def _world():
     return 1
 
 
+def _rank():
+    if DATA_PARALLEL and dist.is_available() and dist.is_initialized():
+        return dist.get_rank()
+    return 0
+
+
 def _allreduce(t):
     if _world() > 1:
         dist.all_reduce(t)
@@ -51,6 +57,11 @@ def enable_peer_exchange(device=None, group=None):
     return PEER
 
 
+def disable_peer_exchange():
+    global PEER
+    PEER = None
+
+
 _SIDE = {}
 
 
@@ -68,13 +79,22 @@ def _xr():
     if _world() <= 1 or not PEER_EXCHANGE:
         return None
     if PEER is None:
+        err = None
         try:
             enable_peer_exchange()
         except Exception as ex:  # noqa: BLE001  (no NVLink peer access / symmetric memory on this system)
+            err = ex
+        # the ranks must AGREE on the path: one rank falling back to NCCL on its own would leave the others spinning
+        # on its flag.  (A rank whose rendezvous itself failed cannot be rescued here; symmetric-memory rendezvous is
+        # collective, so in practice it fails or succeeds everywhere — this guards the allocation / mapping steps.)
+        ok = torch.tensor([0 if err is not None else 1], device=torch.cuda.current_device())
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
             import warnings
             PEER_EXCHANGE = False
-            warnings.warn(f"peer-memory exchange unavailable ({type(ex).__name__}: {ex}); BatchNorm statistics fall "
-                          "back to NCCL all-reduce (still on the GPUs, every rank takes the same path)")
+            disable_peer_exchange()
+            warnings.warn(f"peer-memory exchange unavailable on at least one rank ({type(err).__name__ if err else 'peer'}"
+                          f": {err}); BatchNorm statistics use NCCL all-reduce on EVERY rank (still on the GPUs)")
             return None
     return PEER.args
 
@@ -180,7 +200,7 @@ def _conv_bn_relu(S, P, name, seq, src, n, H, *, first=False, **apply_kw):
     Pn = n * H * H
     sums = _f32(2, cout, dev=dev)
     xr = _xr()
-    if not first and S.mode == L.CONV_MODE_SWAPPED and H % 32 == 0:
+    if not first and S.mode >= L.CONV_MODE_SWAPPED and H % 32 == 0:
         # the batch statistics come out of the convolution's epilogue (+ the cross-rank exchange): one C call
         L.conv3x3(src, P[name + ".f"], S.ones[:cout], bias, z, flags=L.EPI_BNSTATS, mode=S.mode, bn_partial=S.bnp,
                   bn_sums=sums, xr=xr)
@@ -563,6 +583,15 @@ class FusedAdam(torch.optim.Optimizer):
         self._tab = self._key = None  # exp_avg tensors were replaced: rebuild the pointer table
 
 
+def _draw_t(timesteps, n):
+    """t ~ randint(1, T+1) for this rank's n samples (train_diffusion_paper.py:353).  Under data parallelism every
+    rank draws the GLOBAL batch's timesteps and keeps its own slice: with the CPU generators in step (same seed on
+    every rank, which the shared shortcut draw requires anyway) the ranks hold distinct draws — together exactly what
+    the single-process reference draws for the global batch — and the generators stay in step."""
+    w, r = _world(), _rank()
+    return torch.randint(1, timesteps + 1, (n * w,))[r * n:(r + 1) * n]
+
+
 def training_step(model, optim, x, param, timesteps, ab_t, *, noise=None, t=None, shortcut=None):
     """The loop body of code/train_diffusion_paper.py:350-364 on device: noise, t, perturb_input, forward, MSE,
     backward, optimizer step.  Returns the (local) loss as a 0-d tensor; `loss.item()` is left to the caller."""
@@ -570,14 +599,15 @@ def training_step(model, optim, x, param, timesteps, ab_t, *, noise=None, t=None
     n = x.shape[0]
     x = x.to(dev, torch.float32).contiguous()
     if t is None:
-        t = torch.randint(1, timesteps + 1, (n,))
+        t = _draw_t(timesteps, n)
     t = t.to(dev)
     x_pert = torch.empty_like(x)
     ca, cb = ab_t.sqrt().contiguous(), (1 - ab_t).contiguous()
     if noise is None:
         noise = torch.empty_like(x)
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        L.perturb(x, x_pert, ca, cb, t_idx=t.to(torch.int64).contiguous(), seed=seed, noise_out=noise)
+        L.perturb(x, x_pert, ca, cb, t_idx=t.to(torch.int64).contiguous(), seed=seed, noise_out=noise,
+                  sample_offset=_rank() * n)
     else:
         noise = noise.to(dev, torch.float32).contiguous()
         L.perturb(x, x_pert, ca, cb, noise=noise, t_idx=t.to(torch.int64).contiguous())
@@ -685,7 +715,10 @@ class GraphedTrainStep:
         b = self.B if b is None else b
         x, x_pert, noise, dpred, t = self.x[:b], self.x_pert[:b], self.noise[:b], self.dpred[:b], self.t[:b]
         L.step_advance(self.count, 1)
-        L.perturb(x, x_pert, self.ca, self.cb, t_idx=t, step_ptr=self.count, seed=self.seed, noise_out=noise)
+        # the in-kernel noise is keyed by the GLOBAL sample index (rank * B + i): ranks of a data-parallel step never
+        # share noise, as the reference's iid draws over the global batch (train_diffusion_paper.py:352)
+        L.perturb(x, x_pert, self.ca, self.cb, t_idx=t, step_ptr=self.count, seed=self.seed, noise_out=noise,
+                  sample_offset=_rank() * self.B)
         ctx = _Ctx()
         pred = _UnetFn.forward(ctx, m, x_pert, t / self.T, self.param[:b], self.sc, *self.params)
         L.mse_grad(pred, noise, 1.0 / pred.numel(), dpred, self.partial, self.loss_sum)
@@ -733,7 +766,7 @@ class GraphedTrainStep:
             raise L.CdmError(f"batch of {b} samples exceeds the captured capacity {self.B}")
         self.x[:b].copy_(x.reshape(b, *self.x.shape[1:]), non_blocking=True)
         self.param[:b].copy_(param, non_blocking=True)
-        self.t[:b].copy_(torch.randint(1, self.T + 1, (b,)) if t is None else t, non_blocking=True)
+        self.t[:b].copy_(_draw_t(self.T, b) if t is None else t, non_blocking=True)
         self.sc.copy_(m.draw_shortcut() if shortcut is None else shortcut, non_blocking=True)
         if self.use_graph:
             if b not in self.graphs:

@@ -253,3 +253,70 @@ def test_driver_contexts_match_the_reference_statements(n):
     del calls[:]
     _, ctx_b, _ = drivers.parameter_sensitivity(d, base, batched=True)  # same contexts as one batch
     assert len(calls) == 1 and calls[0][0] == 5 * n and torch.equal(calls[0][1], T(g[f"sensitivity/{n}"]))
+
+
+def _header_structs():
+    """{struct typedef name: [field names]} parsed from include/cdm_b200.h (plain C declarations only)."""
+    import re
+    src = open(os.path.join(ROOT, "include", "cdm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for body, name in re.findall(r"typedef struct(?:\s+\w+)?\s*\{(.*?)\}\s*(\w+)\s*;", src, flags=re.S):
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            # "const float* a, *b" / "int H, W" / "cdm_forward_args fwd": the declarators after the type
+            parts = [p.strip() for p in decl.split(",")]
+            first = re.match(r"^(.*?)(\w+)$", parts[0], flags=re.S)
+            fields.append(first.group(2))
+            fields += [re.sub(r"^[\s\*]*", "", p) for p in parts[1:]]
+        out[name] = fields
+    return out
+
+
+def test_ctypes_structs_match_the_c_layout(lib, tmp_path):
+    """Every argument struct of include/cdm_b200.h: sizeof and every field's offsetof, as gcc lays them out, equal the
+    ctypes mirror in _lib.py (a binding that is one field short makes the library read past the caller's struct)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    structs = _header_structs()
+    mirror = {"cdm_conv3x3_args": lib.Conv3x3Args, "cdm_xrank": lib.XrankArgs, "cdm_gemm_args": lib.GemmArgs,
+              "cdm_conv_in_args": lib.ConvInArgs, "cdm_conv_out_args": lib.ConvOutArgs,
+              "cdm_gn_relu_film_args": lib.GnReluFilmArgs, "cdm_ddpm_step_args": lib.DdpmStepArgs,
+              "cdm_perturb_args": lib.PerturbArgs, "cdm_mse_accum_args": lib.MseAccumArgs,
+              "cdm_plan_desc": lib.PlanDesc, "cdm_forward_args": lib.ForwardArgs,
+              "cdm_sample_step_args": lib.SampleStepArgs, "cdm_gemm_tn_args": lib.GemmTnArgs,
+              "cdm_chan_reduce_args": lib.ChanReduceArgs, "cdm_bn_apply_args": lib.BnApplyArgs,
+              "cdm_bn_bwd_args": lib.BnBwdArgs, "cdm_gn_bwd_args": lib.GnBwdArgs,
+              "cdm_outer_wgrad_args": lib.OuterWgradArgs, "cdm_embed_bwd_args": lib.EmbedBwdArgs}
+    assert set(structs) == set(mirror), f"header structs without a ctypes mirror (or vice versa): {set(structs) ^ set(mirror)}"
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "cdm_b200.h"', "int main(void) {"]
+    for name, fields in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        lines += [f'  printf("{name}.{f} %zu\\n", offsetof({name}, {f}));' for f in fields]
+    lines += ["  return 0;", "}"]
+    csrc = tmp_path / "layout.c"
+    csrc.write_text("\n".join(lines))
+    exe = str(tmp_path / "layout")
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(csrc), "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = dict(l.split() for l in subprocess.run([exe], capture_output=True, text=True).stdout.splitlines())
+    for name, cls in mirror.items():
+        assert int(got[name]) == ctypes_sizeof(cls), f"sizeof({name}): C {got[name]} vs ctypes {ctypes_sizeof(cls)}"
+        cfields = structs[name]
+        alias = {"inp": "in"}  # `in` is a Python keyword
+        pyfields = [alias.get(f[0], f[0]) for f in cls._fields_]
+        assert cfields == pyfields, f"{name}: field names/order differ: {cfields} vs {pyfields}"
+        for f in cfields:
+            pf = {v: k for k, v in alias.items()}.get(f, f)
+            assert int(got[f"{name}.{f}"]) == getattr(cls, pf).offset, f"offsetof({name}, {f})"
+
+
+def ctypes_sizeof(cls):
+    import ctypes
+    return ctypes.sizeof(cls)

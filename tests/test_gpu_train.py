@@ -385,7 +385,8 @@ def test_graphed_training_step_equals_eager():
         assert not torch.equal(sd_g[k].cpu(), O.init_state_dict(0, n_cfeat=NCF)[k])
 
 
-def test_conv_epilogue_batchnorm_statistics(L):
+@pytest.mark.parametrize("mode", [3, 4])
+def test_conv_epilogue_batchnorm_statistics(L, mode):
     """CDM_EPI_BNSTATS: per-channel sum / sum of squares of the stored (bf16) conv output come out of the
     convolution launch itself (per-CTA partial rows folded in a fixed order)."""
     for n, H, cin, cout in ((5, 64, 128, 128), (3, 32, 128, 256), (40, 32, 256, 256)):
@@ -397,14 +398,14 @@ def test_conv_epilogue_batchnorm_statistics(L):
         z = torch.empty(n, H, H, cout, device="cuda", dtype=torch.bfloat16)
         part = torch.full((148, 2 * cout), float("nan"), device="cuda")
         sums = torch.empty(2, cout, device="cuda")
-        L.conv3x3(x, w, ones, bias, z, flags=L.EPI_BNSTATS, bn_partial=part, bn_sums=sums)
+        L.conv3x3(x, w, ones, bias, z, flags=L.EPI_BNSTATS, bn_partial=part, bn_sums=sums, mode=mode)
         z_plain = torch.empty_like(z)
-        L.conv3x3(x, w, ones, bias, z_plain, flags=0)
+        L.conv3x3(x, w, ones, bias, z_plain, flags=0, mode=mode)
         assert torch.equal(z, z_plain)
         zf = z.float().reshape(-1, cout).double()
         assert rel_l2(sums[0], zf.sum(0)) < 1e-5 and rel_l2(sums[1], (zf * zf).sum(0)) < 1e-5
         sums2 = torch.empty_like(sums)
-        L.conv3x3(x, w, ones, bias, z, flags=L.EPI_BNSTATS, bn_partial=part, bn_sums=sums2)
+        L.conv3x3(x, w, ones, bias, z, flags=L.EPI_BNSTATS, bn_partial=part, bn_sums=sums2, mode=mode)
         assert torch.equal(sums, sums2), "fixed-order reduction must be deterministic"
 
 

@@ -27,10 +27,12 @@ torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 t0 = time.time()
-nll = P.evaluate_sharded(lambda dl: D.calculate_likelihood(model, dl, T, dev, ab_t, b_t, a_t, seed=7), maps, prm, bs, dev)
+# ONE sweep accumulates both weights over the same forwards (BASELINE config 5); sample_offset keys the noise by global map
+nll, elbo, bpd = P.evaluate_sharded(
+    lambda dl, sample_offset=0: D.calculate_likelihood_and_elbo(model, dl, T, dev, ab_t, b_t, a_t, seed=7,
+                                                                sample_offset=sample_offset), maps, prm, bs, dev)
 torch.cuda.synchronize()
 t_nll = time.time() - t0
-elbo, bpd = P.evaluate_sharded(lambda dl: D.calculate_elbo_and_bpd(model, dl, T, dev, ab_t, b_t, a_t, seed=7), maps, prm, bs, dev)
 if rank == 0:
     fwd = n_maps * T
     print(f"NLL-SHARDED world={world}: {n_maps} maps x {T} timesteps in {t_nll:.2f} s = {fwd / t_nll:.0f} image-forwards/s, "
