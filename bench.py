@@ -41,7 +41,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=1024, help="global number of samples (BASELINE config 2: 1024)")
     ap.add_argument("--guide-w", type=float, default=2.0)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-steps", type=int, default=8, help="steps of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=50, help="steps of the bounded CPU-baseline sample (per guide_w)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary block (configs 3, 4, 5)")
+    ap.add_argument("--no-torch-gpu", action="store_true", help="skip the same-box torch/cuDNN comparator")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--breakdown", default="", help="write the per-kernel CUDA-event breakdown of one step here")
@@ -115,18 +117,45 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU reference arm
+def _reference_modules():
+    """The unmodified reference modules (oracle/_ref, see oracle/build_ref.py) if they travelled with the snapshot."""
+    try:
+        from oracle import build_ref
+        if build_ref.available():
+            return build_ref.load()
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def cpu_reference_steps(steps, warmup, batch=4, guide_w=2.0):
-    """The reference algorithm (oracle port, fp32, torch CPU kernels, all host threads) on a bounded sample
-    of the workload: `batch` samples, CFG (two forwards per step).  Returns (ms_per_step, cores)."""
+    """The reference's CPU path on a bounded sample of the workload: `batch` samples, fp32, all host threads.
+    kind "reference": the reference's own ContextUnet + sample_ddpm (code/sample_power_spectra.py:71-110, imported
+    unmodified from oracle/_ref) run for `steps` reverse-diffusion steps (its `timesteps` argument; per-step cost does
+    not depend on the schedule value).  kind "port": the oracle restatement, when oracle/_ref is not there.
+    Returns (ms_per_step, cores, kind)."""
     import torch
     from oracle import contextunet_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = O.init_state_dict(0, n_cfeat=NCF)
     sched = O.make_schedule(TIMESTEPS)
     g = torch.Generator().manual_seed(0)
-    x = torch.randn(batch, 1, 64, 64, generator=g)
     params = torch.rand(batch, NCF, generator=g)
+    ref = _reference_modules()
+    if ref is not None:
+        CU, sps = ref
+        torch.manual_seed(0)
+        model = CU(in_channels=1, n_feat=128, n_cfeat=NCF, height=64).eval()
+        b_t, a_t, ab_t = sched
+        kw = dict(n_sample=batch, size=64, device=torch.device("cpu"), params=params, guide_w=guide_w, b_t=b_t, a_t=a_t,
+                  ab_t=ab_t)
+        if warmup > 0:
+            sps.sample_ddpm(model, timesteps=warmup, **kw)
+        t0 = time.perf_counter()
+        sps.sample_ddpm(model, timesteps=steps, **kw)
+        return 1e3 * (time.perf_counter() - t0) / steps, cores, "reference"
+    sd = O.init_state_dict(0, n_cfeat=NCF)
+    x = torch.randn(batch, 1, 64, 64, generator=g)
     times = []
     with torch.no_grad():
         for k in range(warmup + steps):
@@ -135,12 +164,26 @@ def cpu_reference_steps(steps, warmup, batch=4, guide_w=2.0):
             z = torch.randn(x.shape, generator=g)
             t = torch.tensor([i / TIMESTEPS])
             e_c = O.unet_forward(sd, x, t, params, O.draw_shortcut(128, g), n_cfeat=NCF)
-            e_u = O.unet_forward(sd, x, t, torch.zeros_like(params), O.draw_shortcut(128, g), n_cfeat=NCF)
-            eps = e_u + guide_w * (e_c - e_u)
-            x = O.denoise_add_noise(x, i, eps, z, *sched)
+            if guide_w > 0:
+                e_u = O.unet_forward(sd, x, t, torch.zeros_like(params), O.draw_shortcut(128, g), n_cfeat=NCF)
+                e_c = e_u + guide_w * (e_c - e_u)
+            x = O.denoise_add_noise(x, i, e_c, z, *sched)
             if k >= warmup:
                 times.append(time.perf_counter() - t0)
-    return 1e3 * sum(times) / len(times), cores
+    return 1e3 * sum(times) / len(times), cores, "port"
+
+
+def cpu_baseline_block(steps, batch=4):
+    """BASELINE.md §4 / SURVEY §8(d) cfg 1: batch 4, fp32, all host cores, >= 50 steps, guide_w = 2.0 (two forwards per
+    step, the headline's workload) and guide_w = 0 (one forward per step), extrapolated to 1500 steps."""
+    ms2, cores, kind = cpu_reference_steps(steps, 2, batch=batch, guide_w=2.0)
+    ms0, _, _ = cpu_reference_steps(steps, 2, batch=batch, guide_w=0.0)
+    what = ("the reference's own ContextUnet + sample_ddpm (oracle/_ref, unmodified)" if kind == "reference"
+            else "the oracle port of the reference loop")
+    return {"value": batch / (ms2 / 1e3 * TIMESTEPS), "unit": "samples/s", "cores": cores, "kind": kind,
+            "ms_per_step": ms2, "guide_w0": {"value": batch / (ms0 / 1e3 * TIMESTEPS), "ms_per_step": ms0},
+            "sample": f"{batch} samples x {steps} steps each at guide_w=2.0 (2 fp32 forwards/step) and guide_w=0 (1 forward"
+                      f"/step) through {what} on {cores} host threads (torch CPU kernels), extrapolated to {TIMESTEPS} steps"}
 
 
 def run_reference(args):
@@ -148,20 +191,92 @@ def run_reference(args):
     if rank != 0:
         return
     batch = 4
-    ms, cores = cpu_reference_steps(args.steps, args.warmup, batch=batch, guide_w=args.guide_w)
+    ms, cores, kind = cpu_reference_steps(args.steps, args.warmup, batch=batch, guide_w=args.guide_w)
     val = batch / (ms / 1e3 * TIMESTEPS)
-    sample = (f"{batch} samples x {args.steps} CFG steps of {TIMESTEPS} (2 forwards/step), fp32, oracle port of the "
-              f"reference loop on {cores} host threads; samples/s extrapolated to 1500 steps")
+    what = ("the reference's own ContextUnet + sample_ddpm (code/sample_power_spectra.py:71-110, unmodified, oracle/_ref)"
+            if kind == "reference" else "oracle port of the reference loop")
+    sample = (f"{batch} samples x {args.steps} CFG steps of {TIMESTEPS} (2 forwards/step), fp32, {what} "
+              f"on {cores} host threads; samples/s extrapolated to 1500 steps")
     print(json.dumps({
         "impl": "reference", "metric": "cfg_ddpm_samples_per_sec_64x64_1500steps", "value": val,
         "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BASELINE config 2 (CFG sampling, 6 params, 1500 timesteps), bounded CPU sample",
                    "batch": batch, "timesteps": TIMESTEPS, "guide_w": args.guide_w},
-        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+# --------------------------------------------------------------------------- same-box GPU comparator
+def torch_gpu_baseline(dev, batch, guide_w, steps=10, warmup=2):
+    """The reference's own module (oracle/_ref; else the oracle port = the same torch ops) on THIS GPU through
+    torch/cuDNN/cuBLAS, same CFG step (2 forwards + mix + denoise_add_noise), same batch: (a) fp32 eager as the
+    reference runs it (torch defaults: TF32 allowed for cuDNN convolutions), (b) bf16 autocast + channels_last.
+    A reported comparator, never part of the product path."""
+    import torch
+    from oracle import contextunet_oracle as O
+    ref = _reference_modules()
+    sched = [s.to(dev) for s in O.make_schedule(TIMESTEPS)]
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.randn(batch, 1, 64, 64, generator=g).to(dev)
+    params = torch.rand(batch, NCF, generator=g).to(dev)
+    zeros = torch.zeros_like(params)
+    if ref is not None:
+        CU, sps = ref
+        torch.manual_seed(0)
+        model = CU(in_channels=1, n_feat=128, n_cfeat=NCF, height=64).to(dev).eval()
+        fwd = lambda x, t, c: model(x, t, c)  # noqa: E731
+        denoise = lambda x, i, e, z: sps.denoise_add_noise(x, i, e, z, *sched)  # noqa: E731
+        kind = "reference module (oracle/_ref)"
+    else:
+        sd = {k: v.to(dev) for k, v in O.init_state_dict(0, n_cfeat=NCF).items()}
+        gs = torch.Generator().manual_seed(1)
+        fwd = lambda x, t, c: O.unet_forward(sd, x, t, c, tuple(v.to(dev) for v in O.draw_shortcut(128, gs)),  # noqa: E731
+                                             n_cfeat=NCF)
+        denoise = lambda x, i, e, z: O.denoise_add_noise(x, i, e, z, *sched)  # noqa: E731
+        model, kind = None, "oracle port"
+
+    def run(n, x):
+        for k in range(n):
+            i = TIMESTEPS - k
+            t = torch.tensor([i / TIMESTEPS], device=dev, dtype=x.dtype)
+            z = torch.randn_like(x)
+            e_c, e_u = fwd(x, t, params), fwd(x, t, zeros)
+            x = denoise(x.float(), i, (e_u + guide_w * (e_c - e_u)).float(), z.float()).to(x.dtype)
+        return x
+
+    out = {"impl": kind, "batch": batch, "steps": steps, "torch": torch.__version__,
+           "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32)}
+    for name in ("fp32_eager", "bf16_autocast_channels_last", "bf16_weights_channels_last"):
+        try:
+            x = x0.clone()
+            if name != "fp32_eager":
+                if model is not None:
+                    model.to(memory_format=torch.channels_last)
+                x = x.contiguous(memory_format=torch.channels_last)
+            if name == "bf16_weights_channels_last":  # the whole module in bf16 (no autocast casts): the strongest
+                if model is None:                      # library-only form of the same network
+                    continue
+                model.to(torch.bfloat16)
+                x, params, zeros = x.to(torch.bfloat16), params.to(torch.bfloat16), zeros.to(torch.bfloat16)
+            ctx = torch.autocast("cuda", dtype=torch.bfloat16, enabled=name == "bf16_autocast_channels_last")
+            with torch.no_grad(), ctx:
+                run(warmup, x)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                xe = run(steps, x)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"ms_per_step": ms, "samples_per_s": batch / (ms / 1e3 * TIMESTEPS),
+                         "finite": bool(torch.isfinite(xe).all())}
+        except Exception as ex:  # noqa: BLE001
+            out[name] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+        torch.cuda.empty_cache()
+    return out
 
 
 # --------------------------------------------------------------------------- B200 arm
@@ -188,6 +303,136 @@ def kernel_breakdown(run):
     ev[2].record()
     torch.cuda.synchronize()
     return recs + [("ddpm_step", ev[0].elapsed_time(ev[1])), ("step_advance", ev[1].elapsed_time(ev[2]))]
+
+
+def secondary_block(dev, rank, world, barrier):
+    """The BASELINE configs that are not the headline, measured after it at every N (device-timed, max over ranks):
+    cfg 3 training step (global batch 256 split over the ranks, CUDA-graph step, cross-rank BatchNorm statistics over
+    NVLink peer memory or NCCL + NCCL gradient all-reduce), cfg 5 all-timestep NLL + ELBO sweep (4096 maps split over
+    the ranks, batches of 512, >= 50 timesteps, both weights accumulated over the same forwards), cfg 4 batch-1 latency."""
+    import torch
+    import torch.distributed as dist
+    import camels_diffusion_model_b200 as cdm
+    from camels_diffusion_model_b200 import _lib as L, diffusion as D, train as TR
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def max_ms(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    out = {}
+    g = torch.Generator().manual_seed(100 + rank)
+    sched = D.make_schedule(TIMESTEPS, device=dev)
+    # ---- cfg 3: training step, global batch 256
+    GB = 256
+    if GB % world == 0:
+        per = GB // world
+        modes = ("peer", "nccl") if world > 1 else ("local",)
+        tr = {"global_batch": GB, "per_gpu_batch": per, "lr": 1e-5,
+              "what": "perturb_input (in-kernel noise) + train-mode forward + MSE + backward + cross-rank reductions + "
+                      "Adam, one CUDA graph per step; reference step: code/train_diffusion_paper.py:349-366"}
+        for mode in modes:
+            try:
+                TR.DATA_PARALLEL, TR.PEER_EXCHANGE = world > 1, mode == "peer"
+                torch.manual_seed(0)
+                model = cdm.ContextUnet(1, 128, NCF, 64).to(dev).train()
+                gs = TR.GraphedTrainStep(model, per, TIMESTEPS, sched[2], lr=1e-5)
+                xb, pb = torch.rand(per, 1, 64, 64, generator=g).to(dev), torch.rand(per, NCF, generator=g).to(dev)
+                torch.manual_seed(7)  # CPU generators in step: same shortcut draw on every rank
+                for _ in range(3):
+                    gs(xb, pb)
+                barrier()
+                K = 20
+                e0, e1 = ev(), ev()
+                e0.record()
+                for _ in range(K):
+                    loss = gs(xb, pb)
+                e1.record()
+                barrier()
+                ms = max_ms(e0.elapsed_time(e1) / K)
+                tr[mode] = {"ms_per_step": ms, "img_per_s": GB / ms * 1e3,
+                            "tflops_per_gpu": 3 * GFLOP_PER_IMAGE_FWD * 1e9 * per / (ms * 1e-3) / 1e12,
+                            "loss": float(loss), "bn_stats_exchange": mode}
+                del gs, model
+            except Exception as ex:  # noqa: BLE001
+                tr[mode] = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
+            torch.cuda.empty_cache()
+        best = min((v for v in tr.values() if isinstance(v, dict) and "ms_per_step" in v),
+                   key=lambda v: v["ms_per_step"], default=None)
+        if best:
+            tr.update(ms_per_step=best["ms_per_step"], img_per_s=best["img_per_s"], tflops_per_gpu=best["tflops_per_gpu"])
+        out["train_step"] = tr
+    # ---- cfg 5: NLL + ELBO sweep
+    N_MAPS, BS, NT = 4096, 512, 50
+    if N_MAPS % (world * BS) == 0:
+        per = N_MAPS // world
+        torch.manual_seed(0)
+        model = cdm.ContextUnet(1, 128, NCF, 64).to(dev).eval()
+        w = 1.0 / (2 * sched[0].float())
+        w2 = 0.5 * (1.0 / (1.0 - sched[2].float()) - 1.0)
+        w2[0] = 0
+        loops = []
+        for bi in range(per // BS):
+            lp = D._EvalLoop(model, torch.rand(BS, 1, 64, 64, generator=g), torch.rand(BS, NCF, generator=g), TIMESTEPS,
+                             sched, "one_minus", w, seed=3, weight_tab2=w2, sample_offset=rank * per + bi * BS)
+            lp.step.fill_(1)
+            lp.one()
+            torch.cuda.synchronize()
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                lp.one()
+                L.step_advance(lp.step, 1)
+            lp.step.fill_(1)
+            lp.acc.zero_()
+            lp.acc2.zero_()
+            loops.append((lp, gph))
+        for lp, gph in loops:
+            for _ in range(2):
+                gph.replay()
+        barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for lp, gph in loops:  # the reference's loop order: all timesteps of one batch, then the next batch
+            for _ in range(NT):
+                gph.replay()
+        e1.record()
+        barrier()
+        ms = max_ms(e0.elapsed_time(e1))
+        fwd = N_MAPS * NT
+        fin = all(bool(torch.isfinite(lp.acc).all() and torch.isfinite(lp.acc2).all()) for lp, _ in loops)
+        out["nll_sweep"] = {"maps": N_MAPS, "maps_per_gpu": per, "batch": BS, "timesteps_timed": NT,
+                            "image_forwards_per_s": fwd / (ms * 1e-3), "tflops_per_gpu":
+                            GFLOP_PER_IMAGE_FWD * 1e9 * fwd / world / (ms * 1e-3) / 1e12,
+                            "maps_per_s_all_1500_timesteps": N_MAPS / (ms * 1e-3 * TIMESTEPS / NT), "finite": fin,
+                            "what": "perturb (in-kernel noise) + eval forward + per-map MSE accumulated with both the NLL "
+                                    "weight 1/(2 b_t) and the ELBO weight 0.5(1/(1-ab_t)-1), graph replay per timestep; "
+                                    "reference: code/train_diffusion_paper.py:142-183, train_diffusion_elbo.py:91-103"}
+        del loops
+        torch.cuda.empty_cache()
+    # ---- cfg 4: batch-1 sampling latency (replicas only: every rank runs the same thing; rank 0's figure)
+    torch.manual_seed(0)
+    model = cdm.ContextUnet(1, 128, NCF, 64).to(dev).eval()
+    b1 = {}
+    for gw in (0.0, 2.0):
+        tab = D.draw_shortcut_table(TIMESTEPS, 2 if gw > 0 else 1, 128)
+        run = D._SamplerRun(model, torch.randn(1, 1, 64, 64, generator=g).to(dev), torch.rand(1, NCF, generator=g).to(dev),
+                            gw, TIMESTEPS, sched, shortcut_tab=tab, seed=1)
+        run.capture()
+        run.run(10)
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        run.run(100)
+        e1.record()
+        torch.cuda.synchronize()
+        b1[f"guide_w_{gw:g}"] = {"ms_per_step": e0.elapsed_time(e1) / 100,
+                                 "s_per_sample_1500_steps": e0.elapsed_time(e1) / 100 * 1.5}
+    out["batch1_latency"] = b1
+    return out
 
 
 def run_b200(args):
@@ -310,12 +555,23 @@ def run_b200(args):
                 fh.write(f"{v:9.4f} ms  {d}\n")
             fh.write(f"{step_ms:9.4f} ms  TOTAL (eager, one CFG step, {n_img} images)\n")
 
+    del run
+    if e2e is not None:
+        del sess, ddpm
+    torch.cuda.empty_cache()
+    secondary = None if args.no_secondary else secondary_block(dev, rank, world, barrier)
+    torch_gpu = None
+    if rank == 0 and world == 1 and not args.no_torch_gpu:
+        try:
+            torch_gpu = torch_gpu_baseline(dev, args.batch, args.guide_w)
+            for k in ("fp32_eager", "bf16_autocast_channels_last", "bf16_weights_channels_last"):
+                if "samples_per_s" in torch_gpu.get(k, {}):
+                    torch_gpu[k]["ours_over_this"] = value / torch_gpu[k]["samples_per_s"]
+        except Exception as ex:  # noqa: BLE001
+            torch_gpu = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cms, cores = cpu_reference_steps(args.cpu_steps, 1, batch=4, guide_w=args.guide_w)
-        cpu = {"value": 4 / (cms / 1e3 * TIMESTEPS), "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": f"4 samples x {args.cpu_steps} CFG steps (2 fp32 forwards/step) of the oracle port on "
-                         f"{cores} host threads, extrapolated to {TIMESTEPS} steps"}
+        cpu = cpu_baseline_block(args.cpu_steps)
     if rank == 0:
         out = {
             "metric": "cfg_ddpm_samples_per_sec_64x64_1500steps", "value": value, "unit": "samples/s",
@@ -329,7 +585,8 @@ def run_b200(args):
                        "parallelism": f"batch-shard x{world}, no collective",
                        "l2_policy": "inputs larger than L2 (activation working set >> 126 MB per step)"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": KERNELS_PER_STEP * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "finite": finite,
+            "roofline": roofline, "cpu_baseline": cpu, "finite": finite, "secondary": secondary,
+            "torch_gpu_baseline": torch_gpu,
         }
         print(json.dumps(out))
     if world > 1:
