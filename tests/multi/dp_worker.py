@@ -147,7 +147,13 @@ nll_s, elbo_s = P.evaluate_sharded(ev, maps, mp, 4, dev)
 nll_1, elbo_1 = ev([(maps, mp)])
 assert abs(nll_s - nll_1) <= 1e-5 * abs(nll_1) and abs(elbo_s - elbo_1) <= 1e-5 * abs(elbo_1), (nll_s, nll_1, elbo_s, elbo_1)
 
+del gs
+torch.cuda.synchronize()
 dist.barrier()
 if rank == 0:
-    print(f"DP-WORKER OK world={world}")
-dist.destroy_process_group()
+    print(f"DP-WORKER OK world={world}", flush=True)
+sys.stdout.flush()
+sys.stderr.flush()
+# every check has passed and every rank has reached the barrier: leave without the interpreter's teardown (destroying
+# the process group under live symmetric-memory mappings and captured NCCL graphs can block at exit)
+os._exit(0)

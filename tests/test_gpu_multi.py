@@ -27,5 +27,5 @@ def test_data_parallel_step_matches_the_single_process_global_batch():
     ranks draw distinct noise / timesteps and keep identical parameters; sharded NLL + ELBO == single process."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "multi", "dp_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
     assert r.returncode == 0 and "DP-WORKER OK world=2" in r.stdout, (r.stdout[-3000:] + r.stderr[-3000:])
