@@ -43,7 +43,7 @@ def save_checkpoint(path, model, optim, epoch, step=0, extra=None):
         return
     ck = {"format": "cdm_b200/1", "epoch": int(epoch), "step": int(step),
           "model": {k: v.detach().cpu() for k, v in model.state_dict().items()},
-          "optim": _to_cpu(optim.state_dict()), "cpu_rng_state": torch.get_rng_state(), "extra": extra or {}}
+          "optim": _to_cpu(optim.state_dict()), "cpu_rng_state": torch.get_rng_state(), "extra": _plain(extra or {})}
     tmp = path + ".tmp"
     torch.save(ck, tmp)
     os.replace(tmp, path)
@@ -73,6 +73,25 @@ def broadcast_model(model, src=0):
             dist.broadcast(t.data, src=src)
     if hasattr(model, "invalidate"):
         model.invalidate()  # .data writes do not bump version counters: re-pack the eval weights on next use
+
+
+def _plain(o):
+    """`extra` as tensors + plain Python containers / scalars only (numpy scalars and arrays become floats / lists), so
+    that the file loads with torch.load(weights_only=True): a resume file never needs arbitrary pickle code."""
+    import numpy as np
+    if torch.is_tensor(o):
+        return o.detach().cpu()
+    if isinstance(o, np.ndarray):
+        return o.tolist()
+    if isinstance(o, np.generic):
+        return o.item()
+    if isinstance(o, dict):
+        return {(k if isinstance(k, (str, int, float, bool)) else str(k)): _plain(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_plain(v) for v in o]
+    if o is None or isinstance(o, (str, int, float, bool)):
+        return o
+    return str(o)
 
 
 def _to_cpu(o):

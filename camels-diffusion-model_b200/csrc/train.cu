@@ -74,21 +74,25 @@ struct ChanReduceP {
   int C;
   float* partial;
 };
-__global__ void __launch_bounds__(256) chan_reduce_kernel(const ChanReduceP p) {
+// Occupancy is what bounds these passes: a thread keeps per-channel constants for its 8 channels in registers, and at
+// 110 registers only two 256-thread blocks fit an SM (ncu: 23 % warps active, 4.2 TB/s).  So the kernel is
+// specialised per mode, mode 1 accumulates sum g and sum g*z and applies (z - mean) * rstd ONCE at the end
+// (sum g*xhat = rstd * (sum g*z - mean * sum g): two constant vectors fewer in the loop), and __launch_bounds__ asks
+// for three blocks per SM: 24 warps x 8 independent 16-byte loads in flight.
+template <int MODE>
+__global__ void __launch_bounds__(256, 3) chan_reduce_kernel(const ChanReduceP p) {
   __shared__ float red[2][256][8];
   const int groups = p.C >> 3, rows = 256 / groups;
   const int cg = threadIdx.x % groups, pr = threadIdx.x / groups;
   float s0[8], s1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
-  float sc[8], sh[8], mu[8], rs[8];
-  if (p.mode == 1) {
+  float sc[8], sh[8];
+  if (MODE == 1) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       sc[j] = p.scale[cg * 8 + j];
       sh[j] = p.shift[cg * 8 + j];
-      mu[j] = p.mean[cg * 8 + j];
-      rs[j] = p.rstd[cg * 8 + j];
     }
   }
   // 4 rows per iteration with all loads issued first (the loop is latency bound otherwise)
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const ChanReduceP p) {
       rz[u] = make_uint4(0u, 0u, 0u, 0u);
       if (r < p.P) {
         ra[u] = ld8(p.a + r * p.lda + cg * 8);
-        if (p.mode == 1) rz[u] = ld8(p.z + r * p.ldz + cg * 8);
+        if (MODE == 1) rz[u] = ld8(p.z + r * p.ldz + cg * 8);
       }
     }
 #pragma unroll
@@ -110,26 +114,30 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const ChanReduceP p) {
       if (r0 + u * stride >= p.P) break;
       float a[8];
       t_unpack8(ra[u], a);
-      if (p.mode == 0) {
+      if (MODE == 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           s0[j] += a[j];
           s1[j] = fmaf(a[j], a[j], s1[j]);
         }
-      } else if (p.mode == 1) {
+      } else if (MODE == 1) {
         float z[8];
         t_unpack8(rz[u], z);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float g = (!p.relu || fmaf(z[j], sc[j], sh[j]) > 0.f) ? a[j] : 0.f;
           s0[j] += g;
-          s1[j] = fmaf(g, (z[j] - mu[j]) * rs[j], s1[j]);
+          s1[j] = fmaf(g, z[j], s1[j]);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) s0[j] += a[j];
       }
     }
+  }
+  if (MODE == 1) {  // sum g*xhat = rstd * (sum g*z - mean * sum g), per thread (linear, so the partials add up)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = (s1[j] - p.mean[cg * 8 + j] * s0[j]) * p.rstd[cg * 8 + j];
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -365,43 +373,56 @@ struct BnApplyP {
   int fb_rows, px_per_img;
   bf16* yf;
 };
-__global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyP p) {
+// Four rows per thread and iteration, all loads issued before the first use (one 16-byte load in flight per thread left
+// the pass at 55-66 % of the copy bandwidth); the shortcut / FiLM extras are compile-time variants so that the plain
+// Conv-BN-ReLU instance stays small enough for four blocks per SM.
+template <bool EXTRAS>
+__global__ void __launch_bounds__(256, 4) bn_apply_kernel(const BnApplyP p) {
   const int groups = p.C >> 3;  // 16 or 32: divides blockDim.x, so a thread keeps the same 8 channels
   const int cg = (int)(threadIdx.x % groups);
-  float sc[8], sh[8], sw[8], sb[8];
+  float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     sc[j] = p.scale[cg * 8 + j];
     sh[j] = p.shift[cg * 8 + j];
-    sw[j] = p.sc_x ? p.sc_w[cg * 8 + j] : 0.f;
-    sb[j] = p.sc_x ? p.sc_b[cg * 8 + j] : 0.f;
   }
   // groups divides blockDim.x, so a thread's row advances by a constant: no 64-bit division in the loop
   const long long r_step = (long long)gridDim.x * (blockDim.x / groups);
-  for (long long r = (long long)blockIdx.x * (blockDim.x / groups) + threadIdx.x / groups; r < p.P; r += r_step) {
-    float f[8];
-    t_unpack8(ld8(p.z + r * p.C + cg * 8), f);
+  for (long long r0 = (long long)blockIdx.x * (blockDim.x / groups) + threadIdx.x / groups; r0 < p.P; r0 += 4 * r_step) {
+    uint4 raw[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float y = fmaf(f[j], sc[j], sh[j]);
-      f[j] = p.relu ? fmaxf(y, 0.f) : y;
+    for (int u = 0; u < 4; ++u) {
+      const long long r = r0 + u * r_step;
+      raw[u] = r < p.P ? ld8(p.z + r * p.C + cg * 8) : make_uint4(0u, 0u, 0u, 0u);
     }
-    if (p.sc_x) {
-      const float xv = p.sc_x[r];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += fmaf(sw[j], xv, sb[j]);
-    }
-    *reinterpret_cast<uint4*>(p.y + r * p.C + cg * 8) = t_pack8(f);
-    if (p.fs) {
-      const long long n = r / p.px_per_img;
-      const float* fs = p.fs + n * p.C + cg * 8;
-      const float* fb = p.fb + (p.fb_rows == 1 ? 0 : n) * p.C + cg * 8;
-      // FiLM acts on the bf16-rounded y the next layer's backward sees
-      float g[8];
-      t_unpack8(t_pack8(f), g);
+    for (int u = 0; u < 4; ++u) {
+      const long long r = r0 + u * r_step;
+      if (r >= p.P) break;
+      float f[8];
+      t_unpack8(raw[u], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = fmaf(fs[j], g[j], fb[j]);
-      *reinterpret_cast<uint4*>(p.yf + r * p.C + cg * 8) = t_pack8(g);
+      for (int j = 0; j < 8; ++j) {
+        float y = fmaf(f[j], sc[j], sh[j]);
+        f[j] = p.relu ? fmaxf(y, 0.f) : y;
+      }
+      if (EXTRAS && p.sc_x) {
+        const float xv = p.sc_x[r];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += fmaf(__ldg(p.sc_w + cg * 8 + j), xv, __ldg(p.sc_b + cg * 8 + j));
+      }
+      *reinterpret_cast<uint4*>(p.y + r * p.C + cg * 8) = t_pack8(f);
+      if (EXTRAS && p.fs) {
+        const long long n = r / p.px_per_img;
+        const float* fs = p.fs + n * p.C + cg * 8;
+        const float* fb = p.fb + (p.fb_rows == 1 ? 0 : n) * p.C + cg * 8;
+        // FiLM acts on the bf16-rounded y the next layer's backward sees
+        float g[8];
+        t_unpack8(t_pack8(f), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = fmaf(fs[j], g[j], fb[j]);
+        *reinterpret_cast<uint4*>(p.yf + r * p.C + cg * 8) = t_pack8(g);
+      }
     }
   }
 }
@@ -421,46 +442,47 @@ struct BnBwdP {
   float count;
   bf16* dz;
 };
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdP p) {
+// dz = scale*g - A*z - B with A = scale*rstd*S1/N and B = scale*S0/N - A*mean (the expression above, expanded so that a
+// thread keeps four constant vectors instead of six: 90 -> <= 85 registers, three blocks per SM instead of two);
+// four rows per iteration, all eight loads issued first.
+__global__ void __launch_bounds__(256, 3) bn_bwd_apply_kernel(const BnBwdP p) {
   const int groups = p.C >> 3;  // divides blockDim.x: a thread keeps the same 8 channels
   const float inv = 1.f / p.count;
   const int cg = (int)(threadIdx.x % groups);
-  float sc[8], sh[8], mu[8], rs[8], m0[8], m1[8];
+  float sc[8], sh[8], ca[8], cb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cg * 8 + j;
     sc[j] = p.scale[c];
     sh[j] = p.shift[c];
-    mu[j] = p.mean[c];
-    rs[j] = p.rstd[c];
-    m0[j] = p.sums[c] * inv;
-    m1[j] = p.sums[p.C + c] * inv;
+    ca[j] = sc[j] * p.rstd[c] * (p.sums[p.C + c] * inv);
+    cb[j] = sc[j] * (p.sums[c] * inv) - ca[j] * p.mean[c];
   }
-  // a thread's row advances by a constant (groups divides blockDim.x): no 64-bit division; two rows per iteration
-  // with all four loads issued first
   const long long r_step = (long long)gridDim.x * (blockDim.x / groups);
-  for (long long r = (long long)blockIdx.x * (blockDim.x / groups) + threadIdx.x / groups; r < p.P; r += 2 * r_step) {
-    const long long r2 = r + r_step;
-    const bool two = r2 < p.P;
-    const uint4 rd0 = ld8(p.dy + r * p.lddy + cg * 8), rz0 = ld8(p.z + r * p.C + cg * 8);
-    uint4 rd1 = make_uint4(0u, 0u, 0u, 0u), rz1 = rd1;
-    if (two) {
-      rd1 = ld8(p.dy + r2 * p.lddy + cg * 8);
-      rz1 = ld8(p.z + r2 * p.C + cg * 8);
+  for (long long r0 = (long long)blockIdx.x * (blockDim.x / groups) + threadIdx.x / groups; r0 < p.P; r0 += 4 * r_step) {
+    uint4 rd[4], rz[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long r = r0 + u * r_step;
+      rd[u] = rz[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (r < p.P) {
+        rd[u] = ld8(p.dy + r * p.lddy + cg * 8);
+        rz[u] = ld8(p.z + r * p.C + cg * 8);
+      }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u == 1 && !two) break;
+    for (int u = 0; u < 4; ++u) {
+      const long long r = r0 + u * r_step;
+      if (r >= p.P) break;
       float d[8], z[8];
-      t_unpack8(u ? rd1 : rd0, d);
-      t_unpack8(u ? rz1 : rz0, z);
+      t_unpack8(rd[u], d);
+      t_unpack8(rz[u], z);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float g = (!p.relu || fmaf(z[j], sc[j], sh[j]) > 0.f) ? d[j] : 0.f;
-        const float xh = (z[j] - mu[j]) * rs[j];
-        d[j] = sc[j] * (g - m0[j] - xh * m1[j]);
+        d[j] = fmaf(sc[j], g, -fmaf(ca[j], z[j], cb[j]));
       }
-      *reinterpret_cast<uint4*>(p.dz + (u ? r2 : r) * p.C + cg * 8) = t_pack8(d);
+      *reinterpret_cast<uint4*>(p.dz + r * p.C + cg * 8) = t_pack8(d);
     }
   }
 }
@@ -975,12 +997,14 @@ __global__ void __launch_bounds__(256) embed_bwd_w2_kernel(const float* __restri
   const int j = blockIdx.x;
   for (int k = threadIdx.x; k < emb; k += blockDim.x) {
     float s = 0.f;
-    for (int r = 0; r < rows; ++r) s = fmaf(dout[(size_t)r * emb + j], h[(size_t)r * emb + k], s);
+#pragma unroll 8
+    for (int r = 0; r < rows; ++r) s = fmaf(__ldg(dout + (size_t)r * emb + j), __ldg(h + (size_t)r * emb + k), s);
     dw2[(size_t)j * emb + k] = s;
   }
   if (threadIdx.x == 0) {
     float s = 0.f;
-    for (int r = 0; r < rows; ++r) s += dout[(size_t)r * emb + j];
+#pragma unroll 8
+    for (int r = 0; r < rows; ++r) s += __ldg(dout + (size_t)r * emb + j);
     db2[j] = s;
   }
 }
@@ -995,7 +1019,8 @@ __global__ void __launch_bounds__(256) embed_bwd_hidden_kernel(const float* __re
   __syncthreads();
   for (int k = threadIdx.x; k < emb; k += blockDim.x) {
     float s = 0.f;
-    for (int j = 0; j < emb; ++j) s = fmaf(s_d[j], w2[(size_t)j * emb + k], s);
+#pragma unroll 8
+    for (int j = 0; j < emb; ++j) s = fmaf(s_d[j], __ldg(w2 + (size_t)j * emb + k), s);
     dpre[r * emb + k] = s * gelu_grad(pre[r * emb + k]);
   }
 }
@@ -1005,11 +1030,13 @@ __global__ void embed_bwd_w1_kernel(const float* __restrict__ dpre, const float*
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= emb) return;
   float sb = 0.f;
-  for (int r = 0; r < rows; ++r) sb += dpre[(size_t)r * emb + k];
+#pragma unroll 8
+  for (int r = 0; r < rows; ++r) sb += __ldg(dpre + (size_t)r * emb + k);
   db1[k] = sb;
   for (int i = 0; i < din; ++i) {
     float s = 0.f;
-    for (int r = 0; r < rows; ++r) s = fmaf(dpre[(size_t)r * emb + k], in[(size_t)r * din + i], s);
+#pragma unroll 8
+    for (int r = 0; r < rows; ++r) s = fmaf(__ldg(dpre + (size_t)r * emb + k), __ldg(in + (size_t)r * din + i), s);
     dw1[(size_t)k * din + i] = s;
   }
 }
@@ -1084,12 +1111,17 @@ extern "C" int cdm_chan_reduce(const cdm_chan_reduce_args* a, void* stream) {
   if (rc) return rc;
   const int rows = 256 / (a->C / 8);
   int blocks = (int)((a->P + rows * 8 - 1) / (rows * 8));
-  if (blocks > num_sms() * 4) blocks = num_sms() * 4;  // the fixed-order final pass walks the partials serially: keep them few
+  if (blocks > num_sms() * 3) blocks = num_sms() * 3;  // three resident blocks per SM = one wave; the final pass walks these partials
   if (blocks > a->workspace_blocks) blocks = a->workspace_blocks;
   if (blocks < 1) blocks = 1;
   ChanReduceP p{(const bf16*)a->a, a->lda, (const bf16*)a->z, a->ldz, a->scale, a->shift, a->mean, a->rstd,
                 a->relu, a->mode, a->P, a->C, a->workspace};
-  chan_reduce_kernel<<<blocks, 256, 0, ST(stream)>>>(p);
+  if (a->mode == 0)
+    chan_reduce_kernel<0><<<blocks, 256, 0, ST(stream)>>>(p);
+  else if (a->mode == 1)
+    chan_reduce_kernel<1><<<blocks, 256, 0, ST(stream)>>>(p);
+  else
+    chan_reduce_kernel<2><<<blocks, 256, 0, ST(stream)>>>(p);
   CDM_CHECK_LAUNCH();
   // fixed-order final pass, fused with the cross-rank exchange when a->xr describes a peer group
   launch_xrank_sum(a->workspace, blocks, 2 * a->C, a->out, a->xr, ST(stream));
@@ -1147,7 +1179,11 @@ extern "C" int cdm_bn_apply(const cdm_bn_apply_args* a, void* stream) {
   if (rc) return rc;
   BnApplyP p{(const bf16*)a->z, a->P, a->C, a->relu, a->scale, a->shift, (bf16*)a->y, a->sc_x, a->sc_w, a->sc_b,
              a->film_scale, a->film_shift, a->film_rows, a->px_per_img, (bf16*)a->yf};
-  bn_apply_kernel<<<grid1d(a->P * (a->C / 8)), 256, 0, ST(stream)>>>(p);
+  const int g_apply = grid1d(a->P * (a->C / 8) / 4, 256, num_sms() * 4);  // four rows per thread, four blocks per SM
+  if (a->sc_x || a->film_scale)
+    bn_apply_kernel<true><<<g_apply, 256, 0, ST(stream)>>>(p);
+  else
+    bn_apply_kernel<false><<<g_apply, 256, 0, ST(stream)>>>(p);
   CDM_CHECK_LAUNCH();
   return CDM_OK;
 }
@@ -1159,7 +1195,7 @@ extern "C" int cdm_bn_bwd_apply(const cdm_bn_bwd_args* a, void* stream) {
   if (rc) return rc;
   BnBwdP p{(const bf16*)a->dy, a->lddy, (const bf16*)a->z, a->P, a->C, a->relu, a->scale, a->shift, a->mean, a->rstd,
            a->sums, a->count, (bf16*)a->dz};
-  bn_bwd_apply_kernel<<<grid1d(a->P * (a->C / 8)), 256, 0, ST(stream)>>>(p);
+  bn_bwd_apply_kernel<<<grid1d(a->P * (a->C / 8) / 4, 256, num_sms() * 3), 256, 0, ST(stream)>>>(p);
   CDM_CHECK_LAUNCH();
   return CDM_OK;
 }

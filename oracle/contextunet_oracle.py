@@ -132,12 +132,12 @@ def unet_forward(sd, x, t, c, shortcut, *, n_feat=128, n_cfeat=6, height=64, tra
 
     u1 = unet_up(_rb(cemb1 * u0 + temb1, rb), d2, "up1")
     u2 = unet_up(_rb(cemb2 * u1 + temb2, rb), d1, "up2")
-    o = _rb(F.conv2d(torch.cat((u2, x0), 1), _rb(sd["out.0.weight"], rb), sd["out.0.bias"], padding=1), rb)
-    o = _rb(F.relu(F.group_norm(o, 8, sd["out.1.weight"], sd["out.1.bias"], GN_EPS)), rb)
+    o_raw = _rb(F.conv2d(torch.cat((u2, x0), 1), _rb(sd["out.0.weight"], rb), sd["out.0.bias"], padding=1), rb)
+    o = _rb(F.relu(F.group_norm(o_raw, 8, sd["out.1.weight"], sd["out.1.bias"], GN_EPS)), rb)
     eps = F.conv2d(o, sd["out.3.weight"], sd["out.3.bias"], padding=1)
     if taps is not None:
         taps.update(x1=x1, x0=x0, d1=d1, d2=d2, hidden=hidden, cemb1=cemb1, temb1=temb1, cemb2=cemb2, temb2=temb2,
-                    u0=u0, u1=u1, u2=u2, o=o)
+                    u0=u0, u1=u1, u2=u2, o=o, o_raw=o_raw)
     return eps
 
 

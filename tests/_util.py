@@ -25,6 +25,13 @@ def rel_l2(a, b):
 
 
 _cache = {}
+PARITY = {}  # measured errors of this session, written to gpurun_out/parity.json at session end (conftest.py)
+
+
+def record(name, value, tol=None):
+    """Keep a measured parity error (and the tolerance it was asserted at) for profiles/rNN_parity.json."""
+    PARITY[name] = {"measured": float(value), "tolerance": tol}
+    return value
 
 
 def raw_sd():

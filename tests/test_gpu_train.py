@@ -11,7 +11,7 @@ import torch
 import torch.nn.functional as F
 
 from oracle import contextunet_oracle as O
-from tests._util import NCF, T, cal_sd, load, rel_l2, split_shortcut
+from tests._util import NCF, T, cal_sd, load, record, rel_l2, split_shortcut
 
 pytestmark = pytest.mark.gpu
 
@@ -296,6 +296,7 @@ def test_training_step_vs_reference_vectors():
     pred = model(x_pert, (t / 1500).cuda(), param.cuda(), shortcut=T(g["shortcut"]))
     err = rel_l2(pred, g["pred_noise"])
     print(f"train-mode pred rel-L2 vs reference = {err:.3e}")
+    record("train_mode_pred_rel_l2/cal/batch4", err, 2e-2)
     assert err < 2e-2
     loss = F.mse_loss(pred, noise.cuda())
     assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 2e-2
@@ -324,6 +325,8 @@ def test_training_step_vs_reference_vectors():
         if cos < 0.85 or abs(float(got.norm() / r32.norm()) - 1) > 0.15 or e_dev > 1.35 * e_emul + 1e-2:
             bad.append((name, round(cos, 3), round(e_dev, 4), round(e_emul, 4)))
     print(f"parameter gradients: min cosine vs fp32 oracle {worst_cos:.4f}; max e_dev/(e_emul+0.01) = {worst_ratio:.3f}")
+    record("train_grad_min_cosine_vs_fp32/cal/batch4", worst_cos, 0.85)
+    record("train_grad_max_edev_over_eemul/cal/batch4", worst_ratio, 1.35)
     assert not bad, bad
     for k in g.files:
         if k.startswith("bn/") and "running" in k:
@@ -549,3 +552,54 @@ def test_training_step_is_bit_reproducible():
             assert torch.equal(runs[0][1][k], runs[it][1][k]), k
         for k in runs[0][2]:
             assert torch.equal(runs[0][2][k], runs[it][2][k]), k
+
+
+def test_training_trajectory_20_steps_vs_fp32_oracle():
+    """20 optimisation steps at batch 32 (the reference's batch size) against the fp32 CPU trajectory stored by
+    oracle/make_golden_train_traj.py (the loop body of code/train_diffusion_paper.py:349-366, Adam defaults, lr 1e-4):
+    the loss curve follows the reference within 2 %, the parameters nearest the loss end within 1e-3 (relative L2 of
+    the weights) and their UPDATE (final - initial) within 10 % of the reference's update; BatchNorm running statistics
+    after 20 momentum updates within 1e-2."""
+    import camels_diffusion_model_b200 as cdm
+    from camels_diffusion_model_b200.train import GraphedTrainStep
+    from oracle.make_golden_train_traj import KEEP, KEEP_BN, draws
+    g = load("train_traj.npz")
+    steps, B, lr = int(g["steps"]), int(g["batch"]), float(g["lr"])
+    x, prm, per_step = draws(int(g["seed"]), steps, B)
+    sd0 = O.init_state_dict(0, n_cfeat=NCF)
+    model = cdm.ContextUnet(1, 128, NCF, 64)
+    model.load_state_dict(sd0)
+    model = model.cuda().train()
+    _, _, ab_t = cdm.make_schedule(1500)
+    losses = []
+    # the reference's step with the reference's own noise: perturb_input -> forward -> mse -> backward -> Adam
+    from camels_diffusion_model_b200.train import FusedAdam, training_step
+    optim = FusedAdam(model.parameters(), lr=lr)
+    for noise, t, sc in per_step:
+        losses.append(float(training_step(model, optim, x, prm.cuda(), 1500, ab_t, noise=noise, t=t, shortcut=sc)))
+    ref = g["losses"]
+    rel = np.abs(np.array(losses) - ref) / ref
+    print("loss curve dev", [round(v, 4) for v in losses], "ref", [round(float(v), 4) for v in ref])
+    record("train_traj20_batch32_max_loss_rel_dev", rel.max(), 2e-2)
+    assert rel.max() < 2e-2, rel
+    sd = model.state_dict()
+    worst_w, worst_d = 0.0, 0.0
+    for k in KEEP:
+        fin, ini = T(g["final/" + k]), sd0[k]
+        if float(ini.norm()) > 0:  # zero-initialised biases: the weight IS its update, checked below
+            e_w = rel_l2(sd[k], fin)
+            worst_w = max(worst_w, e_w)
+            assert e_w < 1e-3, (k, e_w)
+        if k.startswith("out.") or float(ini.norm()) == 0:
+            e_d = rel_l2(sd[k].cpu() - ini, fin - ini)
+            worst_d = max(worst_d, e_d)
+            assert e_d < 0.1, (k, e_d)
+    record("train_traj20_batch32_max_weight_rel_l2", worst_w, 1e-3)
+    record("train_traj20_batch32_max_out_update_rel_l2", worst_d, 0.1)
+    worst_bn = 0.0
+    for pre in KEEP_BN:
+        for nm in ("running_mean", "running_var"):
+            e = rel_l2(sd[f"{pre}.{nm}"], g[f"bn/{pre}.{nm}"])
+            worst_bn = max(worst_bn, e)
+            assert e < 1e-2, (pre, nm, e)
+    record("train_traj20_batch32_max_bn_running_stat_rel_l2", worst_bn, 1e-2)

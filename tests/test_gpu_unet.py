@@ -1,19 +1,22 @@
 """GPU parity of the full ContextUnet forward, the sampler, the likelihood / ELBO loops against
 (a) vectors produced by the unmodified reference (tests/golden) and (b) the CPU oracle run live.
 
-Tolerance (north_star): predicted eps within relative L2 <= 1e-2 of the reference's fp32 path on the
-random-init configuration BASELINE.json names; the 'calibrated' synthetic weights (every layer carries
-signal) are held to 2e-2 and their error is printed."""
+Tolerance (north_star): predicted eps within relative L2 <= 1e-2 of the reference's fp32 path, on the random-init
+configuration BASELINE.json names AND on the 'calibrated' synthetic weights (every layer carries signal, SURVEY
+G12/G13).  Measured (profiles/r2_parity.json): 3.6e-3 .. 5.9e-3, which is the level pure bf16 storage rounding gives in
+a CPU emulation (4.8e-3): the bound is spent by the four roundings nearest the output (out.0 weights and output,
+the GroupNorm+ReLU operand of out.3, init_conv.conv2's output x0 which feeds out.0 directly).  Every intermediate
+tensor, the sampler trajectories and the NLL / ELBO values are held well inside 1e-2 as well."""
 import numpy as np
 import pytest
 import torch
 
 from oracle import contextunet_oracle as O
-from tests._util import NCF, T, cal_sd, load, make_model, raw_sd, rel_l2, split_shortcut
+from tests._util import NCF, T, cal_sd, load, make_model, raw_sd, record, rel_l2, split_shortcut
 
 pytestmark = pytest.mark.gpu
 EPS_TOL_RAW = 1e-2
-EPS_TOL_CAL = 2e-2
+EPS_TOL_CAL = 1e-2
 
 
 @pytest.fixture(scope="module")
@@ -40,6 +43,7 @@ def test_forward_vs_reference_vectors(models, name, tn):
     eps = m(x, t.cuda(), None if tn == "cnone" else c, shortcut=T(g[f"{name}/{tn}/shortcut"]))
     err = rel_l2(eps, g[f"{name}/{tn}/eps"])
     print(f"eps rel-L2 [{name}/{tn}] = {err:.3e}")
+    record(f"eval_eps_rel_l2/{name}/{tn}", err, EPS_TOL_RAW if name == "raw" else EPS_TOL_CAL)
     assert eps.shape == (2, 1, 64, 64) and eps.dtype == torch.float32
     assert err < (EPS_TOL_RAW if name == "raw" else EPS_TOL_CAL)
 
@@ -64,11 +68,13 @@ def test_per_layer_parity_vs_oracle(models):
         "hidden": (ws.hidden, taps["hidden"].view(2, 256)),
         "film(up0)": (ws.u0f.view(2, 16, 16, 256), nhwc(film1)),
         "film(up1)": (ws.u1f, nhwc(film2)), "up2": (ws.p64, nhwc(taps["u2"])),
+        "out.0 (pre-GroupNorm)": (ws.q64, nhwc(taps["o_raw"])),
     }
     for nme, (got, ref) in checks.items():
         err = rel_l2(got.float(), ref)
         print(f"layer {nme}: rel-L2 {err:.3e}")
-        assert err < 2e-2, nme
+        record(f"eval_layer_rel_l2/cal/{nme}", err, 5e-3)
+        assert err < 5e-3, nme
     assert rel_l2(eps, eps_o) < EPS_TOL_CAL
 
 
@@ -190,9 +196,10 @@ def test_sampler_vs_reference_vectors(models, tag, use_graph):
                             shortcut_tab=tab, save_rate=5 if tag == "fromnoise" else 20, use_graph=use_graph)
     err = rel_l2(x, g[f"{tag}/x"])
     print(f"sampler[{tag}, graph={use_graph}] final-x rel-L2 after {Tn} steps = {err:.3e}")
-    assert err < 3e-2
+    record(f"sampler_final_x_rel_l2/cal/{tag}/T{Tn}", err, 2e-3)
+    assert err < 2e-3
     assert inter.shape == g[f"{tag}/inter"].shape
-    assert rel_l2(inter, g[f"{tag}/inter"]) < 3e-2
+    assert rel_l2(inter, g[f"{tag}/inter"]) < 2e-3
 
 
 def test_sampler_graph_equals_eager(models):
@@ -236,14 +243,16 @@ def test_likelihood_and_elbo_vs_reference_vectors(models):
                                    noises=[T(g["nll/noise_b0"]), T(g["nll/noise_b1"])],
                                    shortcuts=[sc[:Tn], sc[Tn:]])
     print("nll", nll, "ref", float(g["nll"]))
-    assert abs(nll - float(g["nll"])) / float(g["nll"]) < 2e-2
+    record("nll_rel_err/cal", abs(nll - float(g["nll"])) / float(g["nll"]), 1e-3)
+    assert abs(nll - float(g["nll"])) / float(g["nll"]) < 1e-3
     sc = [split_shortcut(s) for s in g["elbo/shortcuts"]]
     elbo, bpd = cdm.calculate_elbo_and_bpd(m, loader, Tn, "cuda", ab_t, b_t, a_t,
                                            noises=[T(g["elbo/noise_b0"]), T(g["elbo/noise_b1"])],
                                            shortcuts=[sc[:10], sc[10:]])
     print("elbo", elbo, "ref", float(g["elbo"]))
-    assert abs(elbo - float(g["elbo"])) / float(g["elbo"]) < 2e-2
-    assert abs(bpd - float(g["bpd"])) / float(g["bpd"]) < 2e-2
+    record("elbo_rel_err/cal", abs(elbo - float(g["elbo"])) / float(g["elbo"]), 1e-3)
+    assert abs(elbo - float(g["elbo"])) / float(g["elbo"]) < 1e-3
+    assert abs(bpd - float(g["bpd"])) / float(g["bpd"]) < 1e-3
     e, b = cdm.calculate_elbo_and_bpd_batch(maps, T(g["eb/pred"]), T(g["eb/noise"]), T(g["eb/t"]), b_t, a_t, ab_t,
                                             64 * 64)
     assert abs(float(e) - float(g["eb/elbo"])) / float(g["eb/elbo"]) < 1e-5
