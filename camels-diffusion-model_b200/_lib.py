@@ -419,7 +419,9 @@ class ChanReduceArgs(C.Structure):
 class BnApplyArgs(C.Structure):
     _fields_ = [("z", VP), ("P", LL), ("C", I), ("relu", I), ("scale", VP), ("shift", VP), ("y", VP), ("sc_x", VP),
                 ("sc_w", VP), ("sc_b", VP), ("film_scale", VP), ("film_shift", VP), ("film_rows", I),
-                ("px_per_img", I), ("yf", VP)]
+                ("px_per_img", I), ("yf", VP), ("sums", VP), ("gamma", VP), ("beta", VP), ("count", F), ("eps", F),
+                ("momentum", F), ("running_mean", VP), ("running_var", VP), ("scale_out", VP), ("shift_out", VP),
+                ("mean_out", VP), ("rstd_out", VP)]
 
 
 class BnBwdArgs(C.Structure):
@@ -469,9 +471,16 @@ def bn_finalize(sums, Cn, count, gamma, beta, eps, momentum, rm, rv, scale, shif
 
 
 def bn_apply(z, P, Cn, scale, shift, y, *, relu=1, sc_x=None, sc_w=None, sc_b=None, film_scale=None, film_shift=None,
-             film_rows=1, px_per_img=1, yf=None):
+             film_rows=1, px_per_img=1, yf=None, finalize=None):
+    """finalize = (sums, gamma, beta, count, eps, momentum, running_mean, running_var, mean_out, rstd_out): derive
+    scale / shift from the batch sums inside the launch (they are written to `scale` / `shift`)."""
     g = BnApplyArgs(rawptr(z), P, Cn, relu, rawptr(scale), rawptr(shift), rawptr(y), rawptr(sc_x), rawptr(sc_w),
                     rawptr(sc_b), rawptr(film_scale), rawptr(film_shift), film_rows, px_per_img, rawptr(yf))
+    if finalize is not None:
+        sums, gamma, beta, count, eps, mom, rm, rv, mean_out, rstd_out = finalize
+        g.sums, g.gamma, g.beta, g.count, g.eps, g.momentum = rawptr(sums), rawptr(gamma), rawptr(beta), count, eps, mom
+        g.running_mean, g.running_var = rawptr(rm), rawptr(rv)
+        g.scale_out, g.shift_out, g.mean_out, g.rstd_out = rawptr(scale), rawptr(shift), rawptr(mean_out), rawptr(rstd_out)
     check(lib().cdm_bn_apply(C.byref(g), stream_ptr()), "cdm_bn_apply")
 
 

@@ -372,6 +372,18 @@ struct BnApplyP {
   const float* fb;  // film shift [rows][C]
   int fb_rows, px_per_img;
   bf16* yf;
+  // inline BatchNorm finalisation (sums != null): scale / shift come from the batch sums, block 0 publishes them
+  // (+ mean, rstd for the backward pass) and updates the running statistics — what cdm_bn_finalize would have done
+  const float* sums;
+  const float* gamma;
+  const float* beta;
+  float count, eps, momentum;
+  float* running_mean;
+  float* running_var;
+  float* scale_out;
+  float* shift_out;
+  float* mean_out;
+  float* rstd_out;
 };
 // Four rows per thread and iteration, all loads issued before the first use (one 16-byte load in flight per thread left
 // the pass at 55-66 % of the copy bandwidth); the shortcut / FiLM extras are compile-time variants so that the plain
@@ -381,10 +393,34 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const BnApplyP p) {
   const int groups = p.C >> 3;  // 16 or 32: divides blockDim.x, so a thread keeps the same 8 channels
   const int cg = (int)(threadIdx.x % groups);
   float sc[8], sh[8];
+  if (p.sums) {  // the arithmetic of bn_finalize_kernel, per thread for its own 8 channels (bit-identical results)
+    const bool publish = blockIdx.x == 0 && threadIdx.x < groups;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = p.scale[cg * 8 + j];
-    sh[j] = p.shift[cg * 8 + j];
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      const float mean = p.sums[c] / p.count;
+      const float var = fmaxf(p.sums[p.C + c] / p.count - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + p.eps);
+      sc[j] = p.gamma[c] * rstd;
+      sh[j] = p.beta[c] - mean * sc[j];
+      if (publish) {
+        p.scale_out[c] = sc[j];
+        p.shift_out[c] = sh[j];
+        p.mean_out[c] = mean;
+        p.rstd_out[c] = rstd;
+        if (p.running_mean) {
+          p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
+          p.running_var[c] =
+              (1.f - p.momentum) * p.running_var[c] + p.momentum * var * (p.count / fmaxf(p.count - 1.f, 1.f));
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = p.scale[cg * 8 + j];
+      sh[j] = p.shift[cg * 8 + j];
+    }
   }
   // groups divides blockDim.x, so a thread's row advances by a constant: no 64-bit division in the loop
   const long long r_step = (long long)gridDim.x * (blockDim.x / groups);
@@ -1172,13 +1208,19 @@ extern "C" int cdm_bn_finalize(const float* sums, int C, float count, const floa
 }
 
 extern "C" int cdm_bn_apply(const cdm_bn_apply_args* a, void* stream) {
-  CDM_CHECK_ARG(a && a->z && a->scale && a->shift && a->y && a->P > 0 && a->C % 8 == 0 && 256 % (a->C / 8) == 0);
+  CDM_CHECK_ARG(a && a->z && a->y && a->P > 0 && a->C % 8 == 0 && 256 % (a->C / 8) == 0);
+  CDM_CHECK_ARG((a->scale && a->shift) || a->sums);
+  if (a->sums)
+    CDM_CHECK_ARG(a->gamma && a->beta && a->count > 0 && a->scale_out && a->shift_out && a->mean_out && a->rstd_out &&
+                  (a->running_mean == nullptr) == (a->running_var == nullptr));
   CDM_CHECK_ARG(!a->sc_x || (a->sc_w && a->sc_b));
   CDM_CHECK_ARG(!a->film_scale || (a->film_shift && a->yf && a->px_per_img > 0 && a->film_rows >= 1));
   int rc = check_device();
   if (rc) return rc;
   BnApplyP p{(const bf16*)a->z, a->P, a->C, a->relu, a->scale, a->shift, (bf16*)a->y, a->sc_x, a->sc_w, a->sc_b,
-             a->film_scale, a->film_shift, a->film_rows, a->px_per_img, (bf16*)a->yf};
+             a->film_scale, a->film_shift, a->film_rows, a->px_per_img, (bf16*)a->yf,
+             a->sums, a->gamma, a->beta, a->count, a->eps, a->momentum, a->running_mean, a->running_var,
+             a->scale_out, a->shift_out, a->mean_out, a->rstd_out};
   const int g_apply = grid1d(a->P * (a->C / 8) / 4, 256, num_sms() * 4);  // four rows per thread, four blocks per SM
   if (a->sc_x || a->film_scale)
     bn_apply_kernel<true><<<g_apply, 256, 0, ST(stream)>>>(p);

@@ -217,11 +217,12 @@ def _conv_bn_relu(S, P, name, seq, src, n, H, *, first=False, **apply_kw):
     ly.name, ly.conv, ly.bn, ly.x_in, ly.z, ly.count, ly.H = name, conv, bn, src, z, count, H
     ly.cin, ly.cout = conv.in_channels, cout
     ly.scale, ly.shift, ly.mean, ly.rstd = (_f32(cout, dev=dev) for _ in range(4))
-    L.bn_finalize(sums, cout, count, bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum, bn.running_mean,
-                  bn.running_var, ly.scale, ly.shift, ly.mean, ly.rstd)
-    bn.num_batches_tracked += 1
+    S.nbt.append(bn.num_batches_tracked)  # += 1 for all 18 layers in one multi-tensor launch (end of forward)
     y = _bf(n, H, H, cout, dev=dev)
-    L.bn_apply(z, Pn, cout, ly.scale, ly.shift, y, relu=1, **apply_kw)
+    # one launch: batch statistics -> scale / shift (+ mean, rstd, running statistics), then y = relu(z*scale+shift)
+    L.bn_apply(z, Pn, cout, ly.scale, ly.shift, y, relu=1,
+               finalize=(sums, bn.weight.detach(), bn.bias.detach(), count, bn.eps, bn.momentum, bn.running_mean,
+                         bn.running_var, ly.mean, ly.rstd), **apply_kw)
     ly.y = y
     S.layers[name] = ly
     return y
@@ -240,10 +241,11 @@ class _UnetFn(torch.autograd.Function):
         m = model
         nf, h, n = m.n_feat, m.h, x.shape[0]
         S = _Ctx()
-        S.dev, S.mode, S.layers, S.n = dev, m.conv_mode, {}, n
+        S.dev, S.mode, S.layers, S.n, S.nbt = dev, m.conv_mode, {}, n, []
         S.ones = torch.ones(256, device=dev)
         S.zeros = torch.zeros(65536, device=dev)
-        S.ws = _f32(L.num_sms() * 8, 9 * 256, dev=dev)  # reduction workspace (partials)
+        S.ws = _f32(L.num_sms() * 8, 9 * 256, dev=dev)  # reduction workspace (partials), main stream
+        S.ws2 = _f32(L.num_sms() * 8, 9 * 256, dev=dev)  # the same for the leaf reductions on the side stream
         S.bnp = _f32(L.num_sms(), 2 * 256, dev=dev)  # per-CTA BatchNorm partial sums of the conv epilogue
         S.wgws = _f32(160 * 128 * 384, dev=dev)  # split-K tiles of the 3x3 weight gradients (used on the SIDE stream only)
         S.skws = _f32(160 * 128 * 384, dev=dev)  # split-K tiles of the main-stream GEMMs (transposed convs, up0)
@@ -319,6 +321,7 @@ class _UnetFn(torch.autograd.Function):
                    m.out[3].bias.detach().float().contiguous(), eps.view(n, h, h))
         S.x0, S.d1, S.d2, S.hidden, S.u0raw, S.u0f, S.u1, S.u1f, S.u2, S.o = x0, d1, d2, hidden, u0raw, u0f, u1, u1f, u2, o
         S.pool1_in, S.pool2_in = S.layers["down1.1.c2"].y, S.layers["down2.1.c2"].y
+        torch._foreach_add_(S.nbt, 1)
         ctx.S, ctx.model = S, m
         ctx.names = [nme for nme, _ in m.named_parameters()]
         return eps
@@ -336,6 +339,19 @@ class _UnetFn(torch.autograd.Function):
         # the step is too small to fill the SMs and the two chains overlap (fork / join are CUDA-graph capturable).
         main, side = torch.cuda.current_stream(), _side_stream(dev)
         keep = []  # operands stay referenced until the join: the allocator must not recycle them under the side stream
+
+        def leaf(fn):
+            """Run fn() on the side stream once everything issued so far on the main stream is done.  For the LEAVES
+            of the backward graph (parameter gradients: nothing downstream reads them before the join below): the
+            latency-bound small kernels among them (EmbedFC backward: 16 launches of a few blocks; bias / affine
+            reductions; the K = 9 and N = 1 weight gradients) then run underneath the main dz -> dx chain."""
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                out = fn()
+            keep.append((fn, out))  # the closure keeps its operands referenced until the join
+            return out
 
         def conv_wgrad(dz, srcs, cout):
             cin = sum(s.shape[3] for s in srcs)
@@ -369,9 +385,11 @@ class _UnetFn(torch.autograd.Function):
             L.bn_bwd_apply(dy, lddy, ly.z, Pn, C, ly.scale, ly.shift, ly.mean, ly.rstd, sums, ly.count, dz, relu=1)
             G[prefix + ".0.bias"] = S.zeros[:C]  # a bias in front of train-mode BN has zero gradient
             if ly.cin == 1:
-                w9 = _f32(9, C, dev=dev)
-                L.outer_wgrad(ly.x_in, dz, n, ly.H, ly.H, C, w9, S.ws, flip=0)
-                G[prefix + ".0.weight"] = w9.t().reshape(C, 1, 3, 3).contiguous()
+                def w_first():
+                    w9 = _f32(9, C, dev=dev)
+                    L.outer_wgrad(ly.x_in, dz, n, ly.H, ly.H, C, w9, S.ws2, flip=0)
+                    return w9.t().reshape(C, 1, 3, 3).contiguous()
+                G[prefix + ".0.weight"] = leaf(w_first)
                 return None
             G[prefix + ".0.weight"] = conv_wgrad(dz, [ly.x_in], C)
             if not need_dx:
@@ -390,20 +408,22 @@ class _UnetFn(torch.autograd.Function):
             Mrows = n * Hh * Hh
             s2d = _bf(Mrows, 4 * nf, dev=dev)
             L.space_to_depth(dv, s2d)
-            sums = _f32(2, nf, dev=dev)
-            L.chan_reduce(dv, nf, Mrows * 4, nf, sums, S.ws, mode=2)
-            G[prefix + ".bias"] = sums[0]
             cin = sum(s.shape[-1] for s in srcs)
+
+            def leaves():
+                sums = _f32(2, nf, dev=dev)
+                L.chan_reduce(dv, nf, Mrows * 4, nf, sums, S.ws2, mode=2)
+                dw = _f32(cin, 4 * nf, dev=dev, zero=True)
+                off = 0
+                for s in srcs:
+                    cs = s.shape[-1]
+                    L.gemm_tn(s, s2d, dw[off:], n_img=1, H=1, W=Mrows, a_c=cs, b_c=4 * nf, M=cs, N=4 * nf, ldc=4 * nf,
+                              workspace=S.wgws)
+                    off += cs
+                return sums[0], dw.view(cin, 2, 2, nf).permute(0, 3, 1, 2).contiguous()
+            G[prefix + ".bias"], G[prefix + ".weight"] = leaf(leaves)
             da = _bf(Mrows, cin, dev=dev)
             L.gemm(s2d, P[nm + ".d"], S.zeros[:cin], da, shift_mod=cin)
-            dw = _f32(cin, 4 * nf, dev=dev, zero=True)
-            off = 0
-            for s in srcs:
-                cs = s.shape[-1]
-                L.gemm_tn(s, s2d, dw[off:], n_img=1, H=1, W=Mrows, a_c=cs, b_c=4 * nf, M=cs, N=4 * nf, ldc=4 * nf,
-                          workspace=S.skws)
-                off += cs
-            G[prefix + ".weight"] = dw.view(cin, 2, 2, nf).permute(0, 3, 1, 2).contiguous()
             return da
 
         def embed_bwd(mod, prefix, inp, dout):
@@ -417,24 +437,25 @@ class _UnetFn(torch.autograd.Function):
             G[prefix + ".model.2.weight"], G[prefix + ".model.2.bias"] = dw2, db2
 
         # ---- out.3 (Conv 128->1), out.1 (GroupNorm) + ReLU
-        G["out.3.bias"] = deps.sum().reshape(1)
-        w9 = _f32(9, nf, dev=dev)
-        L.outer_wgrad(deps, S.o, n, h, h, nf, w9, S.ws, flip=1, mean_rstd=S.gn1_mr, gamma=m.out[1].weight.detach(),
-                      beta=m.out[1].bias.detach())
-        G["out.3.weight"] = w9.view(3, 3, nf).permute(2, 0, 1).reshape(1, nf, 3, 3).contiguous()
+        def out3_leaves():
+            w9 = _f32(9, nf, dev=dev)
+            L.outer_wgrad(deps, S.o, n, h, h, nf, w9, S.ws2, flip=1, mean_rstd=S.gn1_mr, gamma=m.out[1].weight.detach(),
+                          beta=m.out[1].bias.detach())
+            return deps.sum().reshape(1), w9.view(3, 3, nf).permute(2, 0, 1).reshape(1, nf, 3, 3).contiguous()
+        G["out.3.bias"], G["out.3.weight"] = leaf(out3_leaves)
         d_a = _bf(n, h, h, nf, dev=dev)
         L.conv_in(deps, P["out3.d"], S.ones[:nf], S.zeros[:nf], d_a, relu=False)
         do = _bf(n, h, h, nf, dev=dev)
         dg_nc, db_nc = _f32(n, nf, dev=dev), _f32(n, nf, dev=dev)
         L.gn_bwd(S.o, d_a, nf, n, h * h, nf, 8, S.gn1_mr, m.out[1].weight.detach(), m.out[1].bias.detach(), do, dg_nc,
                  db_nc)
-        G["out.1.weight"], G["out.1.bias"] = _f32(nf, dev=dev), _f32(nf, dev=dev)
-        L.rows_sum(dg_nc, n, nf, G["out.1.weight"])
-        L.rows_sum(db_nc, n, nf, G["out.1.bias"])
-        # ---- out.0 (Conv 256->128 on cat(u2, x0))
-        sums = _f32(2, nf, dev=dev)
-        L.chan_reduce(do, nf, n * h * h, nf, sums, S.ws, mode=2)
-        G["out.0.bias"] = sums[0]
+        def out1_leaves(dg_nc=dg_nc, db_nc=db_nc):
+            gw, gb, sums = _f32(nf, dev=dev), _f32(nf, dev=dev), _f32(2, nf, dev=dev)
+            L.rows_sum(dg_nc, n, nf, gw)
+            L.rows_sum(db_nc, n, nf, gb)
+            L.chan_reduce(do, nf, n * h * h, nf, sums, S.ws2, mode=2)  # out.0 (Conv 256->128 on cat(u2, x0)): bias
+            return gw, gb, sums[0]
+        G["out.1.weight"], G["out.1.bias"], G["out.0.bias"] = leaf(out1_leaves)
         G["out.0.weight"] = conv_wgrad(do, [S.u2, S.x0], nf)
         d_cat = _bf(n, h, h, 2 * nf, dev=dev)
         L.conv3x3(do, P["out0.d"], S.ones[:2 * nf], S.zeros[:2 * nf], d_cat, flags=0, mode=S.mode)
@@ -447,6 +468,9 @@ class _UnetFn(torch.autograd.Function):
         d_u1 = _bf(n, h2, h2, nf, dev=dev)
         dcemb2, dtemb2 = _f32(n, nf, dev=dev), _f32(n, nf, dev=dev)
         L.film_bwd(da2, 2 * nf, S.u1, n, h2 * h2, nf, S.cemb2, d_u1, dcemb2, dtemb2)
+        trows = S.t.shape[0]
+        leaf(lambda: (embed_bwd(m.contextembed2, "contextembed2", S.c, dcemb2),
+                      embed_bwd(m.timeembed2, "timeembed2", S.t, dtemb2 if trows == n else dtemb2.sum(0, keepdim=True))))
         # ---- up1
         d = rcb_bwd("up1.2", "up1.model.2", d_u1, nf)
         d_v1 = rcb_bwd("up1.1", "up1.model.1", d, nf)
@@ -458,12 +482,15 @@ class _UnetFn(torch.autograd.Function):
         dcemb1, dtemb1 = _f32(n, 2 * nf, dev=dev), _f32(n, 2 * nf, dev=dev)
         L.gn_bwd(S.u0raw, da1, 4 * nf, n, h4 * h4, 2 * nf, 8, S.gn0_mr, m.up0[1].weight.detach(),
                  m.up0[1].bias.detach(), d_u0raw, dg_nc, db_nc, film_scale=S.cemb1, dfs=dcemb1, dfb=dtemb1)
-        G["up0.1.weight"], G["up0.1.bias"] = _f32(2 * nf, dev=dev), _f32(2 * nf, dev=dev)
-        L.rows_sum(dg_nc, n, 2 * nf, G["up0.1.weight"])
-        L.rows_sum(db_nc, n, 2 * nf, G["up0.1.bias"])
-        sums = _f32(2, 2 * nf, dev=dev)
-        L.chan_reduce(d_u0raw, 2 * nf, n * h4 * h4, 2 * nf, sums, S.ws, mode=2)
-        G["up0.0.bias"] = sums[0]
+        def up0_leaves(dg_nc=dg_nc, db_nc=db_nc):
+            gw, gb, sums = _f32(2 * nf, dev=dev), _f32(2 * nf, dev=dev), _f32(2, 2 * nf, dev=dev)
+            L.rows_sum(dg_nc, n, 2 * nf, gw)
+            L.rows_sum(db_nc, n, 2 * nf, gb)
+            L.chan_reduce(d_u0raw, 2 * nf, n * h4 * h4, 2 * nf, sums, S.ws2, mode=2)
+            embed_bwd(m.contextembed1, "contextembed1", S.c, dcemb1)
+            embed_bwd(m.timeembed1, "timeembed1", S.t, dtemb1 if trows == n else dtemb1.sum(0, keepdim=True))
+            return gw, gb, sums[0]
+        G["up0.1.weight"], G["up0.1.bias"], G["up0.0.bias"] = leaf(up0_leaves)
         K0 = h4 * h4 * 2 * nf
         d_hid = _bf(n, 2 * nf, dev=dev)
         L.gemm(d_u0raw.view(n, K0), P["up0.d"], S.zeros[:2 * nf], d_hid, shift_mod=2 * nf, workspace=S.skws)
@@ -503,12 +530,6 @@ class _UnetFn(torch.autograd.Function):
         # ---- init_conv: x0 = y2 + shortcut(x) (the shortcut is not a parameter)
         d_y1 = cbr_bwd("init_conv.c2", "init_conv.conv2", d_x0, nf)
         cbr_bwd("init_conv.c1", "init_conv.conv1", d_y1, nf)
-        # ---- embeddings
-        trows = S.t.shape[0]
-        embed_bwd(m.contextembed1, "contextembed1", S.c, dcemb1)
-        embed_bwd(m.contextembed2, "contextembed2", S.c, dcemb2)
-        embed_bwd(m.timeembed1, "timeembed1", S.t, dtemb1 if trows == n else dtemb1.sum(0, keepdim=True))
-        embed_bwd(m.timeembed2, "timeembed2", S.t, dtemb2 if trows == n else dtemb2.sum(0, keepdim=True))
         main.wait_stream(side)  # join: every weight gradient is complete before it is reduced / handed out
         keep.clear()
         W = _world()

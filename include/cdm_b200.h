@@ -300,7 +300,10 @@ int cdm_bn_finalize(const float* sums, int C, float count, const float* gamma, c
                     float momentum, float* running_mean, float* running_var, float* scale, float* shift,
                     float* mean, float* rstd, void* stream);
 
-/* y = act(z*scale+shift) [+ w_c*x + b_c (init_conv shortcut)]; optional yf = film_scale[n]*y + film_shift[n|0]. */
+/* y = act(z*scale+shift) [+ w_c*x + b_c (init_conv shortcut)]; optional yf = film_scale[n]*y + film_shift[n|0].
+ * sums != NULL: the launch also does cdm_bn_finalize's work — scale / shift are derived from sums[2][C] (same
+ * arithmetic, bit-identical), written with mean / rstd to the *_out vectors for the backward pass, and the running
+ * statistics are updated (one launch per BatchNorm instead of two; `scale` / `shift` are ignored). */
 typedef struct {
   const void* z; long long P; int C, relu;
   const float* scale; const float* shift;
@@ -308,6 +311,10 @@ typedef struct {
   const float* sc_x; const float* sc_w; const float* sc_b;
   const float* film_scale; const float* film_shift; int film_rows, px_per_img;
   void* yf;
+  const float* sums; const float* gamma; const float* beta;
+  float count, eps, momentum;
+  float* running_mean; float* running_var; /* both or neither */
+  float* scale_out; float* shift_out; float* mean_out; float* rstd_out;
 } cdm_bn_apply_args;
 int cdm_bn_apply(const cdm_bn_apply_args* a, void* stream);
 
