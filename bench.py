@@ -100,7 +100,9 @@ class ClockSampler:
         return False
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
+        seq = [int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        tail = sorted(seq[-max(len(seq) // 4, 1):]) if seq else []
+        sm = sorted(seq)
         mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k].lower() == "active" for r in self.rows)]
@@ -112,6 +114,7 @@ class ClockSampler:
         pw = sorted(v for v in (num(r, 6) for r in self.rows) if v is not None)
         lim = [v for v in (num(r, 7) for r in self.rows) if v is not None]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "sm_mhz_min": sm[0] if sm else None, "sm_mhz_settled": tail[len(tail) // 2] if tail else None,
                 "reasons": reasons, "samples": len(sm), "power_w": pw[len(pw) // 2] if pw else None,
                 "power_limit_w": max(lim) if lim else None}
 
@@ -354,6 +357,7 @@ def secondary_block(dev, rank, world, barrier):
                 e1.record()
                 barrier()
                 ms = max_ms(e0.elapsed_time(e1) / K)
+                _phase(f"train_step[{mode}] {ms:.3f} ms")
                 tr[mode] = {"ms_per_step": ms, "img_per_s": GB / ms * 1e3,
                             "tflops_per_gpu": 3 * GFLOP_PER_IMAGE_FWD * 1e9 * per / (ms * 1e-3) / 1e12,
                             "loss": float(loss), "bn_stats_exchange": mode}
@@ -402,6 +406,7 @@ def secondary_block(dev, rank, world, barrier):
         e1.record()
         barrier()
         ms = max_ms(e0.elapsed_time(e1))
+        _phase(f"nll_sweep {ms:.1f} ms")
         fwd = N_MAPS * NT
         fin = all(bool(torch.isfinite(lp.acc).all() and torch.isfinite(lp.acc2).all()) for lp, _ in loops)
         out["nll_sweep"] = {"maps": N_MAPS, "maps_per_gpu": per, "batch": BS, "timesteps_timed": NT,
@@ -433,6 +438,12 @@ def secondary_block(dev, rank, world, barrier):
                                  "s_per_sample_1500_steps": e0.elapsed_time(e1) / 100 * 1.5}
     out["batch1_latency"] = b1
     return out
+
+
+def _phase(msg):
+    """Progress on stderr (the JSON line is the only thing on stdout): a crash is attributable to a phase."""
+    sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')}] {msg}\n")
+    sys.stderr.flush()
 
 
 def run_b200(args):
@@ -470,12 +481,19 @@ def run_b200(args):
     run = D._SamplerRun(model, x_T.to(dev), params.to(dev), args.guide_w, TIMESTEPS, sched, shortcut_tab=sc_tab,
                         seed=1234 + rank, snapshots=True)
     run.capture()
-    run.run(args.warmup)
+    run.run(min(args.warmup, TIMESTEPS))
+    run.reset()  # the timed steps start at i = T (the step index selects schedule / embedding / shortcut rows)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         e0.record()
-        run.run(args.steps)
+        left = args.steps
+        while left > 0:  # more than 1500 steps = several trajectories back to back
+            k = min(left, run.remaining)
+            run.run(k)
+            left -= k
+            if left > 0:
+                run.reset()
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1) / args.steps
@@ -483,6 +501,7 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
+    _phase(f"headline done: {ms_max:.3f} ms/step")
     value = args.batch / (ms_max / 1e3 * TIMESTEPS)
     finite = bool(torch.isfinite(run.x).all())
 
@@ -499,11 +518,12 @@ def run_b200(args):
         barrier()
         t_setup = time.perf_counter() - t0
         d2h = 0
+        e2e_steps = min(args.steps, TIMESTEPS)  # one trajectory
         t1 = time.perf_counter()
-        for k in range(args.steps):
+        for k in range(e2e_steps):
             # this step's noise (pinned host -> device; the next step's upload is handed over now and overlaps this
             # step's kernels); returns the device step counter (D2H)
-            sess.step(z_host[k % nz], z_next=z_host[(k + 1) % nz] if k + 1 < args.steps else None)
+            sess.step(z_host[k % nz], z_next=z_host[(k + 1) % nz] if k + 1 < e2e_steps else None)
             d2h += 4
         x_host, inter = sess.result()  # final samples + the snapshots taken in these steps, back on the host
         d2h += x_host.numel() * 4 + inter.size * 4
@@ -512,15 +532,16 @@ def run_b200(args):
         tt = torch.tensor([dt], device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_e2e = 1e3 * float(tt.item()) / args.steps
-        h2d_step = B * 4096 * 4 + (x_T.numel() * 4 + params.numel() * 4 + sc_tab.numel() * 4) / args.steps
+        ms_e2e = 1e3 * float(tt.item()) / e2e_steps
+        h2d_step = B * 4096 * 4 + (x_T.numel() * 4 + params.numel() * 4 + sc_tab.numel() * 4) / e2e_steps
         e2e = {"value": args.batch / (ms_e2e / 1e3 * TIMESTEPS), "unit": "samples/s",
-               "h2d_bytes_per_step": int(h2d_step) * world, "d2h_bytes_per_step": int(d2h / args.steps) * world,
+               "h2d_bytes_per_step": int(h2d_step) * world, "d2h_bytes_per_step": int(d2h / e2e_steps) * world, "steps": e2e_steps,
                "ms_per_step": ms_e2e, "setup_s": t_setup,
                "note": "public API DDPM.open_sampler(...).step(z, z_next).result(): pinned host x_T/params/per-step z in "
                        "(double-buffered upload), "
                        "step counter every step and x + snapshots out; graph capture/setup reported separately in setup_s"}
 
+    _phase("e2e done")
     # ---- roofline of the dominant kernel (3x3 128->128 conv at 64x64: 9 of 26 launches, ~57% of the FLOPs)
     pk = peaks()
     bd = kernel_breakdown(run)
@@ -559,7 +580,9 @@ def run_b200(args):
     if e2e is not None:
         del sess, ddpm
     torch.cuda.empty_cache()
+    _phase("breakdown done")
     secondary = None if args.no_secondary else secondary_block(dev, rank, world, barrier)
+    _phase("secondary done")
     torch_gpu = None
     if rank == 0 and world == 1 and not args.no_torch_gpu:
         try:
@@ -588,8 +611,15 @@ def run_b200(args):
             "roofline": roofline, "cpu_baseline": cpu, "finite": finite, "secondary": secondary,
             "torch_gpu_baseline": torch_gpu,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
+        # the line is out; do not let process-group teardown (live symmetric-memory mappings, captured NCCL graphs)
+        # hold the launcher: give it 20 s, then leave
+        def _bail():
+            time.sleep(20)
+            os._exit(0)
+        threading.Thread(target=_bail, daemon=True).start()
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -149,6 +149,14 @@ class _SamplerRun:
         self.sample_offset = int(sample_offset)
         self.graph = None
         self.use_graph = use_graph
+        self.x_T = self.x.clone()
+        self.remaining = timesteps  # host mirror of the device step counter: steps left before i reaches 0
+
+    def reset(self):
+        """Back to x_T at step T (a new trajectory over the same graph; snapshots are overwritten)."""
+        self.x.copy_(self.x_T)
+        self.step.fill_(self.T)
+        self.remaining = self.T
 
     def _one_step(self):
         """One reverse-diffusion step = ONE C call (cdm_sample_step: the 26 launches of the reps*B-image forward,
@@ -176,7 +184,10 @@ class _SamplerRun:
         torch.cuda.synchronize()
 
     def run(self, n_steps=None):
-        n_steps = self.T if n_steps is None else n_steps
+        n_steps = self.remaining if n_steps is None else n_steps
+        if n_steps > self.remaining:  # the step index selects table rows on the device: never let it pass 0
+            raise L.CdmError(f"{n_steps} steps requested but only {self.remaining} of {self.T} remain: reset() first")
+        self.remaining -= n_steps
         for _ in range(n_steps):
             if self.graph is not None:
                 self.graph.replay()
@@ -303,6 +314,8 @@ class SamplerSession:
         if z is None or z.numel() != self.run.z.numel():
             raise L.CdmError(f"step(z): z must hold this step's noise, {self.run.z.numel()} values "
                              f"([B,1,H,W] = [{self.run.B},1,{self.run.model.h},{self.run.model.h}])")
+        if self.steps_done >= self.run.T:
+            raise L.CdmError(f"all {self.run.T} steps of this trajectory are done: open a new sampler session")
         main = torch.cuda.current_stream()
         if self._staged_key is not None and self._staged_key == self._key(z):
             main.wait_event(self._staged)
