@@ -173,6 +173,24 @@ def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def on_device(fn):
+    """Decorator for methods of objects with a `.dev` / `.device` attribute (or a ContextUnet): run the body with that
+    device current, so that stream_ptr(), the kernels' attribute caches and every allocation refer to the device the
+    tensors live on even when the caller's current device is another GPU."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        dev = getattr(self, "dev", None) or getattr(self, "device", None)
+        if dev is None and hasattr(self, "_check_supported"):
+            dev = self._check_supported()
+        if dev is None or torch.device(dev).type != "cuda":
+            return fn(self, *a, **k)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrapper
+
+
 _SMS = {}
 
 

@@ -111,10 +111,12 @@ extern "C" int cdm_power_spectrum(const float* maps, int n_maps, int N, const in
   int rc = check_device();
   if (rc) return rc;
   const int smem = (N * N + 2 * N * (N + 1) + 2 * N) * (int)sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64];  // per device: cudaFuncSetAttribute is not process-wide
+  int dev = 0;
+  CDM_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     CDM_CHECK_CUDA(cudaFuncSetAttribute(power_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   power_spectrum_kernel<<<n_maps, 256, smem, (cudaStream_t)stream>>>(maps, N, bin_start, bin_items, n_bins, scale, pk);
   CDM_CHECK_LAUNCH();

@@ -4,6 +4,8 @@
 // All of them are single-pass, vectorised (16 B per thread access) and coalesced.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -215,7 +217,7 @@ static __host__ __device__ inline int co_plane_stride(int R, int W) {
 }
 
 template <int R>
-__global__ void __launch_bounds__(256, 2) conv_out_mma_kernel(const bf16* __restrict__ src, int n_img, int H, int W,
+__global__ void __launch_bounds__(256, R <= 16 ? 3 : 2) conv_out_mma_kernel(const bf16* __restrict__ src, int n_img, int H, int W,
                                                               const float* __restrict__ mean_rstd,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta,
@@ -723,11 +725,13 @@ extern "C" int cdm_conv_in(const cdm_conv_in_args* a, void* stream) {
 
 template <int R>
 static int launch_conv_out(const cdm_conv_out_args* a, cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_set[64];  // per device: cudaFuncSetAttribute is not process-wide
   const int smem = (9 * co_plane_stride(R, a->W) + 2 * kCoC) * (int)sizeof(float) + 8 * 3 * 32 * 8;
-  if (!attr_set) {
+  int dev = 0;
+  CDM_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     CDM_CHECK_CUDA(cudaFuncSetAttribute(conv_out_mma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   conv_out_mma_kernel<R><<<a->n_img * (a->H / R), 256, smem, stream>>>(
       (const bf16*)a->src, a->n_img, a->H, a->W, a->mean_rstd, a->gamma, a->beta, a->weight, a->bias, a->out);
@@ -741,7 +745,13 @@ extern "C" int cdm_conv_out(const cdm_conv_out_args* a, void* stream) {
   int rc = check_device();
   if (rc) return rc;
   // 32-row tiles (6 % halo re-read) once they fill the machine twice over, 8-row tiles for small batches
-  if (a->H % 32 == 0 && a->n_img * (a->H / 32) >= 2 * num_sms()) return launch_conv_out<32>(a, (cudaStream_t)stream);
+  static int r_big = 0;  // CDM_CONV_OUT_ROWS=16|32 selects the large-batch tile height (default 32)
+  if (!r_big) {
+    const char* e = getenv("CDM_CONV_OUT_ROWS");
+    r_big = (e && atoi(e) == 16) ? 16 : 32;
+  }
+  if (a->H % 32 == 0 && a->n_img * (a->H / 32) >= 2 * num_sms())
+    return r_big == 16 ? launch_conv_out<16>(a, (cudaStream_t)stream) : launch_conv_out<32>(a, (cudaStream_t)stream);
   return launch_conv_out<8>(a, (cudaStream_t)stream);
 }
 

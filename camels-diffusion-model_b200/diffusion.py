@@ -105,8 +105,13 @@ def denoise_add_noise(x, t, pred_noise, z=None, b_t=None, a_t=None, ab_t=None):
 class _SamplerRun:
     """Device state of one sampling run + the captured one-step CUDA graph."""
 
-    def __init__(self, model, x_T, params, guide_w, timesteps, sched, *, z_all=None, shortcut_tab=None,
-                 save_rate=20, seed=None, use_graph=True, snapshots=True, sample_offset=0):
+    def __init__(self, model, *a, **k):
+        self.dev = model._check_supported()  # every launch below runs with the model's device current (L.on_device)
+        self._init(model, *a, **k)
+
+    @L.on_device
+    def _init(self, model, x_T, params, guide_w, timesteps, sched, *, z_all=None, shortcut_tab=None,
+              save_rate=20, seed=None, use_graph=True, snapshots=True, sample_offset=0):
         dev = model._check_supported()
         if model.training:
             raise L.CdmError("sampling needs eval mode (BatchNorm running statistics): call model.eval()")
@@ -152,12 +157,14 @@ class _SamplerRun:
         self.x_T = self.x.clone()
         self.remaining = timesteps  # host mirror of the device step counter: steps left before i reaches 0
 
+    @L.on_device
     def reset(self):
         """Back to x_T at step T (a new trajectory over the same graph; snapshots are overwritten)."""
         self.x.copy_(self.x_T)
         self.step.fill_(self.T)
         self.remaining = self.T
 
+    @L.on_device
     def _one_step(self):
         """One reverse-diffusion step = ONE C call (cdm_sample_step: the 26 launches of the reps*B-image forward,
         the CFG mix + x_{t-1} update, the step counter)."""
@@ -167,6 +174,7 @@ class _SamplerRun:
                        self.T, guide_w=self.guide_w, z=self.z, z_iter_stride=self.z_stride, seed=self.seed,
                        sample_offset=self.sample_offset, snap=self.snap, snap_slot=self.snap_slot)
 
+    @L.on_device
     def capture(self):
         """Warm up once on scratch state (sets kernel attributes, fills caches), then capture one step."""
         x_keep = self.x.clone()
@@ -183,6 +191,7 @@ class _SamplerRun:
             self.graph = g
         torch.cuda.synchronize()
 
+    @L.on_device
     def run(self, n_steps=None):
         n_steps = self.remaining if n_steps is None else n_steps
         if n_steps > self.remaining:  # the step index selects table rows on the device: never let it pass 0
@@ -283,7 +292,7 @@ class SamplerSession:
     """One sampling run driven step by step through the captured CUDA graph (see DDPM.open_sampler)."""
 
     def __init__(self, ddpm, noise_images, params, guide_w, save_rate, shortcut_tab, seed):
-        dev = ddpm.device
+        dev = self.dev = ddpm.device
         x_T = noise_images.to(dev, non_blocking=True)
         prm = None if params is None else params.to(dev, non_blocking=True)
         self.run = _SamplerRun(ddpm.nn_model, x_T, prm, guide_w, ddpm.timesteps, ddpm.sched, shortcut_tab=shortcut_tab,
@@ -305,6 +314,7 @@ class SamplerSession:
     def _key(t):
         return (t.data_ptr(), t.numel(), t.device)
 
+    @L.on_device
     def step(self, z, z_next=None):
         """One reverse-diffusion step with the caller's noise `z` [B,1,H,W] (host tensors are copied asynchronously;
         pin them to overlap the copy).  `z_next`, if given, is the NEXT step's noise: its host-to-device copy runs
@@ -347,8 +357,13 @@ class SamplerSession:
 class _EvalLoop:
     """perturb -> U-Net -> per-sample MSE accumulate for one (x, param) batch at a device-resident step t."""
 
-    def __init__(self, model, x, param, timesteps, sched, cb_kind, weight_tab, *, shortcut_tab=None, seed=0,
-                 weight_tab2=None, sample_offset=0):
+    def __init__(self, model, *a, **k):
+        self.dev = model._check_supported()
+        self._init(model, *a, **k)
+
+    @L.on_device
+    def _init(self, model, x, param, timesteps, sched, cb_kind, weight_tab, *, shortcut_tab=None, seed=0,
+              weight_tab2=None, sample_offset=0):
         dev = model._check_supported()
         if model.training:
             raise L.CdmError("likelihood / ELBO evaluation needs eval mode: call model.eval()")
@@ -380,6 +395,7 @@ class _EvalLoop:
         self.sample_offset = int(sample_offset)  # global index of x[0]: in-kernel noise is keyed by the global sample
         self.graph = None
 
+    @L.on_device
     def one(self, noise=None):
         m = self.model
         if noise is not None:
@@ -393,6 +409,7 @@ class _EvalLoop:
         L.mse_accum(eps, self.noise, weight_tab=self.weight, step_ptr=self.step, mse_out=self.mse, acc=self.acc,
                     weight_tab2=self.weight2, acc2=self.acc2)
 
+    @L.on_device
     def sweep_all(self):
         """t = 1..T with in-kernel noise, one captured graph replayed T times."""
         self.step.fill_(1)

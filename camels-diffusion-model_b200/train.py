@@ -702,6 +702,7 @@ class GraphedTrainStep:
     def graph(self):
         return self.graphs.get(self.B)
 
+    @L.on_device
     def _capture(self, b):
         """Capture the step for batch size b <= B (the ragged last batch of an epoch gets its own graph, lazily).
         Warm-up and capture run with lr = 0, and everything a step mutates besides the parameters — BatchNorm
@@ -778,6 +779,7 @@ class GraphedTrainStep:
         self.lr.fill_(float(sd["param_groups"][0]["lr"]))
         self.seed = int(sd.get("seed", self.seed))
 
+    @L.on_device
     def __call__(self, x, param, t=None, shortcut=None):
         """One optimisation step on a batch of b <= B samples; returns the mean-squared-error loss as a 0-d device
         tensor (no host sync).  t / shortcut default to fresh draws from torch's CPU generator, like the reference."""

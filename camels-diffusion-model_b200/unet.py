@@ -297,6 +297,7 @@ class ContextUnet(nn.Module):
         sc = nn.Conv2d(self.in_channels, self.n_feat, kernel_size=1, stride=1, padding=0)
         return torch.cat([sc.weight.detach().view(-1), sc.bias.detach().view(-1)])  # [2*n_feat]: w_c then b_c
 
+    @L.on_device
     def forward(self, x, t, c=None, shortcut=None):
         """ContextUnet.forward (ContextUnet.py:42-60).  x [B,1,64,64]; t numel 1 or B; c [B,n_cfeat] or None.
         `shortcut` ([2*n_feat] = w_c,b_c) overrides the per-call random 1x1 shortcut (tests / replay)."""

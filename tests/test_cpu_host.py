@@ -127,7 +127,9 @@ def test_bench_reference_arm_prints_the_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "cfg_ddpm_samples_per_sec_64x64_1500steps"
     assert d["unit"] == "samples/s" and d["higher_is_better"] is True and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    from oracle import build_ref
+    assert d["cpu_baseline"]["kind"] == ("reference" if build_ref.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                         capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=60)
@@ -320,3 +322,43 @@ def test_ctypes_structs_match_the_c_layout(lib, tmp_path):
 def ctypes_sizeof(cls):
     import ctypes
     return ctypes.sizeof(cls)
+
+
+def test_oracle_equals_the_live_reference_modules():
+    """oracle/_ref (the unmodified reference modules, placed by oracle/build_ref.py) against the oracle restatement,
+    live: same seeded weights, same inputs, the same fresh-shortcut draws -> eps identical to fp32 round-off; and the
+    reference's own denoise_add_noise / sample_ddpm loop equals the oracle's sampler on a 3-step CFG trajectory."""
+    from oracle import build_ref, contextunet_oracle as O
+    if not build_ref.available():
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    CU, sps = build_ref.load()
+    torch.manual_seed(0)
+    ref = CU(in_channels=1, n_feat=128, n_cfeat=6, height=64).eval()
+    sd = O.init_state_dict(0, n_cfeat=6)
+    assert all(torch.equal(v, sd[k]) for k, v in ref.state_dict().items())
+    g = torch.Generator().manual_seed(3)
+    x, c = torch.randn(2, 1, 64, 64, generator=g), torch.rand(2, 6, generator=g)
+    t = torch.tensor([0.3])
+    torch.manual_seed(11)
+    with torch.no_grad():
+        e_ref = ref(x, t, c)
+    torch.manual_seed(11)
+    with torch.no_grad():
+        e_orc = O.unet_forward(sd, x, t, c, O.draw_shortcut(128), n_cfeat=6)
+    assert float((e_ref - e_orc).norm() / e_ref.norm()) < 1e-5
+    # the reference's pure-function sampler (code/sample_power_spectra.py:71-110) vs the oracle's, same draw stream
+    Tn = 3
+    b_t, a_t, ab_t = O.make_schedule(Tn)
+    torch.manual_seed(5)
+    x_ref = sps.sample_ddpm(ref, n_sample=2, size=64, device=torch.device("cpu"), params=c, guide_w=2.0, timesteps=Tn,
+                            b_t=b_t, a_t=a_t, ab_t=ab_t)
+    torch.manual_seed(5)
+    x_T = torch.randn(2, 1, 64, 64)
+    z, shortcuts = torch.zeros(Tn, 2, 1, 64, 64), []
+    for i in range(Tn, 0, -1):
+        if i > 1:
+            z[Tn - i] = torch.randn(2, 1, 64, 64)
+        shortcuts.append([O.draw_shortcut(128), O.draw_shortcut(128)])
+    with torch.no_grad():
+        x_orc, _ = O.sample_ddpm(sd, x_T, c, 2.0, Tn, (b_t, a_t, ab_t), z, shortcuts, n_cfeat=6)
+    assert float((x_ref - x_orc).norm() / x_ref.norm()) < 1e-5
