@@ -539,7 +539,8 @@ def run_b200(args):
                "ms_per_step": ms_e2e, "setup_s": t_setup,
                "note": "public API DDPM.open_sampler(...).step(z, z_next).result(): pinned host x_T/params/per-step z in "
                        "(double-buffered upload), "
-                       "step counter every step and x + snapshots out; graph capture/setup reported separately in setup_s"}
+                       "step counter read back every step (pinned host memory, collected one step later) and x + "
+                       "snapshots out; graph capture/setup reported separately in setup_s"}
 
     _phase("e2e done")
     # ---- roofline of the dominant kernel (3x3 128->128 conv at 64x64: 9 of 26 launches, ~57% of the FLOPs)

@@ -309,13 +309,17 @@ class SamplerSession:
         self._stage_free = torch.cuda.Event()   # the staged noise has been consumed (stage may be overwritten)
         self._stage_free.record()
         self._staged_key, self._staged_ref = None, None
+        # per-step device -> host read of the step counter: copied into pinned memory behind each step's kernels and
+        # collected ONE step later, so the read never drains the GPU's queue (the next graph is already enqueued)
+        self._ctr_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+        self._ctr_ev = [torch.cuda.Event(), torch.cuda.Event()]
 
     @staticmethod
     def _key(t):
         return (t.data_ptr(), t.numel(), t.device)
 
     @L.on_device
-    def step(self, z, z_next=None):
+    def step(self, z, z_next=None, sync=False):
         """One reverse-diffusion step with the caller's noise `z` [B,1,H,W] (host tensors are copied asynchronously;
         pin them to overlap the copy).  `z_next`, if given, is the NEXT step's noise: its host-to-device copy runs
         on a side stream underneath this step's kernels, and the next `step(z_next, ...)` finds it on the device
@@ -344,8 +348,15 @@ class SamplerSession:
                 self._stage.copy_(z_next.reshape(-1), non_blocking=True)
                 self._staged.record(self._copy_stream)
             self._staged_key, self._staged_ref = self._key(z_next), z_next
+        k = self.steps_done & 1
+        self._ctr_host[k:k + 1].copy_(self.run.step, non_blocking=True)
+        self._ctr_ev[k].record(main)
         self.steps_done += 1
-        return int(self.run.step.item())
+        if sync or self.steps_done == 1:
+            self._ctr_ev[k].synchronize()
+            return int(self._ctr_host[k])
+        self._ctr_ev[1 - k].synchronize()  # the previous step's read-back: complete unless the host runs ahead
+        return int(self._ctr_host[1 - k])
 
     def result(self):
         """(x [B,1,H,W], intermediate [n_snapshots_taken,B,1,H,W]) on the host, like the reference's return values."""

@@ -132,15 +132,15 @@ def test_stepwise_sampler_session_equals_batch_sampler(models):
     ddpm = cdm.DDPM(m, Tn)
     ref, inter_ref, _ = D._sample(m, x_T.cuda(), prm.cuda(), 2.0, Tn, ddpm.sched, z_all=z, shortcut_tab=tab, save_rate=4)
     sess = ddpm.open_sampler(x_T.pin_memory(), prm.pin_memory(), guide_w=2.0, save_rate=4, shortcut_tab=tab)
-    left = [sess.step(z[k].pin_memory()) for k in range(Tn)]
+    left = [sess.step(z[k].pin_memory(), sync=True) for k in range(Tn)]
     assert left == list(range(Tn - 1, -1, -1))
     x, inter = sess.result()
     assert torch.equal(x, ref.cpu()) and np.array_equal(inter, inter_ref)
     # double-buffered upload: the next step's noise is handed over one step early (and once not at all)
     zp = z.pin_memory()
     sess = ddpm.open_sampler(x_T.pin_memory(), prm.pin_memory(), guide_w=2.0, save_rate=4, shortcut_tab=tab)
-    for k in range(Tn):
-        sess.step(zp[k], z_next=zp[k + 1] if k + 1 < Tn and k != 4 else None)
+    lag = [sess.step(zp[k], z_next=zp[k + 1] if k + 1 < Tn and k != 4 else None) for k in range(Tn)]
+    assert lag == [Tn - 1] + list(range(Tn - 1, 0, -1))  # the pipelined read-back trails the step by one
     x2, inter2 = sess.result()
     assert torch.equal(x2, ref.cpu()) and np.array_equal(inter2, inter_ref)
     for bad in (None, zp[0][:2]):
