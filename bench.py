@@ -422,10 +422,14 @@ def secondary_block(dev, rank, world, barrier):
     torch.manual_seed(0)
     model = cdm.ContextUnet(1, 128, NCF, 64).to(dev).eval()
     b1 = {}
-    for gw in (0.0, 2.0):
+    # batch-1 runs (the reference's call pattern for the sensitivity sweep: launch-latency bound), then the same work
+    # batched the way drivers.py runs it: 30 sensitivity contexts / 25 grid contexts / 5 guidance samples per launch
+    for B1, gw, tag in ((1, 0.0, "batch1_guide_w_0"), (1, 2.0, "batch1_guide_w_2"),
+                        (30, 0.0, "sensitivity_30_contexts_batched"), (25, 0.0, "parameter_grid_25_batched"),
+                        (5, 2.0, "guidance_sweep_5_samples_cfg")):
         tab = D.draw_shortcut_table(TIMESTEPS, 2 if gw > 0 else 1, 128)
-        run = D._SamplerRun(model, torch.randn(1, 1, 64, 64, generator=g).to(dev), torch.rand(1, NCF, generator=g).to(dev),
-                            gw, TIMESTEPS, sched, shortcut_tab=tab, seed=1)
+        run = D._SamplerRun(model, torch.randn(B1, 1, 64, 64, generator=g).to(dev),
+                            torch.rand(B1, NCF, generator=g).to(dev), gw, TIMESTEPS, sched, shortcut_tab=tab, seed=1)
         run.capture()
         run.run(10)
         torch.cuda.synchronize()
@@ -434,8 +438,10 @@ def secondary_block(dev, rank, world, barrier):
         run.run(100)
         e1.record()
         torch.cuda.synchronize()
-        b1[f"guide_w_{gw:g}"] = {"ms_per_step": e0.elapsed_time(e1) / 100,
-                                 "s_per_sample_1500_steps": e0.elapsed_time(e1) / 100 * 1.5}
+        ms = e0.elapsed_time(e1) / 100
+        b1[tag] = {"batch": B1, "guide_w": gw, "ms_per_step": ms, "s_per_run_1500_steps": ms * 1.5,
+                   "s_per_sample_1500_steps": ms * 1.5 / B1}
+        del run
     out["batch1_latency"] = b1
     return out
 
