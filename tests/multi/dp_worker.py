@@ -90,6 +90,14 @@ for mode in ("nccl", "peer"):
             assert float((b1 - b2).abs().max()) <= 1e-4, f"[{mode}] {k}: running statistics differ from the global batch"
         else:
             assert torch.equal(b1, b2), k
+    if rank == 0 and mode == "nccl":  # diagnostic: batch statistics as seen through the running buffers (momentum 0.1)
+        rows = []
+        for (k, b1), (_, b2) in zip(m_1.named_buffers(), m_dp.named_buffers()):
+            if "running_var" in k:
+                d = ((b1 - b2).abs() / (b1 - 0.9).abs().clamp_min(1e-12)).max()  # relative to 0.1 * batch var
+                rows.append((float(d), k))
+        rows.sort(reverse=True)
+        print("DP-DIAG worst relative batch-variance differences (sharded vs single):", [(f"{d:.1e}", k) for d, k in rows[:4]])
     g1, g2 = dict(m_1.named_parameters()), dict(m_dp.named_parameters())
     # gradients nearest the loss are a sharp check of the exchange logic (deeper ones amplify bf16 ReLU-mask flips
     # ~1.3x per layer in this random-init train-mode BatchNorm stack)
@@ -97,6 +105,11 @@ for mode in ("nccl", "peer"):
                    ("up2.model.2.conv2.1.weight", 2e-2)):
         err = float((g1[k].grad - g2[k].grad).norm() / g1[k].grad.norm())
         assert err <= tol, f"[{mode}] grad {k}: sharded vs single-process rel-L2 {err:.2e} > {tol}"
+    if rank == 0:
+        errs = sorted(((float((g1[k].grad - g2[k].grad).norm() / g1[k].grad.norm()), k) for k in g1
+                       if float(g1[k].grad.norm()) > 1e-7), reverse=True)
+        print(f"DP-DIAG[{mode}] worst gradients (sharded vs single rel-L2):", [(f"{e:.1e}", k) for e, k in errs[:5]],
+              "| out.3.weight", f"{dict((k, e) for e, k in errs)['out.3.weight']:.1e}", flush=True)
     for k, p in g2.items():  # the all-reduced gradients and the updated statistics are the same on every rank
         assert all_equal(p.grad), f"[{mode}] grad {k} differs between ranks"
 
