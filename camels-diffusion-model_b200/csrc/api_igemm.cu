@@ -135,7 +135,7 @@ int conv_prepare(const cdm_conv3x3_args* a, ConvLaunch* L) {
   CDM_CHECK_ARG(a->cout > 0 && a->cout % 128 == 0 && a->cout <= 256);
   CDM_CHECK_ARG(a->mode >= 0 && a->mode <= 4);
 #ifdef CDM_PROBES
-  CDM_CHECK_ARG((a->flags & ~(CDM_EPI_ALL | (31 << 26))) == 0);
+  CDM_CHECK_ARG((a->flags & ~(CDM_EPI_ALL | (127 << 24))) == 0);
 #else
   CDM_CHECK_ARG((a->flags & ~CDM_EPI_ALL) == 0);  // unknown bits are an error, never silently forwarded to the kernel
 #endif

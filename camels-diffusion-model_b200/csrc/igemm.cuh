@@ -608,18 +608,26 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       const int odd = lane & 1;
       const uint32_t base = stg_pair + (uint32_t)((sidx & 1) * kSwStoreBox) + (uint32_t)(odd * 4 * 128 + (lane & 6) * 2);
       const uint32_t jsw = (uint32_t)((q & 1) * 4 + (lane >> 3)) ^ (uint32_t)(odd * 4);
+      if (CDM_PROBE_BIT(p.flags, 25)) {  // probe: no register -> shared-memory staging (stale bytes are stored)
+        float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const int ia = (k >> 2) * 8 + (k & 3), ib = ia + 4;
-        const float recv = __shfl_xor_sync(0xffffffffu, odd ? f[ia] : f[ib], 1);
-        const uint32_t w = odd ? pack_bf16x2(recv, f[ib]) : pack_bf16x2(f[ia], recv);
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)(ia * 128) + ((jsw ^ (uint32_t)(k & 3)) << 4)), "r"(w)
-                     : "memory");
+        for (int i = 0; i < 32; ++i) acc += f[i];
+        if (acc == 123.456f) asm volatile("st.shared.b32 [%0], %1;" ::"r"(base), "r"(__float_as_uint(acc)) : "memory");
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int ia = (k >> 2) * 8 + (k & 3), ib = ia + 4;
+          const float recv = __shfl_xor_sync(0xffffffffu, odd ? f[ia] : f[ib], 1);
+          const uint32_t w = odd ? pack_bf16x2(recv, f[ib]) : pack_bf16x2(f[ia], recv);
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)(ia * 128) + ((jsw ^ (uint32_t)(k & 3)) << 4)),
+                       "r"(w)
+                       : "memory");
+        }
       }
       fence_proxy_async_smem();
       if (st_elect) tma_store_wait_read<0>();  // the OTHER buffer's store (one chunk ago) has left shared memory
       named_bar_sync(2 + pair, 64);
-      if (st_elect) {
+      if (st_elect && !CDM_PROBE_BIT(p.flags, 24)) {  // probe bit 24: staging only, no TMA store
         tma_store_4d(&mapOut, stg_pair + (uint32_t)((sidx & 1) * kSwStoreBox), c_crd, w_crd, h_crd, n_crd);
         tma_store_commit();
       }

@@ -139,7 +139,7 @@ def case_gemm(name, M, k0, k1, N, out_mode=0, H=0, W=0):
     return diag(name, out.float(), r)
 
 
-def case_perf(name, mode, n=256, H=64, cin=128, cout=128, flags=1):
+def case_perf(name, mode, n=256, H=64, cin=128, cout=128, flags=1, iters=10):
     import torch
     L = _load()
     dev = "cuda"
@@ -152,7 +152,6 @@ def case_perf(name, mode, n=256, H=64, cin=128, cout=128, flags=1):
         L.conv3x3(x, w, scale, shift, out, mode=mode, flags=flags)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    iters = 10
     e0.record()
     for _ in range(iters):
         L.conv3x3(x, w, scale, shift, out, mode=mode, flags=flags)
@@ -328,6 +327,11 @@ CASES = {
     "perf_m3_b2048": lambda: case_perf("perf_m3_b2048", 3, n=2048),
     "perf_m4_b2048": lambda: case_perf("perf_m4_b2048", 4, n=2048),
     "waits_m4": lambda: case_waits("waits_m4", mode=4),
+    "perf_m4_long": lambda: case_perf("perf_m4_long", 4, n=1024, iters=600),
+    "perf_m4_nostage": lambda: case_perf("perf_m4_nostage", 4, n=1024, flags=1 | (1 << 25)),
+    "perf_m4_notma": lambda: case_perf("perf_m4_notma", 4, n=1024, flags=1 | (1 << 24)),
+    "perf_m4_nostage_notma": lambda: case_perf("perf_m4_nostage_notma", 4, n=1024, flags=1 | (1 << 24) | (1 << 25)),
+    "perf_m4_noepi": lambda: case_perf("perf_m4_noepi", 4, n=1024, flags=1 | (1 << 29)),
     "perf_m3_nostore": lambda: case_perf("perf_m3_nostore", 3, n=1024, flags=1 | (1 << 30)),
     "perf_m3_noepi": lambda: case_perf("perf_m3_noepi", 3, n=1024, flags=1 | (1 << 29)),
     "perf_m3_l2store": lambda: case_perf("perf_m3_l2store", 3, n=1024, flags=1 | (1 << 26)),
