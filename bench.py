@@ -27,8 +27,8 @@ NCF = 6
 GFLOP_PER_IMAGE_FWD = 19.1785  # conv + transposed-conv MACs x 2 per image per forward
 CONV64_FLOP_PER_IMAGE = 2.0 * 64 * 64 * 128 * 9 * 128  # one 3x3 128->128 conv at 64x64
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE 128->128 @64x64 conv3x3_sw_kernel launch over 2048 images, from
-# the `ncu --set full` capture summarised in profiles/r1_ncu_summary.md (2.150 GB + 2.102 GB; algorithmic: 2 x 2 GiB)
-CONV64_DRAM_BYTES_PER_IMAGE = (2.150360e9 + 2.102144e9) / 2048
+# the `ncu --set full` capture summarised in profiles/r2_ncu_summary.md §2 (2.161 GB + 2.100 GB; algorithmic: 2 x 2 GiB)
+CONV64_DRAM_BYTES_PER_IMAGE = (2.161e9 + 2.100e9) / 2048
 # algorithmic HBM bytes per image of the memory-bound kernels
 HBM_BYTES_PER_IMAGE = {"conv_out": 64 * 64 * 128 * 2 + 64 * 64 * 4, "conv_in": 64 * 64 * 4 + 64 * 64 * 128 * 2}
 
@@ -559,11 +559,11 @@ def run_b200(args):
     conv_ms = sum(conv64) / max(len(conv64), 1)
     achieved = CONV64_FLOP_PER_IMAGE * n_img / (conv_ms * 1e-3) / 1e12
     conv_all_ms = sum(v for d, v in bd if d.startswith("conv3x3") or d.startswith("gemm"))
-    roofline = {"bound": "tensor", "kernel": "conv3x3_sw_kernel (M128 N256 K16) 128->128 @64x64", "achieved": achieved,
+    roofline = {"bound": "tensor", "kernel": "conv3x3_sw_kernel<32, TMA-store epilogue> (M128 N256 K16) 128->128 @64x64", "achieved": achieved,
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
                 "frac_of_burst_peak": achieved / pk["tf_burst"], "peak_source": pk["src"] + ", sustained bf16",
                 "traffic": CONV64_DRAM_BYTES_PER_IMAGE * n_img, "traffic_unit": "bytes per launch (ncu dram read+write, "
-                "profiles/r1_ncu_summary.md, scaled to this launch's image count)",
+                "profiles/r2_ncu_summary.md, scaled to this launch's image count)",
                 "algorithmic_bytes": 2 * 64 * 64 * 128 * 2 * n_img,
                 "launch_ms": conv_ms, "launches_per_step": len(conv64),
                 "share_of_step": sum(conv64) / step_ms, "tensor_kernels_share_of_step": conv_all_ms / step_ms,
