@@ -328,6 +328,9 @@ CASES = {
     "perf_m4_b2048": lambda: case_perf("perf_m4_b2048", 4, n=2048),
     "waits_m4": lambda: case_waits("waits_m4", mode=4),
     "perf_m4_long": lambda: case_perf("perf_m4_long", 4, n=1024, iters=600),
+    "perf_m4_halfw": lambda: case_perf("perf_m4_halfw", 4, n=1024, flags=1 | (1 << 27)),
+    "perf_m4_halfw_notma": lambda: case_perf("perf_m4_halfw_notma", 4, n=1024, flags=1 | (1 << 27) | (1 << 24)),
+    "perf_m4_halfw_noepi": lambda: case_perf("perf_m4_halfw_noepi", 4, n=1024, flags=1 | (1 << 27) | (1 << 29)),
     "perf_m4_nostage": lambda: case_perf("perf_m4_nostage", 4, n=1024, flags=1 | (1 << 25)),
     "perf_m4_notma": lambda: case_perf("perf_m4_notma", 4, n=1024, flags=1 | (1 << 24)),
     "perf_m4_nostage_notma": lambda: case_perf("perf_m4_nostage_notma", 4, n=1024, flags=1 | (1 << 24) | (1 << 25)),
