@@ -264,6 +264,7 @@ def torch_gpu_baseline(dev, batch, guide_w, steps=10, warmup=2):
                     continue
                 model.to(torch.bfloat16)
                 x, params, zeros = x.to(torch.bfloat16), params.to(torch.bfloat16), zeros.to(torch.bfloat16)
+                torch.set_default_dtype(torch.bfloat16)  # the reference builds a fresh nn.Conv2d shortcut per forward
             ctx = torch.autocast("cuda", dtype=torch.bfloat16, enabled=name == "bf16_autocast_channels_last")
             with torch.no_grad(), ctx:
                 run(warmup, x)
@@ -278,6 +279,8 @@ def torch_gpu_baseline(dev, batch, guide_w, steps=10, warmup=2):
                          "finite": bool(torch.isfinite(xe).all())}
         except Exception as ex:  # noqa: BLE001
             out[name] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+        finally:
+            torch.set_default_dtype(torch.float32)
         torch.cuda.empty_cache()
     return out
 

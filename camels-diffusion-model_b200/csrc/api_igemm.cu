@@ -2,6 +2,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
+#include <utility>
+
 #include "common.h"
 #include "igemm.cuh"
 #include "launch.h"
@@ -117,6 +121,31 @@ static int set_smem_attr(K kernel, int variant, int bytes) {
     g_attr_done[dev][variant] = 1;
   }
   return CDM_OK;
+}
+
+// Launch with programmatic stream serialization (PDL): the kernel may become resident while its stream predecessor
+// is still running; conv3x3_sw_kernel orders itself with griddepcontrol.wait.  CDM_PDL=0 disables it (A/B runs).
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CDM_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, int smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)block, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 static int act_tmap(CUtensorMap* m, const void* base, int c, int W, int H, int n, uint32_t bw, uint32_t bh) {
@@ -251,25 +280,25 @@ int conv_launch(const ConvLaunch& L, cudaStream_t st) {
     case kConvSw32: {
       constexpr int smem = conv_sw_smem_bytes<32, false>();
       if ((rc = set_smem_attr(conv3x3_sw_kernel<32, false>, kConvSw32, smem))) return rc;
-      conv3x3_sw_kernel<32, false><<<L.grid, kSwThreads, smem, st>>>(L.a0, L.a1, L.b, L.out, L.p);
+      CDM_CHECK_CUDA(launch_pdl(conv3x3_sw_kernel<32, false>, L.grid, kSwThreads, smem, st, L.a0, L.a1, L.b, L.out, L.p));
       break;
     }
     case kConvSw8: {
       constexpr int smem = conv_sw_smem_bytes<8, false>();
       if ((rc = set_smem_attr(conv3x3_sw_kernel<8, false>, kConvSw8, smem))) return rc;
-      conv3x3_sw_kernel<8, false><<<L.grid, kSwThreads, smem, st>>>(L.a0, L.a1, L.b, L.out, L.p);
+      CDM_CHECK_CUDA(launch_pdl(conv3x3_sw_kernel<8, false>, L.grid, kSwThreads, smem, st, L.a0, L.a1, L.b, L.out, L.p));
       break;
     }
     case kConvSw32 + 2: {
       constexpr int smem = conv_sw_smem_bytes<32, true>();
       if ((rc = set_smem_attr(conv3x3_sw_kernel<32, true>, kConvSw32 + 2, smem))) return rc;
-      conv3x3_sw_kernel<32, true><<<L.grid, kSwThreads, smem, st>>>(L.a0, L.a1, L.b, L.out, L.p);
+      CDM_CHECK_CUDA(launch_pdl(conv3x3_sw_kernel<32, true>, L.grid, kSwThreads, smem, st, L.a0, L.a1, L.b, L.out, L.p));
       break;
     }
     case kConvSw8 + 2: {
       constexpr int smem = conv_sw_smem_bytes<8, true>();
       if ((rc = set_smem_attr(conv3x3_sw_kernel<8, true>, kConvSw8 + 2, smem))) return rc;
-      conv3x3_sw_kernel<8, true><<<L.grid, kSwThreads, smem, st>>>(L.a0, L.a1, L.b, L.out, L.p);
+      CDM_CHECK_CUDA(launch_pdl(conv3x3_sw_kernel<8, true>, L.grid, kSwThreads, smem, st, L.a0, L.a1, L.b, L.out, L.p));
       break;
     }
     default:

@@ -488,10 +488,16 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const int cin = p.chunks * 64;
   const int px_tiles = p.W >> 3, py_tiles = p.H / ROWS;  // patches of 8 px x ROWS rows
   const int units_per_img = px_tiles * py_tiles * p.n_tiles;
+  // PDL: barriers, TMEM and tensor-map prefetch above (and the weight stream below: weights are never written by a
+  // stream predecessor that triggers early) may overlap the tail of the previous kernel; every role that touches
+  // activations — the halo producer, and the epilogue with its table reads and its stores — waits for it first.
+  // Small launches (batch-1 sampling: 64 CTAs on 148 SMs) hide their set-up and the launch latency this way.
+  if (threadIdx.x == 0) griddep_launch();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
     tma_prefetch_desc(&mapA1);
+    griddep_wait();
     int sa = 0;
     uint32_t pa = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
@@ -591,6 +597,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const int q = warp & 3, half = (warp - 4) >> 2;
     const int et = threadIdx.x - 128;  // 0..255 among the epilogue threads
     const int co_l = q * 32 + lane;    // this thread's channel inside the 128-wide tile
+    griddep_wait();
     const int step = p.step_ptr ? *p.step_ptr : 0;
     const bool pool = p.flags & CDM_EPI_POOL;
     float bn_s0 = 0.f, bn_q0 = 0.f, bn_s1 = 0.f, bn_q1 = 0.f;  // CDM_EPI_BNSTATS, per n_tile (cout <= 256)

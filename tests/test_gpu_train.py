@@ -556,12 +556,18 @@ def test_training_step_is_bit_reproducible():
 
 def test_training_trajectory_20_steps_vs_fp32_oracle():
     """20 optimisation steps at batch 32 (the reference's batch size) against the fp32 CPU trajectory stored by
-    oracle/make_golden_train_traj.py (the loop body of code/train_diffusion_paper.py:349-366, Adam defaults, lr 1e-4):
-    the loss curve follows the reference within 2 %, the parameters nearest the loss end within 2e-3 (relative L2 of
-    the weights; the learning rate is 10x the reference's 1e-5, so the weights move 10x further than in its runs) and their UPDATE (final - initial) within 10 % of the reference's update; BatchNorm running statistics
-    after 20 momentum updates within 3e-2."""
+    oracle/make_golden_train_traj.py (the loop body of code/train_diffusion_paper.py:349-366, Adam defaults, lr 1e-4 =
+    ten times the reference's, so that the loss falls from 0.96 to 0.18 and the weights move 10x further than in its
+    runs).  Two-sided, like the single-step gradient test:
+      (a) vs fp32: the loss curve within 2 % at every step; `out.*` weights within 2e-3 (relative L2), their UPDATE
+          (final - initial) within 10 % of the reference's update;
+      (b) the fixture also holds the same trajectory with bf16 rounding emulated at the device path's storage points
+          (pure torch): every tracked weight and BatchNorm running statistic may deviate from fp32 by at most 1.5x what
+          that emulation deviates (+ a small floor).  The deepest BatchNorm (down2.model.1.conv2.1) ends 13 % off in
+          running variance in the EMULATION (Adam turns the noisy tiny gradients of the deep layers into full-size
+          steps), 11 % on the device: a bf16 storage effect, not a kernel error."""
     import camels_diffusion_model_b200 as cdm
-    from camels_diffusion_model_b200.train import GraphedTrainStep
+    from camels_diffusion_model_b200.train import FusedAdam, training_step
     from oracle.make_golden_train_traj import KEEP, KEEP_BN, draws
     g = load("train_traj.npz")
     steps, B, lr = int(g["steps"]), int(g["batch"]), float(g["lr"])
@@ -571,42 +577,48 @@ def test_training_trajectory_20_steps_vs_fp32_oracle():
     model.load_state_dict(sd0)
     model = model.cuda().train()
     _, _, ab_t = cdm.make_schedule(1500)
+    optim = FusedAdam(model.parameters(), lr=lr)
     losses = []
     # the reference's step with the reference's own noise: perturb_input -> forward -> mse -> backward -> Adam
-    from camels_diffusion_model_b200.train import FusedAdam, training_step
-    optim = FusedAdam(model.parameters(), lr=lr)
     for noise, t, sc in per_step:
         losses.append(float(training_step(model, optim, x, prm.cuda(), 1500, ab_t, noise=noise, t=t, shortcut=sc)))
     ref = g["losses"]
     rel = np.abs(np.array(losses) - ref) / ref
+    rel_emul = np.abs(g["emul/losses"] - ref) / ref
     print("loss curve dev", [round(v, 4) for v in losses], "ref", [round(float(v), 4) for v in ref])
+    print(f"max loss deviation from fp32: device {rel.max():.3e}, emulated bf16 {rel_emul.max():.3e}")
     record("train_traj20_batch32_max_loss_rel_dev", rel.max(), 2e-2)
+    record("train_traj20_batch32_max_loss_rel_dev_emulated_bf16", rel_emul.max(), None)
     assert rel.max() < 2e-2, rel
     sd = model.state_dict()
-    worst_w, worst_d = 0.0, 0.0
+    worst_w, worst_d, worst_ratio = 0.0, 0.0, 0.0
     for k in KEEP:
         fin, ini = T(g["final/" + k]), sd0[k]
-        if float(ini.norm()) > 0:  # zero-initialised biases: the weight IS its update, checked below
-            e_w = rel_l2(sd[k], fin)
-            worst_w = max(worst_w, e_w) if k.startswith("out.") else worst_w
-            # out.*: measured 1.04e-3 at lr 1e-4 = 10x the reference's learning rate; tensors in front of a train-mode
-            # BatchNorm (scale-invariant direction, noisier gradients): 3.2e-3
-            assert e_w < (2e-3 if k.startswith("out.") else 1e-2), (k, e_w)
-        if k.startswith("out.") or float(ini.norm()) == 0:
+        e_w = rel_l2(sd[k], fin)
+        e_emul = float(g["emul_dev/" + k])
+        worst_ratio = max(worst_ratio, e_w / (e_emul + 2e-4))
+        assert e_w <= 1.5 * e_emul + 2e-4, (k, e_w, e_emul)
+        if k.startswith("out.") and float(ini.norm()) > 0:
+            worst_w = max(worst_w, e_w)
+            assert e_w < 2e-3, (k, e_w)  # measured 1.04e-3 (out.0.weight; emulated bf16: 1.02e-3)
+        if k.startswith("out."):
             e_d = rel_l2(sd[k].cpu() - ini, fin - ini)
             worst_d = max(worst_d, e_d)
             assert e_d < 0.1, (k, e_d)
     record("train_traj20_batch32_max_weight_rel_l2", worst_w, 2e-3)
     record("train_traj20_batch32_max_out_update_rel_l2", worst_d, 0.1)
-    worst_bn = 0.0
     for pre in KEEP_BN:
-        for nm in ("running_mean", "running_var"):
-            e = rel_l2(sd[f"{pre}.{nm}"], g[f"bn/{pre}.{nm}"])
-            worst_bn = max(worst_bn, e)
-            # batch statistics of bf16-stored train-mode activations (pred itself is within 1.6e-2 at batch 4): measured
-            # 1.4e-2 for the running variance of the last BatchNorm of up2
-            assert e < 3e-2, (pre, nm, e)
-    record("train_traj20_batch32_max_bn_running_stat_rel_l2", worst_bn, 3e-2)
+        var_ref = T(g[f"bn/{pre}.running_var"])
+        # running variance: relative L2; running mean: error in units of the channel's standard deviation
+        e_v = rel_l2(sd[f"{pre}.running_var"], var_ref)
+        e_m = float(((sd[f"{pre}.running_mean"].cpu() - T(g[f"bn/{pre}.running_mean"])).abs() / var_ref.sqrt()).max())
+        ev_emul, em_emul = float(g[f"emul_dev/{pre}.running_var"]), float(g[f"emul_dev/{pre}.running_mean"])
+        print(f"BN {pre}: running_var rel-L2 {e_v:.3e} (emulated {ev_emul:.3e}), running_mean max |diff|/sigma "
+              f"{e_m:.3e} (emulated {em_emul:.3e})")
+        worst_ratio = max(worst_ratio, e_v / (ev_emul + 1e-3), e_m / (em_emul + 1e-3))
+        record(f"train_traj20_batch32_running_var_rel_l2/{pre}", e_v, 1.5 * ev_emul + 1e-3)
+        assert e_v <= 1.5 * ev_emul + 1e-3 and e_m <= 1.5 * em_emul + 1e-3, (pre, e_v, ev_emul, e_m, em_emul)
+    record("train_traj20_batch32_max_deviation_over_emulated_bf16", worst_ratio, 1.5)
 
 
 def test_deep_gradients_are_sensitive_to_summation_order_only():
