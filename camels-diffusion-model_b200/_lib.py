@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CDM_LIB selects another build of the same ABI (tools/gpu_probe.py loads the -DCDM_PROBES library this way)
 LIB_PATH = os.environ.get("CDM_LIB") or os.path.join(_HERE, "libcdm_b200.so")
 
-EPI_RELU, EPI_SHORTCUT, EPI_POOL, EPI_FILM, EPI_GNSTATS, EPI_BNSTATS, EPI_GELU, EPI_RESSCALE = 1, 2, 4, 8, 16, 32, 64, 128
+EPI_RELU, EPI_SHORTCUT, EPI_POOL, EPI_FILM, EPI_GNSTATS, EPI_BNSTATS, EPI_GELU, EPI_RESSCALE, EPI_BNBWD = (
+    1, 2, 4, 8, 16, 32, 64, 128, 256)
 CONV_MODE_COPIES, CONV_MODE_SHIFT24, CONV_MODE_SHIFT18, CONV_MODE_SWAPPED, CONV_MODE_SWAPPED_TMA = 0, 1, 2, 3, 4
 
 
@@ -30,6 +31,8 @@ class Conv3x3Args(C.Structure):
         ("film_scale", C.c_void_p), ("film_shift", C.c_void_p), ("film_shift_rows", C.c_int),
         ("step_ptr", C.c_void_p), ("gn_partial", C.c_void_p), ("mode", C.c_int),
         ("bn_partial", C.c_void_p), ("bn_sums", C.c_void_p), ("xr", C.c_void_p), ("res_scale", C.c_float),
+        ("bwd_z", C.c_void_p), ("bwd_scale", C.c_void_p), ("bwd_shift", C.c_void_p), ("bwd_mean", C.c_void_p),
+        ("bwd_rstd", C.c_void_p),
     ]
 
 
@@ -207,7 +210,7 @@ def num_sms():
 
 def conv3x3(src0, weight, scale, shift, out, *, src1=None, flags=EPI_RELU, sc_x=None, sc_tab=None, sc_reps=1,
             film_scale=None, film_shift=None, film_shift_rows=1, step_ptr=None, gn_partial=None,
-            mode=CONV_MODE_SWAPPED, bn_partial=None, bn_sums=None, xr=None, res_scale=1.0):
+            mode=CONV_MODE_SWAPPED, bn_partial=None, bn_sums=None, xr=None, res_scale=1.0, bwd=None):
     """src*: bf16 [n,H,W,c]; weight bf16 [cout,3,3,cin]; out bf16 NHWC. See cdm_conv3x3 in cdm_b200.h."""
     n, H, W, c0 = src0.shape
     a = Conv3x3Args()
@@ -221,6 +224,8 @@ def conv3x3(src0, weight, scale, shift, out, *, src1=None, flags=EPI_RELU, sc_x=
     a.film_scale, a.film_shift, a.film_shift_rows = ptr(film_scale), ptr(film_shift), film_shift_rows
     a.step_ptr, a.gn_partial, a.mode = ptr(step_ptr), ptr(gn_partial), mode
     a.bn_partial, a.bn_sums, a.xr, a.res_scale = ptr(bn_partial), ptr(bn_sums), _xr_ptr(xr), res_scale
+    if bwd is not None:  # EPI_BNBWD: (z, scale, shift, mean, rstd) of the layer whose dy this launch produces
+        a.bwd_z, a.bwd_scale, a.bwd_shift, a.bwd_mean, a.bwd_rstd = (ptr(t) for t in bwd)
     check(lib().cdm_conv3x3(C.byref(a), stream_ptr()), "cdm_conv3x3")
     return out
 

@@ -175,6 +175,10 @@ int conv_prepare(const cdm_conv3x3_args* a, ConvLaunch* L) {
   if (a->flags & CDM_EPI_BNSTATS)
     CDM_CHECK_ARG(a->bn_partial && a->bn_sums && a->mode >= 3 && a->H % 32 == 0 && a->W % 8 == 0 &&
                   !(a->flags & (CDM_EPI_POOL | CDM_EPI_SHORTCUT)));
+  if (a->flags & CDM_EPI_BNBWD)
+    CDM_CHECK_ARG(a->bn_partial && a->bn_sums && a->mode >= 3 && a->H % 32 == 0 && a->W % 8 == 0 && a->bwd_z &&
+                  a->bwd_scale && a->bwd_shift && a->bwd_mean && a->bwd_rstd &&
+                  !(a->flags & (CDM_EPI_POOL | CDM_EPI_SHORTCUT | CDM_EPI_BNSTATS | CDM_EPI_GNSTATS)));
   int rc = check_device();
   if (rc) return rc;
   memset(L, 0, sizeof(*L));
@@ -215,6 +219,8 @@ int conv_prepare(const cdm_conv3x3_args* a, ConvLaunch* L) {
   p.gn_partial = a->gn_partial;
   p.bn_partial = a->bn_partial;
   p.res_scale = (a->flags & CDM_EPI_RESSCALE) ? a->res_scale : 1.f;
+  p.bwd_z = reinterpret_cast<const bf16*>(a->bwd_z);
+  p.bwd_scale = a->bwd_scale, p.bwd_shift = a->bwd_shift, p.bwd_mean = a->bwd_mean, p.bwd_rstd = a->bwd_rstd;
   const int sms = num_sms();
   uint32_t pitch = 18, box_rows = 18;
   if (swapped) {
@@ -222,13 +228,13 @@ int conv_prepare(const cdm_conv3x3_args* a, ConvLaunch* L) {
     // small launches (batch-1 sampling): when 8 x 32 patches would leave three quarters of the SMs idle, use 8 x 8
     // patches — four times the units (still one wave), a quarter of the MMA chain each.  Not with the statistics
     // epilogues, whose partial-sum layout (and summation order) is tied to the 32-row patch.
-    const bool small = units32 * 4 <= sms && !(a->flags & (CDM_EPI_GNSTATS | CDM_EPI_BNSTATS));
+    const bool small = units32 * 4 <= sms && !(a->flags & (CDM_EPI_GNSTATS | CDM_EPI_BNSTATS | CDM_EPI_BNBWD));
     const bool tma = mode == 4;
     L->variant = (small ? kConvSw8 : kConvSw32) + (tma ? 2 : 0);
     p.n_units = small ? units32 * 4 : units32;
     pitch = 10;
     box_rows = small ? 10 : 34;
-    if (a->flags & CDM_EPI_BNSTATS) {
+    if (a->flags & (CDM_EPI_BNSTATS | CDM_EPI_BNBWD)) {
       L->bn_fold = 1;
       L->bn_sums = a->bn_sums;
       L->xr = a->xr;

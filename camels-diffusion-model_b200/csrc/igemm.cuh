@@ -660,6 +660,11 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         fsv = __ldg(p.film_scale + (size_t)img * p.cout + co);
         fbv = __ldg(p.film_shift + ((size_t)step * p.film_shift_rows + (p.film_shift_rows == 1 ? 0 : img)) * p.cout + co);
       }
+      float bw_sc = 0.f, bw_sh = 0.f;
+      if (p.flags & CDM_EPI_BNBWD) {
+        bw_sc = __ldg(p.bwd_scale + co);
+        bw_sh = __ldg(p.bwd_shift + co);
+      }
       const int reps = (p.flags & CDM_EPI_SHORTCUT) ? p.sc_reps : 1;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kNPix);
       // Classifier-free guidance fan-out (init_conv.conv2: one image -> the conditional and the unconditional copy,
@@ -725,6 +730,15 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           if (CDM_PROBE_BIT(p.flags, 29)) continue;  // probe: no epilogue work at all
           uint32_t v[32];
           tmem_ld_x32(taddr + c8 * 32, v);
+          // CDM_EPI_BNBWD: this thread's channel of the layer's forward z at the chunk's 32 pixels (a warp-level load
+          // covers 32 consecutive channels = 64 bytes of one pixel); issued before the accumulator wait
+          unsigned short zr[32];
+          if (p.flags & CDM_EPI_BNBWD) {
+            const unsigned short* zp = reinterpret_cast<const unsigned short*>(p.bwd_z) +
+                                       (((size_t)img * p.H + oh0 + 4 * c8) * p.W + ow0) * p.cout + co;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) zr[i] = __ldg(zp + ((size_t)(i >> 3) * p.W + (i & 7)) * p.cout);
+          }
           tmem_wait_ld();
           float f[32];
 #pragma unroll
@@ -732,6 +746,24 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             float y = fmaf(__uint_as_float(v[i]), sc, sh);
             if (p.flags & CDM_EPI_RELU) y = fmaxf(y, 0.f);
             f[i] = y;
+          }
+          if (p.flags & CDM_EPI_BNBWD) {  // g = stored (bf16) dy under the ReLU mask of the forward; sum g, sum g*z
+            float ts = 0.f, tq = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float zf = __uint_as_float((uint32_t)zr[i] << 16);
+              const float r = __bfloat162float(__float2bfloat16_rn(f[i]));
+              const float g = fmaf(zf, bw_sc, bw_sh) > 0.f ? r : 0.f;
+              ts += g;
+              tq = fmaf(g, zf, tq);
+            }
+            if (n_tile == 0) {
+              bn_s0 += ts;
+              bn_q0 += tq;
+            } else {
+              bn_s1 += ts;
+              bn_q1 += tq;
+            }
           }
           if (p.flags & CDM_EPI_GELU) {
 #pragma unroll
@@ -849,7 +881,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
     }
     if (st_elect) tma_store_wait_read<0>();  // the staging boxes are read before the CTA (and its shared memory) goes
-    if (p.flags & CDM_EPI_BNSTATS) {
+    if (p.flags & (CDM_EPI_BNSTATS | CDM_EPI_BNBWD)) {
       // the two column halves of a channel live in warps q and q+4: fold them through shared memory (the
       // scale/shift staging area is free once the unit loop is over), then one partial row per CTA
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -863,11 +895,17 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (half == 0) {
         float* dst = p.bn_partial + (size_t)blockIdx.x * 2 * p.cout;
-        dst[co_l] = bn_s0 + fold[(0 * 128 + co_l) * 2];
-        dst[p.cout + co_l] = bn_q0 + fold[(0 * 128 + co_l) * 2 + 1];
+        float s0 = bn_s0 + fold[(0 * 128 + co_l) * 2], q0 = bn_q0 + fold[(0 * 128 + co_l) * 2 + 1];
+        float s1 = bn_s1 + fold[(1 * 128 + co_l) * 2], q1 = bn_q1 + fold[(1 * 128 + co_l) * 2 + 1];
+        if (p.flags & CDM_EPI_BNBWD) {  // sum g*xhat = rstd * (sum g*z - mean * sum g): linear, so the CTA rows add up
+          q0 = (q0 - __ldg(p.bwd_mean + co_l) * s0) * __ldg(p.bwd_rstd + co_l);
+          if (p.n_tiles == 2) q1 = (q1 - __ldg(p.bwd_mean + 128 + co_l) * s1) * __ldg(p.bwd_rstd + 128 + co_l);
+        }
+        dst[co_l] = s0;
+        dst[p.cout + co_l] = q0;
         if (p.n_tiles == 2) {
-          dst[128 + co_l] = bn_s1 + fold[(1 * 128 + co_l) * 2];
-          dst[p.cout + 128 + co_l] = bn_q1 + fold[(1 * 128 + co_l) * 2 + 1];
+          dst[128 + co_l] = s1;
+          dst[p.cout + 128 + co_l] = q1;
         }
       }
     }

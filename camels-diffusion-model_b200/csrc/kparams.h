@@ -26,6 +26,14 @@ struct ConvKParams {
   float* gn_partial;
   float* bn_partial;  // CDM_EPI_BNSTATS: [gridDim.x][2][cout]
   float res_scale;    // CDM_EPI_RESSCALE
+  // CDM_EPI_BNBWD: the launch is the data gradient dy of a Conv-BatchNorm-ReLU layer whose forward z (bf16, same
+  // NHWC shape as `out`), scale / shift (ReLU mask: z*scale+shift > 0), batch mean and rstd are given; the epilogue also
+  // accumulates sum g and sum g*xhat per channel (g = stored dy under the mask) into bn_partial
+  const bf16* bwd_z;
+  const float* bwd_scale;
+  const float* bwd_shift;
+  const float* bwd_mean;
+  const float* bwd_rstd;
 };
 
 struct GemmKParams {

@@ -41,6 +41,12 @@ def _allreduce(t):
     return t
 
 
+# Backward BatchNorm sums in the data-gradient convolution's epilogue (CDM_EPI_BNBWD) instead of a cdm_chan_reduce pass
+# over dy and z: up to this many images per GPU.  Measured: it removes 13 launches from the latency-bound chain of the
+# 32-images-per-GPU step (3.91 -> 3.85 ms), but at batch 256 the extra z loads + mask arithmetic (~200 instructions per
+# 32-pixel chunk on top of ~130) make the epilogue the pacing role of the convolution and cost what the separate pass —
+# which runs at the HBM roofline — would have cost (18.7 vs 18.5-18.9 ms): no gain there, so it stays off.
+FUSE_BN_BWD_MAX_IMAGES = 64
 PEER = None            # parallel.PeerExchange of this process, created on the first data-parallel forward
 PEER_EXCHANGE = True   # False: all-reduce the BatchNorm statistics with NCCL instead (the baseline path)
 
@@ -370,15 +376,20 @@ class _UnetFn(torch.autograd.Function):
             keep.append((dz, srcs, dw, out))
             return out
 
-        def cbr_bwd(name, prefix, dy, lddy, need_dx=True):
+        def cbr_bwd(name, prefix, dy, lddy, need_dx=True, sums=None, fuse_next=None):
+            """Backward of one Conv-BatchNorm-ReLU layer.  `sums` = (sum g, sum g*xhat) of this layer if the producer
+            of `dy` has already computed them; `fuse_next` = the layer whose dy is this layer's dx (its input layer):
+            the data-gradient convolution then accumulates THAT layer's sums in its epilogue (CDM_EPI_BNBWD), which
+            saves the separate pass over dy and z (cdm_chan_reduce mode 1).  Returns (dx, sums of fuse_next or None)."""
             ly = S.layers[name]
             Pn, C = n * ly.H * ly.H, ly.cout
-            sums = _f32(2, C, dev=dev)
             xr = _xr()
-            L.chan_reduce(dy, lddy, Pn, C, sums, S.ws, mode=1, z=ly.z, ldz=C, scale=ly.scale, shift=ly.shift,
-                          mean=ly.mean, rstd=ly.rstd, relu=1, xr=xr)
-            if xr is None:
-                _allreduce(sums)
+            if sums is None:
+                sums = _f32(2, C, dev=dev)
+                L.chan_reduce(dy, lddy, Pn, C, sums, S.ws, mode=1, z=ly.z, ldz=C, scale=ly.scale, shift=ly.shift,
+                              mean=ly.mean, rstd=ly.rstd, relu=1, xr=xr)
+                if xr is None:
+                    _allreduce(sums)
             G[prefix + ".1.weight"], G[prefix + ".1.bias"] = sums[1], sums[0]  # `sums` is this layer's own buffer
             bn_affine.update((prefix + ".1.weight", prefix + ".1.bias"))
             dz = _bf(n, ly.H, ly.H, C, dev=dev)
@@ -390,17 +401,29 @@ class _UnetFn(torch.autograd.Function):
                     L.outer_wgrad(ly.x_in, dz, n, ly.H, ly.H, C, w9, S.ws2, flip=0)
                     return w9.t().reshape(C, 1, 3, 3).contiguous()
                 G[prefix + ".0.weight"] = leaf(w_first)
-                return None
+                return None, None
             G[prefix + ".0.weight"] = conv_wgrad(dz, [ly.x_in], C)
             if not need_dx:
-                return None
+                return None, None
             dx = _bf(n, ly.H, ly.H, ly.cin, dev=dev)
+            nxt = fuse_next
+            if nxt is not None and n <= FUSE_BN_BWD_MAX_IMAGES and S.mode >= L.CONV_MODE_SWAPPED and ly.H % 32 == 0 \
+                    and nxt.cout == ly.cin and nxt.H == ly.H:
+                sums_next = _f32(2, ly.cin, dev=dev)
+                L.conv3x3(dz, P[name + ".d"], S.ones[:ly.cin], S.zeros[:ly.cin], dx, flags=L.EPI_BNBWD, mode=S.mode,
+                          bn_partial=S.bnp, bn_sums=sums_next, xr=xr,
+                          bwd=(nxt.z, nxt.scale, nxt.shift, nxt.mean, nxt.rstd))
+                if xr is None:
+                    _allreduce(sums_next)
+                return dx, sums_next
             L.conv3x3(dz, P[name + ".d"], S.ones[:ly.cin], S.zeros[:ly.cin], dx, flags=0, mode=S.mode)
-            return dx
+            return dx, None
 
-        def rcb_bwd(name, prefix, dy, lddy):
-            d = cbr_bwd(name + ".c2", prefix + ".conv2", dy, lddy)
-            return cbr_bwd(name + ".c1", prefix + ".conv1", d, d.shape[3])
+        def rcb_bwd(name, prefix, dy, lddy, fuse_next=None):
+            """ResidualConvBlock (is_res=False) backward; `fuse_next`: the Conv-BN-ReLU layer that produced this block's
+            input (its backward statistics ride on conv1's data-gradient launch).  Returns (dx, sums for fuse_next)."""
+            d, s1 = cbr_bwd(name + ".c2", prefix + ".conv2", dy, lddy, fuse_next=S.layers[name + ".c1"])
+            return cbr_bwd(name + ".c1", prefix + ".conv1", d, d.shape[3], sums=s1, fuse_next=fuse_next)
 
         def convT_bwd(nm, prefix, dv, srcs):
             """ConvTranspose2d(cin, 128, 2, 2) backward: dv [n,2H,2W,128]; srcs = the two K-split inputs."""
@@ -460,8 +483,9 @@ class _UnetFn(torch.autograd.Function):
         d_cat = _bf(n, h, h, 2 * nf, dev=dev)
         L.conv3x3(do, P["out0.d"], S.ones[:2 * nf], S.zeros[:2 * nf], d_cat, flags=0, mode=S.mode)
         # ---- up2
-        d = rcb_bwd("up2.2", "up2.model.2", d_cat, 2 * nf)  # channels [0,128) of d_cat
-        d_v2 = rcb_bwd("up2.1", "up2.model.1", d, nf)
+        d, sm = rcb_bwd("up2.2", "up2.model.2", d_cat, 2 * nf, fuse_next=S.layers["up2.1.c2"])  # channels [0,128) of d_cat
+        d, sm = cbr_bwd("up2.1.c2", "up2.model.1.conv2", d, nf, sums=sm, fuse_next=S.layers["up2.1.c1"])
+        d_v2, _ = cbr_bwd("up2.1.c1", "up2.model.1.conv1", d, nf, sums=sm)
         h2 = h // 2
         da2 = convT_bwd("up2", "up2.model.0", d_v2, [S.u1f.view(-1, nf), S.d1.view(-1, nf)])  # [n*32*32, 256]
         # FiLM2: u1f = cemb2*u1 + temb2
@@ -472,8 +496,9 @@ class _UnetFn(torch.autograd.Function):
         leaf(lambda: (embed_bwd(m.contextembed2, "contextembed2", S.c, dcemb2),
                       embed_bwd(m.timeembed2, "timeembed2", S.t, dtemb2 if trows == n else dtemb2.sum(0, keepdim=True))))
         # ---- up1
-        d = rcb_bwd("up1.2", "up1.model.2", d_u1, nf)
-        d_v1 = rcb_bwd("up1.1", "up1.model.1", d, nf)
+        d, sm = rcb_bwd("up1.2", "up1.model.2", d_u1, nf, fuse_next=S.layers["up1.1.c2"])
+        d, sm = cbr_bwd("up1.1.c2", "up1.model.1.conv2", d, nf, sums=sm, fuse_next=S.layers["up1.1.c1"])
+        d_v1, _ = cbr_bwd("up1.1.c1", "up1.model.1.conv1", d, nf, sums=sm)
         h4 = h // 4
         da1 = convT_bwd("up1", "up1.model.0", d_v1, [S.u0f.view(-1, 2 * nf), S.d2.view(-1, 2 * nf)])  # [n*256, 512]
         # ---- up0: GroupNorm + ReLU + FiLM backward, then the [B,256]x[256,65536] GEMM
@@ -518,18 +543,20 @@ class _UnetFn(torch.autograd.Function):
         # ---- down2
         dy = _bf(n, h2, h2, 2 * nf, dev=dev)
         L.maxpool2_bwd(d_d2, 2 * nf, S.pool2_in, dy)
-        d = rcb_bwd("down2.1", "down2.model.1", dy, 2 * nf)
-        d_d1 = rcb_bwd("down2.0", "down2.model.0", d, 2 * nf)
+        d, sm = rcb_bwd("down2.1", "down2.model.1", dy, 2 * nf, fuse_next=S.layers["down2.0.c2"])
+        d, sm = cbr_bwd("down2.0.c2", "down2.model.0.conv2", d, 2 * nf, sums=sm, fuse_next=S.layers["down2.0.c1"])
+        d_d1, _ = cbr_bwd("down2.0.c1", "down2.model.0.conv1", d, 2 * nf, sums=sm)
         L.add_bf16(d_d1, nf, da2[:, nf:], 2 * nf, n * h2 * h2, nf)
         # ---- down1
         dy = _bf(n, h, h, nf, dev=dev)
         L.maxpool2_bwd(d_d1, nf, S.pool1_in, dy)
-        d = rcb_bwd("down1.1", "down1.model.1", dy, nf)
-        d_x0 = rcb_bwd("down1.0", "down1.model.0", d, nf)
+        d, sm = rcb_bwd("down1.1", "down1.model.1", dy, nf, fuse_next=S.layers["down1.0.c2"])
+        d, sm = cbr_bwd("down1.0.c2", "down1.model.0.conv2", d, nf, sums=sm, fuse_next=S.layers["down1.0.c1"])
+        d_x0, _ = cbr_bwd("down1.0.c1", "down1.model.0.conv1", d, nf, sums=sm)
         L.add_bf16(d_x0, nf, d_cat.view(-1, 2 * nf)[:, nf:], 2 * nf, n * h * h, nf)
         # ---- init_conv: x0 = y2 + shortcut(x) (the shortcut is not a parameter)
-        d_y1 = cbr_bwd("init_conv.c2", "init_conv.conv2", d_x0, nf)
-        cbr_bwd("init_conv.c1", "init_conv.conv1", d_y1, nf)
+        d_y1, sm = cbr_bwd("init_conv.c2", "init_conv.conv2", d_x0, nf, fuse_next=S.layers["init_conv.c1"])
+        cbr_bwd("init_conv.c1", "init_conv.conv1", d_y1, nf, sums=sm)
         main.wait_stream(side)  # join: every weight gradient is complete before it is reduced / handed out
         keep.clear()
         W = _world()

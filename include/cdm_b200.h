@@ -52,7 +52,11 @@ int cdm_num_sms(void);
                              * comment names, code/diffusion_utilities.py:29,36; the code itself runs nn.ReLU) */
 #define CDM_EPI_RESSCALE 128 /* y *= res_scale after the shortcut add (the reference's disabled `/ 1.414`,
                               * code/diffusion_utilities.py:59: res_scale = 1 / 1.414) */
-#define CDM_EPI_ALL 255     /* every defined bit; any other bit in `flags` is rejected with CDM_ERR_ARG */
+#define CDM_EPI_BNBWD 256   /* the launch computes dy of a Conv-BatchNorm-ReLU layer (a data-gradient convolution):
+                              * its epilogue also accumulates sum g and sum g*xhat per channel (g = dy under the ReLU
+                              * mask of the layer's forward z) -> bn_sums, all ranks of `xr` included: what
+                              * cdm_chan_reduce mode 1 computes with one more pass over dy and z (MODE 3 / 4 only) */
+#define CDM_EPI_ALL 511     /* every defined bit; any other bit in `flags` is rejected with CDM_ERR_ARG */
 
 /* A-operand feeding strategy of cdm_conv3x3. */
 #define CDM_CONV_MODE_COPIES 0  /* three kw-shifted TMA copies, aligned views  */
@@ -100,6 +104,10 @@ typedef struct {
   float* bn_sums;
   const struct cdm_xrank_s* xr;
   float res_scale; /* CDM_EPI_RESSCALE */
+  /* CDM_EPI_BNBWD: forward z of the layer whose dy this launch produces (bf16 NHWC, the shape of `out`), its
+   * scale / shift (mask: z*scale+shift > 0), batch mean and rstd, fp32 [cout]; sums land in bn_partial / bn_sums */
+  const void* bwd_z;
+  const float* bwd_scale; const float* bwd_shift; const float* bwd_mean; const float* bwd_rstd;
 } cdm_conv3x3_args;
 int cdm_conv3x3(const cdm_conv3x3_args* a, void* stream);
 

@@ -412,6 +412,47 @@ def test_conv_epilogue_batchnorm_statistics(L, mode):
         assert torch.equal(sums, sums2), "fixed-order reduction must be deterministic"
 
 
+@pytest.mark.parametrize("mode", [3, 4])
+def test_conv_epilogue_batchnorm_backward_sums(L, mode):
+    """CDM_EPI_BNBWD: the data-gradient convolution's epilogue yields sum g and sum g*xhat of the layer whose dy it
+    produces (g = stored dy under the forward's ReLU mask) — what cdm_chan_reduce mode 1 computes with a separate pass
+    over dy and z; the stored dy itself is unchanged."""
+    for n, H, cin, cout in ((5, 64, 128, 128), (3, 32, 256, 256), (37, 32, 256, 128)):
+        g = torch.Generator(device="cuda").manual_seed(n)
+        dz = (torch.randn(n, H, H, cin, device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+        w = (torch.randn(cout, 3, 3, cin, device="cuda", generator=g) / (3 * cin ** 0.5)).to(torch.bfloat16)
+        ones, zeros = torch.ones(cout, device="cuda"), torch.zeros(cout, device="cuda")
+        z = torch.randn(n, H, H, cout, device="cuda", generator=g).to(torch.bfloat16)
+        scale = torch.rand(cout, device="cuda", generator=g) + 0.5
+        scale[::7] *= -1  # negative gamma flips the mask
+        shift = torch.randn(cout, device="cuda", generator=g) * 0.3
+        mean = torch.randn(cout, device="cuda", generator=g) * 0.2
+        rstd = torch.rand(cout, device="cuda", generator=g) + 0.5
+        dy = torch.empty(n, H, H, cout, device="cuda", dtype=torch.bfloat16)
+        part = torch.full((148, 2 * cout), float("nan"), device="cuda")
+        sums = torch.empty(2, cout, device="cuda")
+        L.conv3x3(dz, w, ones, zeros, dy, flags=L.EPI_BNBWD, bn_partial=part, bn_sums=sums, mode=mode,
+                  bwd=(z, scale, shift, mean, rstd))
+        dy_plain = torch.empty_like(dy)
+        L.conv3x3(dz, w, ones, zeros, dy_plain, flags=0, mode=mode)
+        assert torch.equal(dy, dy_plain)
+        ref = torch.empty(2, cout, device="cuda")
+        ws = torch.empty(148 * 8, 2 * cout, device="cuda")
+        L.chan_reduce(dy, cout, n * H * H, cout, ref, ws, mode=1, z=z, ldz=cout, scale=scale, shift=shift, mean=mean,
+                      rstd=rstd, relu=1)
+        gmask = (z.float() * scale + shift > 0).float() * dy.float()
+        exact0 = gmask.reshape(-1, cout).double().sum(0)
+        exact1 = (gmask * (z.float() - mean) * rstd).reshape(-1, cout).double().sum(0)
+        scale_ref = float(exact1.abs().max())
+        assert float((sums[0].double() - exact0).abs().max()) < 1e-4 * float(exact0.abs().max()) + 1e-5
+        assert float((sums[1].double() - exact1).abs().max()) < 1e-4 * scale_ref + 1e-5
+        assert float((ref[1].double() - exact1).abs().max()) < 1e-4 * scale_ref + 1e-5
+        sums2 = torch.empty_like(sums)
+        L.conv3x3(dz, w, ones, zeros, dy, flags=L.EPI_BNBWD, bn_partial=part, bn_sums=sums2, mode=mode,
+                  bwd=(z, scale, shift, mean, rstd))
+        assert torch.equal(sums, sums2), "fixed-order reduction must be deterministic"
+
+
 def test_xrank_sum_single_rank(L):
     g = torch.Generator(device="cuda").manual_seed(0)
     part = torch.randn(592, 512, device="cuda", generator=g)
