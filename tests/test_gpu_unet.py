@@ -318,7 +318,7 @@ def test_blocks_standalone_forward():
     assert rel_l2(same(x), ref) < 1e-2
 
 
-@pytest.mark.parametrize("ncf", [1, 3])
+@pytest.mark.parametrize("ncf", [1, 2, 3, 4, 5])
 def test_other_context_widths(ncf):
     """BASELINE config 4: n_cfeat 1..6 only changes the first EmbedFC layer of the two context embeddings."""
     import camels_diffusion_model_b200 as cdm
@@ -333,6 +333,23 @@ def test_other_context_widths(ncf):
     with torch.no_grad():
         ref = O.unet_forward(sd, x, t, c, (sc[:128], sc[128:]), n_cfeat=ncf)
     assert rel_l2(m(x.cuda(), t.cuda(), c.cuda(), shortcut=sc), ref) < EPS_TOL_RAW
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("tn", ["t1", "tB"])
+def test_other_context_widths_vs_reference_vectors(n, tn):
+    """BASELINE config 4 against the REFERENCE module's own outputs at context widths 1..5 (tests/golden/unet_widths.npz,
+    written by oracle/make_golden_widths.py from the unmodified ContextUnet): calibrated norm layers, both t shapes."""
+    import camels_diffusion_model_b200 as cdm
+    g = load("unet_widths.npz")
+    sd = O.calibrate_state_dict(O.init_state_dict(5, n_cfeat=n))
+    m = cdm.ContextUnet(1, 128, n, 64)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    eps = m(T(g[f"{n}/x"]).cuda(), T(g[f"{n}/{tn}/t"]).cuda(), T(g[f"{n}/c"]).cuda(), shortcut=T(g[f"{n}/{tn}/shortcut"]))
+    err = rel_l2(eps, g[f"{n}/{tn}/eps"])
+    record(f"eval_eps_rel_l2/width{n}/{tn}", err, EPS_TOL_CAL)
+    assert err < EPS_TOL_CAL
 
 
 def test_drivers_grid_guidance_sensitivity(models):
