@@ -298,7 +298,37 @@ def case_hbm_rates(name, gib=2):
     return True
 
 
+def case_tmem_layout(name):
+    """Register <- TMEM element mapping of tcgen05.ld.16x256b.x4 (probe library only)."""
+    import ctypes as C
+    import torch
+    L = _load()
+    out = torch.zeros(4, 2, 32, 16, device="cuda")
+    rc = L.lib().cdm_probe_tmem_layout(C.c_void_p(out.data_ptr()), L.stream_ptr())
+    torch.cuda.synchronize()
+    assert rc == 0, L.lib().cdm_last_error()
+    o = out.cpu()
+    lane, col = (o // 1000).long(), (o % 1000).long()
+    ok = True
+    for w in range(4):
+        for h in range(2):
+            for t in range(32):
+                for i in range(16):
+                    j, k = i // 4, i % 4
+                    exp_lane = w * 32 + h * 16 + t // 4 + (8 if k >= 2 else 0)
+                    exp_col = 8 * j + 2 * (t % 4) + (k & 1)
+                    if int(lane[w, h, t, i]) != exp_lane or int(col[w, h, t, i]) != exp_col:
+                        if ok:
+                            print(f"   first mismatch: warp {w} half {h} thread {t} reg {i}: got lane {int(lane[w, h, t, i])} "
+                                  f"col {int(col[w, h, t, i])}, expected lane {exp_lane} col {exp_col}")
+                        ok = False
+    print(f"CASE {name}: {'PASS' if ok else 'FAIL'} (reg 4j+k of thread t <- lane t/4 + 8*(k>=2) [+16*half], column 8j + 2(t%4) + (k&1))")
+    print("   thread 5, half 0, regs:", [(int(lane[0, 0, 5, i]), int(col[0, 0, 5, i])) for i in range(16)])
+    return ok
+
+
 CASES = {
+    "tmem_layout": lambda: case_tmem_layout("tmem_layout"),
     "hbm_rates": lambda: case_hbm_rates("hbm_rates"),
     "gemm_basic": lambda: case_gemm("gemm_basic", 256, 64, 0, 128),
     "gemm_ragged": lambda: case_gemm("gemm_ragged", 300, 128, 64, 256),
