@@ -714,3 +714,44 @@ def test_deep_gradients_are_sensitive_to_summation_order_only():
     record("train_grad_rel_l2_permuted_batch_order/out.0.weight", near["out.0.weight"], 1e-2)
     assert near["out.3.weight"] < 2e-3 and near["out.1.weight"] < 5e-3 and near["out.0.weight"] < 1e-2
     assert worst_cos > 0.5
+
+
+def test_fused_backward_statistics_equal_the_separate_pass():
+    """The training step with the backward BatchNorm sums taken from the data-gradient convolution's epilogue
+    (CDM_EPI_BNBWD, the default up to 64 images) against the same step with the separate cdm_chan_reduce pass: identical
+    forward, and the first fused layer's sums — which are its BatchNorm affine gradients — agree to fp32 summation
+    order (everything upstream of them is bit-identical; deeper layers inherit last-bit differences and the usual
+    amplification, so they are only required to stay direction-consistent)."""
+    import camels_diffusion_model_b200 as cdm
+    from camels_diffusion_model_b200 import train as TR
+    sd = cal_sd()
+    _, _, ab_t = cdm.make_schedule(1500)
+    g = torch.Generator().manual_seed(21)
+    B = 6
+    x, prm = torch.rand(B, 1, 64, 64, generator=g), torch.rand(B, NCF, generator=g)
+    noise, t = torch.randn(B, 1, 64, 64, generator=g), torch.randint(1, 1501, (B,), generator=g)
+    sc = torch.rand(256, generator=g) * 2 - 1
+    res = {}
+    old = TR.FUSE_BN_BWD_MAX_IMAGES
+    try:
+        for tag, lim in (("fused", 64), ("separate", 0)):
+            TR.FUSE_BN_BWD_MAX_IMAGES = lim
+            m = cdm.ContextUnet(1, 128, NCF, 64)
+            m.load_state_dict(sd)
+            m = m.cuda().train()
+            pred = m(cdm.perturb_input(x, t, noise, ab_t), (t / 1500).cuda(), prm.cuda(), shortcut=sc)
+            loss = F.mse_loss(pred, noise.cuda())
+            loss.backward()
+            res[tag] = (pred.detach().clone(), {k: p.grad.detach().clone() for k, p in m.named_parameters()})
+    finally:
+        TR.FUSE_BN_BWD_MAX_IMAGES = old
+    (p_f, g_f), (p_s, g_s) = res["fused"], res["separate"]
+    assert torch.equal(p_f, p_s)
+    for k in ("out.3.weight", "out.0.weight", "up2.model.2.conv2.1.weight", "up2.model.2.conv2.0.weight"):
+        assert torch.equal(g_f[k], g_s[k]), k  # upstream of the first fused layer: the same kernels on the same data
+    for k in ("up2.model.2.conv1.1.weight", "up2.model.2.conv1.1.bias"):  # = the first fused layer's sums
+        assert rel_l2(g_f[k], g_s[k]) < 1e-5, (k, rel_l2(g_f[k], g_s[k]))
+    cos = min(float(torch.dot(g_f[k].flatten().double(), g_s[k].flatten().double()) /
+                    (g_f[k].double().norm() * g_s[k].double().norm()))
+              for k in g_f if float(g_s[k].norm()) > 1e-7)
+    assert cos > 0.8, cos
