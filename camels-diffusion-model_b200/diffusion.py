@@ -313,6 +313,17 @@ class SamplerSession:
         # collected ONE step later, so the read never drains the GPU's queue (the next graph is already enqueued)
         self._ctr_host = torch.zeros(2, dtype=torch.int32).pin_memory()
         self._ctr_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        # results leave through pinned host memory: each snapshot is copied out on the side stream as soon as the step
+        # that takes it has run (the reference copies `x` to numpy at every 20th step, paper.py:617-618), the final x at
+        # result().  If the host cannot pin that much memory the copies fall back to pageable memory at result().
+        self._snap_slot_of = {i: k for k, i in enumerate(self.run.snap_steps)}
+        try:
+            self._x_host = torch.empty(self.run.x.shape, dtype=torch.float32).pin_memory()
+            self._snap_host = (torch.empty(self.run.snap.shape, dtype=torch.float32).pin_memory()
+                               if self.run.snap is not None else None)
+        except RuntimeError:
+            self._x_host, self._snap_host = None, None
+        self._snap_done = torch.cuda.Event()
 
     @staticmethod
     def _key(t):
@@ -323,8 +334,11 @@ class SamplerSession:
         """One reverse-diffusion step with the caller's noise `z` [B,1,H,W] (host tensors are copied asynchronously;
         pin them to overlap the copy).  `z_next`, if given, is the NEXT step's noise: its host-to-device copy runs
         on a side stream underneath this step's kernels, and the next `step(z_next, ...)` finds it on the device
-        (keep the tensor alive and unchanged until then).  Returns the remaining step count read back from the
-        device (one 4-byte device-to-host read: the caller's per-step synchronisation point)."""
+        (keep the tensor alive and unchanged until then).  Every step also reads the device step counter back (4 bytes,
+        pinned host memory); the call returns the value read back by the PREVIOUS step (the current one is still in
+        flight — waiting for it would drain the GPU's queue between steps); `sync=True` waits for this step's own value.
+        A snapshot taken by this step starts its device-to-host copy (pinned memory, side stream) right away.
+        `result()` synchronises."""
         if z is None or z.numel() != self.run.z.numel():
             raise L.CdmError(f"step(z): z must hold this step's noise, {self.run.z.numel()} values "
                              f"([B,1,H,W] = [{self.run.B},1,{self.run.model.h},{self.run.model.h}])")
@@ -348,6 +362,14 @@ class SamplerSession:
                 self._stage.copy_(z_next.reshape(-1), non_blocking=True)
                 self._staged.record(self._copy_stream)
             self._staged_key, self._staged_ref = self._key(z_next), z_next
+        slot = self._snap_slot_of.get(self.run.T - self.steps_done)  # this step ran at i = T - steps_done
+        if slot is not None and self._snap_host is not None:
+            taken = torch.cuda.Event()
+            taken.record(main)
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(taken)
+                self._snap_host[slot].copy_(self.run.snap[slot], non_blocking=True)
+                self._snap_done.record(self._copy_stream)
         k = self.steps_done & 1
         self._ctr_host[k:k + 1].copy_(self.run.step, non_blocking=True)
         self._ctr_ev[k].record(main)
@@ -361,7 +383,14 @@ class SamplerSession:
     def result(self):
         """(x [B,1,H,W], intermediate [n_snapshots_taken,B,1,H,W]) on the host, like the reference's return values."""
         n_snap = sum(1 for i in self.run.snap_steps if i > self.run.T - self.steps_done)
-        return self.run.x.cpu(), self.run.snap[:n_snap].cpu().numpy()
+        if self._x_host is None:
+            return self.run.x.cpu(), self.run.snap[:n_snap].cpu().numpy()
+        self._x_host.copy_(self.run.x, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self._snap_done.synchronize()
+        inter = self._snap_host[:n_snap].numpy() if self._snap_host is not None else \
+            np.zeros((0,) + tuple(self.run.x.shape), np.float32)
+        return self._x_host, inter
 
 
 # --------------------------------------------------------------------------- likelihood / ELBO
