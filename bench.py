@@ -36,7 +36,9 @@ HBM_BYTES_PER_IMAGE = {"conv_out": 64 * 64 * 128 * 2 + 64 * 64 * 4, "conv_in": 6
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100,
+                    help="timed steps (default 100 = 3 s on one GPU: long enough for the board's power cap to engage; the "
+                         "metric's own length is 1500, profiles/r2_bench_full1500_*gpu.json)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1024, help="global number of samples (BASELINE config 2: 1024)")
     ap.add_argument("--guide-w", type=float, default=2.0)
