@@ -381,7 +381,9 @@ class SamplerSession:
         return int(self._ctr_host[1 - k])
 
     def result(self):
-        """(x [B,1,H,W], intermediate [n_snapshots_taken,B,1,H,W]) on the host, like the reference's return values."""
+        """(x [B,1,H,W], intermediate [n_snapshots_taken,B,1,H,W]) on the host, like the reference's return values.
+        Both are views of the session's pinned result buffers: copy them if the session goes on stepping (later
+        snapshots fill later rows; a later result() call overwrites x)."""
         n_snap = sum(1 for i in self.run.snap_steps if i > self.run.T - self.steps_done)
         if self._x_host is None:
             return self.run.x.cpu(), self.run.snap[:n_snap].cpu().numpy()
