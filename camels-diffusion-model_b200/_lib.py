@@ -151,7 +151,7 @@ EXPORTS = [
     "cdm_maxpool2_bwd", "cdm_add_bf16", "cdm_space_to_depth", "cdm_film_bwd", "cdm_gn_bwd", "cdm_rows_sum",
     "cdm_avgpool_gelu_train", "cdm_avgpool_gelu_bwd", "cdm_outer_wgrad", "cdm_embed_bwd", "cdm_mse_grad",
     "cdm_adam_step", "cdm_power_spectrum", "cdm_pixel_histogram",
-    "cdm_minmax", "cdm_preprocess_maps", "cdm_normalize_params", "cdm_xrank_sum", "cdm_xrank_set_timeout", "cdm_pack_bf16",
+    "cdm_minmax", "cdm_preprocess_maps", "cdm_normalize_params", "cdm_xrank_sum", "cdm_xrank_set_timeout", "cdm_pack_bf16", "cdm_pack_transpose_bf16",
     "cdm_plan_n_tensors", "cdm_plan_tensor_name", "cdm_plan_tensor_numel", "cdm_plan_arena_bytes",
     "cdm_plan_workspace_bytes", "cdm_plan_create", "cdm_plan_refresh", "cdm_plan_destroy", "cdm_plan_buffer",
     "cdm_plan_embed", "cdm_forward_eval", "cdm_sample_step", "cdm_plan_n_launches", "cdm_plan_launch_name",
@@ -637,6 +637,13 @@ def xrank_sum(partial, out, xr=None):
 
 def xrank_set_timeout(seconds):
     check(lib().cdm_xrank_set_timeout(C.c_double(seconds)), "cdm_xrank_set_timeout")
+
+
+def pack_transpose_bf16(src, dst, batches, R, Cc, sb, sr, db, dc):
+    """dst[b][c][r] (bf16) = src[b][r][c] (fp32), strides in elements (cdm_pack_transpose_bf16)."""
+    LLc = C.c_longlong
+    check(lib().cdm_pack_transpose_bf16(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), batches, R, Cc, LLc(sb),
+                                        LLc(sr), LLc(db), LLc(dc), stream_ptr()), "cdm_pack_transpose_bf16")
 
 
 def pack_bf16(table, n_rows, total_vec):

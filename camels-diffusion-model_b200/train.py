@@ -157,9 +157,21 @@ class _PackPlan:
         w = m.out[0].weight.detach()
         add("out0.f", w, (0, 2, 3, 1))
         add("out0.d", w, (1, 2, 3, 0), flips=(2, 3))
+        self.transposes = []  # (src, dst, batches, R, C, sb, sr, db, dc): cdm_pack_transpose_bf16 launches
         for nm, mod in (("up0", m.up0[0]), ("up1", m.up1.model[0]), ("up2", m.up2.model[0])):
             w = mod.weight.detach()  # IOHW
             ci, co, kh, kw = w.shape
+            khw = kh * kw
+            if khw % 64 == 0 and ci % 64 == 0 and co % 64 == 0:
+                # up0 (78 % of all parameters): both layouts are batched 2-D transposes of [ci][co][khw] with contiguous
+                # innermost dimensions -> tiled through shared memory instead of the strided gather of the table
+                assert w.is_contiguous() and w.dtype == torch.float32
+                f = torch.empty(khw * co, ci, device=w.device, dtype=torch.bfloat16)   # [(khw, co)][ci]
+                d = torch.empty(ci, khw * co, device=w.device, dtype=torch.bfloat16)   # [ci][(khw, co)]
+                self.transposes.append((w, f, co, ci, khw, khw, co * khw, ci, co * ci))   # b = co, r = ci, c = khw
+                self.transposes.append((w, d, ci, co, khw, co * khw, khw, co * khw, co))  # b = ci, r = co, c = khw
+                self.P[nm + ".f"], self.P[nm + ".d"] = f, d
+                continue
             add(nm + ".f", w, (2, 3, 1, 0))
             add(nm + ".d", w, (0, 2, 3, 1))
             self.P[nm + ".f"] = self.P[nm + ".f"].view(kh * kw * co, ci)
@@ -173,6 +185,8 @@ class _PackPlan:
 
     def refresh(self):
         L.pack_bf16(self.table, self.n_rows, self.total_vec)
+        for t in self.transposes:
+            L.pack_transpose_bf16(*t)
 
 
 def _pack_train(m):
@@ -565,6 +579,7 @@ class _UnetFn(torch.autograd.Function):
             # captured step: gradients land in ONE flat buffer that the parameters' .grad views alias ([all-reduced
             # tensors | BatchNorm affine tensors, already global]): cat + all-reduce + scale = 3 launches, not ~300
             assert set(flat_out["order"][flat_out["n_reduce"]:]) == bn_affine
+            G["__pad__"] = S.zeros[:flat_out["pad"]]  # alignment filler in front of up0.0.weight's slot
             for names, dst in flat_out["segments"]:  # the tensors around the directly written ones
                 torch.cat([G[k].reshape(-1) for k in names], out=dst)
             if W > 1:
@@ -702,19 +717,26 @@ class GraphedTrainStep:
         big = "up0.0.weight"  # written by its producer directly (never copied through the concatenation)
         order = [k for k, _ in named if not is_bn(k) and k != big] + [big] + [k for k, _ in named if is_bn(k)]
         by_name = dict(named)
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev)
+        # out.3.bias has ONE element: without padding everything behind it — 78 % of the buffer is up0.0.weight's
+        # gradient — sits at an address that is not a multiple of 16 bytes and the optimizer's float4 path is lost.
+        # "__pad__" is a pseudo-tensor of zeros in front of `big` (backward supplies it to the concatenation).
+        i_big = order.index(big)
+        pad = (-sum(by_name[k].numel() for k in order[:i_big])) % 4
+        self.flat = torch.zeros(sum(p.numel() for p in self.params) + pad, device=dev)
         o, start = 0, {}
         for k in order:
+            if k == big:
+                o += pad
             p = by_name[k]
             start[k] = o
             p.grad = self.flat[o:o + p.numel()].view_as(p)
             o += p.numel()
-        i_big = order.index(big)
         end_big = start[big] + by_name[big].numel()
         self.flat_out = {"flat": self.flat, "order": order, "n_reduce": sum(1 for k in order if not is_bn(k)),
                          "numel_reduce": sum(by_name[k].numel() for k in order if not is_bn(k)),
-                         "direct": {big: by_name[big].grad},
-                         "segments": [(order[:i_big], self.flat[:start[big]]), (order[i_big + 1:], self.flat[end_big:])]}
+                         "direct": {big: by_name[big].grad}, "pad": pad,
+                         "segments": [(order[:i_big] + (["__pad__"] if pad else []), self.flat[:start[big]]),
+                                      (order[i_big + 1:], self.flat[end_big:])]}
         self.m = [torch.zeros_like(p) for p in self.params]
         self.v = [torch.zeros_like(p) for p in self.params]
         rows = [[p.data_ptr(), p.grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()]

@@ -460,6 +460,12 @@ int cdm_normalize_params(const float* x, int rows, int cols, int repeat, int out
  * vec_start = running count of 8-element output vectors, total_vec their total.  Replaces the per-tensor
  * w.permute(..).contiguous().to(bf16) / w.flip(2,3).permute(..) chains of the torch path. */
 int cdm_pack_bf16(const void* table, int n_rows, long long total_vec, void* stream);
+/* dst[b][c][r] (bf16) = src[b][r][c] (fp32): batched transposing cast through shared memory, both innermost dimensions
+ * contiguous (strides in elements; R, Cc multiples of 64).  The two tensor-core layouts of up0.0.weight
+ * (ConvTranspose2d IOHW [ci][co][16*16]) are such transposes: [ci][khw][co] (b = ci, r = co, c = khw) and
+ * [khw][co][ci] (b = co, r = ci, c = khw). */
+int cdm_pack_transpose_bf16(const float* src, void* dst, int batches, int R, int Cc, long long src_batch_stride,
+                            long long src_row_stride, long long dst_batch_stride, long long dst_col_stride, void* stream);
 
 /* ======================= composite entry points: one eval forward / one sampling step per C call ===============
  * ContextUnet.forward in eval mode (ContextUnet.py:42-60) and one iteration of sample_ddpm's loop

@@ -199,10 +199,19 @@ def test_pack_plan_table_addresses_the_torch_layouts(monkeypatch):
     for nm, mod in (("up0", m.up0[0]), ("up1", m.up1.model[0]), ("up2", m.up2.model[0])):
         w = mod.weight.detach()
         refs[nm + ".f"], refs[nm + ".d"] = w.permute(2, 3, 1, 0).contiguous(), w.permute(0, 2, 3, 1).contiguous()
-    assert list(plan.P) == list(refs) and len(tab) == 42 and tab.shape[1] == 12
+    # up0.0.weight (both layouts) goes through cdm_pack_transpose_bf16 instead of the table: emulate its addressing
+    # dst[b][c][r] = src[b][r][c] on the stride arguments
+    assert list(plan.P) == list(refs) and len(tab) == 40 and tab.shape[1] == 12 and len(plan.transposes) == 2
     rng = np.random.RandomState(0)
+    for key, (src, dst, nb, R, Cc, sb, sr, db, dc) in zip(("up0.f", "up0.d"), plan.transposes):
+        flat, ref = by_ptr[src.data_ptr()], refs[key].reshape(-1).numpy()
+        assert dst is plan.P[key] and dst.numel() == ref.size == nb * R * Cc
+        for _ in range(64):
+            b, r, c = rng.randint(nb), rng.randint(R), rng.randint(Cc)
+            assert flat[b * sb + r * sr + c] == ref[b * db + c * dc + r], key
     vec = 0
-    for key, row in zip(plan.P, tab):
+    table_keys = [k for k in plan.P if not k.startswith("up0.")]
+    for key, row in zip(table_keys, tab):
         src, _, d1, d2, d3, s0, s1, s2, s3, off, v0, _ = (int(v) for v in row)
         ref = refs[key].reshape(-1).numpy()
         assert v0 == vec and d3 % 8 == 0 and plan.P[key].numel() == ref.size
