@@ -671,17 +671,34 @@ __global__ void __launch_bounds__(256) film_bwd_kernel(const bf16* __restrict__ 
     a0[j] = a1[j] = 0.f;
     s[j] = fs[n * C + cg * 8 + j];
   }
-  for (int r = pr; r < px; r += rows) {
-    float d[8], v[8];
-    t_unpack8(ld8(dyf + (n * px + r) * lddyf + cg * 8), d);
-    t_unpack8(ld8(y + (n * px + r) * C + cg * 8), v);
+  // four rows per iteration, all eight loads issued first (one block per image: at 32 images per GPU the kernel is a
+  // latency chain, 42 us with one row in flight); the order of the additions per thread is unchanged
+  for (int r0 = pr; r0 < px; r0 += 4 * rows) {
+    uint4 rd[4], rv[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      a0[j] = fmaf(d[j], v[j], a0[j]);
-      a1[j] += d[j];
-      d[j] *= s[j];
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u * rows;
+      rd[u] = rv[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (r < px) {
+        rd[u] = ld8(dyf + (n * px + r) * lddyf + cg * 8);
+        rv[u] = ld8(y + (n * px + r) * C + cg * 8);
+      }
     }
-    *reinterpret_cast<uint4*>(dy + (n * px + r) * C + cg * 8) = t_pack8(d);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u * rows;
+      if (r >= px) break;
+      float d[8], v[8];
+      t_unpack8(rd[u], d);
+      t_unpack8(rv[u], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a0[j] = fmaf(d[j], v[j], a0[j]);
+        a1[j] += d[j];
+        d[j] *= s[j];
+      }
+      *reinterpret_cast<uint4*>(dy + (n * px + r) * C + cg * 8) = t_pack8(d);
+    }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -943,7 +960,8 @@ __global__ void __launch_bounds__(256) avgpool_gelu_bwd_kernel(const float* __re
                                                                bf16* __restrict__ dx) {
   const size_t n = blockIdx.x;
   const int groups = C >> 3;
-  for (int i = threadIdx.x; i < P * groups; i += blockDim.x) {
+  // grid.y slices the image's pixels: at 32 images per GPU one block per image left 116 SMs idle for 44 us
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < P * groups; i += gridDim.y * blockDim.x) {
     const int cg = i % groups, px = i / groups;
     float d[8];
     t_unpack8(ld8(dx + (n * P + px) * C + cg * 8), d);
@@ -1444,7 +1462,11 @@ extern "C" int cdm_avgpool_gelu_bwd(const float* pre, const float* dh, int n_img
   CDM_CHECK_ARG(pre && dh && dx && n_img > 0 && P > 0 && C % 8 == 0);
   int rc = check_device();
   if (rc) return rc;
-  avgpool_gelu_bwd_kernel<<<n_img, 256, 0, ST(stream)>>>(pre, dh, P, C, (bf16*)dx);
+  int slices = (num_sms() * 4 + n_img - 1) / n_img;  // ~4 blocks per SM in total
+  const int max_slices = (P * (C / 8) + 255) / 256;
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  avgpool_gelu_bwd_kernel<<<dim3(n_img, slices), 256, 0, ST(stream)>>>(pre, dh, P, C, (bf16*)dx);
   CDM_CHECK_LAUNCH();
   return CDM_OK;
 }

@@ -280,7 +280,16 @@ class _UnetFn(torch.autograd.Function):
             raise L.CdmError(f"t must have 1 or {n} elements")
         S.x, S.c, S.t = x3, c, tt
         sc = (m.draw_shortcut() if shortcut is None else shortcut).detach().to(dev, torch.float32).contiguous()
-        S.cemb1, S.temb1, S.cemb2, S.temb2 = m.embed(tt, c)
+        # the four EmbedFC forwards (latency-bound: ~20 us each) are first needed by up0's FiLM, after the whole down
+        # path: they run on the side stream underneath it
+        main_s, side_s = torch.cuda.current_stream(), _side_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(main_s)
+        with torch.cuda.stream(side_s):
+            side_s.wait_event(fork)
+            S.cemb1, S.temb1, S.cemb2, S.temb2 = m.embed(tt, c)
+            emb_done = torch.cuda.Event()
+            emb_done.record(side_s)
         trows = tt.shape[0]
         # ---- init_conv (ContextUnet.py:43): conv1, conv2, + fresh 1x1 shortcut
         y1 = _conv_bn_relu(S, P, "init_conv.c1", m.init_conv.conv1, x3, n, h, first=True)
@@ -307,6 +316,7 @@ class _UnetFn(torch.autograd.Function):
         L.gemm(hidden, P["up0.f"], m.up0[0].bias.detach().float().contiguous(), u0raw, shift_mod=2 * nf)
         u0f = _bf(n, h4 * h4, 2 * nf, dev=dev)
         S.gn0_mr = _f32(n, 8, 2, dev=dev)
+        main_s.wait_event(emb_done)  # join: the embeddings are ready
         L.gn_relu_film(u0raw, m.up0[1].weight.detach(), m.up0[1].bias.detach(), u0f, groups=8, eps=GN_EPS,
                        film_scale=S.cemb1, film_shift=S.temb1.view(1, trows, 2 * nf), film_rows=trows,
                        mean_rstd_out=S.gn0_mr)
