@@ -55,11 +55,17 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // [pixels x 9] x [9 x C] GEMM, so it runs on mma.sync with the fp32 operands split into bf16 hi + lo parts:
 // w' = scale*w = wh + wl, x = xh + xl, K = 29 of 32: xh*wh (9) + xl*wh (9) + xh*wl (9) + 1*shift_hi + 1*shift_lo,
 // fp32 accumulate.  The dropped xl*wl term is 2^-16 of a product, i.e. the result keeps fp32-level accuracy
-// before the one bf16 rounding of the output, and the whole epilogue is "round, max(.,0), store".
-// A CTA stages a zero-bordered (4+2)-row halo of the image in shared memory (row pitch = 10 mod 32: the
-// three tap rows land in disjoint banks); one warp = 16 consecutive pixels x 128 channels = 32 MMAs.  The N
-// (channel) order of the MMA is permuted so that a thread owns 8 CONSECUTIVE channels per 16-byte store and
-// a warp-level store covers 8 pixels x 64 contiguous bytes.  Bound by the 256 B/pixel write.
+// before the one bf16 rounding of the output, and the whole epilogue is "max(.,0) + round (one F2FP.RELU), store".
+// Every WARP is an independent worker (no block-wide barrier after the set-up): it stages the zero-bordered
+// (4+2)-row halo of its unit in a warp-private shared-memory buffer (row pitch = 12 mod 32: the three tap rows
+// land in disjoint banks), and the NEXT unit's halo is copied into the warp's second buffer (cp.async) under the
+// current unit's MMAs, so the only global-load latency a warp ever waits for is its first.  (Round 1 staged per CTA behind a
+// __syncthreads: ncu attributed 24 % of the warp-cycles to the wait for that load and 13 % to the barrier, and a
+// register spill reload — the 64 weight-fragment registers — another 12 %; the fragments now live in shared
+// memory, read as one 16-byte load per two MMAs.)  One unit = 16/parts groups of 16 consecutive pixels x 128
+// channels (32 MMAs each) of a 4-row tile; `parts` > 1 spreads small launches over the machine.  The N (channel)
+// order of the MMA is permuted so that a thread owns 8 CONSECUTIVE channels per 16-byte store and a warp-level
+// store covers 8 pixels x 64 contiguous bytes.  Bound by the 256 B/pixel write.
 __device__ __forceinline__ void mma_bf16_m16n8k16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                   uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -70,20 +76,23 @@ __device__ __forceinline__ void mma_bf16_m16n8k16(float (&d)[4], uint32_t a0, ui
 }
 __device__ __forceinline__ float bf16_hi(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-constexpr int kCiRows = 4;     // output rows per CTA tile
+constexpr int kCiRows = 4;     // output rows per tile
 constexpr int kCiMaxW = 64;
-constexpr int kCiPitch = kCiMaxW + 10;
+constexpr int kCiPitch = kCiMaxW + 12;                         // image column c <-> index c + 4 (16-byte aligned rows)
+constexpr int kCiHalo = (kCiRows + 2) * kCiPitch;              // floats per warp-private halo buffer
+constexpr int kCiLoads = (kCiRows + 2) * (kCiMaxW / 4) / 32;   // 16-byte halo chunks per lane (W = 64)
+constexpr int kCiCtasPerSm = 3;
 
 template <bool RELU>
-__global__ void __launch_bounds__(256, 2) conv_in_mma_kernel(const float* __restrict__ x, int n_img, int H, int W, int C,
-                                                             const float* __restrict__ wgt,
-                                                             const float* __restrict__ scale,
-                                                             const float* __restrict__ shift,
-                                                             bf16* __restrict__ out) {
-  __shared__ float s_x[2][(kCiRows + 2) * kCiPitch];  // column 0 <-> image column -1
+__global__ void __launch_bounds__(256, kCiCtasPerSm)
+conv_in_mma_kernel(const float* __restrict__ x, int n_img, int H, int W, int C, const float* __restrict__ wgt,
+                   const float* __restrict__ scale, const float* __restrict__ shift, bf16* __restrict__ out, int parts) {
+  __shared__ uint4 s_bw[4][4][32];     // B fragments [s4][q][lane] = {k-step 0: b0, b1; k-step 1: b0, b1}
+  __shared__ __align__(16) float s_x[8][2][kCiHalo];  // warp-private, double-buffered; index 3 <-> image column -1
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int slice = blockIdx.y;  // 128-channel slice of the output
-  for (int i = threadIdx.x; i < 2 * (kCiRows + 2) * kCiPitch; i += blockDim.x) (&s_x[0][0])[i] = 0.f;
+  float* sx = s_x[warp][0];
+  for (int i = lane; i < 2 * kCiHalo; i += 32) sx[i] = 0.f;
   // this thread's 8 A-fragment slots: slot i <-> k = 16*(i>>2) + 8*((i>>1)&1) + 2t + (i&1);
   // k in [0,9): xh, [9,18): xl, [18,27): xh (times wl), 27/28: the constant 1 (times shift hi / lo), 29..31: 0
   int aoff[8], akind[8];  // shared-memory offset of the tap relative to the pixel; 0 = hi, 1 = lo, 2 = one, 3 = zero
@@ -91,15 +100,17 @@ __global__ void __launch_bounds__(256, 2) conv_in_mma_kernel(const float* __rest
   for (int i = 0; i < 8; ++i) {
     const int k = 16 * (i >> 2) + 8 * ((i >> 1) & 1) + 2 * t + (i & 1);
     const int tap = k % 9;
-    aoff[i] = k < 27 ? (tap / 3) * kCiPitch + tap % 3 : 0;  // halo row 0 <-> image row y-1, column 0 <-> x-1
+    aoff[i] = k < 27 ? (tap / 3) * kCiPitch + tap % 3 + 3 : 0;  // halo row 0 <-> image row y-1, index 3 <-> column -1
     akind[i] = k < 27 ? (k / 9 == 1 ? 1 : 0) : (k < 29 ? 2 : 3);
   }
-  // B fragments: n-tile jj (0..15) column g <-> channel 128*slice + 32*(jj>>2) + 8*(g>>1) + 2*(jj&3) + (g&1)
-  uint32_t bw[2][16][2];
+  // B fragments: n-tile jj = 4*s4 + q (0..15), column g <-> channel 128*slice + 32*s4 + 8*(g>>1) + 2*q + (g&1);
+  // warp w prepares n-tiles 2w and 2w+1
 #pragma unroll
-  for (int jj = 0; jj < 16; ++jj) {
+  for (int u = 0; u < 2; ++u) {
+    const int jj = 2 * warp + u;
     const int ch = 128 * slice + 32 * (jj >> 2) + 8 * (g >> 1) + 2 * (jj & 3) + (g & 1);
     const float sc = __ldg(scale + ch), sh = __ldg(shift + ch);
+    uint32_t bw[2][2];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
@@ -118,22 +129,45 @@ __global__ void __launch_bounds__(256, 2) conv_in_mma_kernel(const float* __rest
             v[e] = sh - bf16_hi(sh);
           }
         }
-        bw[ks][jj][r] = pack_bf16x2(v[0], v[1]);
+        bw[ks][r] = pack_bf16x2(v[0], v[1]);
       }
+    s_bw[jj >> 2][jj & 3][lane] = make_uint4(bw[0][0], bw[0][1], bw[1][0], bw[1][1]);
   }
-  const int mtx = W >> 4, tiles_y = H / kCiRows, n_tiles = n_img * tiles_y;
-  int buf = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
-    const int n = tile / tiles_y, y0 = (tile - n * tiles_y) * kCiRows;
-    float* sx = s_x[buf];
-    for (int i = threadIdx.x; i < (kCiRows + 2) * W; i += blockDim.x) {
-      const int rr = i / W, cc = i - rr * W, yy = y0 - 1 + rr;
-      sx[rr * kCiPitch + cc + 1] = (yy >= 0 && yy < H) ? __ldg(x + ((size_t)n * H + yy) * W + cc) : 0.f;
+  __syncthreads();  // the only block-wide barrier: the weight fragments
+  const int mtx = W >> 4, tiles_y = H / kCiRows;
+  const int n_units = n_img * tiles_y * parts, groups = kCiRows * mtx / parts;
+  const int csh = 29 - __clz(W);  // log2(W / 4): 16-byte chunks per row (W = 16 / 32 / 64)
+  const int halo_chunks = (kCiRows + 2) << csh;
+  const int stride = gridDim.x * 8;
+  // the unit's halo rows -> shared memory in 16-byte cp.async chunks (rows outside the image are zero-filled by a
+  // zero source size; the border columns keep the zeros written above)
+  auto fetch = [&](int unit, float* dst) {
+    const int tile = unit / parts, n = tile / tiles_y, y0 = (tile - n * tiles_y) * kCiRows;
+    const float* img = x + (size_t)n * H * W;
+#pragma unroll
+    for (int j = 0; j < kCiLoads; ++j) {
+      const int i = lane + 32 * j, rr = i >> csh, cc = (i - (rr << csh)) * 4, yy = y0 - 1 + rr;
+      if (i < halo_chunks) {
+        const bool in = yy >= 0 && yy < H;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst + rr * kCiPitch + cc + 4)),
+                     "l"(img + (in ? yy * W + cc : 0)), "r"(in ? 16 : 0)
+                     : "memory");
+      }
     }
-    __syncthreads();  // one barrier per tile: the other buffer is rewritten only after the NEXT barrier
-    for (int tk = warp; tk < kCiRows * mtx; tk += 8) {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int unit = blockIdx.x * 8 + warp, buf = 0;
+  if (unit < n_units) fetch(unit, sx);
+  for (; unit < n_units; unit += stride, buf ^= 1) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();  // this unit's halo is visible to every lane, and every lane has left the previous unit's buffer
+    if (unit + stride < n_units) fetch(unit + stride, sx + (buf ^ 1) * kCiHalo);  // in flight under the MMAs below
+    const float* sxb = sx + buf * kCiHalo;
+    const int tile = unit / parts, part = unit - tile * parts;
+    const int n = tile / tiles_y, y0 = (tile - n * tiles_y) * kCiRows;
+    for (int tk = part * groups; tk < (part + 1) * groups; ++tk) {
       const int r_loc = tk / mtx, x0 = (tk - r_loc * mtx) * 16 + g;
-      const float* px = sx + r_loc * kCiPitch + x0;
+      const float* px = sxb + r_loc * kCiPitch + x0;
       float av[2][8];  // [pixel row g / g+8][slot]
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -156,22 +190,24 @@ __global__ void __launch_bounds__(256, 2) conv_in_mma_kernel(const float* __rest
         float acc[4][4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+          const uint4 b = s_bw[s4][q][lane];
           acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
-          mma_bf16_m16n8k16(acc[q], a[0][0], a[0][1], a[0][2], a[0][3], bw[0][4 * s4 + q][0], bw[0][4 * s4 + q][1]);
-          mma_bf16_m16n8k16(acc[q], a[1][0], a[1][1], a[1][2], a[1][3], bw[1][4 * s4 + q][0], bw[1][4 * s4 + q][1]);
+          mma_bf16_m16n8k16(acc[q], a[0][0], a[0][1], a[0][2], a[0][3], b.x, b.y);
+          mma_bf16_m16n8k16(acc[q], a[1][0], a[1][1], a[1][2], a[1][3], b.z, b.w);
         }
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           uint4 v;
-          v.x = pack_bf16x2(acc[0][2 * r], acc[0][2 * r + 1]);
-          v.y = pack_bf16x2(acc[1][2 * r], acc[1][2 * r + 1]);
-          v.z = pack_bf16x2(acc[2][2 * r], acc[2][2 * r + 1]);
-          v.w = pack_bf16x2(acc[3][2 * r], acc[3][2 * r + 1]);
           if (RELU) {
-            v.x = bf16x2_max(v.x, 0u);
-            v.y = bf16x2_max(v.y, 0u);
-            v.z = bf16x2_max(v.z, 0u);
-            v.w = bf16x2_max(v.w, 0u);
+            v.x = pack_bf16x2_relu(acc[0][2 * r], acc[0][2 * r + 1]);
+            v.y = pack_bf16x2_relu(acc[1][2 * r], acc[1][2 * r + 1]);
+            v.z = pack_bf16x2_relu(acc[2][2 * r], acc[2][2 * r + 1]);
+            v.w = pack_bf16x2_relu(acc[3][2 * r], acc[3][2 * r + 1]);
+          } else {
+            v.x = pack_bf16x2(acc[0][2 * r], acc[0][2 * r + 1]);
+            v.y = pack_bf16x2(acc[1][2 * r], acc[1][2 * r + 1]);
+            v.z = pack_bf16x2(acc[2][2 * r], acc[2][2 * r + 1]);
+            v.w = pack_bf16x2(acc[3][2 * r], acc[3][2 * r + 1]);
           }
           *reinterpret_cast<uint4*>(o0 + (size_t)(8 * r) * C + 32 * s4) = v;
         }
@@ -193,18 +229,15 @@ __global__ void __launch_bounds__(256, 2) conv_in_mma_kernel(const float* __rest
 // 8 pixels x 64 contiguous bytes.  HBM-bound: 1 MiB in + 16 KiB out per image.
 constexpr int kCoC = 128;
 
-// relu(a * x + b) on 8 bf16 channels, re-packed to bf16x2 (the one rounding of this layer's input).
+// relu(a * x + b) on 8 bf16 channels, re-packed to bf16x2 (the one rounding of this layer's input); the ReLU rides
+// on the conversion (F2FP.RELU), which takes 8 of the 28 instructions per 16 bytes out of an issue-limited loop.
 __device__ __forceinline__ uint4 gn_relu8(const uint4& v, const float4& a0, const float4& a1, const float4& b0,
                                           const float4& b1) {
   uint4 r;
-  r.x = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v.x << 16), a0.x, b0.x), 0.f),
-                    fmaxf(fmaf(__uint_as_float(v.x & 0xffff0000u), a0.y, b0.y), 0.f));
-  r.y = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v.y << 16), a0.z, b0.z), 0.f),
-                    fmaxf(fmaf(__uint_as_float(v.y & 0xffff0000u), a0.w, b0.w), 0.f));
-  r.z = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v.z << 16), a1.x, b1.x), 0.f),
-                    fmaxf(fmaf(__uint_as_float(v.z & 0xffff0000u), a1.y, b1.y), 0.f));
-  r.w = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v.w << 16), a1.z, b1.z), 0.f),
-                    fmaxf(fmaf(__uint_as_float(v.w & 0xffff0000u), a1.w, b1.w), 0.f));
+  r.x = pack_bf16x2_relu(fmaf(__uint_as_float(v.x << 16), a0.x, b0.x), fmaf(__uint_as_float(v.x & 0xffff0000u), a0.y, b0.y));
+  r.y = pack_bf16x2_relu(fmaf(__uint_as_float(v.y << 16), a0.z, b0.z), fmaf(__uint_as_float(v.y & 0xffff0000u), a0.w, b0.w));
+  r.z = pack_bf16x2_relu(fmaf(__uint_as_float(v.z << 16), a1.x, b1.x), fmaf(__uint_as_float(v.z & 0xffff0000u), a1.y, b1.y));
+  r.w = pack_bf16x2_relu(fmaf(__uint_as_float(v.w << 16), a1.z, b1.z), fmaf(__uint_as_float(v.w & 0xffff0000u), a1.w, b1.w));
   return r;
 }
 
@@ -707,18 +740,26 @@ using namespace cdm;
 
 extern "C" int cdm_conv_in(const cdm_conv_in_args* a, void* stream) {
   CDM_CHECK_ARG(a && a->x && a->weight && a->scale && a->shift && a->out);
-  CDM_CHECK_ARG(a->n_img > 0 && a->H > 0 && a->H % kCiRows == 0 && a->W > 0 && a->W % 16 == 0 && a->W <= kCiMaxW);
+  CDM_CHECK_ARG(a->n_img > 0 && a->H > 0 && a->H % kCiRows == 0 && (a->W == 16 || a->W == 32 || a->W == kCiMaxW));
+  CDM_CHECK_ARG(((uintptr_t)a->x & 15) == 0);  // the halo rows are copied in 16-byte chunks
   CDM_CHECK_ARG(a->cout > 0 && a->cout % 128 == 0 && a->cout <= 512);
   int rc = check_device();
   if (rc) return rc;
-  const int tiles = a->n_img * (a->H / kCiRows);
-  const dim3 grid(tiles < num_sms() * 2 ? tiles : num_sms() * 2, a->cout / 128);
+  // Work unit = 1/parts of a 4-row tile, one warp each.  Large launches take whole tiles (the halo is staged once per
+  // tile); `parts` doubles while the units would not give every resident warp about six turns (tail quantisation)
+  // and for small launches (batch-1 sampling: 16 tiles) until the units spread over the machine.
+  const int tiles = a->n_img * (a->H / kCiRows), groups = kCiRows * (a->W / 16);
+  const int warps = num_sms() * kCiCtasPerSm * 8;
+  int parts = 1;
+  while (groups % (parts * 2) == 0 && (long long)tiles * parts < 6LL * warps) parts *= 2;
+  const int units = tiles * parts, ctas = (units + 7) / 8;
+  const dim3 grid(ctas < num_sms() * kCiCtasPerSm ? ctas : num_sms() * kCiCtasPerSm, a->cout / 128);
   if (a->relu)
     conv_in_mma_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(a->x, a->n_img, a->H, a->W, a->cout, a->weight,
-                                                                     a->scale, a->shift, (bf16*)a->out);
+                                                                     a->scale, a->shift, (bf16*)a->out, parts);
   else
     conv_in_mma_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(a->x, a->n_img, a->H, a->W, a->cout, a->weight,
-                                                                      a->scale, a->shift, (bf16*)a->out);
+                                                                      a->scale, a->shift, (bf16*)a->out, parts);
   CDM_CHECK_LAUNCH();
   return CDM_OK;
 }
