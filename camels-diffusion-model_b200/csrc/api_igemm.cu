@@ -387,6 +387,18 @@ int gemm_prepare(const cdm_gemm_args* a, GemmLaunch* G) {
     const int groups_per_cta = (q.n_groups + sms - 1) / sms;
     G->grid = many_n ? (q.n_groups + groups_per_cta - 1) / groups_per_cta : (sms / q.n_groups) * q.n_groups;
     G->variant = 1;
+    G->out = G->a0;
+    if (a->out_mode == 1) {
+      // out[img][2h + kh][2w + kw][128] = five dimensions {c, kw, w, kh, img*H + h}; an epilogue warp stores its 32
+      // consecutive rows m (pixels) x 64 channels as one box
+      const int W = a->W, bw = W >= 32 ? 32 : W;
+      CDM_CHECK_ARG(32 % bw == 0 && a->M % bw == 0);
+      uint64_t dims[5] = {128, 2, (uint64_t)W, 2, (uint64_t)(a->M / W)};
+      uint64_t str[4] = {256, 512, (uint64_t)512 * W, (uint64_t)1024 * W};
+      uint32_t box[5] = {64, 1, (uint32_t)bw, 1, (uint32_t)(32 / bw)};
+      rc = make_tmap_bf16(&G->out, a->out, 5, dims, str, box);
+      if (rc) return rc;
+    }
     return CDM_OK;
   }
   GemmKParams& p = G->p;
@@ -428,7 +440,7 @@ int gemm_launch(const GemmLaunch& G, cudaStream_t st) {
   if (G.variant == 1) {
     constexpr int smem_b = gemm_bres_smem_bytes();
     if ((rc = set_smem_attr(gemm_bres_kernel, 8, smem_b))) return rc;
-    gemm_bres_kernel<<<G.grid, kBresThreads, smem_b, st>>>(G.a0, G.a1, G.b, G.q);
+    gemm_bres_kernel<<<G.grid, kBresThreads, smem_b, st>>>(G.a0, G.a1, G.b, G.out, G.q);
     CDM_CHECK_LAUNCH();
     return CDM_OK;
   }

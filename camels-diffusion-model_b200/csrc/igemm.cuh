@@ -1130,18 +1130,20 @@ __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const float* __
 constexpr int kBresStages = 4;
 constexpr int kBresStageTile = 32 * 128;  // per epilogue warp: 32 rows x 128 B of bf16 output, 16-byte chunks XOR-swizzled
 constexpr int gemm_bres_smem_bytes() {
-  return 131072 + kBresStages * 16384 + 256 + 1024 + 8 * kBresStageTile + 1024;
+  return 131072 + kBresStages * 16384 + 8 * kBresStageTile + 256 + 1024 + 1024;
 }
 
 constexpr int kBresThreads = 128 + 8 * 32;  // 4 role warps + 8 epilogue warps (one set of 4 per resident n-tile)
 __global__ void __launch_bounds__(kBresThreads, 1)
 gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                 const __grid_constant__ CUtensorMap mapB, const GemmBresKParams p) {
+                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
+                 const GemmBresKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smemW = smem;            // [n_res][chunks][128 rows][64 ch]
   uint8_t* smemA = smem + 131072;   // ring of [128 rows][64 ch]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smemA + kBresStages * 16384);
+  uint8_t* smemStage = smemA + kBresStages * 16384;  // 8 x kBresStageTile, 1024-byte aligned (TMA-store source boxes)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemStage + 8 * kBresStageTile);
   uint64_t* full = bars;
   uint64_t* empty = full + kBresStages;
   uint64_t* t_full = empty + kBresStages;
@@ -1150,7 +1152,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint64_t* w_free = w_ready + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_free + 1);
   float* s_shift = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);  // [n_res][128], 16-byte aligned
-  const uint32_t stage_base = smem_u32(reinterpret_cast<uint8_t*>(bars) + 256 + 1024);  // 8 x kBresStageTile
+  const uint32_t stage_base = smem_u32(smemStage);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < p.n_res * 128; i += blockDim.x)
     s_shift[i] = p.shift[(((blockIdx.x % p.n_groups) * p.n_res) * 128 + i) % p.shift_mod];
@@ -1262,19 +1264,50 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         const int n_tile = n_tile0 + nt;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.n_res + nt) * 128);
         const float* shift = s_shift + nt * 128;  // shared memory: broadcast reads, no global-load latency
+        if (p.out_mode == 1) {
+          // Pixel-shuffle output through the TMA engine (UTMASTG): the staging tile in the layout above IS a
+          // 128-byte-swizzle box {64 ch, kw 1, 32 px (or W px x 32/W rows), kh 1} of the output seen as
+          // [img*H + h][kh][w][kw][128 ch]: this warp's 32 consecutive rows m are 32 consecutive pixels.  One elected
+          // lane stores 4 KB per half instead of eight 16-byte loads + stores per lane (the LSU's shared-memory
+          // wavefronts, at 50 % of their peak in ncu, halve), and the store leaves while the next half is read.
+          const int m0 = mt * 128 + q * 32;
+          const int w0 = p.W >= 32 ? (m0 & (p.W - 1)) : 0, hh0 = m0 >> p.w_shift;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            if (lane == 0) tma_store_wait_read<0>();  // the previous store has left the staging tile
+            __syncwarp();
+#pragma unroll 1
+            for (int c2 = 0; c2 < 2; ++c2) {
+              const int col0 = (half * 2 + c2) * 32;
+              uint32_t v[32];
+              tmem_ld_x32(taddr + col0, v);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 s0 = *reinterpret_cast<const float4*>(shift + col0 + j * 8);
+                const float4 s1 = *reinterpret_cast<const float4*>(shift + col0 + j * 8 + 4);
+                const int chunk = c2 * 4 + j;
+                st_shared_v4(stage + (uint32_t)(lane * 128 + ((chunk ^ (lane & 7)) << 4)),
+                             pack_bf16x2(__uint_as_float(v[j * 8 + 0]) + s0.x, __uint_as_float(v[j * 8 + 1]) + s0.y),
+                             pack_bf16x2(__uint_as_float(v[j * 8 + 2]) + s0.z, __uint_as_float(v[j * 8 + 3]) + s0.w),
+                             pack_bf16x2(__uint_as_float(v[j * 8 + 4]) + s1.x, __uint_as_float(v[j * 8 + 5]) + s1.y),
+                             pack_bf16x2(__uint_as_float(v[j * 8 + 6]) + s1.z, __uint_as_float(v[j * 8 + 7]) + s1.w));
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && m0 < p.M) {
+              tma_store_5d(&mapOut, stage, half * 64, n_tile & 1, w0, n_tile >> 1, hh0);
+              tma_store_commit();
+            }
+          }
+          continue;
+        }
         size_t row_off[8];  // element offset of the eight rows this lane stores (row = sub_row + 4*it); ~0 = beyond M
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int m = mt * 128 + q * 32 + sub_row + 4 * it;
-          if (m >= p.M) {
-            row_off[it] = ~(size_t)0;
-          } else if (p.out_mode == 0) {
-            row_off[it] = (size_t)m * p.N + n_tile * 128;
-          } else {
-            const int w = m & (p.W - 1), h = (m >> p.w_shift) & (p.H - 1), img = m >> (p.w_shift + p.h_shift);
-            const int kh = n_tile >> 1, kw = n_tile & 1;
-            row_off[it] = (((size_t)img * 2 * p.H + 2 * h + kh) * (2 * p.W) + 2 * w + kw) * 128;
-          }
+          row_off[it] = m >= p.M ? ~(size_t)0 : (size_t)m * p.N + n_tile * 128;  // out_mode 0: plain row-major
         }
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
@@ -1311,6 +1344,7 @@ gemm_bres_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[buf]);
     }
+    if (lane == 0) tma_store_wait_read<0>();  // the staging tiles are read before the CTA's shared memory goes
   }
   tc_fence_before();
   __syncthreads();

@@ -21,6 +21,7 @@ int conv_launch(const ConvLaunch& L, cudaStream_t st);
 
 struct GemmLaunch {
   CUtensorMap a0, a1, b;
+  CUtensorMap out;    // variant 1, out_mode 1: the pixel-shuffled output as [img*H + h][kh][w][kw][128 ch] (TMA store)
   GemmKParams p;      // variant 0: streaming gemm_kernel (+ split-K reduce)
   GemmBresKParams q;  // variant 1: resident-weight gemm_bres_kernel
   int variant, grid, M;
