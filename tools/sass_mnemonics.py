@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "camels-diffusion-model_b200", "libcdm_b200.so")
 KEEP = ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR", "HMMA", "SYNCS", "REDUX", "RED", "ATOM", "ATOMG")
 HEAD = """SASS mnemonics per kernel of libcdm_b200.so (cuobjdump -sass, sm_100a), tensor/TMA-relevant ones only:
-UTCHMMA = tcgen05.mma (kind::f16), UTMALDG = TMA tensor load, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit,
+UTCHMMA = tcgen05.mma (kind::f16), UTMALDG = TMA tensor load, UTMASTG = TMA tensor store, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit,
 HMMA = mma.sync (first/last convolution), SYNCS = mbarrier ops, RED/ATOM = global reductions / atomics.
 """
 
