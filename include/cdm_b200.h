@@ -142,9 +142,11 @@ typedef struct {
 int cdm_gemm(const cdm_gemm_args* a, void* stream);
 
 /* init_conv.conv1: nn.Conv2d(1, cout, 3, 1, 1) + eval BatchNorm2d + ReLU
- * (code/diffusion_utilities.py:26-30 with in_channels=1, ContextUnet.py:14). fp32 math. */
+ * (code/diffusion_utilities.py:26-30 with in_channels=1, ContextUnet.py:14). fp32 math.
+ * W is 16, 32 or 64, H a multiple of 4, cout a multiple of 128 (<= 512); x is 16-byte aligned (its rows are copied
+ * in 16-byte chunks); anything else returns CDM_ERR_ARG. */
 typedef struct {
-  const float* x; /* fp32 [n_img][H][W] */
+  const float* x; /* fp32 [n_img][H][W], 16-byte aligned */
   int n_img, H, W;
   const float* weight; /* fp32 [9][cout], tap-major */
   int cout;
