@@ -333,6 +333,18 @@ def ctypes_sizeof(cls):
     return ctypes.sizeof(cls)
 
 
+def test_integration_md_stub_is_the_real_struct(lib):
+    """The ctypes stub INTEGRATION.md shows a maintainer (cdm_conv3x3_args) has the fields of the binding that the
+    layout test above holds to the header — a stub one field short makes the library read past the caller's struct
+    (round-1 finding)."""
+    import re
+    txt = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blk = txt[txt.index("class Conv3x3Args"):txt.index("def conv_bn_relu")]
+    doc = re.findall(r'\("(\w+)", C\.(\w+)\)', blk)
+    real = [(n, t.__name__) for n, t in lib.Conv3x3Args._fields_]
+    assert doc == real
+
+
 def test_oracle_equals_the_live_reference_modules():
     """oracle/_ref (the unmodified reference modules, placed by oracle/build_ref.py) against the oracle restatement,
     live: same seeded weights, same inputs, the same fresh-shortcut draws -> eps identical to fp32 round-off; and the
