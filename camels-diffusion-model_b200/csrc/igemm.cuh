@@ -417,13 +417,18 @@ template <int ROWS>
 struct SwCfg {
   static constexpr int kHalo = ROWS + 2, kNPix = 8 * ROWS, kABytes = kHalo * kSwPitch * 128;
   static constexpr int kAStride = (kABytes + 1023) / 1024 * 1024, kChunksPerHalf = ROWS / 8;
+  // Weight ring depth.  ROWS = 32: 4 stages (see below).  ROWS = 8 (the latency shape: one unit per CTA, N = 64): a
+  // 16 KB weight tile is consumed in 4 short MMAs (~70 ns) but takes an L2 round trip (~1 us) to arrive, so with 4
+  // stages the 18 (K = 1152) or 36 (K = 2304) tiles of a unit arrive in 4.5 / 9 latency-bound turns of the ring;
+  // the small halo tiles leave room for 9 stages = 144 KB in flight, which turns the stream bandwidth-bound (and,
+  // under PDL, lets half of a layer's weights arrive while the previous kernel drains).
+  static constexpr int kNB = ROWS == 8 ? 9 : 4;
 };
 constexpr int kSwEpiWarps = 8, kSwThreads = 128 + 32 * kSwEpiWarps;
-// Weight ring: 4 stages.  The issuer is blocked on it ~30 % of its cycles (tools/gpu_probe.py waits), but that is
+// Weight ring (ROWS = 32): 4 stages.  The issuer is blocked on it ~30 % of its cycles (tools/gpu_probe.py waits), but that is
 // back-pressure from the tensor pipe, not TMA latency: 6 stages changed neither the wait share nor the run time.
 // The shape itself is at the shared-memory limit: operand reads 12 KB / 128 clk = 96 B/clk plus TMA fills
 // (16 KB weights / 512 clk + 43.5 KB halo / 4608 clk = 41 B/clk) against 128 B/clk per SM.
-constexpr int kSwNB = 4;
 // TMAST (TMA-store epilogue): the NHWC output leaves through shared memory + cp.async.bulk.tensor stores.  A store box
 // is {64 ch, 8 px, 4 rows} = 32 rows of 128 B (one 32-pixel accumulator chunk of one channel half), written by the
 // two epilogue warps that own those 64 channels; 4 warp pairs x 2 buffers x 4 KB of staging replace the scale/shift
@@ -431,7 +436,7 @@ constexpr int kSwNB = 4;
 constexpr int kSwStoreBox = 32 * 128, kSwStageBytes = 4 * 2 * kSwStoreBox;
 template <int ROWS, bool TMAST = false>
 constexpr int conv_sw_smem_bytes() {
-  return kSwNA * SwCfg<ROWS>::kAStride + kSwNB * kBBytes + (TMAST ? kSwStageBytes : 2 * 256 * 4) + 256 + 1024;
+  return kSwNA * SwCfg<ROWS>::kAStride + SwCfg<ROWS>::kNB * kBBytes + (TMAST ? kSwStageBytes : 2 * 256 * 4) + 256 + 1024;
 }
 
 template <int ROWS, bool TMAST = false>
@@ -440,6 +445,7 @@ conv3x3_sw_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                   const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
                   const ConvKParams p) {
   constexpr int kSwABytes = SwCfg<ROWS>::kABytes, kSwAStride = SwCfg<ROWS>::kAStride, kNPix = SwCfg<ROWS>::kNPix;
+  constexpr int kSwNB = SwCfg<ROWS>::kNB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smemA = smem;  // pixel halo tiles

@@ -388,43 +388,59 @@ __global__ void __launch_bounds__(256) avgpool_gelu_kernel(const bf16* __restric
   }
 }
 
-// Vectorised form for C % 8 == 0 and 256 % (C / 8) == 0 (C = 128, 256): a thread owns 8 consecutive channels
-// (one 16-byte load per pixel) of every (256 / (C/8))-th pixel, four loads in flight; the row groups are then
-// added in a fixed order through shared memory (deterministic).
-__global__ void __launch_bounds__(256) avgpool_gelu_vec_kernel(const bf16* __restrict__ src, int P, int C,
-                                                               bf16* __restrict__ out) {
-  __shared__ float red[256][8];
+// Vectorised form for C % 8 == 0 and C / 8 a divisor of 256 (C = 128, 256): a thread owns 8 consecutive channels
+// (one 16-byte load per pixel) of the pixels p = j (mod 32) for JPT of the 32 residues j; each residue's pixels are
+// added in increasing order into ITS OWN partial sum, and the 32 partials are then added in the order j = 0..31
+// through shared memory.  The arithmetic is therefore the same for every JPT: the launch picks 32 / JPT * (C / 8)
+// threads per image — 256 threads (JPT = 4 at C = 256, four loads in flight) when there are images enough to fill the
+// machine, 1024 (JPT = 1, all of a thread's pixels in flight at once) for small batches, where one block per image
+// walking 128 KB in eight dependent round trips took 21 us of the 245 us batch-1 sampling step.
+template <int JPT>
+__global__ void __launch_bounds__(1024 / JPT) avgpool_gelu_vec_kernel(const bf16* __restrict__ src, int P, int C,
+                                                                      bf16* __restrict__ out) {
+  extern __shared__ float av_red[];  // [32][C]
   const size_t n = blockIdx.x;
-  const int vecs = C >> 3, rows = 256 / vecs;
+  const int vecs = C >> 3, rows = 32 / JPT;
   const int v = threadIdx.x % vecs, r = threadIdx.x / vecs;
   const bf16* base = src + n * P * C + v * 8;
-  float s[8];
+  float s[JPT][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s[j] = 0.f;
-  for (int p0 = r; p0 < P; p0 += 4 * rows) {
-    uint4 raw[4];
+  for (int u = 0; u < JPT; ++u)
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int p = p0 + u * rows;
-      raw[u] = p < P ? __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * C)) : make_uint4(0u, 0u, 0u, 0u);
-    }
+    for (int j = 0; j < 8; ++j) s[u][j] = 0.f;
+  constexpr int kDepth = JPT == 1 ? 8 : 1;  // pixels of one residue in flight together
+  for (int p0 = r; p0 < P; p0 += 32 * kDepth) {
+    uint4 raw[kDepth][JPT];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float f[8];
-      unpack8(raw[u], f);
+    for (int d = 0; d < kDepth; ++d)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s[j] += f[j];
-    }
+      for (int u = 0; u < JPT; ++u) {
+        const int p = p0 + 32 * d + u * rows;
+        raw[d][u] = p < P ? __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * C)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d)
+#pragma unroll
+      for (int u = 0; u < JPT; ++u) {
+        float f[8];
+        unpack8(raw[d][u], f);
+        if (p0 + 32 * d + u * rows < P) {  // (an absent pixel must not even add +0: -0 + +0 would flip a sign bit)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s[u][j] += f[j];
+        }
+      }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = s[j];
+  for (int u = 0; u < JPT; ++u)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) av_red[((r + u * rows) * vecs + v) * 8 + j] = s[u][j];
   __syncthreads();
   if (r == 0) {
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float t = 0.f;
-      for (int q = 0; q < rows; ++q) t += red[q * vecs + v][j];
+      for (int q = 0; q < 32; ++q) t += av_red[(q * vecs + v) * 8 + j];
       f[j] = gelu_erf(t / (float)P);
     }
     *reinterpret_cast<uint4*>(out + n * C + v * 8) = pack8(f);
@@ -806,8 +822,14 @@ extern "C" int cdm_avgpool_gelu(const void* src, int n_img, int P, int C, void* 
   CDM_CHECK_ARG(src && out && n_img > 0 && P > 0 && C > 0);
   int rc = check_device();
   if (rc) return rc;
-  if (C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0)
-    avgpool_gelu_vec_kernel<<<n_img, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, P, C, (bf16*)out);
+  if (C % 8 == 0 && C / 8 <= 32 && 32 % (C / 8) == 0) {  // C = 8 .. 256: 32 residues x C / 8 vectors <= 1024 threads
+    const int vecs = C / 8;
+    const size_t smem = (size_t)32 * C * sizeof(float);
+    if (n_img > 2 * num_sms() && (8 * vecs) % 32 == 0)
+      avgpool_gelu_vec_kernel<4><<<n_img, 8 * vecs, smem, (cudaStream_t)stream>>>((const bf16*)src, P, C, (bf16*)out);
+    else
+      avgpool_gelu_vec_kernel<1><<<n_img, 32 * vecs, smem, (cudaStream_t)stream>>>((const bf16*)src, P, C, (bf16*)out);
+  }
   else
     avgpool_gelu_kernel<<<n_img, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, P, C, (bf16*)out);
   CDM_CHECK_LAUNCH();
